@@ -1,0 +1,55 @@
+/*
+ * dorktracer_host.h — C ABI of the host-side mirror ("libdthost.so") of the reference's scene layer.
+ *
+ * The reference keeps its own tinyxml2/happly parser and Scene/Camera/Material/light classes
+ * (src/parser.cpp, src/scene.h); a maintainer wires those to dorktracer.h with the stub in INTEGRATION.md.
+ * /root/reference does not travel to the GPU box and its sources may not be copied, so this library is an
+ * independent C++ restatement of exactly that layer — Scene::loadFromXml (parser.cpp:26-577), the face /
+ * transform / bbox helpers (parser.cpp:579-826), parse{Cameras,Lights,BRDFs,Materials,Meshes}
+ * (parser.cpp:828-1636), Camera::Setup* (camera.cpp:5-72) and Mesh::ConstructBVH (mesh.cpp:23-156) — whose
+ * only output is the flat dt_scene_desc / dt_camera_desc the hot path consumes.  It does no rendering.
+ */
+#ifndef DORKTRACER_HOST_H
+#define DORKTRACER_HOST_H
+
+#include "dorktracer.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dth_scene dth_scene;     /* opaque: owns every array the returned descs point into */
+
+/* Scene::loadFromXml (parser.cpp:26).  Relative plyFile / image paths are tried against the current
+ * directory first (as the reference does) and then against the XML file's directory. */
+int dth_scene_load_xml(const char* xml_path, dth_scene** out);
+void dth_scene_free(dth_scene* scene);
+
+const dt_scene_desc* dth_scene_desc(const dth_scene* scene);
+int dth_scene_num_cameras(const dth_scene* scene);
+const dt_camera_desc* dth_scene_camera(const dth_scene* scene, int index);
+const char* dth_scene_camera_image_name(const dth_scene* scene, int index);
+
+/* Replace the pixel data of image `index` (for image formats this library does not decode itself:
+ * the caller decodes and hands over raw pixels; the data is copied). */
+int dth_scene_set_image(dth_scene* scene, int index, int width, int height, int channels, int is_hdr,
+                        const void* data);
+/* File name of image `index` as written in the XML, and whether the loader could decode it itself. */
+const char* dth_scene_image_path(const dth_scene* scene, int index);
+int dth_scene_image_loaded(const dth_scene* scene, int index);
+
+/* Camera::SetupLookAt / SetupDefault (camera.cpp:5-72) for callers that build cameras programmatically. */
+int dth_camera_look_at(const float pos[3], const float gaze_point[3], const float up[3], float near_dist,
+                       float fov_y, int width, int height, dt_camera_desc* out);
+int dth_camera_default(const float pos[3], const float gaze_dir[3], const float up[3], const float near_plane[4],
+                       float near_dist, int width, int height, dt_camera_desc* out);
+
+/* Minimal image writers for the stand-alone driver (main.cpp:191-195 uses stb_image_write). */
+int dth_write_png(const char* path, int width, int height, const uint8_t* rgb);
+
+const char* dth_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,140 @@
+"""Checker-side helpers: the C oracle (oracle/libdtoracle.so) and the compiled reference (oracle/_ref).
+
+TEST INFRASTRUCTURE ONLY — nothing under advanced-cpu-raytracing_b200/ imports this.
+"""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(REPO, "advanced-cpu-raytracing_b200"))
+
+from dtb200 import capi  # noqa: E402
+
+REF_DIR = os.path.join(REPO, "oracle", "_ref")
+REF_BIN = os.path.join(REF_DIR, "raytracer")
+REF_PROBE = os.path.join(REF_DIR, "raytracer_probe")
+
+
+def have_ref():
+    return os.path.exists(REF_BIN) and os.path.exists(REF_PROBE)
+
+
+def oracle_render(host_scene, cam, seed=1234, threads=None, want_hdr=True):
+    lib = capi.load_dtoracle()
+    W, H = cam.width, cam.height
+    ldr = np.zeros((H, W, 3), np.uint8)
+    hdr = np.zeros((H, W, 3), np.float32) if want_hdr else None
+    stats = capi.dt_stats()
+    rc = lib.dto_render(host_scene.desc_ptr, C.byref(cam), seed, threads or (os.cpu_count() or 1),
+                        ldr.ctypes.data_as(C.c_void_p), hdr.ctypes.data_as(C.c_void_p) if hdr is not None else None, C.byref(stats))
+    if rc != 0:
+        raise RuntimeError("dto_render failed %d" % rc)
+    return ldr, hdr, stats
+
+
+def oracle_primary_hits(host_scene, cam):
+    lib = capi.load_dtoracle()
+    n = cam.width * cam.height
+    shape = np.empty(n, np.int32); face = np.empty(n, np.int32); t = np.empty(n, np.float32)
+    rc = lib.dto_primary_hits(host_scene.desc_ptr, C.byref(cam), shape.ctypes.data_as(C.c_void_p),
+                              face.ctypes.data_as(C.c_void_p), t.ctypes.data_as(C.c_void_p))
+    if rc != 0:
+        raise RuntimeError("dto_primary_hits failed %d" % rc)
+    return shape, face, t
+
+
+def oracle_trace_closest(host_scene, origins, dirs):
+    lib = capi.load_dtoracle()
+    origins = np.ascontiguousarray(origins, np.float32); dirs = np.ascontiguousarray(dirs, np.float32)
+    n = origins.shape[0]
+    shape = np.empty(n, np.int32); face = np.empty(n, np.int32); t = np.empty(n, np.float32)
+    rc = lib.dto_trace_closest(host_scene.desc_ptr, origins.ctypes.data_as(C.c_void_p), dirs.ctypes.data_as(C.c_void_p), n,
+                               shape.ctypes.data_as(C.c_void_p), face.ctypes.data_as(C.c_void_p), t.ctypes.data_as(C.c_void_p))
+    assert rc == 0
+    return shape, face, t
+
+
+def oracle_trace_occluded(host_scene, origins, dirs, tmax):
+    lib = capi.load_dtoracle()
+    origins = np.ascontiguousarray(origins, np.float32); dirs = np.ascontiguousarray(dirs, np.float32)
+    tmax = np.ascontiguousarray(tmax, np.float32)
+    n = origins.shape[0]
+    occ = np.empty(n, np.uint8)
+    rc = lib.dto_trace_occluded(host_scene.desc_ptr, origins.ctypes.data_as(C.c_void_p), dirs.ctypes.data_as(C.c_void_p),
+                                tmax.ctypes.data_as(C.c_void_p), n, occ.ctypes.data_as(C.c_void_p))
+    assert rc == 0
+    return occ
+
+
+def oracle_tonemap(hdr, key, burn, saturation, gamma):
+    lib = capi.load_dtoracle()
+    hdr = np.ascontiguousarray(hdr, np.float32)
+    H, W = hdr.shape[:2]
+    ldr = np.zeros((H, W, 3), np.uint8)
+    rc = lib.dto_tonemap(hdr.ctypes.data_as(C.c_void_p), W, H, key, burn, saturation, gamma, ldr.ctypes.data_as(C.c_void_p))
+    assert rc == 0
+    return ldr
+
+
+def run_reference(xml_path, probe=True, threads=None, cwd=None, timeout=3600, width_height=None):
+    """Run the compiled reference on an XML scene.  Returns dict(png, hits, hdr, seconds, closest, shadow).
+
+    The reference resolves plyFile / inputs/<image> against the cwd and writes <ImageName> into it, so it is
+    run inside `cwd` (default: the XML's directory if writable, else a temp dir with symlinks)."""
+    from PIL import Image
+    xml_path = os.path.abspath(xml_path)
+    src_dir = os.path.dirname(xml_path)
+    tmp = tempfile.mkdtemp(prefix="dt_refrun_")
+    # mirror the scene directory (symlinks) so relative assets resolve and outputs land in tmp
+    for f in os.listdir(src_dir):
+        os.symlink(os.path.join(src_dir, f), os.path.join(tmp, f))
+    env = dict(os.environ)
+    if threads:
+        env["DT_THREADS"] = str(threads)
+    hits_p = os.path.join(tmp, "_hits.bin"); hdr_p = os.path.join(tmp, "_hdr.bin")
+    if probe:
+        env["DT_DUMP_HITS"] = hits_p
+        env["DT_DUMP_HDR"] = hdr_p
+    exe = REF_PROBE if probe else REF_BIN
+    before = set(os.listdir(tmp))
+    p = subprocess.run([exe, os.path.basename(xml_path)], cwd=tmp, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=timeout)
+    out = p.stdout.decode(errors="replace")
+    if p.returncode != 0:
+        raise RuntimeError("reference failed (%d): %s" % (p.returncode, out[-2000:]))
+    res = {"stdout": out[-4000:]}
+    m = re.search(r"Rendering took: ([0-9.eE+-]+)s", out)
+    res["seconds"] = float(m.group(1)) if m else None
+    m = re.search(r"DT_RAYS closest=(\d+) shadow=(\d+)", out)
+    if m:
+        res["closest"] = int(m.group(1)); res["shadow"] = int(m.group(2))
+    pngs = [f for f in set(os.listdir(tmp)) - before if f.endswith(".png")]
+    if pngs:
+        res["png"] = np.array(Image.open(os.path.join(tmp, pngs[0])).convert("RGB"))
+        H, W = res["png"].shape[:2]
+        if probe and os.path.exists(hits_p):
+            raw = np.fromfile(hits_p, dtype=np.int32).reshape(-1, 3)
+            res["hit_shape"] = raw[:, 0].copy(); res["hit_face"] = raw[:, 1].copy()
+            res["hit_t"] = raw[:, 2].copy().view(np.float32)
+        if probe and os.path.exists(hdr_p):
+            res["hdr"] = np.fromfile(hdr_p, dtype=np.float32).reshape(H, W, 3)
+    import shutil
+    shutil.rmtree(tmp, ignore_errors=True)
+    return res
+
+
+def ldr_mismatch_fraction(a, b, tol=1):
+    d = np.abs(a.astype(np.int32) - b.astype(np.int32)).max(axis=2)
+    return float((d > tol).mean()), int(d.max())
+
+
+def psnr(a, b):
+    mse = np.mean((a.astype(np.float64) - b.astype(np.float64)) ** 2)
+    if mse == 0:
+        return 99.0
+    return float(10 * np.log10(255.0 ** 2 / mse))
