@@ -1,0 +1,641 @@
+// C ABI of the render hot path (include/dorktracer.h): scene upload, wavefront driver, outputs.
+#include "dt_flatten.h"
+#include "dt_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_err;
+int g_device = -1;
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { g_err = std::string(#call) + ": " + cudaGetErrorString(e_); return DT_ERR_CUDA; } } while (0)
+
+int ensure_device() {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        g_err = std::string("no CUDA device available (") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0") + "); this library has no CPU fallback";
+        return DT_ERR_NO_DEVICE;
+    }
+    if (g_device < 0) g_device = 0;
+    if (g_device >= n) { g_err = "CUDA device index out of range"; return DT_ERR_NO_DEVICE; }
+    e = cudaSetDevice(g_device);
+    if (e != cudaSuccess) { g_err = std::string("cudaSetDevice: ") + cudaGetErrorString(e); return DT_ERR_CUDA; }
+    return DT_OK;
+}
+
+template <class T>
+int upload(std::vector<void*>& allocs, const T* src, size_t n, const T** dst, size_t pad_elems = 0) {
+    *dst = nullptr;
+    size_t bytes = std::max<size_t>((n + pad_elems) * sizeof(T), 16);
+    void* p = nullptr;
+    CK(cudaMalloc(&p, bytes));
+    allocs.push_back(p);
+    CK(cudaMemset(p, 0, bytes));
+    if (n) CK(cudaMemcpy(p, src, n * sizeof(T), cudaMemcpyHostToDevice));
+    *dst = (const T*)p;
+    return DT_OK;
+}
+
+struct Timer {
+    cudaEvent_t a = nullptr, b = nullptr;
+    bool armed = false;
+    int init() { CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b)); return DT_OK; }
+    void start(cudaStream_t s) { cudaEventRecord(a, s); }
+    void stop(cudaStream_t s) { cudaEventRecord(b, s); armed = true; }
+    float take() { if (!armed) return 0.f; float ms = 0.f; cudaEventElapsedTime(&ms, a, b); armed = false; return ms; }
+    void destroy() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); a = b = nullptr; }
+};
+
+}  // namespace
+
+struct dt_scene {
+    int device = 0;
+    int num_sms = 148;
+    cudaStream_t stream = nullptr;
+    DtSceneDev dev;
+    std::vector<void*> allocs;
+    uint64_t n_triangles = 0;
+    int lights_shadowed = 0;          // shadow rays per shaded hit
+    int fanout_hint = 0;
+    bool has_env = false;
+
+    // render-time buffers
+    int capacity = 0, shadow_capacity = 0;
+    DtRayQueue q[2];
+    float4* miss[2] = {nullptr, nullptr};
+    DtShadowQueue sq;
+    std::vector<void*> qallocs;
+    int* counters = nullptr;
+    int* h_counters = nullptr;
+    float4* accum = nullptr; size_t accum_pix = 0;
+    float* hdr = nullptr; uint8_t* ldr = nullptr; size_t out_pix = 0;
+    double* tm_logsum = nullptr; unsigned int* tm_hist = nullptr; unsigned long long* tm_rank = nullptr; uint32_t* tm_prefix = nullptr;
+    Timer t_total, t_gen, t_closest, t_shadow, t_shade, t_resolve, t_tm;
+    int grid_closest = 0, grid_shadow = 0;
+
+    void free_queues() { for (void* p : qallocs) cudaFree(p); qallocs.clear(); capacity = shadow_capacity = 0; }
+};
+
+namespace {
+
+template <class T>
+int qalloc(dt_scene* s, T** p, size_t n) {
+    void* v = nullptr;
+    CK(cudaMalloc(&v, std::max<size_t>(n * sizeof(T), 16)));
+    s->qallocs.push_back(v);
+    *p = (T*)v;
+    return DT_OK;
+}
+
+int ensure_queues(dt_scene* s, int capacity, int shadow_capacity) {
+    if (s->capacity >= capacity && s->shadow_capacity >= shadow_capacity) return DT_OK;
+    s->free_queues();
+    for (int k = 0; k < 2; k++) {
+        DtRayQueue& q = s->q[k];
+        int rc;
+        if ((rc = qalloc(s, &q.o_time, capacity))) return rc;
+        if ((rc = qalloc(s, &q.d_tmax, capacity))) return rc;
+        if ((rc = qalloc(s, &q.hit0, capacity))) return rc;
+        if ((rc = qalloc(s, &q.hit_face, capacity))) return rc;
+        if ((rc = qalloc(s, &q.pixel, capacity))) return rc;
+        if ((rc = qalloc(s, &q.weight_n, capacity))) return rc;
+        if ((rc = qalloc(s, &q.thr_beer, capacity))) return rc;
+        if ((rc = qalloc(s, &q.misc, capacity))) return rc;
+        q.sort_key = nullptr;
+        s->miss[k] = nullptr;
+        if (s->has_env) { if ((rc = qalloc(s, &s->miss[k], capacity))) return rc; }
+    }
+    int rc;
+    if ((rc = qalloc(s, &s->sq.o_time, shadow_capacity))) return rc;
+    if ((rc = qalloc(s, &s->sq.d_tmax, shadow_capacity))) return rc;
+    if ((rc = qalloc(s, &s->sq.contrib_pix, shadow_capacity))) return rc;
+    if ((rc = qalloc(s, &s->sq.defer, shadow_capacity))) return rc;
+    s->capacity = capacity; s->shadow_capacity = shadow_capacity;
+    return DT_OK;
+}
+
+int ensure_outputs(dt_scene* s, size_t n_pix) {
+    if (s->accum_pix < n_pix) {
+        if (s->accum) cudaFree(s->accum);
+        if (s->hdr) cudaFree(s->hdr);
+        if (s->ldr) cudaFree(s->ldr);
+        s->accum = nullptr; s->hdr = nullptr; s->ldr = nullptr; s->accum_pix = 0;
+        CK(cudaMalloc(&s->accum, n_pix * sizeof(float4)));
+        CK(cudaMalloc(&s->hdr, n_pix * 3 * sizeof(float)));
+        CK(cudaMalloc(&s->ldr, n_pix * 3));
+        s->accum_pix = n_pix;
+    }
+    return DT_OK;
+}
+
+DtCamDev make_cam(const dt_camera_desc* c) {
+    DtCamDev d;
+    memcpy(d.position, c->position, 12); memcpy(d.gaze, c->gaze, 12); memcpy(d.up, c->up, 12); memcpy(d.right, c->right, 12); memcpy(d.q, c->q, 12);
+    d.left = c->left; d.right_ = c->right_; d.bottom = c->bottom; d.top = c->top;
+    d.width = c->width; d.height = c->height; d.spp = c->samples_per_pixel < 1 ? 1 : c->samples_per_pixel;
+    d.focus_distance = c->focus_distance; d.aperture_size = c->aperture_size;
+    d.path_tracing = c->path_tracing; d.importance_sampling = c->importance_sampling; d.nee = c->next_event_estimation; d.russian_roulette = c->russian_roulette;
+    return d;
+}
+
+int check_cam(const dt_camera_desc* c) {
+    if (!c) { g_err = "null camera"; return DT_ERR_INVALID; }
+    if (c->width <= 0 || c->height <= 0 || (long long)c->width * c->height > 0x0FFFFFFF) { g_err = "bad image resolution"; return DT_ERR_INVALID; }
+    return DT_OK;
+}
+
+// Tonemap a device radiance buffer into a device LDR buffer.
+int tonemap_device(dt_scene* s, const float* hdr, int W, int H, float key, float burn, float sat, float gamma, uint8_t* ldr, uint32_t* launches) {
+    const int n_pix = W * H;
+    const size_t n_vals = (size_t)n_pix * 3;
+    cudaStream_t st = s->stream;
+    CK(cudaMemsetAsync(s->tm_logsum, 0, sizeof(double), st));
+    k_tm_logsum<<<s->num_sms * 4, 256, 0, st>>>(hdr, n_pix, s->tm_logsum);
+    (*launches)++;
+    CK(cudaMemsetAsync(s->tm_prefix, 0, sizeof(uint32_t), st));
+    if (burn > 0.01) {
+        // index of the white point in the sorted list of all channel values (tonemapper.h:100-104): evaluated in
+        // FLOAT, (int)(thresholdPerct * lastIdx), so it is itself rounded above 2^24.
+        float thresholdPerct = (100.0f - burn) / 100;
+        int lastIdx = (int)n_vals - 1;
+        int bi = (int)(thresholdPerct * lastIdx);
+        if (bi > lastIdx) bi = lastIdx;
+        if (bi < 0) bi = 0;
+        unsigned long long rank = (unsigned long long)bi;
+        CK(cudaMemcpyAsync(s->tm_rank, &rank, sizeof rank, cudaMemcpyHostToDevice, st));
+        CK(cudaMemsetAsync(s->tm_hist, 0, 256 * sizeof(unsigned int), st));
+        uint32_t mask = 0;
+        for (int pass = 0; pass < 4; pass++) {
+            const int shift = 24 - 8 * pass;
+            // prefix lives on the device; k_tm_hist needs it by value -> read it back (4 tiny syncs per frame)
+            uint32_t prefix = 0;
+            CK(cudaMemcpyAsync(&prefix, s->tm_prefix, 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            k_tm_hist<<<s->num_sms * 8, 256, 0, st>>>(hdr, n_vals, prefix, mask, shift, s->tm_hist);
+            k_tm_pick<<<1, 1, 0, st>>>(s->tm_hist, s->tm_rank, s->tm_prefix, shift);
+            *launches += 2;
+            mask |= 0xFFu << shift;
+        }
+    }
+    k_tm_map<<<(n_pix + 255) / 256, 256, 0, st>>>(hdr, n_pix, s->tm_logsum, s->tm_prefix, key, burn, sat, gamma, ldr);
+    (*launches)++;
+    CK(cudaGetLastError());
+    return DT_OK;
+}
+
+struct RenderOut { float* hdr_dev; };
+
+int render_core(dt_scene* s, const dt_camera_desc* cam, const dt_render_params* params, dt_stats* stats, bool primary_only) {
+    int rc = check_cam(cam);
+    if (rc) return rc;
+    CK(cudaSetDevice(s->device));
+    dt_render_params P; memset(&P, 0, sizeof P); P.seed = 1234; P.tile_world = 1;
+    if (params) P = *params;
+    if (P.tile_world < 1 || P.tile_rank < 0 || P.tile_rank >= P.tile_world) { g_err = "bad tile_rank/tile_world"; return DT_ERR_INVALID; }
+    DtCamDev dc = make_cam(cam);
+    if (primary_only) { dc.spp = 1; }
+    const int W = cam->width, H = cam->height;
+    const size_t n_pix = (size_t)W * H;
+    if ((rc = ensure_outputs(s, n_pix))) return rc;
+
+    DtWaveParams wp;
+    wp.seed_lo = (uint32_t)P.seed; wp.seed_hi = (uint32_t)(P.seed >> 32);
+    wp.tile_rank = P.tile_rank; wp.tile_world = P.tile_world;
+    wp.tiles_x = (W + 7) / 8; wp.tiles_y = (H + 3) / 4;
+    const long long n_tiles = (long long)wp.tiles_x * wp.tiles_y;
+    const long long my_tiles = (n_tiles - P.tile_rank + P.tile_world - 1) / P.tile_world;
+    wp.per_sample = my_tiles * 32;
+    const long long total = wp.per_sample * dc.spp;
+
+    const bool pt = dc.path_tracing != 0 && !primary_only;
+    const bool defer_mode = pt && dc.nee && s->dev.n_mesh_lights > 0;
+    int wave_max = P.max_wave_rays > 0 ? P.max_wave_rays : (1 << 23);
+    wave_max = (int)std::min<long long>(wave_max, std::max<long long>(total, 32));
+    wave_max = (wave_max + 31) & ~31;
+    const int fan = s->fanout_hint + (pt ? 1 : 0);
+    uint32_t retries = 0;
+
+    cudaStream_t st = s->stream;
+    dt_stats S; memset(&S, 0, sizeof S);
+    s->t_total.start(st);
+
+retry:
+    {
+        const int capacity = primary_only ? wave_max : (fan <= 1 ? wave_max : (int)std::min<long long>((long long)wave_max * 4, 1ll << 28));
+        const long long shcap = primary_only ? 32 : std::max<long long>(32, (long long)wave_max * std::max(1, s->lights_shadowed));
+        if (shcap > (1ll << 29)) { g_err = "shadow queue too large; lower max_wave_rays"; return DT_ERR_INVALID; }
+        if ((rc = ensure_queues(s, capacity, (int)shcap))) return rc;
+    }
+    CK(cudaMemsetAsync(s->accum, 0, n_pix * sizeof(float4), st));
+    CK(cudaMemsetAsync(s->counters, 0, DT_CNT_COUNT * sizeof(int), st));
+    {
+        long long next_primary = 0;
+        int count = 0, cur = 0;
+        int prev_shadow = 0;
+        bool overflow = false;
+        S.rays_closest = 0; S.rays_shadow = 0; S.waves = 0; S.kernel_launches = 0; S.launches_traverse_closest = 0;
+        S.ms_generate = S.ms_traverse_closest = S.ms_traverse_shadow = S.ms_shade = 0.f;
+        while (next_primary < total || count > 0) {
+            int n_new = 0;
+            if (count < wave_max && next_primary < total) {
+                n_new = (int)std::min<long long>(wave_max - count, total - next_primary);
+                s->t_gen.start(st);
+                k_generate<<<(n_new + 255) / 256, 256, 0, st>>>(dc, wp, s->q[cur], count, next_primary, n_new, s->accum);
+                s->t_gen.stop(st);
+                S.kernel_launches++;
+                count += n_new; next_primary += n_new;
+            }
+            CK(cudaMemsetAsync(s->counters + DT_CNT_NEXT, 0, sizeof(int), st));
+            CK(cudaMemsetAsync(s->counters + DT_CNT_FETCH_A, 0, 2 * sizeof(int), st));
+            s->t_closest.start(st);
+            k_traverse<false><<<s->grid_closest, 128, 0, st>>>(s->dev, s->q[cur], s->sq, nullptr, count, s->counters + DT_CNT_FETCH_A, s->accum);
+            s->t_closest.stop(st);
+            S.kernel_launches++; S.launches_traverse_closest++;
+            if (primary_only) { CK(cudaStreamSynchronize(st)); S.ms_traverse_closest += s->t_closest.take(); S.ms_generate += s->t_gen.take(); S.waves++; break; }
+            bool shadow_timed = false;
+            if (defer_mode && prev_shadow > 0) {
+                k_filter_deferred<<<(prev_shadow + 255) / 256, 256, 0, st>>>(s->dev, s->sq, prev_shadow, s->q[cur]);
+                s->t_shadow.start(st);
+                k_traverse<true><<<s->grid_shadow, 128, 0, st>>>(s->dev, s->q[cur], s->sq, nullptr, prev_shadow, s->counters + DT_CNT_FETCH_B, s->accum);
+                s->t_shadow.stop(st);
+                shadow_timed = true;
+                S.kernel_launches += 2;
+            }
+            CK(cudaMemsetAsync(s->counters + DT_CNT_SHADOW, 0, sizeof(int), st));
+            s->t_shade.start(st);
+            k_shade<<<(count + 127) / 128, 128, 0, st>>>(s->dev, dc, s->q[cur], s->miss[cur], count, s->q[1 - cur], s->miss[1 - cur], s->capacity,
+                                                         s->sq, s->shadow_capacity, s->counters, s->accum);
+            s->t_shade.stop(st);
+            S.kernel_launches++;
+            if (!defer_mode) {
+                s->t_shadow.start(st);
+                k_traverse<true><<<s->grid_shadow, 128, 0, st>>>(s->dev, s->q[cur], s->sq, s->counters + DT_CNT_SHADOW, 0, s->counters + DT_CNT_FETCH_B, s->accum);
+                s->t_shadow.stop(st);
+                shadow_timed = true;
+                S.kernel_launches++;
+            }
+            CK(cudaMemcpyAsync(s->h_counters, s->counters, DT_CNT_COUNT * sizeof(int), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            CK(cudaGetLastError());
+            S.ms_generate += s->t_gen.take();
+            S.ms_traverse_closest += s->t_closest.take();
+            S.ms_shade += s->t_shade.take();
+            if (shadow_timed) S.ms_traverse_shadow += s->t_shadow.take();
+            S.waves++;
+            if (s->h_counters[DT_CNT_OVERFLOW] != 0) { overflow = true; break; }
+            const int next_count = s->h_counters[DT_CNT_NEXT];
+            const int shadow_count = std::min(s->h_counters[DT_CNT_SHADOW], s->shadow_capacity);
+            S.rays_closest += (uint64_t)next_count;
+            S.rays_shadow += (uint64_t)shadow_count;
+            prev_shadow = defer_mode ? shadow_count : 0;
+            count = next_count;
+            cur = 1 - cur;
+        }
+        if (!overflow && defer_mode && prev_shadow > 0) {
+            CK(cudaMemsetAsync(s->counters + DT_CNT_FETCH_B, 0, sizeof(int), st));
+            k_traverse<true><<<s->grid_shadow, 128, 0, st>>>(s->dev, s->q[cur], s->sq, nullptr, prev_shadow, s->counters + DT_CNT_FETCH_B, s->accum);
+            S.kernel_launches++;
+        }
+        if (overflow) {
+            if (retries >= 6 || wave_max <= 4096) { g_err = "wavefront queue overflow (ray-tree fan-out too large even for small waves)"; return DT_ERR_OVERFLOW; }
+            retries++;
+            wave_max = std::max(4096, (wave_max / 4 + 31) & ~31);
+            CK(cudaStreamSynchronize(st));
+            goto retry;
+        }
+        // valid primary rays: every in-image pixel of the owned tiles, spp times
+        long long valid = 0;
+        for (long long j = 0; j < my_tiles; j++) {
+            long long tile = j * P.tile_world + P.tile_rank;
+            int tx = (int)(tile % wp.tiles_x), ty = (int)(tile / wp.tiles_x);
+            int w = std::min(8, W - tx * 8), h = std::min(4, H - ty * 4);
+            if (w > 0 && h > 0) valid += (long long)w * h;
+        }
+        S.rays_closest += (uint64_t)(valid * (primary_only ? 1 : dc.spp));
+    }
+    S.retries = retries;
+    if (stats) *stats = S;
+    return DT_OK;
+}
+
+int finish_core(dt_scene* s, const dt_camera_desc* cam, const float* hdr_dev, int flags, uint8_t* ldr_host, dt_stats* S) {
+    const int W = cam->width, H = cam->height;
+    const size_t n_pix = (size_t)W * H;
+    cudaStream_t st = s->stream;
+    if (cam->has_tonemapper && !(flags & DT_FLAG_SKIP_TONEMAP)) {
+        s->t_tm.start(st);
+        uint32_t l = 0;
+        int rc = tonemap_device(s, hdr_dev, W, H, cam->tm_key, cam->tm_burn, cam->tm_saturation, cam->tm_gamma, s->ldr, &l);
+        if (rc) return rc;
+        s->t_tm.stop(st);
+        if (S) S->kernel_launches += l;
+    }
+    if (ldr_host) CK(cudaMemcpyAsync(ldr_host, s->ldr, n_pix * 3, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (S) S->ms_tonemap = s->t_tm.take();
+    return DT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dt_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int dt_gpu_init(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) { g_err = "no CUDA device available; this library has no CPU fallback"; return DT_ERR_NO_DEVICE; }
+    if (device < 0 || device >= n) { g_err = "device index out of range"; return DT_ERR_INVALID; }
+    g_device = device;
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) { g_err = std::string("cudaSetDevice: ") + cudaGetErrorString(e); return DT_ERR_CUDA; }
+    return n;
+}
+
+int dt_scene_create(const dt_scene_desc* desc, dt_scene** out) {
+    if (!desc || !out) { g_err = "null argument"; return DT_ERR_INVALID; }
+    *out = nullptr;
+    DtHostScene hs;
+    std::string err;
+    if (!dt_flatten_scene(desc, hs, err)) { g_err = "scene description rejected: " + err; return DT_ERR_INVALID; }
+    int rc = ensure_device();
+    if (rc) return rc;
+    dt_scene* s = new dt_scene();
+    s->device = g_device;
+    memset(&s->dev, 0, sizeof s->dev);
+    memset(&s->q, 0, sizeof s->q);
+    memset(&s->sq, 0, sizeof s->sq);
+    auto fail = [&](int code) { dt_scene_destroy(s); return code; };
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, s->device) != cudaSuccess) { g_err = "cudaGetDeviceProperties failed"; return fail(DT_ERR_CUDA); }
+    s->num_sms = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) { g_err = "cudaStreamCreate failed"; return fail(DT_ERR_CUDA); }
+    DtSceneDev& D = s->dev;
+    {
+        const uint4* p = nullptr;
+        if ((rc = upload<uint4>(s->allocs, (const uint4*)hs.tlas_nodes.data(), hs.tlas_nodes.size() * 5, &p))) return fail(rc);
+        D.tlas_nodes = p;
+        if ((rc = upload<uint4>(s->allocs, (const uint4*)hs.blas_nodes.data(), hs.blas_nodes.size() * 5, &p))) return fail(rc);
+        D.blas_nodes = p;
+    }
+    if ((rc = upload<int32_t>(s->allocs, hs.tlas_prims.data(), hs.tlas_prims.size(), &D.tlas_prims))) return fail(rc);
+    if ((rc = upload<float4>(s->allocs, hs.tris.data(), hs.tris.size(), &D.tris))) return fail(rc);
+    if ((rc = upload<float4>(s->allocs, hs.leaf_boxes.data(), hs.leaf_boxes.size(), &D.leaf_boxes))) return fail(rc);
+    if ((rc = upload<DtShapeDev>(s->allocs, hs.shapes.data(), hs.shapes.size(), &D.shapes))) return fail(rc);
+    if ((rc = upload<DtMeshDev>(s->allocs, hs.meshes.data(), hs.meshes.size(), &D.meshes))) return fail(rc);
+    if ((rc = upload<DtFaceDev>(s->allocs, hs.faces.data(), hs.faces.size(), &D.faces))) return fail(rc);
+    if ((rc = upload<float>(s->allocs, hs.verts.data(), hs.verts.size(), &D.verts))) return fail(rc);
+    if ((rc = upload<float>(s->allocs, hs.uvs.data(), hs.uvs.size(), &D.uvs))) return fail(rc);
+    if ((rc = upload<dt_material>(s->allocs, desc->materials, (size_t)desc->n_materials, &D.materials))) return fail(rc);
+    if ((rc = upload<dt_brdf>(s->allocs, desc->brdfs, (size_t)desc->n_brdfs, &D.brdfs))) return fail(rc);
+    if ((rc = upload<dt_point_light>(s->allocs, desc->point_lights, (size_t)desc->n_point_lights, &D.point_lights))) return fail(rc);
+    if ((rc = upload<dt_area_light>(s->allocs, desc->area_lights, (size_t)desc->n_area_lights, &D.area_lights))) return fail(rc);
+    if ((rc = upload<dt_directional_light>(s->allocs, desc->directional_lights, (size_t)desc->n_directional_lights, &D.directional_lights))) return fail(rc);
+    if ((rc = upload<dt_spot_light>(s->allocs, desc->spot_lights, (size_t)desc->n_spot_lights, &D.spot_lights))) return fail(rc);
+    if ((rc = upload<dt_env_light>(s->allocs, desc->env_lights, (size_t)desc->n_env_lights, &D.env_lights))) return fail(rc);
+    if ((rc = upload<dt_mesh_light>(s->allocs, desc->mesh_lights, (size_t)desc->n_mesh_lights, &D.mesh_lights))) return fail(rc);
+    if ((rc = upload<dt_texture>(s->allocs, desc->textures, (size_t)desc->n_textures, &D.textures))) return fail(rc);
+    if ((rc = upload<DtImageDev>(s->allocs, hs.images.data(), hs.images.size(), &D.images))) return fail(rc);
+    if ((rc = upload<uint8_t>(s->allocs, hs.image_u8.data(), hs.image_u8.size(), &D.image_u8, 16))) return fail(rc);
+    if ((rc = upload<float>(s->allocs, hs.image_f32.data(), hs.image_f32.size(), &D.image_f32, 16))) return fail(rc);
+    D.n_shapes = desc->n_shapes; D.n_mesh_shapes = desc->n_mesh_shapes; D.n_materials = desc->n_materials;
+    D.n_point_lights = desc->n_point_lights; D.n_area_lights = desc->n_area_lights; D.n_directional_lights = desc->n_directional_lights;
+    D.n_spot_lights = desc->n_spot_lights; D.n_env_lights = desc->n_env_lights; D.n_mesh_lights = desc->n_mesh_lights;
+    D.bg_texture = desc->bg_texture; D.max_recursion_depth = desc->max_recursion_depth;
+    memcpy(D.background_color, desc->background_color, 12);
+    D.shadow_ray_epsilon = desc->shadow_ray_epsilon;
+    memcpy(D.ambient_light, desc->ambient_light, 12);
+    s->n_triangles = hs.n_triangles;
+    s->lights_shadowed = desc->n_point_lights + desc->n_area_lights + desc->n_directional_lights + desc->n_spot_lights + desc->n_mesh_lights;
+    s->has_env = desc->n_env_lights > 0;
+    bool any_diel = false, any_refl = false;
+    for (int i = 0; i < desc->n_materials; i++) {
+        if (desc->materials[i].type == DT_MAT_DIELECTRIC) any_diel = true;
+        if (desc->materials[i].type == DT_MAT_MIRROR || desc->materials[i].type == DT_MAT_CONDUCTOR) any_refl = true;
+    }
+    s->fanout_hint = desc->max_recursion_depth > 0 ? (any_diel ? 2 : (any_refl ? 1 : 0)) : 0;
+
+    if (cudaMalloc(&s->counters, DT_CNT_COUNT * sizeof(int)) != cudaSuccess || cudaMallocHost(&s->h_counters, DT_CNT_COUNT * sizeof(int)) != cudaSuccess ||
+        cudaMalloc(&s->tm_logsum, sizeof(double)) != cudaSuccess || cudaMalloc(&s->tm_hist, 256 * sizeof(unsigned int)) != cudaSuccess ||
+        cudaMalloc(&s->tm_rank, sizeof(unsigned long long)) != cudaSuccess || cudaMalloc(&s->tm_prefix, sizeof(uint32_t)) != cudaSuccess) {
+        g_err = "cudaMalloc of control buffers failed"; return fail(DT_ERR_CUDA);
+    }
+    for (Timer* t : {&s->t_total, &s->t_gen, &s->t_closest, &s->t_shadow, &s->t_shade, &s->t_resolve, &s->t_tm}) if (t->init()) return fail(DT_ERR_CUDA);
+    int bps = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_traverse<false>, 128, 0);
+    s->grid_closest = s->num_sms * std::max(1, bps);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_traverse<true>, 128, 0);
+    s->grid_shadow = s->num_sms * std::max(1, bps);
+    if (cudaDeviceSynchronize() != cudaSuccess) { g_err = "device sync after upload failed"; return fail(DT_ERR_CUDA); }
+    *out = s;
+    return DT_OK;
+}
+
+void dt_scene_destroy(dt_scene* s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    s->free_queues();
+    for (void* p : s->allocs) cudaFree(p);
+    if (s->counters) cudaFree(s->counters);
+    if (s->h_counters) cudaFreeHost(s->h_counters);
+    if (s->accum) cudaFree(s->accum);
+    if (s->hdr) cudaFree(s->hdr);
+    if (s->ldr) cudaFree(s->ldr);
+    if (s->tm_logsum) cudaFree(s->tm_logsum);
+    if (s->tm_hist) cudaFree(s->tm_hist);
+    if (s->tm_rank) cudaFree(s->tm_rank);
+    if (s->tm_prefix) cudaFree(s->tm_prefix);
+    for (Timer* t : {&s->t_total, &s->t_gen, &s->t_closest, &s->t_shadow, &s->t_shade, &s->t_resolve, &s->t_tm}) t->destroy();
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+int dt_render_device(dt_scene* s, const dt_camera_desc* cam, const dt_render_params* params, float** hdr_dev, dt_stats* stats) {
+    if (!s || !hdr_dev) { g_err = "null argument"; return DT_ERR_INVALID; }
+    dt_stats S; memset(&S, 0, sizeof S);
+    int rc = render_core(s, cam, params, &S, false);
+    if (rc) return rc;
+    cudaStream_t st = s->stream;
+    const int n_pix = cam->width * cam->height;
+    const int spp = cam->samples_per_pixel < 1 ? 1 : cam->samples_per_pixel;
+    s->t_resolve.start(st);
+    k_resolve<<<(n_pix + 255) / 256, 256, 0, st>>>(s->accum, n_pix, spp, s->hdr, s->ldr, s->counters);
+    s->t_resolve.stop(st);
+    S.kernel_launches++;
+    s->t_total.stop(st);
+    CK(cudaMemcpyAsync(s->h_counters, s->counters, DT_CNT_COUNT * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    S.nan_pixels = (uint64_t)s->h_counters[DT_CNT_NAN];
+    S.ms_resolve = s->t_resolve.take();
+    S.ms_total = s->t_total.take();
+    *hdr_dev = s->hdr;
+    if (stats) *stats = S;
+    return DT_OK;
+}
+
+int dt_finish_device(dt_scene* s, const dt_camera_desc* cam, const float* hdr_dev, uint8_t* ldr_rgb, dt_stats* stats) {
+    if (!s || !cam || !hdr_dev || !ldr_rgb) { g_err = "null argument"; return DT_ERR_INVALID; }
+    int rc = check_cam(cam);
+    if (rc) return rc;
+    CK(cudaSetDevice(s->device));
+    const size_t n_pix = (size_t)cam->width * cam->height;
+    if ((rc = ensure_outputs(s, n_pix))) return rc;
+    dt_stats S; memset(&S, 0, sizeof S);
+    cudaStream_t st = s->stream;
+    s->t_total.start(st);
+    // copy into our own hdr buffer if it is a foreign pointer, then finish
+    if (hdr_dev != s->hdr) CK(cudaMemcpyAsync(s->hdr, hdr_dev, n_pix * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (!cam->has_tonemapper) {
+        // clamp from s->hdr
+        k_clamp_hdr<<<((int)n_pix + 255) / 256, 256, 0, st>>>(s->hdr, (int)n_pix, s->ldr);
+        S.kernel_launches++;
+    }
+    rc = finish_core(s, cam, s->hdr, 0, ldr_rgb, &S);
+    if (rc) return rc;
+    s->t_total.stop(st);
+    CK(cudaStreamSynchronize(st));
+    S.ms_total = s->t_total.take();
+    if (stats) *stats = S;
+    return DT_OK;
+}
+
+int dt_render(dt_scene* s, const dt_camera_desc* cam, const dt_render_params* params, uint8_t* ldr_rgb, float* hdr_rgb, dt_stats* stats) {
+    if (!s || !ldr_rgb) { g_err = "null argument"; return DT_ERR_INVALID; }
+    float* hdr_dev = nullptr;
+    dt_stats S; memset(&S, 0, sizeof S);
+    int rc = dt_render_device(s, cam, params, &hdr_dev, &S);
+    if (rc) return rc;
+    const size_t n_pix = (size_t)cam->width * cam->height;
+    cudaStream_t st = s->stream;
+    const int flags = params ? params->flags : 0;
+    if (hdr_rgb) CK(cudaMemcpyAsync(hdr_rgb, hdr_dev, n_pix * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    rc = finish_core(s, cam, hdr_dev, flags, ldr_rgb, &S);
+    if (rc) return rc;
+    S.ms_total += S.ms_tonemap;
+    if (stats) *stats = S;
+    return DT_OK;
+}
+
+int dt_primary_hits(dt_scene* s, const dt_camera_desc* cam, int32_t* shape, int32_t* face, float* t) {
+    if (!s || !shape || !face || !t) { g_err = "null argument"; return DT_ERR_INVALID; }
+    dt_render_params P; memset(&P, 0, sizeof P); P.seed = 1234; P.tile_world = 1;
+    const long long n_slots = (long long)((cam->width + 7) / 8) * ((cam->height + 3) / 4) * 32;
+    if (n_slots > (1ll << 28)) { g_err = "image too large for dt_primary_hits"; return DT_ERR_INVALID; }
+    P.max_wave_rays = (int)n_slots;
+    dt_stats S;
+    int rc = render_core(s, cam, &P, &S, true);
+    if (rc) return rc;
+    const int n_pix = cam->width * cam->height;
+    int32_t *d_shape = nullptr, *d_face = nullptr; float* d_t = nullptr;
+    CK(cudaMalloc(&d_shape, (size_t)n_pix * 4)); CK(cudaMalloc(&d_face, (size_t)n_pix * 4)); CK(cudaMalloc(&d_t, (size_t)n_pix * 4));
+    cudaStream_t st = s->stream;
+    k_unpack_hits<<<((int)n_slots + 255) / 256, 256, 0, st>>>(s->q[0].hit0, s->q[0].hit_face, s->q[0].pixel, (int)n_slots, d_shape, d_face, d_t, 1);
+    cudaMemcpyAsync(shape, d_shape, (size_t)n_pix * 4, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(face, d_face, (size_t)n_pix * 4, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(t, d_t, (size_t)n_pix * 4, cudaMemcpyDeviceToHost, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    cudaFree(d_shape); cudaFree(d_face); cudaFree(d_t);
+    if (e != cudaSuccess) { g_err = std::string("dt_primary_hits: ") + cudaGetErrorString(e); return DT_ERR_CUDA; }
+    return DT_OK;
+}
+
+static int trace_generic(dt_scene* s, const float* origins, const float* dirs, const float* tmax, int64_t n, bool any,
+                         int32_t* shape, int32_t* face, float* t, uint8_t* occluded) {
+    if (!s || !origins || !dirs || n < 0) { g_err = "bad argument"; return DT_ERR_INVALID; }
+    if (n == 0) return DT_OK;
+    if (n > (1ll << 28)) { g_err = "too many rays in one call"; return DT_ERR_INVALID; }
+    CK(cudaSetDevice(s->device));
+    cudaStream_t st = s->stream;
+    float *d_o = nullptr, *d_d = nullptr, *d_tm = nullptr; float4 *o4 = nullptr, *d4 = nullptr, *hit0 = nullptr; int32_t* hface = nullptr;
+    int32_t *d_shape = nullptr, *d_face = nullptr; float* d_t = nullptr; uint8_t* d_occ = nullptr; int* fetch = nullptr;
+    std::vector<void*> tmp;
+    auto A = [&](void** p, size_t b) -> int { CK(cudaMalloc(p, std::max<size_t>(b, 16))); tmp.push_back(*p); return DT_OK; };
+    int rc = DT_OK;
+    do {
+        if ((rc = A((void**)&d_o, (size_t)n * 12)) || (rc = A((void**)&d_d, (size_t)n * 12)) || (rc = A((void**)&o4, (size_t)n * 16)) || (rc = A((void**)&d4, (size_t)n * 16)) || (rc = A((void**)&fetch, 16))) break;
+        cudaMemcpyAsync(d_o, origins, (size_t)n * 12, cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(d_d, dirs, (size_t)n * 12, cudaMemcpyHostToDevice, st);
+        if (tmax) { if ((rc = A((void**)&d_tm, (size_t)n * 4))) break; cudaMemcpyAsync(d_tm, tmax, (size_t)n * 4, cudaMemcpyHostToDevice, st); }
+        cudaMemsetAsync(fetch, 0, 16, st);
+        k_pack_rays<<<((int)n + 255) / 256, 256, 0, st>>>(d_o, d_d, d_tm, (int)n, o4, d4);
+        if (any) {
+            if ((rc = A((void**)&d_occ, (size_t)n))) break;
+            k_traverse_occluded<<<((int)n + 127) / 128, 128, 0, st>>>(s->dev, o4, d4, (int)n, d_occ);
+            cudaMemcpyAsync(occluded, d_occ, (size_t)n, cudaMemcpyDeviceToHost, st);
+        } else {
+            if ((rc = A((void**)&hit0, (size_t)n * 16)) || (rc = A((void**)&hface, (size_t)n * 4)) || (rc = A((void**)&d_shape, (size_t)n * 4)) || (rc = A((void**)&d_face, (size_t)n * 4)) || (rc = A((void**)&d_t, (size_t)n * 4))) break;
+            DtRayQueue q; memset(&q, 0, sizeof q);
+            q.o_time = o4; q.d_tmax = d4; q.hit0 = hit0; q.hit_face = hface; q.pixel = nullptr;
+            DtShadowQueue sq; memset(&sq, 0, sizeof sq);
+            k_traverse<false><<<s->grid_closest, 128, 0, st>>>(s->dev, q, sq, nullptr, (int)n, fetch, nullptr);
+            k_unpack_hits<<<((int)n + 255) / 256, 256, 0, st>>>(hit0, hface, nullptr, (int)n, d_shape, d_face, d_t, 0);
+            cudaMemcpyAsync(shape, d_shape, (size_t)n * 4, cudaMemcpyDeviceToHost, st);
+            cudaMemcpyAsync(face, d_face, (size_t)n * 4, cudaMemcpyDeviceToHost, st);
+            cudaMemcpyAsync(t, d_t, (size_t)n * 4, cudaMemcpyDeviceToHost, st);
+        }
+    } while (0);
+    cudaError_t e = cudaStreamSynchronize(st);
+    cudaError_t e2 = cudaGetLastError();
+    for (void* p : tmp) cudaFree(p);
+    if (rc) return rc;
+    if (e != cudaSuccess || e2 != cudaSuccess) { g_err = std::string("trace: ") + cudaGetErrorString(e != cudaSuccess ? e : e2); return DT_ERR_CUDA; }
+    return DT_OK;
+}
+
+int dt_trace_closest(dt_scene* s, const float* origins, const float* dirs, int64_t n, int32_t* shape, int32_t* face, float* t) {
+    if (!shape || !face || !t) { g_err = "null output"; return DT_ERR_INVALID; }
+    return trace_generic(s, origins, dirs, nullptr, n, false, shape, face, t, nullptr);
+}
+int dt_trace_occluded(dt_scene* s, const float* origins, const float* dirs, const float* tmax, int64_t n, uint8_t* occluded) {
+    if (!occluded || !tmax) { g_err = "null argument"; return DT_ERR_INVALID; }
+    return trace_generic(s, origins, dirs, tmax, n, true, nullptr, nullptr, nullptr, occluded);
+}
+
+int dt_tonemap(const float* hdr_rgb, int32_t width, int32_t height, float key, float burn, float saturation, float gamma, uint8_t* ldr_rgb) {
+    if (!hdr_rgb || !ldr_rgb || width <= 0 || height <= 0) { g_err = "bad argument"; return DT_ERR_INVALID; }
+    int rc = ensure_device();
+    if (rc) return rc;
+    // a throw-away scene-less context: allocate just what the tonemapper needs
+    dt_scene tmp;
+    tmp.device = g_device;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, tmp.device));
+    tmp.num_sms = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&tmp.stream, cudaStreamNonBlocking));
+    const size_t n_pix = (size_t)width * height;
+    float* d_hdr = nullptr; uint8_t* d_ldr = nullptr;
+    rc = DT_OK;
+    do {
+        if (cudaMalloc(&d_hdr, n_pix * 12) != cudaSuccess || cudaMalloc(&d_ldr, n_pix * 3) != cudaSuccess || cudaMalloc(&tmp.tm_logsum, 8) != cudaSuccess ||
+            cudaMalloc(&tmp.tm_hist, 1024) != cudaSuccess || cudaMalloc(&tmp.tm_rank, 8) != cudaSuccess || cudaMalloc(&tmp.tm_prefix, 4) != cudaSuccess) { g_err = "cudaMalloc failed"; rc = DT_ERR_CUDA; break; }
+        cudaMemcpyAsync(d_hdr, hdr_rgb, n_pix * 12, cudaMemcpyHostToDevice, tmp.stream);
+        uint32_t l = 0;
+        rc = tonemap_device(&tmp, d_hdr, width, height, key, burn, saturation, gamma, d_ldr, &l);
+        if (rc) break;
+        cudaMemcpyAsync(ldr_rgb, d_ldr, n_pix * 3, cudaMemcpyDeviceToHost, tmp.stream);
+        if (cudaStreamSynchronize(tmp.stream) != cudaSuccess) { g_err = "tonemap sync failed"; rc = DT_ERR_CUDA; }
+    } while (0);
+    cudaFree(d_hdr); cudaFree(d_ldr); cudaFree(tmp.tm_logsum); cudaFree(tmp.tm_hist); cudaFree(tmp.tm_rank); cudaFree(tmp.tm_prefix);
+    cudaStreamDestroy(tmp.stream);
+    return rc;
+}
+
+const char* dt_last_error(void) { return g_err.c_str(); }
+const char* dt_version(void) { return "dorktracer-b200 0.1 (sm_100a, abi 1)"; }
+
+}  // extern "C"
+

@@ -1,0 +1,613 @@
+// Wavefront kernels of the render hot path (sm_100a).  One wave =
+//   k_generate (top-up with new camera samples) -> k_traverse<closest> -> k_shade (accumulate local terms,
+//   emit shadow rays + child rays) -> k_traverse<shadow> (accumulate unoccluded light terms)
+// replacing the per-pixel recursion of Raytracer::PerPixel / PerformShading (raytracer.cpp:38-134).
+// The recursion is linear in child radiance, so every tree node carries its RGB weight W and adds
+// W * Local(node) straight into the pixel accumulator (SURVEY.md 8a "Ray-tree semantics").
+#pragma once
+#include "dt_device.h"
+#include "dt_math.cuh"
+#include "dt_traverse.cuh"
+#include "dt_shade.cuh"
+
+struct DtCamDev {
+    float position[3], gaze[3], up[3], right[3], q[3];
+    float left, right_, bottom, top;
+    int width, height, spp;
+    float focus_distance, aperture_size;
+    int path_tracing, importance_sampling, nee, russian_roulette;
+};
+
+struct DtWaveParams {
+    uint32_t seed_lo, seed_hi;
+    int tile_rank, tile_world;
+    int tiles_x, tiles_y;
+    long long per_sample;          // primary slots per sample on this rank (tiles owned * 32)
+};
+
+// counters[] layout (device ints)
+enum { DT_CNT_NEXT = 0, DT_CNT_SHADOW = 1, DT_CNT_FETCH_A = 2, DT_CNT_FETCH_B = 3, DT_CNT_NAN = 4, DT_CNT_OVERFLOW = 5, DT_CNT_DEFER = 6, DT_CNT_COUNT = 8 };
+
+#define DT_DEAD_PIXEL 0xFFFFFFFFu
+
+__device__ __forceinline__ int dt_agg_inc(int* counter) {
+    const unsigned active = __activemask();
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(active) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(counter, __popc(active));
+    base = __shfl_sync(active, base, leader);
+    return base + __popc(active & ((1u << lane) - 1u));
+}
+
+__device__ __forceinline__ void dt_accum(float4* accum, uint32_t pix, v3 c) {
+    float* p = reinterpret_cast<float*>(accum + pix);
+    atomicAdd(p + 0, c.x); atomicAdd(p + 1, c.y); atomicAdd(p + 2, c.z);
+}
+
+// ------------------------------------------------------------------ generate
+// Camera::GetImagePlanePosition (camera.cpp:74-80) + Raytracer::GenerateRay (raytracer.cpp:661-699) + the
+// stratified-sample / Gaussian-weight part of renderThreadMain (main.cpp:59-96).
+__device__ inline void dt_camera_ray(const DtCamDev& cam, int i, int j, DtRng& rng, v3& o, v3& d, float& mb_time) {
+    float su = (float)((i + 0.5) * (double)(cam.right_ - cam.left) / cam.width);
+    float sv = (float)((j + 0.5) * (double)(cam.top - cam.bottom) / cam.height);
+    v3 ipp = vadd(vadd(F3(cam.q), vscale(F3(cam.right), su)), vscale(F3(cam.up), -sv));
+    o = F3(cam.position);
+    if (cam.aperture_size > 0.0001) {
+        v3 ap = o;
+        float first01 = -1.0f + 2.0f * rng01(rng);
+        ap = vadd(ap, vscale(F3(cam.up), (first01 * cam.aperture_size * 0.5f)));
+        float second01 = -1.0f + 2.0f * rng01(rng);
+        ap = vadd(ap, vscale(F3(cam.right), (second01 * cam.aperture_size * 0.5f)));
+        v3 dir = vunit(vsub(o, ipp));
+        float tFd = cam.focus_distance / vdot(dir, F3(cam.gaze));
+        v3 bent = vadd(o, vscale(dir, tFd));
+        d = vunit(vsub(bent, ap));
+        o = ap;
+    } else {
+        d = vunit(vsub(ipp, o));
+    }
+    mb_time = rng01(rng);
+}
+
+__global__ void k_generate(DtCamDev cam, DtWaveParams wp, DtRayQueue q, int base, long long k0, int n, float4* accum) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    const long long k = k0 + idx;
+    const int s = (int)(k / wp.per_sample);
+    const long long rem = k % wp.per_sample;
+    const long long tile = (rem >> 5) * wp.tile_world + wp.tile_rank;
+    const int lane = (int)(rem & 31);
+    const int x = (int)(tile % wp.tiles_x) * 8 + (lane & 7);
+    const int y = (int)(tile / wp.tiles_x) * 4 + (lane >> 3);
+    const int slot = base + idx;
+    if (x >= cam.width || y >= cam.height) {
+        q.pixel[slot] = DT_DEAD_PIXEL;
+        return;
+    }
+    const uint32_t pix = (uint32_t)(x + y * cam.width);
+    DtRng rng; rng.key = dt_hash(dt_hash(pix, (uint32_t)s) ^ wp.seed_lo, wp.seed_hi); rng.ctr = 0;
+    int px = x, py = y;
+    float w = 1.0f;
+    if (cam.spp > 1) {
+        const int nRows = (int)sqrt((double)cam.spp), nCols = nRows;
+        const int st = s % (nRows * nCols);
+        const int row = st / nCols, col = st % nCols;
+        float psi1 = rng01(rng), psi2 = rng01(rng);
+        float sx = (col + psi1) / nCols;
+        float sy = (row + psi2) / nRows;
+        px = (int)(sx + x);          // RenderPixel(int,int,...) truncates the float sample position (main.cpp:83)
+        py = (int)(sy + y);
+        const float sigma = 1.0f / 6.0f;                     // gaussian.h:3-21, main.cpp:52
+        const float sigmaSqr = sigma * sigma;
+        const float c1 = (float)(1.0f / (2.0f * DT_PI * sigmaSqr));
+        float xd = sx - 0.5f, yd = sy - 0.5f;
+        float exponent = (float)(-0.5 * (double)((xd * xd + yd * yd) / sigmaSqr));
+        w = c1 * expf(exponent);
+        atomicAdd(reinterpret_cast<float*>(accum + pix) + 3, w);
+    }
+    v3 o, d; float mb;
+    dt_camera_ray(cam, px, py, rng, o, d, mb);
+    q.o_time[slot] = make_float4(o.x, o.y, o.z, mb);
+    q.d_tmax[slot] = make_float4(d.x, d.y, d.z, CUDART_INF_F);
+    q.pixel[slot] = pix;
+    q.weight_n[slot] = make_float4(w, w, w, 1.0f);
+    q.thr_beer[slot] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+    q.misc[slot] = make_int4(0x7FFFFFFF /* set by shade from the scene */, 0, (int)dt_hash(rng.key, 0x9E37u), DT_FLAG_PRIMARY);
+}
+
+// ------------------------------------------------------------------ traversal (persistent warps, warp-level fetch)
+template <bool ANY>
+__global__ void __launch_bounds__(128) k_traverse(DtSceneDev S, DtRayQueue q, DtShadowQueue sq, const int* n_ptr, int n_fixed, int* fetch_counter, float4* accum) {
+    const int n = n_ptr ? *n_ptr : n_fixed;
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(fetch_counter, 32);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (base >= n) break;
+        const int i = base + lane;
+        if (i < n) {
+            if (ANY) {
+                const float4 o = sq.o_time[i], d = sq.d_tmax[i];
+                DtHit h;
+                dt_trace<true>(S, V(o.x, o.y, o.z), V(d.x, d.y, d.z), o.w, d.w, h);
+                if (h.shape < 0) {
+                    const float4 c = sq.contrib_pix[i];
+                    dt_accum(accum, (uint32_t)__float_as_int(c.w), V(c.x, c.y, c.z));
+                }
+            } else {
+                if (q.pixel && q.pixel[i] == DT_DEAD_PIXEL) continue;
+                const float4 o = q.o_time[i], d = q.d_tmax[i];
+                DtHit h;
+                dt_trace<false>(S, V(o.x, o.y, o.z), V(d.x, d.y, d.z), o.w, CUDART_INF_F, h);
+                q.hit0[i] = make_float4(h.t, h.beta, h.gamma, __int_as_float(h.shape));
+                q.hit_face[i] = h.face;
+            }
+        }
+    }
+}
+
+// occlusion query with an explicit result array (dt_trace_occluded)
+__global__ void __launch_bounds__(128) k_traverse_occluded(DtSceneDev S, const float4* o_time, const float4* d_tmax, int n, uint8_t* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 o = o_time[i], d = d_tmax[i];
+    DtHit h;
+    dt_trace<true>(S, V(o.x, o.y, o.z), V(d.x, d.y, d.z), o.w, d.w, h);
+    out[i] = h.shape >= 0 ? 1 : 0;
+}
+
+// ------------------------------------------------------------------ shade
+struct DtChild {
+    v3 o, d; float mb;
+    v3 W; float n_medium;
+    v3 thr; float beer_thr;
+    int depth, beer_mat; uint32_t rng_key; int flags;
+    v3 miss;
+};
+
+__device__ __forceinline__ int dt_emit_child(const DtRayQueue& out, float4* out_miss, int* counters, int capacity, uint32_t pix, const DtChild& c) {
+    const int slot = dt_agg_inc(counters + DT_CNT_NEXT);
+    if (slot >= capacity) { atomicAdd(counters + DT_CNT_OVERFLOW, 1); return -1; }
+    out.o_time[slot] = make_float4(c.o.x, c.o.y, c.o.z, c.mb);
+    out.d_tmax[slot] = make_float4(c.d.x, c.d.y, c.d.z, CUDART_INF_F);
+    out.pixel[slot] = pix;
+    out.weight_n[slot] = make_float4(c.W.x, c.W.y, c.W.z, c.n_medium);
+    out.thr_beer[slot] = make_float4(c.thr.x, c.thr.y, c.thr.z, c.beer_thr);
+    out.misc[slot] = make_int4(c.depth, c.beer_mat, (int)c.rng_key, c.flags);
+    if (out_miss) out_miss[slot] = make_float4(c.miss.x, c.miss.y, c.miss.z, 0.f);
+    return slot;
+}
+
+__device__ __forceinline__ void dt_emit_shadow(const DtShadowQueue& sq, int* counters, int capacity, v3 o, v3 d, float mb, float tmax,
+                                               v3 contrib, uint32_t pix, int defer_slot, int defer_light) {
+    const int slot = dt_agg_inc(counters + DT_CNT_SHADOW);
+    if (slot >= capacity) { atomicAdd(counters + DT_CNT_OVERFLOW, 1); return; }
+    sq.o_time[slot] = make_float4(o.x, o.y, o.z, mb);
+    sq.d_tmax[slot] = make_float4(d.x, d.y, d.z, tmax);
+    sq.contrib_pix[slot] = make_float4(contrib.x, contrib.y, contrib.z, __int_as_float((int)pix));
+    if (sq.defer) sq.defer[slot] = make_int2(defer_slot, defer_light);
+}
+
+// One thread per traced ray: Raytracer::PerPixel miss handling (raytracer.cpp:49-62) and PerformShading
+// (:65-134) with ComputeGlobalIllumination (:135-191), SampleDirectLighting (:701-806), mirror / conductor /
+// dielectric children (:208-472) turned into queue emissions.
+__global__ void __launch_bounds__(128) k_shade(DtSceneDev S, DtCamDev cam, DtRayQueue in, const float4* in_miss, int n,
+                                               DtRayQueue out, float4* out_miss, int out_capacity,
+                                               DtShadowQueue sq, int shadow_capacity, int* counters, float4* accum) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t pix = in.pixel[i];
+    if (pix == DT_DEAD_PIXEL) return;
+    const float4 o4 = in.o_time[i], d4 = in.d_tmax[i];
+    const float4 h0 = in.hit0[i];
+    const float4 wn = in.weight_n[i];
+    const int4 misc = in.misc[i];
+    const v3 o = V(o4.x, o4.y, o4.z), d = V(d4.x, d4.y, d4.z);
+    const float mb = o4.w;
+    v3 W = V(wn.x, wn.y, wn.z);
+    const float n_medium = wn.w;
+    const int hit_shape = __float_as_int(h0.w);
+    const int flags = misc.w;
+    const bool primary = (flags & DT_FLAG_PRIMARY) != 0;
+    const int depth = primary ? S.max_recursion_depth : misc.x;
+
+    if (hit_shape < 0) {
+        if (primary) {
+            v3 c;
+            if (S.bg_texture >= 0) {
+                const int x = (int)(pix % (uint32_t)cam.width), y = (int)(pix / (uint32_t)cam.width);
+                c = tex_rgb_sample(S, S.textures[S.bg_texture], x / (float)cam.width, y / (float)cam.height);
+            } else if (S.n_env_lights > 0) c = env_sample(S, 0, d);
+            else c = V((float)S.background_color[0], (float)S.background_color[1], (float)S.background_color[2]);
+            dt_accum(accum, pix, vmul(W, c));
+        } else if ((flags & DT_FLAG_ENV_ON_MISS) && in_miss) {
+            const float4 m = in_miss[i];
+            dt_accum(accum, pix, vmul(W, V(m.x, m.y, m.z)));
+        }
+        return;
+    }
+
+    const float t = h0.x;
+    const DtShapeDev& sh = S.shapes[hit_shape];
+    const v3 hitPoint = vadd(o, vscale(d, t));                                   // raytracer.cpp:69
+    // ---- surface at the winning hit ----
+    DtSurface sf;
+    {
+        v3 lo = apply_transform(sh.inv, o, 1.0f);
+        v3 ld = apply_transform(sh.inv, d, 0.0f);
+        if (sh.has_motion_blur) lo = vadd(lo, vscale(F3(sh.motion_blur), mb));
+        if (sh.kind == DT_SHAPE_SPHERE) sphere_surface(S, sh, t, lo, ld, V(0.f, 0.f, 0.f), sf);
+        else mesh_surface(S, sh, in.hit_face[i], t, h0.y, h0.z, lo, ld, sf);
+    }
+    const v3 normal = sf.normal;
+    const dt_material mat = S.materials[sh.material - 1];
+
+    // Beer's law applied by the parent to everything this child returns (raytracer.cpp:306-309,345-349,398-402)
+    const float4 tb = in.thr_beer[i];
+    if (tb.w > 0.0f && n_medium > tb.w) {
+        const dt_material& pm = S.materials[misc.y - 1];
+        W = V(W.x * expf(-pm.absorption_coefficient[0] * t), W.y * expf(-pm.absorption_coefficient[1] * t), W.z * expf(-pm.absorption_coefficient[2] * t));
+    }
+
+    const v3 eye = primary ? F3(cam.position) : o;
+    const v3 w_o = vunit(vsub(eye, hitPoint));
+    const float vac = 1.00001f;
+    const bool inside = n_medium > vac;
+
+    if (mat.type == DT_MAT_EMISSIVE) {                                            // raytracer.cpp:81-84
+        dt_accum(accum, pix, vmul(W, vscale(vscale(F3(mat.radiance), 2.0f), DT_PI_F)));
+        return;
+    }
+    if (sh.tex_replace_all >= 0) {                                                // raytracer.cpp:87-89
+        dt_accum(accum, pix, vmul(W, tex_rgb_sample(S, S.textures[sh.tex_replace_all], sf.u, sf.v)));
+        return;
+    }
+
+    DtRng rng; rng.key = (uint32_t)misc.z; rng.ctr = 0;
+    v3 thr = V(tb.x, tb.y, tb.z);
+    int gi_slot = -1;
+
+    // ---- ComputeGlobalIllumination (raytracer.cpp:135-191) ----
+    if (cam.path_tracing) {
+        bool go = true;
+        if (cam.russian_roulette) {
+            float probTest = rng01(rng);
+            float maxT = fmaxf(thr.x, fmaxf(thr.x, thr.z));
+            if (probTest > maxT && depth <= 0) go = false;
+            else thr = vdiv(thr, maxT);
+        } else if (depth <= 0) go = false;
+        if (go) {
+            float rand1 = rng01(rng), rand2 = rng01(rng);
+            float phi = (float)(2 * DT_PI * rand1);
+            float theta = cam.importance_sampling ? asinf(sqrtf(rand2)) : acosf(rand2);
+            v3 u, v;
+            orthonormal_basis(normal, u, v);
+            v3 nd = vadd(vadd(vscale(vscale(u, sinf(theta)), cosf(phi)), vscale(normal, cosf(theta))), vscale(vscale(v, sinf(theta)), sinf(phi)));
+            nd = vunit(nd);
+            DtChild c;
+            c.o = vadd(hitPoint, vscale(normal, (float)0.0001)); c.d = nd; c.mb = mb;
+            v3 res = V(1.f, 1.f, 1.f);
+            v3 f = shade_term(S, sh, mat, hitPoint, normal, sf.u, sf.v, nd, w_o, V(1.f, 1.f, 1.f), &res);
+            c.W = vmul(W, vscale(vscale(f, 2.0f), DT_PI_F));
+            c.n_medium = n_medium; c.thr = thr; c.beer_thr = 0.f;
+            c.depth = depth - 1; c.beer_mat = 0; c.rng_key = dt_hash(rng.key, 0xA511E9B3u); c.flags = 0; c.miss = V(0, 0, 0);
+            gi_slot = dt_emit_child(out, out_miss, counters, out_capacity, pix, c);
+            if (mat.brdf >= 0) thr = vmul(thr, res);                              // Shade(): ray.throughput *= res
+        }
+    }
+
+    // ---- ambient + SampleDirectLighting (raytracer.cpp:98-108, 701-806) ----
+    const bool sampleDirect = !cam.path_tracing || cam.nee;
+    if (!inside && sampleDirect) {
+        v3 local = vmul(F3(S.ambient_light), F3(mat.ambient));
+        const v3 so = vadd(hitPoint, vscale(normal, S.shadow_ray_epsilon));
+        for (int l = 0; l < S.n_point_lights; l++) {
+            const dt_point_light& L = S.point_lights[l];
+            v3 lp = F3(L.position);
+            v3 dir = vsub(lp, hitPoint);
+            float lightT = vlen(dir);
+            v3 sdir = vdiv(dir, lightT);
+            v3 w_i = sdir;                                                        // makeUnit(lp - hitPoint) == the same three divisions
+            v3 E = vdiv(F3(L.intensity), (lightT * lightT));
+            v3 res = V(1.f, 1.f, 1.f);
+            v3 c = shade_term(S, sh, mat, hitPoint, normal, sf.u, sf.v, w_i, w_o, E, &res);
+            if (mat.brdf >= 0) thr = vmul(thr, res);
+            dt_emit_shadow(sq, counters, shadow_capacity, so, sdir, mb, lightT, vmul(W, c), pix, -1, -1);
+        }
+        for (int l = 0; l < S.n_area_lights; l++) {
+            const dt_area_light& L = S.area_lights[l];
+            float offU = -0.5f + rng01(rng), offV = -0.5f + rng01(rng);          // areaLight.h:34-40
+            v3 sp = vadd(vadd(F3(L.position), vscale(F3(L.u), (L.extent * offU))), vscale(F3(L.v), (L.extent * offV)));
+            v3 dir = vsub(sp, hitPoint);
+            float lightT = vlen(dir);
+            v3 w_i = vdiv(dir, lightT);
+            float dSqr = lightT * lightT;
+            float lCos = vdot(F3(L.normal), vneg(w_i));
+            if (lCos < 0) lCos = vdot(F3(L.normal), w_i);
+            float area = L.extent * L.extent;
+            v3 E = vscale(F3(L.radiance), (area * lCos / dSqr));
+            v3 res = V(1.f, 1.f, 1.f);
+            v3 c = shade_term(S, sh, mat, hitPoint, normal, sf.u, sf.v, w_i, w_o, E, &res);
+            if (mat.brdf >= 0) thr = vmul(thr, res);
+            dt_emit_shadow(sq, counters, shadow_capacity, so, w_i, mb, lightT, vmul(W, c), pix, -1, -1);
+        }
+        for (int l = 0; l < S.n_env_lights; l++) {                                // no shadow ray (raytracer.cpp:741-755)
+            v3 nn = vunit(normal);
+            v3 cand = V(0, 0, 0);
+            for (int guard = 0; guard < 4096; guard++) {                          // rejection sampling, un-normalised result
+                cand.x = -1.0f + 2.0f * rng01(rng); cand.y = -1.0f + 2.0f * rng01(rng); cand.z = -1.0f + 2.0f * rng01(rng);
+                if (vlen(cand) <= 1.0f && vdot(nn, cand) > 0.0f) break;
+            }
+            v3 E = env_sample(S, l, cand);
+            v3 res = V(1.f, 1.f, 1.f);
+            v3 c = shade_term(S, sh, mat, hitPoint, normal, sf.u, sf.v, normal, w_o, E, &res);
+            if (mat.brdf >= 0) thr = vmul(thr, res);
+            local = vadd(local, c);
+        }
+        for (int l = 0; l < S.n_directional_lights; l++) {
+            const dt_directional_light& L = S.directional_lights[l];
+            v3 w_i = vneg(F3(L.dir));
+            v3 res = V(1.f, 1.f, 1.f);
+            v3 c = shade_term(S, sh, mat, hitPoint, normal, sf.u, sf.v, w_i, w_o, F3(L.radiance), &res);
+            if (mat.brdf >= 0) thr = vmul(thr, res);
+            dt_emit_shadow(sq, counters, shadow_capacity, so, w_i, mb, CUDART_INF_F, vmul(W, c), pix, -1, -1);
+        }
+        for (int l = 0; l < S.n_spot_lights; l++) {
+            const dt_spot_light& L = S.spot_lights[l];
+            v3 dir = vsub(F3(L.pos), hitPoint);
+            float lightT = vlen(dir);
+            v3 w_i = vdiv(dir, lightT);
+            v3 E = spot_irradiance(L, hitPoint);
+            v3 res = V(1.f, 1.f, 1.f);
+            v3 c = shade_term(S, sh, mat, hitPoint, normal, sf.u, sf.v, w_i, w_o, E, &res);
+            if (mat.brdf >= 0) thr = vmul(thr, res);
+            dt_emit_shadow(sq, counters, shadow_capacity, so, w_i, mb, lightT, vmul(W, c), pix, -1, -1);
+        }
+        for (int l = 0; l < S.n_mesh_lights; l++) {
+            const dt_mesh_light& L = S.mesh_lights[l];
+            const DtShapeDev& lsh = S.shapes[L.shape];
+            const DtMeshDev& lm = S.meshes[lsh.mesh];
+            int fi = (int)(rng01(rng) * lm.n_faces);                              // meshLight.h:27-47 (+P2)
+            if (fi >= lm.n_faces) fi = lm.n_faces - 1;
+            const DtFaceDev fc = S.faces[lm.face_base + fi];
+            float rand1 = rng01(rng), rand2 = rng01(rng);
+            const float* vp = S.verts + (size_t)lm.vert_base * 3;
+            v3 a = F3(vp + (size_t)fc.v0 * 3), b = F3(vp + (size_t)fc.v1 * 3), cc = F3(vp + (size_t)fc.v2 * 3);
+            v3 qq = vadd(vscale(b, (1 - rand2)), vscale(cc, rand2));
+            float sr = sqrtf(rand1);
+            v3 pos = vadd(vscale(a, (1 - sr)), vscale(qq, sr));
+            pos = apply_transform(lsh.fwd, pos, 1.0f);
+            v3 dir = vsub(pos, hitPoint);
+            float lightT = vlen(dir);
+            v3 w_i = vdiv(dir, lightT);
+            v3 rad = vscale(vscale(vscale(F3(L.radiance), fc.light_weight), 2.f), DT_PI_F);
+            v3 res = V(1.f, 1.f, 1.f);
+            v3 c = shade_term(S, sh, mat, hitPoint, normal, sf.u, sf.v, w_i, w_o, rad, &res);
+            if (mat.brdf >= 0) thr = vmul(thr, res);
+            // hitMeshLightId (raytracer.cpp:91-95,107,781): this light is skipped when the GI child of this very
+            // hit lands on the emissive shape with the same id -> decided one wave later (deferred entry).
+            dt_emit_shadow(sq, counters, shadow_capacity, so, w_i, mb, lightT, vmul(W, c), pix, gi_slot, L.id);
+        }
+        dt_accum(accum, pix, vmul(W, local));
+    }
+
+    if (depth <= 0) return;        // all three recursive helpers start with `if(recDepth <= 0) return 0`
+
+    if (mat.type == DT_MAT_MIRROR) {                                              // raytracer.cpp:442-472
+        DtChild c;
+        c.d = reflect_dir(rng, normal, w_o, mat.roughness);
+        c.o = vadd(hitPoint, vscale(normal, S.shadow_ray_epsilon)); c.mb = mb;
+        c.W = vmul(W, F3(mat.mirror)); c.n_medium = 1.0f; c.thr = thr; c.beer_thr = 0.f;
+        c.depth = depth - 1; c.beer_mat = 0; c.rng_key = dt_hash(rng.key, 0x1B873593u); c.flags = 0; c.miss = V(0, 0, 0);
+        if (S.n_env_lights > 0) { c.flags |= DT_FLAG_ENV_ON_MISS; c.miss = env_sample(S, 0, c.d); }
+        dt_emit_child(out, out_miss, counters, out_capacity, pix, c);
+    } else if (mat.type == DT_MAT_CONDUCTOR) {                                    // raytracer.cpp:208-254
+        v3 dd = vneg(w_o);
+        float cosTheta = -vdot(dd, normal);
+        float n2 = mat.refractive_index, k2 = mat.conductor_absorption_index;
+        float n2k2 = n2 * n2 + k2 * k2;
+        float n2cosTheta2 = 2 * n2 * cosTheta;
+        float cosThetaSqr = cosTheta * cosTheta;
+        float rs = (n2k2 - n2cosTheta2 + cosThetaSqr) / (n2k2 + n2cosTheta2 + cosThetaSqr);
+        float rp = (n2k2 * cosThetaSqr - n2cosTheta2 + 1) / (n2k2 * cosThetaSqr + n2cosTheta2 + 1);
+        float reflectRatio = (float)(0.5 * (double)(rs + rp));
+        if (reflectRatio > 0.0001) {
+            DtChild c;
+            c.d = reflect_dir(rng, normal, w_o, mat.roughness);
+            c.o = vadd(hitPoint, vscale(normal, S.shadow_ray_epsilon)); c.mb = mb;
+            c.W = vscale(vmul(W, F3(mat.mirror)), reflectRatio); c.n_medium = 1.0f; c.thr = thr; c.beer_thr = 0.f;
+            c.depth = depth - 1; c.beer_mat = 0; c.rng_key = dt_hash(rng.key, 0x2C1B3C6Du); c.flags = 0; c.miss = V(0, 0, 0);
+            dt_emit_child(out, out_miss, counters, out_capacity, pix, c);
+        }
+    } else if (mat.type == DT_MAT_DIELECTRIC) {                                   // raytracer.cpp:261-415
+        float n1 = n_medium, n2 = mat.refractive_index;
+        v3 dd = vneg(w_o);
+        v3 mn = normal;
+        float cosTheta = -vdot(dd, mn);
+        const bool isEntering = cosTheta > 0.f;
+        float objN = n2;
+        if (!isEntering) { n1 = n2; n2 = 1.0f; objN = 1.0f; cosTheta = fabsf(cosTheta); mn = vneg(mn); }
+        float r = n1 / n2;
+        float sinThetaSqr = 1 - (cosTheta * cosTheta);
+        float criticalTerm = r * r * sinThetaSqr;
+        const int mat_id = sh.material;
+        if (criticalTerm > 1) {
+            DtChild c;
+            c.d = reflect_dir(rng, mn, w_o, mat.roughness);
+            c.o = vadd(hitPoint, vscale(mn, S.shadow_ray_epsilon)); c.mb = mb;
+            c.W = W; c.n_medium = n_medium; c.thr = thr; c.beer_thr = 1.0001f;
+            c.depth = depth - 1; c.beer_mat = mat_id; c.rng_key = dt_hash(rng.key, 0x3D4D51CBu); c.flags = 0; c.miss = V(0, 0, 0);
+            dt_emit_child(out, out_miss, counters, out_capacity, pix, c);
+        } else {
+            float cosPhi = sqrtf(1 - criticalTerm);
+            float n2cosTheta = n2 * cosTheta;
+            float n1cosPhi = n1 * cosPhi;
+            float rparallel = (n2cosTheta - n1cosPhi) / (n2cosTheta + n1cosPhi);
+            float rperp = (n1 * cosTheta - n2 * cosPhi) / (n1 * cosTheta + n2 * cosPhi);
+            float rReflect = (rparallel * rparallel + rperp * rperp) / 2;
+            float rRefract = 1 - rReflect;
+            const float child_n = isEntering ? objN : 1.0f;
+            DtChild c;
+            c.d = reflect_dir(rng, mn, w_o, mat.roughness);
+            const v3 refl_dir = c.d;
+            c.o = vadd(hitPoint, vscale(mn, S.shadow_ray_epsilon)); c.mb = mb;
+            c.W = vscale(W, rReflect); c.n_medium = child_n; c.thr = thr; c.beer_thr = 1.00001f;
+            c.depth = depth - 1; c.beer_mat = mat_id; c.rng_key = dt_hash(rng.key, 0x4CF5AD43u); c.flags = 0; c.miss = V(0, 0, 0);
+            v3 env = V(0, 0, 0);
+            if (S.n_env_lights > 0) { env = env_sample(S, 0, refl_dir); c.flags |= DT_FLAG_ENV_ON_MISS; c.miss = env; }
+            dt_emit_child(out, out_miss, counters, out_capacity, pix, c);
+
+            v3 w_t = vsub(vscale(vadd(dd, vscale(mn, cosTheta)), r), vscale(mn, cosPhi));
+            if (mat.roughness > 0.001) {
+                v3 u, v;
+                orthonormal_basis(w_t, u, v);
+                float psi1 = rng01(rng) - 0.5f, psi2 = rng01(rng) - 0.5f;
+                w_t = vunit(vadd(w_t, vscale(vadd(vscale(u, psi1), vscale(v, psi2)), mat.roughness)));
+            } else w_t = vunit(w_t);
+            c.d = w_t;
+            c.o = vadd(hitPoint, vscale(vneg(mn), S.shadow_ray_epsilon));
+            c.W = vscale(W, rRefract); c.beer_thr = 1.001f;
+            c.rng_key = dt_hash(rng.key, 0x5A27B1E9u);
+            // a refracted ray that misses reads the environment along the REFLECTED direction (raytracer.cpp:408)
+            dt_emit_child(out, out_miss, counters, out_capacity, pix, c);
+        }
+    }
+}
+
+// Deferred mesh-light NEE (see k_shade): after the next wave's closest-hit pass, drop the entries whose GI
+// child hit the emissive shape carrying the same light id; the survivors are traced like any shadow ray.
+__global__ void k_filter_deferred(DtSceneDev S, DtShadowQueue sq, int n, DtRayQueue next) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int2 df = sq.defer[i];
+    if (df.x < 0) return;
+    const int hs = __float_as_int(next.hit0[df.x].w);
+    if (hs < 0) return;
+    const DtShapeDev& sh = S.shapes[hs];
+    if (S.materials[sh.material - 1].type == DT_MAT_EMISSIVE && sh.id == df.y)
+        sq.contrib_pix[i] = make_float4(0.f, 0.f, 0.f, sq.contrib_pix[i].w);
+}
+
+// ------------------------------------------------------------------ resolve
+// main.cpp:97-125: Gaussian-weighted resolve, HDR store, LDR clamp((int)c) with cvttss2si semantics
+__device__ __forceinline__ int dt_clamp_channel(float f) {
+    int v;
+    if (!(f > -2147483904.0f && f < 2147483648.0f)) v = (int)0x80000000; else v = (int)f;
+    return v < 0 ? 0 : (v > 255 ? 255 : v);
+}
+__global__ void k_resolve(const float4* accum, int n_pix, int spp, float* hdr, uint8_t* ldr, int* counters) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pix) return;
+    const float4 a = accum[i];
+    float r = a.x, g = a.y, b = a.z;
+    if (spp > 1 && a.w > 0.f) { r = r / a.w; g = g / a.w; b = b / a.w; }
+    if (isnan(r) || isnan(g) || isnan(b)) atomicAdd(counters + DT_CNT_NAN, 1);
+    if (hdr) { hdr[3 * (size_t)i] = r; hdr[3 * (size_t)i + 1] = g; hdr[3 * (size_t)i + 2] = b; }
+    if (ldr) {
+        ldr[3 * (size_t)i] = (uint8_t)dt_clamp_channel(r);
+        ldr[3 * (size_t)i + 1] = (uint8_t)dt_clamp_channel(g);
+        ldr[3 * (size_t)i + 2] = (uint8_t)dt_clamp_channel(b);
+    }
+}
+
+// LDR clamp of an already resolved radiance buffer (main.cpp:118-125)
+__global__ void k_clamp_hdr(const float* hdr, int n_pix, uint8_t* ldr) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pix) return;
+    ldr[3 * (size_t)i] = (uint8_t)dt_clamp_channel(hdr[3 * (size_t)i]);
+    ldr[3 * (size_t)i + 1] = (uint8_t)dt_clamp_channel(hdr[3 * (size_t)i + 1]);
+    ldr[3 * (size_t)i + 2] = (uint8_t)dt_clamp_channel(hdr[3 * (size_t)i + 2]);
+}
+
+// ------------------------------------------------------------------ tonemap (tonemapper.h:28-119)
+// pass 1: sum of log(delta + Y) in double;  pass 2: exact k-th smallest of all 3N channel values by 4-pass
+// radix select on order-preserving keys (the reference sorts all 3N floats, tonemapper.h:51);  pass 3: map.
+__device__ __forceinline__ uint32_t dt_float_key(float f) { uint32_t u = __float_as_uint(f); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
+__device__ __forceinline__ float dt_key_float(uint32_t k) { uint32_t u = (k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k; return __uint_as_float(u); }
+
+__global__ void k_tm_logsum(const float* hdr, int n_pix, double* sum) {
+    double local = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pix; i += gridDim.x * blockDim.x) {
+        double r = hdr[3 * (size_t)i], g = hdr[3 * (size_t)i + 1], b = hdr[3 * (size_t)i + 2];
+        double lum = 0.2126 * r + 0.7152 * g + 0.0722 * b;
+        local += log((double)0.01f + lum);
+    }
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xFFFFFFFFu, local, o);
+    __shared__ double ws[32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) ws[wid] = local;
+    __syncthreads();
+    if (wid == 0) {
+        local = lane < (blockDim.x >> 5) ? ws[lane] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xFFFFFFFFu, local, o);
+        if (lane == 0) atomicAdd(sum, local);
+    }
+}
+// histogram of byte `shift/8` of the keys whose higher bytes equal `prefix`
+__global__ void k_tm_hist(const float* vals, size_t n, uint32_t prefix, uint32_t prefix_mask, int shift, unsigned int* hist) {
+    __shared__ unsigned int sh[256];
+    for (int k = threadIdx.x; k < 256; k += blockDim.x) sh[k] = 0;
+    __syncthreads();
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        uint32_t key = dt_float_key(vals[i]);
+        if ((key & prefix_mask) == prefix) atomicAdd(&sh[(key >> shift) & 0xFFu], 1u);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < 256; k += blockDim.x) if (sh[k]) atomicAdd(&hist[k], sh[k]);
+}
+// single-thread step of the select: pick the bucket holding rank `*rank`, refine prefix
+__global__ void k_tm_pick(unsigned int* hist, unsigned long long* rank, uint32_t* prefix, int shift) {
+    unsigned long long r = *rank;
+    uint32_t b = 0;
+    for (; b < 256; b++) { unsigned int c = hist[b]; if (r < c) break; r -= c; }
+    if (b > 255) b = 255;
+    *rank = r;
+    *prefix |= (b << shift);
+    for (int k = 0; k < 256; k++) hist[k] = 0;
+}
+__global__ void k_tm_map(const float* hdr, int n_pix, const double* logsum, const uint32_t* white_key, float key, float burn,
+                         float saturation, float gamma, uint8_t* ldr) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pix) return;
+    const double avgLum = exp(*logsum / (double)n_pix);
+    double R = hdr[3 * (size_t)i], G = hdr[3 * (size_t)i + 1], B = hdr[3 * (size_t)i + 2];
+    double y_i = 0.2126 * R + 0.7152 * G + 0.0722 * B;
+    float y_of;
+    {
+        double Lxy = ((double)key * y_i) / avgLum;
+        if (burn > 0.01) {
+            double thr = (double)dt_key_float(*white_key);
+            thr = thr * (double)key / avgLum;
+            double LwhiteSqr = thr * thr;
+            y_of = (float)((Lxy * (1 + (Lxy / LwhiteSqr))) / (1.0f + Lxy));
+        } else y_of = (float)(Lxy / (1 + Lxy));
+    }
+    double y_o = y_of;
+    double r_o = clipf((float)(y_o * pow((R / y_i), (double)saturation)), 0.0f, 1.0f);
+    double g_o = clipf((float)(y_o * pow((G / y_i), (double)saturation)), 0.0f, 1.0f);
+    double b_o = clipf((float)(y_o * pow((B / y_i), (double)saturation)), 0.0f, 1.0f);
+    double gammaInv = 1.0f / gamma;
+    int cr = (int)floor(fmin(255.0, 255 * pow(r_o, gammaInv)));
+    int cg = (int)floor(fmin(255.0, 255 * pow(g_o, gammaInv)));
+    int cb = (int)floor(fmin(255.0, 255 * pow(b_o, gammaInv)));
+    ldr[3 * (size_t)i] = (uint8_t)cr; ldr[3 * (size_t)i + 1] = (uint8_t)cg; ldr[3 * (size_t)i + 2] = (uint8_t)cb;
+}
+
+// ------------------------------------------------------------------ small utility kernels
+__global__ void k_pack_rays(const float* origins, const float* dirs, const float* tmax, int n, float4* o_time, float4* d_tmax) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    o_time[i] = make_float4(origins[3 * (size_t)i], origins[3 * (size_t)i + 1], origins[3 * (size_t)i + 2], 0.f);
+    d_tmax[i] = make_float4(dirs[3 * (size_t)i], dirs[3 * (size_t)i + 1], dirs[3 * (size_t)i + 2], tmax ? tmax[i] : CUDART_INF_F);
+}
+__global__ void k_unpack_hits(const float4* hit0, const int32_t* hit_face, const uint32_t* pixel, int n, int32_t* shape, int32_t* face, float* t, int by_pixel) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int dst = i;
+    if (by_pixel) { if (pixel[i] == DT_DEAD_PIXEL) return; dst = (int)pixel[i]; }
+    const float4 h = hit0[i];
+    const int s = __float_as_int(h.w);
+    shape[dst] = s; face[dst] = s >= 0 ? hit_face[i] : -1; t[dst] = s >= 0 ? h.x : CUDART_INF_F;
+}

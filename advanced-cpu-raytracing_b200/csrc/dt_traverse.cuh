@@ -1,0 +1,259 @@
+// Closest-hit / any-hit traversal of the two-level wide BVH (device functions).
+//
+// Replaces: Raytracer::IntersectObjects (raytracer.cpp:625-643), Raytracer::CastShadowRay (:585-623),
+// Mesh::Intersect (mesh.cpp:158-188), InstancedMesh::Intersect (instancedMesh.cpp:16-66),
+// BVH::IntersectBVH (bvh.cpp:5-31), the hit test of Mesh::IntersectFace (mesh.cpp:201-236) and
+// Sphere::Intersect (sphere.cpp:13-72).
+//
+// Parity design: box tests against the quantised BVH8 are conservative (outward-rounded boxes, FMA with
+// slack) and only select candidates; every accept/reject decision that the reference makes in float —
+// per-shape slab tests, the double-precision ray transform, Cramer's rule, the sphere quadratic — is
+// re-evaluated op-for-op.  Ties: the reference keeps the first hit in scan order (strict `<`), i.e. lowest
+// shape index then lowest canonical face index; we replace iff (t, shape, face) is lexicographically smaller.
+#pragma once
+#include "dt_device.h"
+#include "dt_math.cuh"
+
+struct DtHit {
+    float t;
+    float beta, gamma;
+    int shape;
+    int face;
+};
+
+// helperMath.cpp:132-138 with m = [a b c] as columns (rows x,y,z): exact association, no contraction.
+__device__ __forceinline__ float det3(v3 a, v3 b, v3 c) {
+    float first = __fmul_rn(a.x, __fsub_rn(__fmul_rn(b.y, c.z), __fmul_rn(c.y, b.z)));
+    float second = __fmul_rn(a.y, __fsub_rn(__fmul_rn(c.x, b.z), __fmul_rn(b.x, c.z)));
+    float third = __fmul_rn(a.z, __fsub_rn(__fmul_rn(b.x, c.y), __fmul_rn(b.y, c.x)));
+    return __fadd_rn(__fadd_rn(first, second), third);
+}
+
+// Mesh::IntersectFace hit test (mesh.cpp:203-236).  e1 = v0-v1, e2 = v0-v2 are stored precomputed (they are
+// the same single float subtractions the reference performs per test).
+__device__ __forceinline__ bool tri_test_exact(v3 o, v3 d, v3 v0, v3 e1, v3 e2, float& t, float& beta, float& gamma) {
+    float detA = det3(e1, e2, d);
+    if (detA == 0) return false;
+    v3 s = vsub(v0, o);
+    beta = __fdiv_rn(det3(s, e2, d), detA);
+    if (beta < 0) return false;
+    gamma = __fdiv_rn(det3(e1, s, d), detA);
+    if (gamma < 0 || __fadd_rn(gamma, beta) > 1) return false;
+    t = __fdiv_rn(det3(e1, e2, s), detA);
+    return true;      // caller applies: t > 0 && t < minT
+}
+
+// Sphere::Intersect hit distance (sphere.cpp:13-72) for a ray already in the sphere's local space.
+__device__ __forceinline__ bool sphere_test_exact(v3 o, v3 d, v3 center, float radius, float& t) {
+    v3 oc = vsub(o, center);
+    float c = __fsub_rn(vdot(oc, oc), __fmul_rn(radius, radius));
+    float b = __fmul_rn(2.0f, vdot(d, oc));
+    float a = vdot(d, d);
+    float delta = __fsub_rn(__fmul_rn(b, b), __fmul_rn(__fmul_rn(4.0f, a), c));
+    if (delta < 0.0f) return false;
+    delta = __fsqrt_rn(delta);
+    a = (float)(2.0 * (double)a);
+    float t1 = __fdiv_rn(__fadd_rn(-b, delta), a);
+    float t2 = __fdiv_rn(__fsub_rn(-b, delta), a);
+    t = t1 < t2 ? t1 : t2;
+    if (t1 < t2) { if (t1 > 0.0f) t = t1; else t = t2; }
+    else if (t2 < t1) { if (t2 > 0.0f) t = t2; else t = t1; }
+    return true;      // caller applies: t < minT && t > 0
+}
+
+struct DtRayPrep {
+    v3 o, d;
+    float idx, idy, idz;    // clamped reciprocal direction
+    uint32_t oct_inv4;
+};
+
+__device__ __forceinline__ float dt_safe_rcp(float d) {
+    return fabsf(d) < 1e-30f ? copysignf(1e30f, d) : __frcp_rn(d);
+}
+__device__ __forceinline__ void dt_prep(DtRayPrep& r, v3 o, v3 d) {
+    r.o = o; r.d = d;
+    r.idx = dt_safe_rcp(d.x); r.idy = dt_safe_rcp(d.y); r.idz = dt_safe_rcp(d.z);
+    uint32_t oct = (d.x < 0.f ? 0u : 4u) | (d.y < 0.f ? 0u : 2u) | (d.z < 0.f ? 0u : 1u);   // 7 - octant
+    r.oct_inv4 = oct * 0x01010101u;
+}
+
+__device__ __forceinline__ uint32_t dt_sign_extend_s8x4(uint32_t x) {
+    // each byte's top bit replicated over the byte
+    return ((x >> 7) & 0x01010101u) * 0xFFu;
+}
+__device__ __forceinline__ uint32_t dt_byte(uint32_t w, int j) { return (w >> (j * 8)) & 0xFFu; }
+
+#define DT_SLACK_HI 1.0000019f     // 1 + 2^-19: conservative inflation of the slab interval against FMA/rcp rounding
+#define DT_SLACK_LO 0.9999981f
+
+// Test the 8 quantised child boxes of a node; returns the hit mask (top 8 bits: internal children in
+// traversal-priority order, low 24 bits: primitives of hit leaf children).
+__device__ __forceinline__ uint32_t dt_node_hits(const uint4 n0, const uint4 n1, const uint4 n2, const uint4 n3, const uint4 n4,
+                                                 const DtRayPrep& r, float tmax) {
+    const uint32_t e_imask = n0.w;
+    const float ax = __fmul_rn(__uint_as_float((e_imask & 0xFFu) << 23), r.idx);
+    const float ay = __fmul_rn(__uint_as_float(((e_imask >> 8) & 0xFFu) << 23), r.idy);
+    const float az = __fmul_rn(__uint_as_float(((e_imask >> 16) & 0xFFu) << 23), r.idz);
+    const float bx = __fmul_rn(__fsub_rn(__uint_as_float(n0.x), r.o.x), r.idx);
+    const float by = __fmul_rn(__fsub_rn(__uint_as_float(n0.y), r.o.y), r.idy);
+    const float bz = __fmul_rn(__fsub_rn(__uint_as_float(n0.z), r.o.z), r.idz);
+    uint32_t hitmask = 0;
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+        const uint32_t meta4 = half ? n1.w : n1.z;
+        const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+        const uint32_t inner_mask4 = dt_sign_extend_s8x4(is_inner4 << 3);
+        const uint32_t bit_index4 = (meta4 ^ (r.oct_inv4 & inner_mask4)) & 0x1F1F1F1Fu;
+        const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
+        const uint32_t qlox = half ? n2.y : n2.x, qloy = half ? n2.w : n2.z, qloz = half ? n3.y : n3.x;
+        const uint32_t qhix = half ? n3.w : n3.z, qhiy = half ? n4.y : n4.x, qhiz = half ? n4.w : n4.z;
+        const uint32_t nx = r.idx < 0.f ? qhix : qlox, fx = r.idx < 0.f ? qlox : qhix;
+        const uint32_t ny = r.idy < 0.f ? qhiy : qloy, fy = r.idy < 0.f ? qloy : qhiy;
+        const uint32_t nz = r.idz < 0.f ? qhiz : qloz, fz = r.idz < 0.f ? qloz : qhiz;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const float tnx = __fmaf_rn((float)dt_byte(nx, j), ax, bx);
+            const float tny = __fmaf_rn((float)dt_byte(ny, j), ay, by);
+            const float tnz = __fmaf_rn((float)dt_byte(nz, j), az, bz);
+            const float tfx = __fmaf_rn((float)dt_byte(fx, j), ax, bx);
+            const float tfy = __fmaf_rn((float)dt_byte(fy, j), ay, by);
+            const float tfz = __fmaf_rn((float)dt_byte(fz, j), az, bz);
+            // fminf/fmaxf drop NaNs (0*inf on axis-parallel rays): a NaN constraint is ignored = conservative
+            const float tn = __fmul_rn(fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f)), DT_SLACK_LO);
+            const float tf = __fmul_rn(fminf(fminf(tfx, tfy), fminf(tfz, tmax)), DT_SLACK_HI);
+            if (tn <= tf) hitmask |= dt_byte(child_bits4, j) << dt_byte(bit_index4, j);
+        }
+    }
+    return hitmask;
+}
+
+// (t, shape, face) lexicographic "strictly better" — the reference's scan order with strict `<`.
+__device__ __forceinline__ bool dt_better(float t, int shape, int face, const DtHit& best) {
+    if (t < best.t) return true;
+    if (t > best.t || !(t == best.t)) return false;
+    if (best.shape < 0) return true;            // best.t == INFINITY and t == INFINITY cannot be a hit; defensive
+    if (shape != best.shape) return shape < best.shape;
+    return face < best.face;
+}
+
+// ANY = true: occlusion query (CastShadowRay): returns as soon as any hit with 0 < t < tmax_in exists,
+// skipping Emissive mesh shapes; best.shape >= 0 marks "occluded".
+template <bool ANY>
+__device__ __forceinline__ void dt_trace(const DtSceneDev& S, v3 wo, v3 wd, float mb_time, float tmax_in, DtHit& best) {
+    uint2 stack[DT_STACK_SIZE];
+    int sp = 0;
+    best.t = ANY ? tmax_in : CUDART_INF_F;
+    const float any_min_t = __fadd_rn(tmax_in, 0.01f);     // shadowRay.hitInfo.minT (raytracer.cpp:580)
+    best.shape = -1; best.face = -1; best.beta = 0.f; best.gamma = 0.f;
+
+    DtRayPrep r;
+    dt_prep(r, wo, wd);
+    bool in_blas = false;
+    int blas_sp = 0;
+    int cur_shape = -1;
+    const uint4* nodes = S.tlas_nodes;
+    uint2 ng = make_uint2(0u, 0x80000000u);     // root as the single "child" of a virtual group
+    uint2 tg = make_uint2(0u, 0u);
+
+    for (;;) {
+        if (ng.y > 0x00FFFFFFu) {
+            const uint32_t hits = ng.y;
+            const uint32_t imask = ng.y & 0xFFu;
+            const int child_bit = 31 - __clz(hits);
+            ng.y &= ~(1u << child_bit);
+            if (ng.y > 0x00FFFFFFu) { if (sp < DT_STACK_SIZE) stack[sp++] = ng; }
+            const uint32_t slot = (uint32_t)(child_bit - 24) ^ (r.oct_inv4 & 0xFFu);
+            const uint32_t rel = __popc(imask & ~(0xFFFFFFFFu << slot));
+            const uint32_t ni = ng.x + rel;
+            const uint4* np = nodes + (size_t)ni * 5;
+            const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+            const uint32_t hm = dt_node_hits(n0, n1, n2, n3, n4, r, best.t);
+            ng.x = n1.x;
+            ng.y = (hm & 0xFF000000u) | (n0.w >> 24);
+            tg.x = n1.y;
+            tg.y = hm & 0x00FFFFFFu;
+        } else {
+            tg = ng;
+            ng = make_uint2(0u, 0u);
+        }
+
+        while (tg.y != 0u) {
+            const int bit = __ffs(tg.y) - 1;
+            tg.y &= ~(1u << bit);
+            const uint32_t prim = tg.x + (uint32_t)bit;
+            if (in_blas) {
+                const float4* tp = S.tris + (size_t)prim * 3;
+                const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+                float t, beta, gamma;
+                if (tri_test_exact(r.o, r.d, V(a.x, a.y, a.z), V(a.w, b.x, b.y), V(b.z, b.w, c.x), t, beta, gamma)) {
+                    const int face = __float_as_int(c.y);
+                    const bool cand = ANY ? (t > 0.0f && t < best.t) : (t > 0.0f && dt_better(t, cur_shape, face, best));
+                    if (cand) {
+                        // The reference only reaches this face if the float slab test of its BVH2 leaf passes
+                        // (bvh.cpp:7-10); every ancestor box contains the leaf box, and the float slab interval is
+                        // monotone in the box, so the leaf test implies the ancestors'.  Rare path: runs only for
+                        // would-be winners.
+                        const float4 lb0 = __ldg(S.leaf_boxes + (size_t)prim * 2), lb1 = __ldg(S.leaf_boxes + (size_t)prim * 2 + 1);
+                        const float lmn[3] = {lb0.x, lb0.y, lb0.z}, lmx[3] = {lb1.x, lb1.y, lb1.z};
+                        if (box_intersect_exact(lmn, lmx, r.o, r.d, ANY ? any_min_t : best.t)) {
+                            if (ANY) { best.shape = cur_shape; best.face = face; best.t = t; return; }
+                            best.t = t; best.beta = beta; best.gamma = gamma; best.shape = cur_shape; best.face = face;
+                        }
+                    }
+                }
+            } else {
+                const int si = __ldg(S.tlas_prims + prim);
+                const DtShapeDev* sh = S.shapes + si;
+                if (ANY && sh->skip_shadow) continue;
+                const int kind = sh->kind;
+                if (kind == DT_SHAPE_SPHERE) {
+                    v3 lo = apply_transform(sh->inv, wo, 1.0f);
+                    v3 ld = apply_transform(sh->inv, wd, 0.0f);
+                    if (sh->has_motion_blur) lo = vadd(lo, vscale(F3(sh->motion_blur), mb_time));
+                    float t;
+                    if (sphere_test_exact(lo, ld, F3(sh->center), sh->radius, t)) {
+                        if (ANY) {
+                            if (t > 0.0f && t < best.t) { best.shape = si; best.face = -1; best.t = t; return; }
+                        } else if (t > 0.0f && dt_better(t, si, -1, best)) {
+                            best.t = t; best.beta = 0.f; best.gamma = 0.f; best.shape = si; best.face = -1;
+                        }
+                    }
+                    continue;
+                }
+                // Mesh / InstancedMesh: the reference's exact per-shape pre-tests, then descend into the BLAS.
+                if (kind == DT_SHAPE_INSTANCE) {
+                    v3 so = wo;
+                    if (sh->has_motion_blur) so = vadd(so, vscale(F3(sh->motion_blur), mb_time));
+                    if (!box_intersect_exact(sh->bbox_min, sh->bbox_max, so, wd, best.t)) continue;     // instancedMesh.cpp:29
+                }
+                v3 lo = apply_transform(sh->inv, wo, 1.0f);
+                v3 ld = apply_transform(sh->inv, wd, 0.0f);
+                if (sh->has_motion_blur) lo = vadd(lo, vscale(F3(sh->motion_blur), mb_time));
+                const DtMeshDev* m = S.meshes + sh->mesh;
+                // mesh.cpp:172 (Mesh::bbox) and the root node of BVH::IntersectBVH (same box) in local space
+                if (!box_intersect_exact(m->bbox_min, m->bbox_max, lo, ld, best.t)) continue;
+                if (ng.y > 0x00FFFFFFu) { if (sp < DT_STACK_SIZE) stack[sp++] = ng; }
+                if (tg.y != 0u) { if (sp < DT_STACK_SIZE) stack[sp++] = tg; }
+                blas_sp = sp;
+                in_blas = true;
+                cur_shape = si;
+                dt_prep(r, lo, ld);
+                nodes = S.blas_nodes;
+                ng = make_uint2(m->node_root, 0x80000000u);
+                tg = make_uint2(0u, 0u);
+                break;
+            }
+        }
+
+        if (ng.y <= 0x00FFFFFFu) {
+            if (in_blas && sp == blas_sp) {
+                in_blas = false;
+                dt_prep(r, wo, wd);
+                nodes = S.tlas_nodes;
+            }
+            if (sp == 0) break;
+            ng = stack[--sp];
+        }
+    }
+    if (ANY) best.shape = -1;
+}

@@ -1,0 +1,71 @@
+// raytracer_gpu — the reference's command line (src/main.cpp:132-202: `raytracer scene.xml`) on the GPU path.
+// Parse with the host mirror, hand the flat scene to the C ABI once, render every camera with one dt_render
+// call each (replacing the thread spawn / join / tonemap block, main.cpp:164-192), write <ImageName>.png.
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/dorktracer_host.h"
+
+static void write_rgbe(const char* path, int w, int h, const float* rgb) {     // main.cpp:191 (stbi_write_hdr): flat RGBE
+    FILE* f = fopen(path, "wb");
+    if (!f) return;
+    fprintf(f, "#?RADIANCE\nFORMAT=32-bit_rle_rgbe\n\n-Y %d +X %d\n", h, w);
+    std::vector<unsigned char> row((size_t)w * 4);
+    for (int y = 0; y < h; y++) {
+        for (int x = 0; x < w; x++) {
+            const float* p = rgb + ((size_t)y * w + x) * 3;
+            float m = p[0] > p[1] ? p[0] : p[1]; if (p[2] > m) m = p[2];
+            unsigned char* o = &row[(size_t)x * 4];
+            if (!(m > 1e-32f)) { o[0] = o[1] = o[2] = o[3] = 0; continue; }
+            int e; float n = frexpf(m, &e) * 256.0f / m;
+            o[0] = (unsigned char)(p[0] * n); o[1] = (unsigned char)(p[1] * n); o[2] = (unsigned char)(p[2] * n); o[3] = (unsigned char)(e + 128);
+        }
+        fwrite(row.data(), 1, row.size(), f);
+    }
+    fclose(f);
+}
+
+int main(int argc, char* argv[]) {
+    if (argc < 2) { fprintf(stderr, "usage: %s scene.xml [--device N] [--seed S]\n", argv[0]); return 2; }
+    int device = 0; unsigned long long seed = 1234;
+    for (int i = 2; i + 1 < argc; i++) {
+        if (!strcmp(argv[i], "--device")) device = atoi(argv[i + 1]);
+        if (!strcmp(argv[i], "--seed")) seed = strtoull(argv[i + 1], nullptr, 10);
+    }
+    dth_scene* hs = nullptr;
+    if (dth_scene_load_xml(argv[1], &hs) != DT_OK) { fprintf(stderr, "%s\n", dth_last_error()); return 1; }
+    for (int i = 0; i < dth_scene_desc(hs)->n_images; i++)
+        if (!dth_scene_image_loaded(hs, i)) { fprintf(stderr, "image '%s' could not be decoded (PNG/EXR only in the stand-alone driver)\n", dth_scene_image_path(hs, i)); return 1; }
+    if (dt_gpu_init(device) < 0) { fprintf(stderr, "%s\n", dt_last_error()); return 1; }
+    dt_scene* gs = nullptr;
+    if (dt_scene_create(dth_scene_desc(hs), &gs) != DT_OK) { fprintf(stderr, "%s\n", dt_last_error()); return 1; }
+    auto start = std::chrono::steady_clock::now();
+    for (int c = 0; c < dth_scene_num_cameras(hs); c++) {
+        const dt_camera_desc* cam = dth_scene_camera(hs, c);
+        std::vector<uint8_t> ldr((size_t)cam->width * cam->height * 3);
+        std::vector<float> hdr;
+        if (cam->has_tonemapper) hdr.resize((size_t)cam->width * cam->height * 3);
+        dt_render_params p; memset(&p, 0, sizeof p); p.seed = seed; p.tile_world = 1;
+        dt_stats st;
+        printf("Resolution: %dx%d, Running on: GPU %d\n", cam->width, cam->height, device);
+        if (dt_render(gs, cam, &p, ldr.data(), hdr.empty() ? nullptr : hdr.data(), &st) != DT_OK) { fprintf(stderr, "%s\n", dt_last_error()); return 1; }
+        std::string name = dth_scene_camera_image_name(hs, c);
+        if (cam->has_tonemapper) write_rgbe(name.c_str(), cam->width, cam->height, hdr.data());
+        size_t dot = name.find_last_of('.');
+        std::string png = name.substr(0, dot) + ".png";
+        if (dth_write_png(png.c_str(), cam->width, cam->height, ldr.data()) != DT_OK) { fprintf(stderr, "%s\n", dth_last_error()); return 1; }
+        printf("%s: %llu closest + %llu shadow rays, %.3f ms on device (%.1f Mrays/s), %u waves\n", png.c_str(),
+               (unsigned long long)st.rays_closest, (unsigned long long)st.rays_shadow, st.ms_total,
+               (st.rays_closest + st.rays_shadow) / (st.ms_total * 1e3), st.waves);
+    }
+    auto end = std::chrono::steady_clock::now();
+    printf("Rendering took: %gs\n", std::chrono::duration<double>(end - start).count());
+    dt_scene_destroy(gs);
+    dth_scene_free(hs);
+    return 0;
+}
