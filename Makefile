@@ -4,8 +4,8 @@
 #   oracle/libdtoracle.so                            CPU restatement of the reference algorithm (TEST INFRASTRUCTURE ONLY)
 PKG      := advanced-cpu-raytracing_b200
 NVCC     ?= /usr/local/cuda/bin/nvcc
-CXX      ?= g++
-CC       ?= gcc
+CXX      := /usr/bin/g++
+CC       := /usr/bin/gcc
 
 # -fmad=false: the reference build has no FMA instructions; bit-exact hit parity needs unfused float math
 # (SURVEY.md 8a).  Device code that wants FMAs (conservative box tests) uses explicit __fmaf_* intrinsics.

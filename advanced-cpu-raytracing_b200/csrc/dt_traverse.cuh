@@ -195,7 +195,11 @@ __device__ __forceinline__ void dt_trace(const DtSceneDev& S, v3 wo, v3 wd, floa
                         // would-be winners.
                         const float4 lb0 = __ldg(S.leaf_boxes + (size_t)prim * 2), lb1 = __ldg(S.leaf_boxes + (size_t)prim * 2 + 1);
                         const float lmn[3] = {lb0.x, lb0.y, lb0.z}, lmx[3] = {lb1.x, lb1.y, lb1.z};
-                        if (box_intersect_exact(lmn, lmx, r.o, r.d, ANY ? any_min_t : best.t)) {
+                        // minT the reference would hold when it reaches this face: it scans in (shape, face) order, so a
+                        // candidate that precedes the current best was tested BEFORE that best existed.
+                        const bool after_best = best.shape >= 0 && (cur_shape > best.shape || (cur_shape == best.shape && face > best.face));
+                        const float ref_min_t = ANY ? any_min_t : (after_best ? best.t : CUDART_INF_F);
+                        if (box_intersect_exact(lmn, lmx, r.o, r.d, ref_min_t)) {
                             if (ANY) { best.shape = cur_shape; best.face = face; best.t = t; return; }
                             best.t = t; best.beta = beta; best.gamma = gamma; best.shape = cur_shape; best.face = face;
                         }
@@ -221,17 +225,19 @@ __device__ __forceinline__ void dt_trace(const DtSceneDev& S, v3 wo, v3 wd, floa
                     continue;
                 }
                 // Mesh / InstancedMesh: the reference's exact per-shape pre-tests, then descend into the BLAS.
+                // ray.hitInfo.minT at the time the reference scans shape si: only hits of lower-index shapes exist.
+                const float shape_min_t = ANY ? any_min_t : ((best.shape >= 0 && si > best.shape) ? best.t : CUDART_INF_F);
                 if (kind == DT_SHAPE_INSTANCE) {
                     v3 so = wo;
                     if (sh->has_motion_blur) so = vadd(so, vscale(F3(sh->motion_blur), mb_time));
-                    if (!box_intersect_exact(sh->bbox_min, sh->bbox_max, so, wd, best.t)) continue;     // instancedMesh.cpp:29
+                    if (!box_intersect_exact(sh->bbox_min, sh->bbox_max, so, wd, shape_min_t)) continue; // instancedMesh.cpp:29
                 }
                 v3 lo = apply_transform(sh->inv, wo, 1.0f);
                 v3 ld = apply_transform(sh->inv, wd, 0.0f);
                 if (sh->has_motion_blur) lo = vadd(lo, vscale(F3(sh->motion_blur), mb_time));
                 const DtMeshDev* m = S.meshes + sh->mesh;
                 // mesh.cpp:172 (Mesh::bbox) and the root node of BVH::IntersectBVH (same box) in local space
-                if (!box_intersect_exact(m->bbox_min, m->bbox_max, lo, ld, best.t)) continue;
+                if (!box_intersect_exact(m->bbox_min, m->bbox_max, lo, ld, shape_min_t)) continue;
                 if (ng.y > 0x00FFFFFFu) { if (sp < DT_STACK_SIZE) stack[sp++] = ng; }
                 if (tg.y != 0u) { if (sp < DT_STACK_SIZE) stack[sp++] = tg; }
                 blas_sp = sp;
