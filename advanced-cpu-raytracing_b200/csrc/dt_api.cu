@@ -634,6 +634,8 @@ int dt_tonemap(const float* hdr_rgb, int32_t width, int32_t height, float key, f
     return rc;
 }
 
+void* dt_scene_stream(dt_scene* s) { return s ? (void*)s->stream : nullptr; }
+
 const char* dt_last_error(void) { return g_err.c_str(); }
 const char* dt_version(void) { return "dorktracer-b200 0.1 (sm_100a, abi 1)"; }
 

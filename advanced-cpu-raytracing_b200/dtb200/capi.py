@@ -144,7 +144,7 @@ class dt_stats(C.Structure):
 DORKTRACER_SYMBOLS = [
     "dt_gpu_init", "dt_device_count", "dt_scene_create", "dt_scene_destroy", "dt_render", "dt_render_device",
     "dt_finish_device", "dt_primary_hits", "dt_trace_closest", "dt_trace_occluded", "dt_tonemap",
-    "dt_last_error", "dt_version",
+    "dt_scene_stream", "dt_last_error", "dt_version",
 ]
 DTHOST_SYMBOLS = [
     "dth_scene_load_xml", "dth_scene_free", "dth_scene_desc", "dth_scene_num_cameras", "dth_scene_camera",
@@ -224,6 +224,8 @@ def load_dorktracer():
     lib.dt_trace_occluded.restype = C.c_int
     lib.dt_tonemap.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]
     lib.dt_tonemap.restype = C.c_int
+    lib.dt_scene_stream.argtypes = [vp]
+    lib.dt_scene_stream.restype = C.c_void_p
     lib.dt_last_error.argtypes = []
     lib.dt_last_error.restype = C.c_char_p
     lib.dt_version.argtypes = []

@@ -160,6 +160,10 @@ class GpuScene:
             self._err("dt_trace_occluded", rc)
         return occ
 
+    @property
+    def stream_ptr(self):
+        return self.lib.dt_scene_stream(self.handle)
+
     def close(self):
         if self.handle:
             self.lib.dt_scene_destroy(self.handle)

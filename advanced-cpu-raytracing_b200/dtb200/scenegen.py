@@ -223,9 +223,12 @@ def gen_config4(out_dir, width=1920, height=1080, spp=256, depth=4, blob=(0, 0),
         return ("        <Material id=\"%d\"%s>\n            <AmbientReflectance>0 0 0</AmbientReflectance>\n            <DiffuseReflectance>%g %g %g</DiffuseReflectance>\n"
                 "            <SpecularReflectance>%g %g %g</SpecularReflectance>\n            <PhongExponent>10</PhongExponent>\n%s        </Material>\n" % ((i, attrs) + tuple(kd) + tuple(ks) + (more,)))
     xml += "    <Materials>\n"
-    xml += mat(1, (0.7, 0.7, 0.7))                                         # white walls
-    xml += mat(2, (0.7, 0.15, 0.12))                                       # red
-    xml += mat(3, (0.15, 0.6, 0.2))                                        # green
+    # The reference's GI estimator multiplies every bounce by f*cos*2pi whatever the sampling pdf (raytracer.cpp:187-188)
+    # and Russian roulette never shortens pure GI chains (throughput stays 1), so un-normalised Phong materials with
+    # kd > ~0.24 make its radiance diverge.  The diffuse surfaces therefore use the normalised (kd/pi) BRDF.
+    xml += mat(1, (0.5, 0.5, 0.5), (0, 0, 0), ' BRDF="2"')                # white walls
+    xml += mat(2, (0.5, 0.1, 0.08), (0, 0, 0), ' BRDF="2"')               # red
+    xml += mat(3, (0.1, 0.45, 0.15), (0, 0, 0), ' BRDF="2"')              # green
     xml += mat(4, (0.4, 0.35, 0.2), (0.5, 0.5, 0.5), ' BRDF="1"', "            <RefractionIndex>1.8</RefractionIndex>\n")    # Torrance-Sparrow
     xml += mat(5, (0.2, 0.3, 0.6), (0.4, 0.4, 0.4), ' BRDF="2"')         # modified Blinn-Phong
     xml += mat(6, (0, 0, 0))                                               # emissive (set by LightMesh)

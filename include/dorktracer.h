@@ -280,6 +280,10 @@ int dt_trace_occluded(dt_scene* scene, const float* origins, const float* dirs, 
 int dt_tonemap(const float* hdr_rgb, int32_t width, int32_t height, float key, float burn, float saturation,
                float gamma, uint8_t* ldr_rgb);
 
+/* The CUDA stream (cudaStream_t) all device work of this scene is enqueued on, so callers can bracket calls
+ * with their own CUDA events / order collectives after a render without a device-wide sync. */
+void* dt_scene_stream(dt_scene* scene);
+
 const char* dt_last_error(void);
 const char* dt_version(void);
 
