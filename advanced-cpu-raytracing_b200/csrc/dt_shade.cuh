@@ -19,7 +19,8 @@ __device__ __forceinline__ v3 image_sample(const DtSceneDev& S, const DtImageDev
     const uint8_t* p = S.image_u8 + im.offset + k;
     return V((float)p[0], (float)p[1], (float)p[2]);
 }
-__device__ __forceinline__ float clipf(float n, float lo, float hi) { return fmaxf(lo, fminf(n, hi)); }
+// std::max(lower, std::min(n, upper)) with the std:: NaN behaviour (a NaN input yields `lower`): imageTexture.h:107-109, tonemapper.h:121-124
+__device__ __forceinline__ float clipf(float n, float lo, float hi) { float m = (hi < n) ? hi : n; return (lo < m) ? m : lo; }
 
 // ImageTexture::GetRGBSample / interpolateBilinear (imageTexture.h:60-73, 111-133); PerlinTexture returns a
 // constant (perlinTexture.h:41-50).

@@ -151,7 +151,6 @@ DTHOST_SYMBOLS = [
     "dth_scene_camera_image_name", "dth_scene_set_image", "dth_scene_image_path", "dth_scene_image_loaded",
     "dth_camera_look_at", "dth_camera_default", "dth_write_png", "dth_last_error",
 ]
-DTORACLE_SYMBOLS = ["dto_render", "dto_primary_hits", "dto_tonemap", "dto_trace_closest", "dto_trace_occluded"]
 
 _libs = {}
 
@@ -230,20 +229,4 @@ def load_dorktracer():
     lib.dt_last_error.restype = C.c_char_p
     lib.dt_version.argtypes = []
     lib.dt_version.restype = C.c_char_p
-    return lib
-
-
-def load_dtoracle():
-    """CPU restatement of the reference algorithm — TEST INFRASTRUCTURE ONLY (tests/, smoke(), bench cpu_baseline)."""
-    lib = _load(os.path.join(REPO_DIR, "oracle", "libdtoracle.so"), "oracle library")
-    lib.dto_render.argtypes = [C.POINTER(dt_scene_desc), C.POINTER(dt_camera_desc), C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(dt_stats)]
-    lib.dto_render.restype = C.c_int
-    lib.dto_primary_hits.argtypes = [C.POINTER(dt_scene_desc), C.POINTER(dt_camera_desc), C.c_void_p, C.c_void_p, C.c_void_p]
-    lib.dto_primary_hits.restype = C.c_int
-    lib.dto_tonemap.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]
-    lib.dto_tonemap.restype = C.c_int
-    lib.dto_trace_closest.argtypes = [C.POINTER(dt_scene_desc), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
-    lib.dto_trace_closest.restype = C.c_int
-    lib.dto_trace_occluded.argtypes = [C.POINTER(dt_scene_desc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
-    lib.dto_trace_occluded.restype = C.c_int
     return lib

@@ -147,7 +147,9 @@ static v3 image_sample(const dt_image* im, int i, int j) {      /* LDRImage.h:16
     const uint8_t* p = (const uint8_t*)im->data;
     return V((float)p[k], (float)p[k + 1], (float)p[k + 2]);
 }
-static float clipf(float n, float lo, float hi) { return fmaxf(lo, fminf(n, hi)); }
+/* std::max(lower, std::min(n, upper)) with the std:: NaN behaviour: min(a,b) = (b<a)?b:a, max(a,b) = (a<b)?b:a, so a NaN
+   input yields `lower` (imageTexture.h:107-109, tonemapper.h:121-124) */
+static float clipf(float n, float lo, float hi) { float m = (hi < n) ? hi : n; return (lo < m) ? m : lo; }
 
 static v3 tex_rgb_sample(const dt_scene_desc* sc, const dt_texture* t, float u, float v) {
     if (t->kind == DT_TEX_PERLIN) return V(180, 30, 180);        /* perlinTexture.h:46-50 */

@@ -16,6 +16,25 @@ sys.path.insert(0, os.path.join(REPO, "advanced-cpu-raytracing_b200"))
 
 from dtb200 import capi  # noqa: E402
 
+DTORACLE_SYMBOLS = ["dto_render", "dto_primary_hits", "dto_tonemap", "dto_trace_closest", "dto_trace_occluded"]
+
+
+def load_dtoracle():
+    """CPU restatement of the reference algorithm — TEST INFRASTRUCTURE ONLY (tests/, smoke(), bench cpu_baseline)."""
+    lib = capi._load(os.path.join(REPO, "oracle", "libdtoracle.so"), "oracle library")
+    lib.dto_render.argtypes = [C.POINTER(capi.dt_scene_desc), C.POINTER(capi.dt_camera_desc), C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(capi.dt_stats)]
+    lib.dto_render.restype = C.c_int
+    lib.dto_primary_hits.argtypes = [C.POINTER(capi.dt_scene_desc), C.POINTER(capi.dt_camera_desc), C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.dto_primary_hits.restype = C.c_int
+    lib.dto_tonemap.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]
+    lib.dto_tonemap.restype = C.c_int
+    lib.dto_trace_closest.argtypes = [C.POINTER(capi.dt_scene_desc), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.dto_trace_closest.restype = C.c_int
+    lib.dto_trace_occluded.argtypes = [C.POINTER(capi.dt_scene_desc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    lib.dto_trace_occluded.restype = C.c_int
+    return lib
+
+
 REF_DIR = os.path.join(REPO, "oracle", "_ref")
 REF_BIN = os.path.join(REF_DIR, "raytracer")
 REF_PROBE = os.path.join(REF_DIR, "raytracer_probe")
@@ -26,7 +45,7 @@ def have_ref():
 
 
 def oracle_render(host_scene, cam, seed=1234, threads=None, want_hdr=True):
-    lib = capi.load_dtoracle()
+    lib = load_dtoracle()
     W, H = cam.width, cam.height
     ldr = np.zeros((H, W, 3), np.uint8)
     hdr = np.zeros((H, W, 3), np.float32) if want_hdr else None
@@ -39,7 +58,7 @@ def oracle_render(host_scene, cam, seed=1234, threads=None, want_hdr=True):
 
 
 def oracle_primary_hits(host_scene, cam):
-    lib = capi.load_dtoracle()
+    lib = load_dtoracle()
     n = cam.width * cam.height
     shape = np.empty(n, np.int32); face = np.empty(n, np.int32); t = np.empty(n, np.float32)
     rc = lib.dto_primary_hits(host_scene.desc_ptr, C.byref(cam), shape.ctypes.data_as(C.c_void_p),
@@ -50,7 +69,7 @@ def oracle_primary_hits(host_scene, cam):
 
 
 def oracle_trace_closest(host_scene, origins, dirs):
-    lib = capi.load_dtoracle()
+    lib = load_dtoracle()
     origins = np.ascontiguousarray(origins, np.float32); dirs = np.ascontiguousarray(dirs, np.float32)
     n = origins.shape[0]
     shape = np.empty(n, np.int32); face = np.empty(n, np.int32); t = np.empty(n, np.float32)
@@ -61,7 +80,7 @@ def oracle_trace_closest(host_scene, origins, dirs):
 
 
 def oracle_trace_occluded(host_scene, origins, dirs, tmax):
-    lib = capi.load_dtoracle()
+    lib = load_dtoracle()
     origins = np.ascontiguousarray(origins, np.float32); dirs = np.ascontiguousarray(dirs, np.float32)
     tmax = np.ascontiguousarray(tmax, np.float32)
     n = origins.shape[0]
@@ -73,7 +92,7 @@ def oracle_trace_occluded(host_scene, origins, dirs, tmax):
 
 
 def oracle_tonemap(hdr, key, burn, saturation, gamma):
-    lib = capi.load_dtoracle()
+    lib = load_dtoracle()
     hdr = np.ascontiguousarray(hdr, np.float32)
     H, W = hdr.shape[:2]
     ldr = np.zeros((H, W, 3), np.uint8)

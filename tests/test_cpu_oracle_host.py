@@ -260,8 +260,6 @@ def test_product_path_never_touches_the_oracle():
         for f in files:
             if f.endswith((".py", ".cpp", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(root, f), errors="replace").read()
-                if f == "capi.py":
-                    text = text.split("def load_dtoracle")[0]        # the loader stub itself is used by tests only
-                assert "dtoracle" not in text and "oracle_util" not in text and "dto_" not in text.replace("DTORACLE_SYMBOLS", ""), os.path.join(root, f)
+                assert "dtoracle" not in text and "oracle_util" not in text and "dto_" not in text, os.path.join(root, f)
     deps = subprocess.run(["ldd", os.path.join(pkg, "libdorktracer.so")], stdout=subprocess.PIPE).stdout.decode()
     assert "dtoracle" not in deps
