@@ -78,12 +78,25 @@ struct dt_scene {
     float* hdr = nullptr; uint8_t* ldr = nullptr; size_t out_pix = 0;
     double* tm_logsum = nullptr; unsigned int* tm_hist = nullptr; unsigned long long* tm_rank = nullptr; uint32_t* tm_prefix = nullptr;
     Timer t_total, t_gen, t_closest, t_shadow, t_shade, t_resolve, t_tm;
-    int grid_closest = 0, grid_shadow = 0;
+    int grid_trav[4][2] = {};
+    int trav_mode = 3, refill_threshold = 20;
 
     void free_queues() { for (void* p : qallocs) cudaFree(p); qallocs.clear(); capacity = shadow_capacity = 0; }
 };
 
 namespace {
+
+template <bool ANY>
+void launch_traverse(dt_scene* s, const DtRayQueue& q, const DtShadowQueue& sq, const int* n_ptr, int n_fixed, int* fetch, float4* accum) {
+    const int grid = s->grid_trav[s->trav_mode][ANY ? 1 : 0];
+    cudaStream_t st = s->stream;
+    switch (s->trav_mode) {
+        case 0: k_traverse<ANY, false><<<grid, 128, 0, st>>>(s->dev, q, sq, n_ptr, n_fixed, fetch, accum); break;
+        case 1: k_traverse<ANY, true><<<grid, 128, 0, st>>>(s->dev, q, sq, n_ptr, n_fixed, fetch, accum); break;
+        case 2: k_traverse_dyn<ANY, false><<<grid, 128, 0, st>>>(s->dev, q, sq, n_ptr, n_fixed, fetch, accum, s->refill_threshold); break;
+        default: k_traverse_dyn<ANY, true><<<grid, 128, 0, st>>>(s->dev, q, sq, n_ptr, n_fixed, fetch, accum, s->refill_threshold); break;
+    }
+}
 
 template <class T>
 int qalloc(dt_scene* s, T** p, size_t n) {
@@ -255,7 +268,7 @@ retry:
             CK(cudaMemsetAsync(s->counters + DT_CNT_NEXT, 0, sizeof(int), st));
             CK(cudaMemsetAsync(s->counters + DT_CNT_FETCH_A, 0, 2 * sizeof(int), st));
             s->t_closest.start(st);
-            k_traverse<false><<<s->grid_closest, 128, 0, st>>>(s->dev, s->q[cur], s->sq, nullptr, count, s->counters + DT_CNT_FETCH_A, s->accum);
+            launch_traverse<false>(s, s->q[cur], s->sq, nullptr, count, s->counters + DT_CNT_FETCH_A, s->accum);
             s->t_closest.stop(st);
             S.kernel_launches++; S.launches_traverse_closest++;
             if (primary_only) { CK(cudaStreamSynchronize(st)); S.ms_traverse_closest += s->t_closest.take(); S.ms_generate += s->t_gen.take(); S.waves++; break; }
@@ -263,7 +276,7 @@ retry:
             if (defer_mode && prev_shadow > 0) {
                 k_filter_deferred<<<(prev_shadow + 255) / 256, 256, 0, st>>>(s->dev, s->sq, prev_shadow, s->q[cur]);
                 s->t_shadow.start(st);
-                k_traverse<true><<<s->grid_shadow, 128, 0, st>>>(s->dev, s->q[cur], s->sq, nullptr, prev_shadow, s->counters + DT_CNT_FETCH_B, s->accum);
+                launch_traverse<true>(s, s->q[cur], s->sq, nullptr, prev_shadow, s->counters + DT_CNT_FETCH_B, s->accum);
                 s->t_shadow.stop(st);
                 shadow_timed = true;
                 S.kernel_launches += 2;
@@ -276,7 +289,7 @@ retry:
             S.kernel_launches++;
             if (!defer_mode) {
                 s->t_shadow.start(st);
-                k_traverse<true><<<s->grid_shadow, 128, 0, st>>>(s->dev, s->q[cur], s->sq, s->counters + DT_CNT_SHADOW, 0, s->counters + DT_CNT_FETCH_B, s->accum);
+                launch_traverse<true>(s, s->q[cur], s->sq, s->counters + DT_CNT_SHADOW, 0, s->counters + DT_CNT_FETCH_B, s->accum);
                 s->t_shadow.stop(st);
                 shadow_timed = true;
                 S.kernel_launches++;
@@ -300,7 +313,7 @@ retry:
         }
         if (!overflow && defer_mode && prev_shadow > 0) {
             CK(cudaMemsetAsync(s->counters + DT_CNT_FETCH_B, 0, sizeof(int), st));
-            k_traverse<true><<<s->grid_shadow, 128, 0, st>>>(s->dev, s->q[cur], s->sq, nullptr, prev_shadow, s->counters + DT_CNT_FETCH_B, s->accum);
+            launch_traverse<true>(s, s->q[cur], s->sq, nullptr, prev_shadow, s->counters + DT_CNT_FETCH_B, s->accum);
             S.kernel_launches++;
         }
         if (overflow) {
@@ -433,11 +446,20 @@ int dt_scene_create(const dt_scene_desc* desc, dt_scene** out) {
         g_err = "cudaMalloc of control buffers failed"; return fail(DT_ERR_CUDA);
     }
     for (Timer* t : {&s->t_total, &s->t_gen, &s->t_closest, &s->t_shadow, &s->t_shade, &s->t_resolve, &s->t_tm}) if (t->init()) return fail(DT_ERR_CUDA);
-    int bps = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_traverse<false>, 128, 0);
-    s->grid_closest = s->num_sms * std::max(1, bps);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_traverse<true>, 128, 0);
-    s->grid_shadow = s->num_sms * std::max(1, bps);
+    // traversal variant (A/B measurement): 0 static if-if, 1 static while-while, 2 dynamic if-if, 3 dynamic while-while
+    if (const char* e = getenv("DT_TRAVERSE_MODE")) s->trav_mode = std::min(3, std::max(0, atoi(e)));
+    if (const char* e = getenv("DT_REFILL_THRESHOLD")) s->refill_threshold = std::min(32, std::max(1, atoi(e)));
+    {
+        int bps = 0;
+        const void* fns[4][2] = {{(const void*)k_traverse<false, false>, (const void*)k_traverse<true, false>},
+                                 {(const void*)k_traverse<false, true>, (const void*)k_traverse<true, true>},
+                                 {(const void*)k_traverse_dyn<false, false>, (const void*)k_traverse_dyn<true, false>},
+                                 {(const void*)k_traverse_dyn<false, true>, (const void*)k_traverse_dyn<true, true>}};
+        for (int m = 0; m < 4; m++) for (int a = 0; a < 2; a++) {
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, fns[m][a], 128, 0);
+            s->grid_trav[m][a] = s->num_sms * std::max(1, bps);
+        }
+    }
     if (cudaDeviceSynchronize() != cudaSuccess) { g_err = "device sync after upload failed"; return fail(DT_ERR_CUDA); }
     *out = s;
     return DT_OK;
@@ -581,7 +603,7 @@ static int trace_generic(dt_scene* s, const float* origins, const float* dirs, c
             DtRayQueue q; memset(&q, 0, sizeof q);
             q.o_time = o4; q.d_tmax = d4; q.hit0 = hit0; q.hit_face = hface; q.pixel = nullptr;
             DtShadowQueue sq; memset(&sq, 0, sizeof sq);
-            k_traverse<false><<<s->grid_closest, 128, 0, st>>>(s->dev, q, sq, nullptr, (int)n, fetch, nullptr);
+            launch_traverse<false>(s, q, sq, nullptr, (int)n, fetch, nullptr);
             k_unpack_hits<<<((int)n + 255) / 256, 256, 0, st>>>(hit0, hface, nullptr, (int)n, d_shape, d_face, d_t, 0);
             cudaMemcpyAsync(shape, d_shape, (size_t)n * 4, cudaMemcpyDeviceToHost, st);
             cudaMemcpyAsync(face, d_face, (size_t)n * 4, cudaMemcpyDeviceToHost, st);
@@ -633,6 +655,14 @@ int dt_tonemap(const float* hdr_rgb, int32_t width, int32_t height, float key, f
     cudaStreamDestroy(tmp.stream);
     return rc;
 }
+
+#ifdef DT_TRAV_STATS
+void dt_debug_stats(unsigned long long* out, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, g_dt_stats, sizeof(unsigned long long) * 8);
+    if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_dt_stats, z, sizeof z); }
+}
+#endif
 
 void* dt_scene_stream(dt_scene* s) { return s ? (void*)s->stream : nullptr; }
 

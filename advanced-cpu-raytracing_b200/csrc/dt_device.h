@@ -40,7 +40,7 @@ struct DtShapeDev {
     float motion_blur[3];
     float radius;
     float center[3];
-    float pad0;
+    int32_t inv_is_identity;      // inverseTransform == I exactly: the double transform is a no-op up to -0 -> +0
     float bbox_min[3], bbox_max[3];   // MESH: Mesh::bbox (local); INSTANCE: InstancedMesh::bbox (world)
     float pad1[2];
     double inv[12];               // rows 0..2 of inverseTransform

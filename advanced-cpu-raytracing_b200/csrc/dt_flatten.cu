@@ -328,6 +328,12 @@ bool dt_flatten_scene(const dt_scene_desc* d, DtHostScene& out, std::string& err
         for (int t : {s.tex_diffuse, s.tex_specular, s.tex_normal, s.tex_bump, s.tex_replace_all}) if (t >= d->n_textures) { err = "shape texture index out of range"; return false; }
         sd.has_motion_blur = s.has_motion_blur; memcpy(sd.motion_blur, s.motion_blur, 12);
         rows012(sd.inv, s.inverse_transform); rows012(sd.invT, s.inverse_transpose_transform); rows012(sd.fwd, s.transform);
+        {
+            static const double I16[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+            bool id = true;
+            for (int k = 0; k < 12; k++) if (!(s.inverse_transform[k] == I16[k])) id = false;
+            sd.inv_is_identity = id ? 1 : 0;
+        }
         sd.skip_shadow = (si < d->n_mesh_shapes && d->materials[s.material - 1].type == DT_MAT_EMISSIVE) ? 1 : 0;
         if (s.kind == DT_SHAPE_MESH) {
             if (s.mesh < 0 || s.mesh >= d->n_meshes) { err = "shape mesh index out of range"; return false; }

@@ -116,8 +116,20 @@ __global__ void k_generate(DtCamDev cam, DtWaveParams wp, DtRayQueue q, int base
     q.misc[slot] = make_int4(0x7FFFFFFF /* set by shade from the scene */, 0, (int)dt_hash(rng.key, 0x9E37u), DT_FLAG_PRIMARY);
 }
 
-// ------------------------------------------------------------------ traversal (persistent warps, warp-level fetch)
-template <bool ANY>
+// ------------------------------------------------------------------ traversal (persistent warps)
+__device__ __forceinline__ void dt_store_closest(const DtRayQueue& q, int i, const DtHit& h) {
+    q.hit0[i] = make_float4(h.t, h.beta, h.gamma, __int_as_float(h.shape));
+    q.hit_face[i] = h.face;
+}
+__device__ __forceinline__ void dt_store_shadow(const DtShadowQueue& sq, int i, const DtHit& h, float4* accum) {
+    if (h.shape < 0) {
+        const float4 c = sq.contrib_pix[i];
+        dt_accum(accum, (uint32_t)__float_as_int(c.w), V(c.x, c.y, c.z));
+    }
+}
+
+// Static variant: a warp fetches 32 consecutive rays and runs them to completion.
+template <bool ANY, bool WW>
 __global__ void __launch_bounds__(128) k_traverse(DtSceneDev S, DtRayQueue q, DtShadowQueue sq, const int* n_ptr, int n_fixed, int* fetch_counter, float4* accum) {
     const int n = n_ptr ? *n_ptr : n_fixed;
     const int lane = threadIdx.x & 31;
@@ -128,22 +140,61 @@ __global__ void __launch_bounds__(128) k_traverse(DtSceneDev S, DtRayQueue q, Dt
         if (base >= n) break;
         const int i = base + lane;
         if (i < n) {
-            if (ANY) {
-                const float4 o = sq.o_time[i], d = sq.d_tmax[i];
-                DtHit h;
-                dt_trace<true>(S, V(o.x, o.y, o.z), V(d.x, d.y, d.z), o.w, d.w, h);
-                if (h.shape < 0) {
-                    const float4 c = sq.contrib_pix[i];
-                    dt_accum(accum, (uint32_t)__float_as_int(c.w), V(c.x, c.y, c.z));
+            if (!ANY && q.pixel && q.pixel[i] == DT_DEAD_PIXEL) continue;
+            const float4 o = ANY ? sq.o_time[i] : q.o_time[i];
+            const float4 d = ANY ? sq.d_tmax[i] : q.d_tmax[i];
+            DtTrav T;
+            dt_trav_init<ANY>(T, S, V(o.x, o.y, o.z), V(d.x, d.y, d.z), o.w, ANY ? d.w : CUDART_INF_F);
+            while (!dt_trav_step<ANY, WW>(T, S)) {}
+            if (ANY) dt_store_shadow(sq, i, T.best, accum); else dt_store_closest(q, i, T.best);
+        }
+    }
+}
+
+// Dynamic variant: every lane is a resumable traversal state machine; when fewer than `refill_threshold`
+// lanes of the warp still hold a ray, the idle lanes fetch new rays with ONE warp-aggregated atomic
+// (Aila-Laine style persistent threads).  Keeps SIMT lanes busy on incoherent secondary / shadow rays.
+template <bool ANY, bool WW>
+__global__ void __launch_bounds__(128) k_traverse_dyn(DtSceneDev S, DtRayQueue q, DtShadowQueue sq, const int* n_ptr, int n_fixed, int* fetch_counter,
+                                                      float4* accum, int refill_threshold) {
+    const int n = n_ptr ? *n_ptr : n_fixed;
+    const int lane = threadIdx.x & 31;
+    const unsigned FULL = 0xFFFFFFFFu;
+    DtTrav T;
+    int ray = -1;
+    bool drained = false;
+    for (;;) {
+        if (!drained) {
+            const unsigned idle = __ballot_sync(FULL, ray < 0);
+            if (idle) {
+                const int leader = __ffs(idle) - 1;
+                int base = 0;
+                if (lane == leader) base = atomicAdd(fetch_counter, __popc(idle));
+                base = __shfl_sync(FULL, base, leader);
+                if (ray < 0) {
+                    const int i = base + __popc(idle & ((1u << lane) - 1u));
+                    if (i < n && (ANY || !q.pixel || q.pixel[i] != DT_DEAD_PIXEL)) {
+                        const float4 o = ANY ? sq.o_time[i] : q.o_time[i];
+                        const float4 d = ANY ? sq.d_tmax[i] : q.d_tmax[i];
+                        dt_trav_init<ANY>(T, S, V(o.x, o.y, o.z), V(d.x, d.y, d.z), o.w, ANY ? d.w : CUDART_INF_F);
+                        ray = i;
+                    }
                 }
-            } else {
-                if (q.pixel && q.pixel[i] == DT_DEAD_PIXEL) continue;
-                const float4 o = q.o_time[i], d = q.d_tmax[i];
-                DtHit h;
-                dt_trace<false>(S, V(o.x, o.y, o.z), V(d.x, d.y, d.z), o.w, CUDART_INF_F, h);
-                q.hit0[i] = make_float4(h.t, h.beta, h.gamma, __int_as_float(h.shape));
-                q.hit_face[i] = h.face;
+                if (base + __popc(idle) >= n) drained = true;
             }
+        }
+        unsigned act = __ballot_sync(FULL, ray >= 0);
+        if (act == 0u) { if (drained) break; else continue; }
+        for (;;) {
+            if (ray >= 0) {
+                if (dt_trav_step<ANY, WW>(T, S)) {
+                    if (ANY) dt_store_shadow(sq, ray, T.best, accum); else dt_store_closest(q, ray, T.best);
+                    ray = -1;
+                }
+            }
+            act = __ballot_sync(FULL, ray >= 0);
+            if (act == 0u) break;
+            if (!drained && __popc(act) < refill_threshold) break;
         }
     }
 }

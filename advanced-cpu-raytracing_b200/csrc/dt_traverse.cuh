@@ -82,6 +82,10 @@ __device__ __forceinline__ uint32_t dt_sign_extend_s8x4(uint32_t x) {
     return ((x >> 7) & 0x01010101u) * 0xFFu;
 }
 __device__ __forceinline__ uint32_t dt_byte(uint32_t w, int j) { return (w >> (j * 8)) & 0xFFu; }
+// byte j of w as an exact float without the slow I2F pipe: PRMT builds 0x4B0000qq = 2^23 + q, one FADD removes 2^23.
+__device__ __forceinline__ float dt_byte_f(uint32_t w, int j) {
+    return __fadd_rn(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440u | (uint32_t)j)), -8388608.0f);
+}
 
 #define DT_SLACK_HI 1.0000019f     // 1 + 2^-19: conservative inflation of the slab interval against FMA/rcp rounding
 #define DT_SLACK_LO 0.9999981f
@@ -112,12 +116,12 @@ __device__ __forceinline__ uint32_t dt_node_hits(const uint4 n0, const uint4 n1,
         const uint32_t nz = r.idz < 0.f ? qhiz : qloz, fz = r.idz < 0.f ? qloz : qhiz;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            const float tnx = __fmaf_rn((float)dt_byte(nx, j), ax, bx);
-            const float tny = __fmaf_rn((float)dt_byte(ny, j), ay, by);
-            const float tnz = __fmaf_rn((float)dt_byte(nz, j), az, bz);
-            const float tfx = __fmaf_rn((float)dt_byte(fx, j), ax, bx);
-            const float tfy = __fmaf_rn((float)dt_byte(fy, j), ay, by);
-            const float tfz = __fmaf_rn((float)dt_byte(fz, j), az, bz);
+            const float tnx = __fmaf_rn(dt_byte_f(nx, j), ax, bx);
+            const float tny = __fmaf_rn(dt_byte_f(ny, j), ay, by);
+            const float tnz = __fmaf_rn(dt_byte_f(nz, j), az, bz);
+            const float tfx = __fmaf_rn(dt_byte_f(fx, j), ax, bx);
+            const float tfy = __fmaf_rn(dt_byte_f(fy, j), ay, by);
+            const float tfz = __fmaf_rn(dt_byte_f(fz, j), az, bz);
             // fminf/fmaxf drop NaNs (0*inf on axis-parallel rays): a NaN constraint is ignored = conservative
             const float tn = __fmul_rn(fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f)), DT_SLACK_LO);
             const float tf = __fmul_rn(fminf(fminf(tfx, tfy), fminf(tfz, tmax)), DT_SLACK_HI);
@@ -136,130 +140,192 @@ __device__ __forceinline__ bool dt_better(float t, int shape, int face, const Dt
     return face < best.face;
 }
 
-// ANY = true: occlusion query (CastShadowRay): returns as soon as any hit with 0 < t < tmax_in exists,
+#ifdef DT_TRAV_STATS
+__device__ unsigned long long g_dt_stats[8];     // 0 nodes, 1 tri tests, 2 shape visits, 3 blas entries, 4 leaf confirms, 5 steps, 6 rays
+#define DT_STAT(i) atomicAdd(&g_dt_stats[i], 1ull)
+#else
+#define DT_STAT(i)
+#endif
+
+// Per-ray traversal state: a resumable state machine so that persistent warps can refill finished lanes
+// (dynamic fetch) instead of idling until the slowest ray of the warp is done.
+struct DtTrav {
+    v3 wo, wd;                  // world-space ray
+    float mb_time;
+    float any_min_t;            // ANY: shadowRay.hitInfo.minT = lightT + 0.01 (raytracer.cpp:580)
+    DtRayPrep r;                // ray of the current level (world in the TLAS, local inside a BLAS)
+    DtHit best;
+    uint2 ng, tg;               // current node group / primitive group
+    const uint4* nodes;
+    int sp, blas_sp, cur_shape;
+    bool in_blas;
+    uint2 stack[DT_STACK_SIZE];
+};
+
+template <bool ANY>
+__device__ __forceinline__ void dt_trav_init(DtTrav& T, const DtSceneDev& S, v3 wo, v3 wd, float mb_time, float tmax_in) {
+    T.wo = wo; T.wd = wd; T.mb_time = mb_time;
+    T.best.t = ANY ? tmax_in : CUDART_INF_F;
+    T.any_min_t = __fadd_rn(tmax_in, 0.01f);
+    T.best.shape = -1; T.best.face = -1; T.best.beta = 0.f; T.best.gamma = 0.f;
+    dt_prep(T.r, wo, wd);
+    DT_STAT(6);
+    T.in_blas = false; T.blas_sp = 0; T.cur_shape = -1; T.sp = 0;
+    T.nodes = S.tlas_nodes;
+    T.ng = make_uint2(0u, 0x80000000u);         // root as the single "child" of a virtual group
+    T.tg = make_uint2(0u, 0u);
+}
+
+// Visit the nearest pending child node of the current group: load 80 B, test 8 boxes, refill ng / tg.
+__device__ __forceinline__ void dt_trav_node(DtTrav& T) {
+    DT_STAT(0);
+    const uint32_t hits = T.ng.y;
+    const uint32_t imask = T.ng.y & 0xFFu;
+    const int child_bit = 31 - __clz(hits);
+    T.ng.y &= ~(1u << child_bit);
+    if (T.ng.y > 0x00FFFFFFu) { if (T.sp < DT_STACK_SIZE) T.stack[T.sp++] = T.ng; }
+    const uint32_t slot = (uint32_t)(child_bit - 24) ^ (T.r.oct_inv4 & 0xFFu);
+    const uint32_t rel = __popc(imask & ~(0xFFFFFFFFu << slot));
+    const uint32_t ni = T.ng.x + rel;
+    const uint4* np = T.nodes + (size_t)ni * 5;
+    const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+    const uint32_t hm = dt_node_hits(n0, n1, n2, n3, n4, T.r, T.best.t);
+    T.ng.x = n1.x;
+    // a group without node hits must read as empty (a remnant imask would look like a primitive group)
+    T.ng.y = (hm & 0xFF000000u) ? ((hm & 0xFF000000u) | (n0.w >> 24)) : 0u;
+    T.tg.x = n1.y;
+    T.tg.y = hm & 0x00FFFFFFu;
+}
+
+// World -> local ray (mesh.cpp:164-170, sphere.cpp:23-30, instancedMesh.cpp:33-39).  For an identity inverseTransform the
+// double-precision product reduces to x*1 + 0 + 0 + 0: the value is unchanged except that -0 becomes +0, which `x + 0.0f`
+// reproduces exactly, so the 24 DMUL/DADD are skipped (the common case: untransformed meshes and spheres).
+__device__ __forceinline__ void dt_to_local(const DtShapeDev* sh, v3 wo, v3 wd, float mb_time, v3& lo, v3& ld) {
+    if (sh->inv_is_identity) {
+        lo = V(__fadd_rn(wo.x, 0.0f), __fadd_rn(wo.y, 0.0f), __fadd_rn(wo.z, 0.0f));
+        ld = V(__fadd_rn(wd.x, 0.0f), __fadd_rn(wd.y, 0.0f), __fadd_rn(wd.z, 0.0f));
+    } else {
+        lo = apply_transform(sh->inv, wo, 1.0f);
+        ld = apply_transform(sh->inv, wd, 0.0f);
+    }
+    if (sh->has_motion_blur) lo = vadd(lo, vscale(F3(sh->motion_blur), mb_time));
+}
+
+// One primitive of the current primitive group.  Returns true when an ANY query is decided (occluded).
+template <bool ANY>
+__device__ __forceinline__ bool dt_trav_prim(DtTrav& T, const DtSceneDev& S, bool& entered_blas) {
+    DtHit& best = T.best;
+    const int bit = __ffs(T.tg.y) - 1;
+    T.tg.y &= ~(1u << bit);
+    const uint32_t prim = T.tg.x + (uint32_t)bit;
+    if (T.in_blas) {
+        DT_STAT(1);
+        const float4* tp = S.tris + (size_t)prim * 3;
+        const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+        float t, beta, gamma;
+        if (tri_test_exact(T.r.o, T.r.d, V(a.x, a.y, a.z), V(a.w, b.x, b.y), V(b.z, b.w, c.x), t, beta, gamma)) {
+            const int face = __float_as_int(c.y);
+            const bool cand = ANY ? (t > 0.0f && t < best.t) : (t > 0.0f && dt_better(t, T.cur_shape, face, best));
+            if (cand) {
+                // The reference only reaches this face if the float slab test of its BVH2 leaf passes (bvh.cpp:7-10);
+                // every ancestor box contains the leaf box and the float slab interval is monotone in the box, so the
+                // leaf test implies the ancestors'.  Rare path: runs only for would-be winners.
+                DT_STAT(4);
+                const float4 lb0 = __ldg(S.leaf_boxes + (size_t)prim * 2), lb1 = __ldg(S.leaf_boxes + (size_t)prim * 2 + 1);
+                const float lmn[3] = {lb0.x, lb0.y, lb0.z}, lmx[3] = {lb1.x, lb1.y, lb1.z};
+                // minT the reference would hold when it reaches this face: it scans in (shape, face) order, so a
+                // candidate that precedes the current best was tested BEFORE that best existed.
+                const bool after_best = best.shape >= 0 && (T.cur_shape > best.shape || (T.cur_shape == best.shape && face > best.face));
+                const float ref_min_t = ANY ? T.any_min_t : (after_best ? best.t : CUDART_INF_F);
+                if (box_intersect_exact(lmn, lmx, T.r.o, T.r.d, ref_min_t)) {
+                    best.t = t; best.beta = beta; best.gamma = gamma; best.shape = T.cur_shape; best.face = face;
+                    if (ANY) return true;
+                }
+            }
+        }
+        return false;
+    }
+    DT_STAT(2);
+    const int si = __ldg(S.tlas_prims + prim);
+    const DtShapeDev* sh = S.shapes + si;
+    if (ANY && sh->skip_shadow) return false;
+    const int kind = sh->kind;
+    if (kind == DT_SHAPE_SPHERE) {
+        v3 lo, ld;
+        dt_to_local(sh, T.wo, T.wd, T.mb_time, lo, ld);
+        float t;
+        if (sphere_test_exact(lo, ld, F3(sh->center), sh->radius, t)) {
+            if (ANY) {
+                if (t > 0.0f && t < best.t) { best.shape = si; best.face = -1; best.t = t; return true; }
+            } else if (t > 0.0f && dt_better(t, si, -1, best)) {
+                best.t = t; best.beta = 0.f; best.gamma = 0.f; best.shape = si; best.face = -1;
+            }
+        }
+        return false;
+    }
+    // Mesh / InstancedMesh: the reference's exact per-shape pre-tests, then descend into the BLAS.
+    // ray.hitInfo.minT at the time the reference scans shape si: only hits of lower-index shapes exist.
+    const float shape_min_t = ANY ? T.any_min_t : ((best.shape >= 0 && si > best.shape) ? best.t : CUDART_INF_F);
+    if (kind == DT_SHAPE_INSTANCE) {
+        v3 so = T.wo;
+        if (sh->has_motion_blur) so = vadd(so, vscale(F3(sh->motion_blur), T.mb_time));
+        if (!box_intersect_exact(sh->bbox_min, sh->bbox_max, so, T.wd, shape_min_t)) return false;   // instancedMesh.cpp:29
+    }
+    v3 lo, ld;
+    dt_to_local(sh, T.wo, T.wd, T.mb_time, lo, ld);
+    const DtMeshDev* m = S.meshes + sh->mesh;
+    // mesh.cpp:172 (Mesh::bbox) and the root node of BVH::IntersectBVH (same box) in local space
+    if (!box_intersect_exact(m->bbox_min, m->bbox_max, lo, ld, shape_min_t)) return false;
+    if (T.ng.y > 0x00FFFFFFu) { if (T.sp < DT_STACK_SIZE) T.stack[T.sp++] = T.ng; }
+    if (T.tg.y != 0u) { if (T.sp < DT_STACK_SIZE) T.stack[T.sp++] = T.tg; }
+    DT_STAT(3);
+    T.blas_sp = T.sp;
+    T.in_blas = true;
+    T.cur_shape = si;
+    dt_prep(T.r, lo, ld);
+    T.nodes = S.blas_nodes;
+    T.ng = make_uint2(m->node_root, 0x80000000u);
+    T.tg = make_uint2(0u, 0u);
+    entered_blas = true;
+    return false;
+}
+
+// One step of the state machine.  WW = false: one node visit + its primitives ("if-if");
+// WW = true: descend nodes until some primitive group is pending, then drain it ("while-while").
+// Returns true when the ray is finished (ANY: best.shape >= 0 <=> occluded).
+template <bool ANY, bool WW>
+__device__ __forceinline__ bool dt_trav_step(DtTrav& T, const DtSceneDev& S) {
+    DT_STAT(5);
+    if (WW) {
+        while (T.ng.y > 0x00FFFFFFu && T.tg.y == 0u) dt_trav_node(T);
+        if (T.tg.y == 0u && T.ng.y != 0u && T.ng.y <= 0x00FFFFFFu) { T.tg = T.ng; T.ng = make_uint2(0u, 0u); }
+    } else {
+        if (T.ng.y > 0x00FFFFFFu) dt_trav_node(T);
+        else { T.tg = T.ng; T.ng = make_uint2(0u, 0u); }
+    }
+    while (T.tg.y != 0u) {
+        bool entered = false;
+        if (dt_trav_prim<ANY>(T, S, entered)) return true;
+        if (entered) break;
+    }
+    if (T.ng.y <= 0x00FFFFFFu && T.tg.y == 0u) {
+        if (T.in_blas && T.sp == T.blas_sp) {
+            T.in_blas = false;
+            dt_prep(T.r, T.wo, T.wd);
+            T.nodes = S.tlas_nodes;
+        }
+        if (T.sp == 0) { if (ANY) T.best.shape = -1; return true; }
+        T.ng = T.stack[--T.sp];
+    }
+    return false;
+}
+
+// ANY = true: occlusion query (CastShadowRay): finishes as soon as any hit with 0 < t < tmax_in exists,
 // skipping Emissive mesh shapes; best.shape >= 0 marks "occluded".
 template <bool ANY>
 __device__ __forceinline__ void dt_trace(const DtSceneDev& S, v3 wo, v3 wd, float mb_time, float tmax_in, DtHit& best) {
-    uint2 stack[DT_STACK_SIZE];
-    int sp = 0;
-    best.t = ANY ? tmax_in : CUDART_INF_F;
-    const float any_min_t = __fadd_rn(tmax_in, 0.01f);     // shadowRay.hitInfo.minT (raytracer.cpp:580)
-    best.shape = -1; best.face = -1; best.beta = 0.f; best.gamma = 0.f;
-
-    DtRayPrep r;
-    dt_prep(r, wo, wd);
-    bool in_blas = false;
-    int blas_sp = 0;
-    int cur_shape = -1;
-    const uint4* nodes = S.tlas_nodes;
-    uint2 ng = make_uint2(0u, 0x80000000u);     // root as the single "child" of a virtual group
-    uint2 tg = make_uint2(0u, 0u);
-
-    for (;;) {
-        if (ng.y > 0x00FFFFFFu) {
-            const uint32_t hits = ng.y;
-            const uint32_t imask = ng.y & 0xFFu;
-            const int child_bit = 31 - __clz(hits);
-            ng.y &= ~(1u << child_bit);
-            if (ng.y > 0x00FFFFFFu) { if (sp < DT_STACK_SIZE) stack[sp++] = ng; }
-            const uint32_t slot = (uint32_t)(child_bit - 24) ^ (r.oct_inv4 & 0xFFu);
-            const uint32_t rel = __popc(imask & ~(0xFFFFFFFFu << slot));
-            const uint32_t ni = ng.x + rel;
-            const uint4* np = nodes + (size_t)ni * 5;
-            const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
-            const uint32_t hm = dt_node_hits(n0, n1, n2, n3, n4, r, best.t);
-            ng.x = n1.x;
-            ng.y = (hm & 0xFF000000u) | (n0.w >> 24);
-            tg.x = n1.y;
-            tg.y = hm & 0x00FFFFFFu;
-        } else {
-            tg = ng;
-            ng = make_uint2(0u, 0u);
-        }
-
-        while (tg.y != 0u) {
-            const int bit = __ffs(tg.y) - 1;
-            tg.y &= ~(1u << bit);
-            const uint32_t prim = tg.x + (uint32_t)bit;
-            if (in_blas) {
-                const float4* tp = S.tris + (size_t)prim * 3;
-                const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
-                float t, beta, gamma;
-                if (tri_test_exact(r.o, r.d, V(a.x, a.y, a.z), V(a.w, b.x, b.y), V(b.z, b.w, c.x), t, beta, gamma)) {
-                    const int face = __float_as_int(c.y);
-                    const bool cand = ANY ? (t > 0.0f && t < best.t) : (t > 0.0f && dt_better(t, cur_shape, face, best));
-                    if (cand) {
-                        // The reference only reaches this face if the float slab test of its BVH2 leaf passes
-                        // (bvh.cpp:7-10); every ancestor box contains the leaf box, and the float slab interval is
-                        // monotone in the box, so the leaf test implies the ancestors'.  Rare path: runs only for
-                        // would-be winners.
-                        const float4 lb0 = __ldg(S.leaf_boxes + (size_t)prim * 2), lb1 = __ldg(S.leaf_boxes + (size_t)prim * 2 + 1);
-                        const float lmn[3] = {lb0.x, lb0.y, lb0.z}, lmx[3] = {lb1.x, lb1.y, lb1.z};
-                        // minT the reference would hold when it reaches this face: it scans in (shape, face) order, so a
-                        // candidate that precedes the current best was tested BEFORE that best existed.
-                        const bool after_best = best.shape >= 0 && (cur_shape > best.shape || (cur_shape == best.shape && face > best.face));
-                        const float ref_min_t = ANY ? any_min_t : (after_best ? best.t : CUDART_INF_F);
-                        if (box_intersect_exact(lmn, lmx, r.o, r.d, ref_min_t)) {
-                            if (ANY) { best.shape = cur_shape; best.face = face; best.t = t; return; }
-                            best.t = t; best.beta = beta; best.gamma = gamma; best.shape = cur_shape; best.face = face;
-                        }
-                    }
-                }
-            } else {
-                const int si = __ldg(S.tlas_prims + prim);
-                const DtShapeDev* sh = S.shapes + si;
-                if (ANY && sh->skip_shadow) continue;
-                const int kind = sh->kind;
-                if (kind == DT_SHAPE_SPHERE) {
-                    v3 lo = apply_transform(sh->inv, wo, 1.0f);
-                    v3 ld = apply_transform(sh->inv, wd, 0.0f);
-                    if (sh->has_motion_blur) lo = vadd(lo, vscale(F3(sh->motion_blur), mb_time));
-                    float t;
-                    if (sphere_test_exact(lo, ld, F3(sh->center), sh->radius, t)) {
-                        if (ANY) {
-                            if (t > 0.0f && t < best.t) { best.shape = si; best.face = -1; best.t = t; return; }
-                        } else if (t > 0.0f && dt_better(t, si, -1, best)) {
-                            best.t = t; best.beta = 0.f; best.gamma = 0.f; best.shape = si; best.face = -1;
-                        }
-                    }
-                    continue;
-                }
-                // Mesh / InstancedMesh: the reference's exact per-shape pre-tests, then descend into the BLAS.
-                // ray.hitInfo.minT at the time the reference scans shape si: only hits of lower-index shapes exist.
-                const float shape_min_t = ANY ? any_min_t : ((best.shape >= 0 && si > best.shape) ? best.t : CUDART_INF_F);
-                if (kind == DT_SHAPE_INSTANCE) {
-                    v3 so = wo;
-                    if (sh->has_motion_blur) so = vadd(so, vscale(F3(sh->motion_blur), mb_time));
-                    if (!box_intersect_exact(sh->bbox_min, sh->bbox_max, so, wd, shape_min_t)) continue; // instancedMesh.cpp:29
-                }
-                v3 lo = apply_transform(sh->inv, wo, 1.0f);
-                v3 ld = apply_transform(sh->inv, wd, 0.0f);
-                if (sh->has_motion_blur) lo = vadd(lo, vscale(F3(sh->motion_blur), mb_time));
-                const DtMeshDev* m = S.meshes + sh->mesh;
-                // mesh.cpp:172 (Mesh::bbox) and the root node of BVH::IntersectBVH (same box) in local space
-                if (!box_intersect_exact(m->bbox_min, m->bbox_max, lo, ld, shape_min_t)) continue;
-                if (ng.y > 0x00FFFFFFu) { if (sp < DT_STACK_SIZE) stack[sp++] = ng; }
-                if (tg.y != 0u) { if (sp < DT_STACK_SIZE) stack[sp++] = tg; }
-                blas_sp = sp;
-                in_blas = true;
-                cur_shape = si;
-                dt_prep(r, lo, ld);
-                nodes = S.blas_nodes;
-                ng = make_uint2(m->node_root, 0x80000000u);
-                tg = make_uint2(0u, 0u);
-                break;
-            }
-        }
-
-        if (ng.y <= 0x00FFFFFFu) {
-            if (in_blas && sp == blas_sp) {
-                in_blas = false;
-                dt_prep(r, wo, wd);
-                nodes = S.tlas_nodes;
-            }
-            if (sp == 0) break;
-            ng = stack[--sp];
-        }
-    }
-    if (ANY) best.shape = -1;
+    DtTrav T;
+    dt_trav_init<ANY>(T, S, wo, wd, mb_time, tmax_in);
+    while (!dt_trav_step<ANY, true>(T, S)) {}
+    best = T.best;
 }

@@ -1,0 +1,9 @@
+import sys, os
+R=os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0,R+'/tests'); sys.path.insert(0,R+'/advanced-cpu-raytracing_b200')
+from dtb200.scene import GpuScene, HostScene
+from dtb200 import scenegen
+p=scenegen.gen_config2('/tmp/gen/c2'); hs=HostScene(p); cam=hs.camera(0)
+gs=GpuScene(hs)
+for _ in range(int(sys.argv[1]) if len(sys.argv)>1 else 2):
+    ldr,hdr,st=gs.render(cam)
+print(st.ms_total, st.rays_closest, st.rays_shadow)
