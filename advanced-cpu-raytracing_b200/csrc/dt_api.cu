@@ -71,6 +71,12 @@ struct dt_scene {
     DtRayQueue q[2];
     float4* miss[2] = {nullptr, nullptr};
     DtShadowQueue sq;
+    DtShadowQueue sq2;            // second shadow queue: shadow(k) on stream2 overlaps closest(k+1)/shade(k+1)
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t ev_shade[2] = {nullptr, nullptr}, ev_shadow[2] = {nullptr, nullptr};
+    std::vector<cudaEvent_t> ev_pool;    // timing events of the sync-free loop
+    int grid_shade = 0;
+    int sync_waves = 0;           // DT_SYNC_WAVES=1 forces the host-synchronised wave loop (A/B)
     std::vector<void*> qallocs;
     int* counters = nullptr;
     int* h_counters = nullptr;
@@ -87,9 +93,9 @@ struct dt_scene {
 namespace {
 
 template <bool ANY>
-void launch_traverse(dt_scene* s, const DtRayQueue& q, const DtShadowQueue& sq, const int* n_ptr, int n_fixed, int* fetch, float4* accum) {
+void launch_traverse(dt_scene* s, const DtRayQueue& q, const DtShadowQueue& sq, const int* n_ptr, int n_fixed, int* fetch, float4* accum, cudaStream_t st = nullptr) {
     const int grid = s->grid_trav[s->trav_mode][ANY ? 1 : 0];
-    cudaStream_t st = s->stream;
+    if (!st) st = s->stream;
     switch (s->trav_mode) {
         case 0: k_traverse<ANY, false><<<grid, 128, 0, st>>>(s->dev, q, sq, n_ptr, n_fixed, fetch, accum); break;
         case 1: k_traverse<ANY, true><<<grid, 128, 0, st>>>(s->dev, q, sq, n_ptr, n_fixed, fetch, accum); break;
@@ -130,6 +136,10 @@ int ensure_queues(dt_scene* s, int capacity, int shadow_capacity) {
     if ((rc = qalloc(s, &s->sq.d_tmax, shadow_capacity))) return rc;
     if ((rc = qalloc(s, &s->sq.contrib_pix, shadow_capacity))) return rc;
     if ((rc = qalloc(s, &s->sq.defer, shadow_capacity))) return rc;
+    if ((rc = qalloc(s, &s->sq2.o_time, shadow_capacity))) return rc;
+    if ((rc = qalloc(s, &s->sq2.d_tmax, shadow_capacity))) return rc;
+    if ((rc = qalloc(s, &s->sq2.contrib_pix, shadow_capacity))) return rc;
+    s->sq2.defer = nullptr;
     s->capacity = capacity; s->shadow_capacity = shadow_capacity;
     return DT_OK;
 }
@@ -248,6 +258,78 @@ retry:
     }
     CK(cudaMemsetAsync(s->accum, 0, n_pix * sizeof(float4), st));
     CK(cudaMemsetAsync(s->counters, 0, DT_CNT_COUNT * sizeof(int), st));
+    // ---- sync-free wave loop: every ray of the frame fits one batch and the ray tree has a known depth bound, so all
+    // waves are enqueued back to back (wave sizes live in device memory) and shadow(k) runs on a second stream while
+    // closest(k+1) / shade(k+1) proceed.  One host synchronisation per frame.
+    const bool bounded = !(pt && dc.russian_roulette) && s->dev.max_recursion_depth <= 16;
+    if (!primary_only && !defer_mode && bounded && total <= (long long)wave_max && !s->sync_waves) {
+        const int n_waves = s->dev.max_recursion_depth + 1;
+        cudaStream_t A = s->stream, B = s->stream2;
+        int* c = s->counters;
+        const int n0 = (int)total;
+        size_t ev_i = 0;
+        auto ev = [&]() -> cudaEvent_t { if (ev_i >= s->ev_pool.size()) { cudaEvent_t e; cudaEventCreate(&e); s->ev_pool.push_back(e); } return s->ev_pool[ev_i++]; };
+        std::vector<cudaEvent_t> tg, tc, th, ts;      // (start, stop) pairs per stage
+        { cudaEvent_t a = ev(), b = ev(); cudaEventRecord(a, A);
+          k_generate<<<(n0 + 255) / 256, 256, 0, A>>>(dc, wp, s->q[0], 0, 0, n0, s->accum);
+          cudaEventRecord(b, A); tg.push_back(a); tg.push_back(b); }
+        s->h_counters[DT_CNT_COUNT] = n0;              // pinned scratch slot past the readback area
+        CK(cudaMemcpyAsync(c + DT_CNT_CUR, s->h_counters + DT_CNT_COUNT, sizeof(int), cudaMemcpyHostToDevice, A));
+        int cur = 0;
+        for (int k = 0; k < n_waves; k++) {
+            const int slot = k & 1;
+            DtShadowQueue& sq = slot ? s->sq2 : s->sq;
+            { cudaEvent_t a = ev(), b = ev(); cudaEventRecord(a, A);
+              launch_traverse<false>(s, s->q[cur], sq, c + DT_CNT_CUR, 0, c + DT_CNT_FETCH_A, s->accum, A);
+              cudaEventRecord(b, A); tc.push_back(a); tc.push_back(b); }
+            if (k >= 2) CK(cudaStreamWaitEvent(A, s->ev_shadow[slot], 0));       // shadow(k-2) must have drained this queue
+            { cudaEvent_t a = ev(), b = ev(); cudaEventRecord(a, A);
+              DtShadeCounters sc = {c + DT_CNT_NEXT, c + (slot ? DT_CNT_SHADOW2 : DT_CNT_SHADOW), c + DT_CNT_OVERFLOW};
+              k_shade<<<s->grid_shade, 128, 0, A>>>(s->dev, dc, s->q[cur], s->miss[cur], c + DT_CNT_CUR, 0, s->q[1 - cur], s->miss[1 - cur], s->capacity,
+                                                    sq, s->shadow_capacity, sc, s->accum);
+              cudaEventRecord(b, A); th.push_back(a); th.push_back(b); }
+            CK(cudaEventRecord(s->ev_shade[slot], A));
+            CK(cudaStreamWaitEvent(B, s->ev_shade[slot], 0));
+            { cudaEvent_t a = ev(), b = ev(); cudaEventRecord(a, B);
+              launch_traverse<true>(s, s->q[cur], sq, c + (slot ? DT_CNT_SHADOW2 : DT_CNT_SHADOW), 0, c + (slot ? DT_CNT_FETCH_B2 : DT_CNT_FETCH_B), s->accum, B);
+              cudaEventRecord(b, B); ts.push_back(a); ts.push_back(b); }
+            CK(cudaEventRecord(s->ev_shadow[slot], B));
+            if (k >= 1) CK(cudaStreamWaitEvent(A, s->ev_shadow[1 - slot], 0));    // the other queue's counters are about to be reset
+            k_wave_advance<<<1, 1, 0, A>>>(c, 1 - slot, 1 - slot);
+            S.kernel_launches += 4; S.launches_traverse_closest++;
+            cur = 1 - cur;
+        }
+        S.kernel_launches++;
+        CK(cudaStreamWaitEvent(A, s->ev_shadow[0], 0));
+        if (n_waves > 1) CK(cudaStreamWaitEvent(A, s->ev_shadow[1], 0));
+        CK(cudaMemcpyAsync(s->h_counters, c, DT_CNT_COUNT * sizeof(int), cudaMemcpyDeviceToHost, A));
+        CK(cudaStreamSynchronize(A));
+        CK(cudaGetLastError());
+        auto sum = [&](std::vector<cudaEvent_t>& v) { float t = 0.f; for (size_t i = 0; i + 1 < v.size(); i += 2) { float ms = 0.f; cudaEventElapsedTime(&ms, v[i], v[i + 1]); t += ms; } return t; };
+        S.ms_generate = sum(tg); S.ms_traverse_closest = sum(tc); S.ms_shade = sum(th); S.ms_traverse_shadow = sum(ts);
+        S.waves = (uint32_t)n_waves;
+        if (s->h_counters[DT_CNT_OVERFLOW] != 0) {
+            if (retries >= 6 || wave_max <= 4096) { g_err = "wavefront queue overflow (ray-tree fan-out too large even for small waves)"; return DT_ERR_OVERFLOW; }
+            retries++;
+            wave_max = std::max(4096, (wave_max / 4 + 31) & ~31);      // smaller batches -> falls back to the synchronised loop
+            goto retry;
+        }
+        unsigned long long tot_c = 0, tot_s = 0;
+        memcpy(&tot_c, s->h_counters + DT_CNT_TOT_CLOSEST, 8); memcpy(&tot_s, s->h_counters + DT_CNT_TOT_SHADOW, 8);
+        tot_s += (unsigned long long)s->h_counters[((n_waves - 1) & 1) ? DT_CNT_SHADOW2 : DT_CNT_SHADOW];     // last wave's queue
+        S.rays_closest = tot_c; S.rays_shadow = tot_s;
+        long long valid = 0;
+        for (long long j = 0; j < my_tiles; j++) {
+            long long tile = j * P.tile_world + P.tile_rank;
+            int tx = (int)(tile % wp.tiles_x), ty = (int)(tile / wp.tiles_x);
+            int w = std::min(8, W - tx * 8), h = std::min(4, H - ty * 4);
+            if (w > 0 && h > 0) valid += (long long)w * h;
+        }
+        S.rays_closest += (uint64_t)(valid * dc.spp);
+        S.retries = retries;
+        if (stats) *stats = S;
+        return DT_OK;
+    }
     {
         long long next_primary = 0;
         int count = 0, cur = 0;
@@ -283,8 +365,11 @@ retry:
             }
             CK(cudaMemsetAsync(s->counters + DT_CNT_SHADOW, 0, sizeof(int), st));
             s->t_shade.start(st);
-            k_shade<<<(count + 127) / 128, 128, 0, st>>>(s->dev, dc, s->q[cur], s->miss[cur], count, s->q[1 - cur], s->miss[1 - cur], s->capacity,
-                                                         s->sq, s->shadow_capacity, s->counters, s->accum);
+            {
+                DtShadeCounters sc = {s->counters + DT_CNT_NEXT, s->counters + DT_CNT_SHADOW, s->counters + DT_CNT_OVERFLOW};
+                k_shade<<<(count + 127) / 128, 128, 0, st>>>(s->dev, dc, s->q[cur], s->miss[cur], nullptr, count, s->q[1 - cur], s->miss[1 - cur], s->capacity,
+                                                             s->sq, s->shadow_capacity, sc, s->accum);
+            }
             s->t_shade.stop(st);
             S.kernel_launches++;
             if (!defer_mode) {
@@ -390,11 +475,13 @@ int dt_scene_create(const dt_scene_desc* desc, dt_scene** out) {
     memset(&s->dev, 0, sizeof s->dev);
     memset(&s->q, 0, sizeof s->q);
     memset(&s->sq, 0, sizeof s->sq);
+    memset(&s->sq2, 0, sizeof s->sq2);
     auto fail = [&](int code) { dt_scene_destroy(s); return code; };
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, s->device) != cudaSuccess) { g_err = "cudaGetDeviceProperties failed"; return fail(DT_ERR_CUDA); }
     s->num_sms = prop.multiProcessorCount;
-    if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) { g_err = "cudaStreamCreate failed"; return fail(DT_ERR_CUDA); }
+    if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&s->stream2, cudaStreamNonBlocking) != cudaSuccess) { g_err = "cudaStreamCreate failed"; return fail(DT_ERR_CUDA); }
+    for (int k = 0; k < 2; k++) if (cudaEventCreateWithFlags(&s->ev_shade[k], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&s->ev_shadow[k], cudaEventDisableTiming) != cudaSuccess) { g_err = "cudaEventCreate failed"; return fail(DT_ERR_CUDA); }
     DtSceneDev& D = s->dev;
     {
         const uint4* p = nullptr;
@@ -440,7 +527,7 @@ int dt_scene_create(const dt_scene_desc* desc, dt_scene** out) {
     }
     s->fanout_hint = desc->max_recursion_depth > 0 ? (any_diel ? 2 : (any_refl ? 1 : 0)) : 0;
 
-    if (cudaMalloc(&s->counters, DT_CNT_COUNT * sizeof(int)) != cudaSuccess || cudaMallocHost(&s->h_counters, DT_CNT_COUNT * sizeof(int)) != cudaSuccess ||
+    if (cudaMalloc(&s->counters, DT_CNT_COUNT * sizeof(int)) != cudaSuccess || cudaMallocHost(&s->h_counters, (DT_CNT_COUNT + 4) * sizeof(int)) != cudaSuccess ||
         cudaMalloc(&s->tm_logsum, sizeof(double)) != cudaSuccess || cudaMalloc(&s->tm_hist, 256 * sizeof(unsigned int)) != cudaSuccess ||
         cudaMalloc(&s->tm_rank, sizeof(unsigned long long)) != cudaSuccess || cudaMalloc(&s->tm_prefix, sizeof(uint32_t)) != cudaSuccess) {
         g_err = "cudaMalloc of control buffers failed"; return fail(DT_ERR_CUDA);
@@ -448,6 +535,7 @@ int dt_scene_create(const dt_scene_desc* desc, dt_scene** out) {
     for (Timer* t : {&s->t_total, &s->t_gen, &s->t_closest, &s->t_shadow, &s->t_shade, &s->t_resolve, &s->t_tm}) if (t->init()) return fail(DT_ERR_CUDA);
     // traversal variant (A/B measurement): 0 static if-if, 1 static while-while, 2 dynamic if-if, 3 dynamic while-while
     if (const char* e = getenv("DT_TRAVERSE_MODE")) s->trav_mode = std::min(3, std::max(0, atoi(e)));
+    if (const char* e = getenv("DT_SYNC_WAVES")) s->sync_waves = atoi(e);
     if (const char* e = getenv("DT_REFILL_THRESHOLD")) s->refill_threshold = std::min(32, std::max(1, atoi(e)));
     {
         int bps = 0;
@@ -460,6 +548,7 @@ int dt_scene_create(const dt_scene_desc* desc, dt_scene** out) {
             s->grid_trav[m][a] = s->num_sms * std::max(1, bps);
         }
     }
+    { int bps = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_shade, 128, 0); s->grid_shade = s->num_sms * std::max(1, bps); }
     if (cudaDeviceSynchronize() != cudaSuccess) { g_err = "device sync after upload failed"; return fail(DT_ERR_CUDA); }
     *out = s;
     return DT_OK;
@@ -481,6 +570,9 @@ void dt_scene_destroy(dt_scene* s) {
     if (s->tm_rank) cudaFree(s->tm_rank);
     if (s->tm_prefix) cudaFree(s->tm_prefix);
     for (Timer* t : {&s->t_total, &s->t_gen, &s->t_closest, &s->t_shadow, &s->t_shade, &s->t_resolve, &s->t_tm}) t->destroy();
+    for (cudaEvent_t e : s->ev_pool) cudaEventDestroy(e);
+    for (int k = 0; k < 2; k++) { if (s->ev_shade[k]) cudaEventDestroy(s->ev_shade[k]); if (s->ev_shadow[k]) cudaEventDestroy(s->ev_shadow[k]); }
+    if (s->stream2) cudaStreamDestroy(s->stream2);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }

@@ -26,7 +26,12 @@ struct DtWaveParams {
 };
 
 // counters[] layout (device ints)
-enum { DT_CNT_NEXT = 0, DT_CNT_SHADOW = 1, DT_CNT_FETCH_A = 2, DT_CNT_FETCH_B = 3, DT_CNT_NAN = 4, DT_CNT_OVERFLOW = 5, DT_CNT_DEFER = 6, DT_CNT_COUNT = 8 };
+enum { DT_CNT_NEXT = 0, DT_CNT_SHADOW = 1, DT_CNT_FETCH_A = 2, DT_CNT_FETCH_B = 3, DT_CNT_NAN = 4, DT_CNT_OVERFLOW = 5, DT_CNT_DEFER = 6,
+       DT_CNT_CUR = 7,            // rays in the current wave (device-resident loop)
+       DT_CNT_SHADOW2 = 8, DT_CNT_FETCH_B2 = 9,   // second shadow queue (shadow(k) overlaps closest(k+1))
+       DT_CNT_TOT_CLOSEST = 10, DT_CNT_TOT_SHADOW = 12,   // 64-bit totals (two ints each)
+       DT_CNT_COUNT = 16 };
+struct DtShadeCounters { int* next; int* shadow; int* overflow; };
 
 #define DT_DEAD_PIXEL 0xFFFFFFFFu
 
@@ -218,9 +223,9 @@ struct DtChild {
     v3 miss;
 };
 
-__device__ __forceinline__ int dt_emit_child(const DtRayQueue& out, float4* out_miss, int* counters, int capacity, uint32_t pix, const DtChild& c) {
-    const int slot = dt_agg_inc(counters + DT_CNT_NEXT);
-    if (slot >= capacity) { atomicAdd(counters + DT_CNT_OVERFLOW, 1); return -1; }
+__device__ __forceinline__ int dt_emit_child(const DtRayQueue& out, float4* out_miss, const DtShadeCounters& counters, int capacity, uint32_t pix, const DtChild& c) {
+    const int slot = dt_agg_inc(counters.next);
+    if (slot >= capacity) { atomicAdd(counters.overflow, 1); return -1; }
     out.o_time[slot] = make_float4(c.o.x, c.o.y, c.o.z, c.mb);
     out.d_tmax[slot] = make_float4(c.d.x, c.d.y, c.d.z, CUDART_INF_F);
     out.pixel[slot] = pix;
@@ -231,10 +236,10 @@ __device__ __forceinline__ int dt_emit_child(const DtRayQueue& out, float4* out_
     return slot;
 }
 
-__device__ __forceinline__ void dt_emit_shadow(const DtShadowQueue& sq, int* counters, int capacity, v3 o, v3 d, float mb, float tmax,
+__device__ __forceinline__ void dt_emit_shadow(const DtShadowQueue& sq, const DtShadeCounters& counters, int capacity, v3 o, v3 d, float mb, float tmax,
                                                v3 contrib, uint32_t pix, int defer_slot, int defer_light) {
-    const int slot = dt_agg_inc(counters + DT_CNT_SHADOW);
-    if (slot >= capacity) { atomicAdd(counters + DT_CNT_OVERFLOW, 1); return; }
+    const int slot = dt_agg_inc(counters.shadow);
+    if (slot >= capacity) { atomicAdd(counters.overflow, 1); return; }
     sq.o_time[slot] = make_float4(o.x, o.y, o.z, mb);
     sq.d_tmax[slot] = make_float4(d.x, d.y, d.z, tmax);
     sq.contrib_pix[slot] = make_float4(contrib.x, contrib.y, contrib.z, __int_as_float((int)pix));
@@ -244,11 +249,9 @@ __device__ __forceinline__ void dt_emit_shadow(const DtShadowQueue& sq, int* cou
 // One thread per traced ray: Raytracer::PerPixel miss handling (raytracer.cpp:49-62) and PerformShading
 // (:65-134) with ComputeGlobalIllumination (:135-191), SampleDirectLighting (:701-806), mirror / conductor /
 // dielectric children (:208-472) turned into queue emissions.
-__global__ void __launch_bounds__(128) k_shade(DtSceneDev S, DtCamDev cam, DtRayQueue in, const float4* in_miss, int n,
-                                               DtRayQueue out, float4* out_miss, int out_capacity,
-                                               DtShadowQueue sq, int shadow_capacity, int* counters, float4* accum) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+__device__ __forceinline__ void dt_shade_ray(const int i, const DtSceneDev& S, const DtCamDev& cam, const DtRayQueue& in, const float4* in_miss,
+                                             const DtRayQueue& out, float4* out_miss, int out_capacity,
+                                             const DtShadowQueue& sq, int shadow_capacity, const DtShadeCounters& counters, float4* accum) {
     const uint32_t pix = in.pixel[i];
     if (pix == DT_DEAD_PIXEL) return;
     const float4 o4 = in.o_time[i], d4 = in.d_tmax[i];
@@ -525,6 +528,28 @@ __global__ void __launch_bounds__(128) k_shade(DtSceneDev S, DtCamDev cam, DtRay
             dt_emit_child(out, out_miss, counters, out_capacity, pix, c);
         }
     }
+}
+
+// Grid-stride launch: the wave size lives in device memory (n_ptr) so consecutive waves need no host round trip.
+__global__ void __launch_bounds__(128) k_shade(DtSceneDev S, DtCamDev cam, DtRayQueue in, const float4* in_miss, const int* n_ptr, int n_fixed,
+                                               DtRayQueue out, float4* out_miss, int out_capacity,
+                                               DtShadowQueue sq, int shadow_capacity, DtShadeCounters counters, float4* accum) {
+    const int n = n_ptr ? *n_ptr : n_fixed;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        dt_shade_ray(i, S, cam, in, in_miss, out, out_miss, out_capacity, sq, shadow_capacity, counters, accum);
+}
+
+// Device-side bookkeeping between two waves of the sync-free loop (one thread).
+__global__ void k_wave_advance(int* c, int shadow_slot_done, int shadow_slot_next) {
+    unsigned long long* tot_c = reinterpret_cast<unsigned long long*>(c + DT_CNT_TOT_CLOSEST);
+    unsigned long long* tot_s = reinterpret_cast<unsigned long long*>(c + DT_CNT_TOT_SHADOW);
+    *tot_c += (unsigned long long)c[DT_CNT_NEXT];
+    *tot_s += (unsigned long long)c[shadow_slot_done ? DT_CNT_SHADOW2 : DT_CNT_SHADOW];
+    c[DT_CNT_CUR] = c[DT_CNT_NEXT];
+    c[DT_CNT_NEXT] = 0;
+    c[DT_CNT_FETCH_A] = 0;
+    c[shadow_slot_next ? DT_CNT_SHADOW2 : DT_CNT_SHADOW] = 0;
+    c[shadow_slot_next ? DT_CNT_FETCH_B2 : DT_CNT_FETCH_B] = 0;
 }
 
 // Deferred mesh-light NEE (see k_shade): after the next wave's closest-hit pass, drop the entries whose GI
