@@ -42,3 +42,7 @@ clean:
 	rm -f $(PKG)/*.so oracle/*.so $(PKG)/raytracer_gpu
 
 .PHONY: all host oracle cuda cli clean
+
+# A/B variants of the CUDA library for on-GPU measurements (tests/_perf_ab.py): make variant NAME=x DEFS="-DFOO"
+variant:
+	$(NVCC) $(NVCCFLAGS) $(DEFS) -shared -o $(PKG)/libdorktracer_$(NAME).so $(CUDA_SRCS) -lcudart

@@ -3,6 +3,7 @@
 #include "dt_kernels.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -55,6 +56,22 @@ struct Timer {
 
 }  // namespace
 
+#define DT_MAX_PIPES 8
+
+struct DtPipe {
+    DtRayQueue q[2];
+    float4* miss[2] = {nullptr, nullptr};
+    DtShadowQueue sq[2];          // shadow(k) on stream B overlaps closest(k+1) / shade(k+1) on stream A
+    int capacity = 0, shadow_capacity = 0;
+    bool has_miss = false, has_defer = false;
+    std::vector<void*> allocs;
+    cudaStream_t A = nullptr, B = nullptr;
+    cudaEvent_t ev_shade[2] = {nullptr, nullptr}, ev_shadow[2] = {nullptr, nullptr}, ev_done = nullptr;
+    int* counters = nullptr;      // this pipe's block of dt_scene::counters
+    DtPipe() { memset(q, 0, sizeof q); memset(sq, 0, sizeof sq); }
+    void free_queues() { for (void* p : allocs) cudaFree(p); allocs.clear(); capacity = shadow_capacity = 0; }
+};
+
 struct dt_scene {
     int device = 0;
     int num_sms = 148;
@@ -66,28 +83,27 @@ struct dt_scene {
     int fanout_hint = 0;
     bool has_env = false;
 
-    // render-time buffers
-    int capacity = 0, shadow_capacity = 0;
-    DtRayQueue q[2];
-    float4* miss[2] = {nullptr, nullptr};
-    DtShadowQueue sq;
-    DtShadowQueue sq2;            // second shadow queue: shadow(k) on stream2 overlaps closest(k+1)/shade(k+1)
-    cudaStream_t stream2 = nullptr;
-    cudaEvent_t ev_shade[2] = {nullptr, nullptr}, ev_shadow[2] = {nullptr, nullptr};
+    // render-time buffers: up to DT_MAX_PIPES independent wavefront pipelines (queues, counters, two streams each).
+    // The frame's tiles are dealt round-robin to the pipelines; their waves run concurrently so that the tail of one
+    // pipeline's persistent traversal kernel is filled by the bulk of another's.  Pipe 0 also serves the
+    // host-synchronised loop (path tracing with Russian roulette / multi-batch frames).
+    DtPipe pipes[DT_MAX_PIPES];
+    cudaEvent_t ev_fork = nullptr;
     std::vector<cudaEvent_t> ev_pool;    // timing events of the sync-free loop
     int grid_shade = 0;
     int sync_waves = 0;           // DT_SYNC_WAVES=1 forces the host-synchronised wave loop (A/B)
-    std::vector<void*> qallocs;
-    int* counters = nullptr;
-    int* h_counters = nullptr;
+    int n_pipes_env = 0;          // DT_PIPES=n forces the pipeline count (0 = auto)
+    int debug_timing = 0;         // DT_DEBUG_TIMING=1 prints host-side enqueue times to stderr
+    int* counters = nullptr;      // DT_MAX_PIPES x DT_CNT_COUNT device ints (pipe p owns block p)
+    int* h_counters = nullptr;    // pinned mirror (+ scratch)
     float4* accum = nullptr; size_t accum_pix = 0;
     float* hdr = nullptr; uint8_t* ldr = nullptr; size_t out_pix = 0;
     double* tm_logsum = nullptr; unsigned int* tm_hist = nullptr; unsigned long long* tm_rank = nullptr; uint32_t* tm_prefix = nullptr;
     Timer t_total, t_gen, t_closest, t_shadow, t_shade, t_resolve, t_tm;
     int grid_trav[4][2] = {};
-    int trav_mode = 3, refill_threshold = 20;
+    int trav_mode = 2, refill_threshold = 16;
 
-    void free_queues() { for (void* p : qallocs) cudaFree(p); qallocs.clear(); capacity = shadow_capacity = 0; }
+    void free_queues() { for (DtPipe& p : pipes) p.free_queues(); }
 };
 
 namespace {
@@ -105,42 +121,41 @@ void launch_traverse(dt_scene* s, const DtRayQueue& q, const DtShadowQueue& sq, 
 }
 
 template <class T>
-int qalloc(dt_scene* s, T** p, size_t n) {
+int qalloc(DtPipe& pp, T** p, size_t n) {
     void* v = nullptr;
     CK(cudaMalloc(&v, std::max<size_t>(n * sizeof(T), 16)));
-    s->qallocs.push_back(v);
+    pp.allocs.push_back(v);
     *p = (T*)v;
     return DT_OK;
 }
 
-int ensure_queues(dt_scene* s, int capacity, int shadow_capacity) {
-    if (s->capacity >= capacity && s->shadow_capacity >= shadow_capacity) return DT_OK;
-    s->free_queues();
-    for (int k = 0; k < 2; k++) {
-        DtRayQueue& q = s->q[k];
-        int rc;
-        if ((rc = qalloc(s, &q.o_time, capacity))) return rc;
-        if ((rc = qalloc(s, &q.d_tmax, capacity))) return rc;
-        if ((rc = qalloc(s, &q.hit0, capacity))) return rc;
-        if ((rc = qalloc(s, &q.hit_face, capacity))) return rc;
-        if ((rc = qalloc(s, &q.pixel, capacity))) return rc;
-        if ((rc = qalloc(s, &q.weight_n, capacity))) return rc;
-        if ((rc = qalloc(s, &q.thr_beer, capacity))) return rc;
-        if ((rc = qalloc(s, &q.misc, capacity))) return rc;
-        q.sort_key = nullptr;
-        s->miss[k] = nullptr;
-        if (s->has_env) { if ((rc = qalloc(s, &s->miss[k], capacity))) return rc; }
-    }
+int ensure_queues(dt_scene* s, DtPipe& pp, int capacity, int shadow_capacity, bool need_defer) {
+    if (pp.capacity >= capacity && pp.shadow_capacity >= shadow_capacity && pp.has_miss == s->has_env && (pp.has_defer || !need_defer)) return DT_OK;
+    pp.free_queues();
     int rc;
-    if ((rc = qalloc(s, &s->sq.o_time, shadow_capacity))) return rc;
-    if ((rc = qalloc(s, &s->sq.d_tmax, shadow_capacity))) return rc;
-    if ((rc = qalloc(s, &s->sq.contrib_pix, shadow_capacity))) return rc;
-    if ((rc = qalloc(s, &s->sq.defer, shadow_capacity))) return rc;
-    if ((rc = qalloc(s, &s->sq2.o_time, shadow_capacity))) return rc;
-    if ((rc = qalloc(s, &s->sq2.d_tmax, shadow_capacity))) return rc;
-    if ((rc = qalloc(s, &s->sq2.contrib_pix, shadow_capacity))) return rc;
-    s->sq2.defer = nullptr;
-    s->capacity = capacity; s->shadow_capacity = shadow_capacity;
+    for (int k = 0; k < 2; k++) {
+        DtRayQueue& q = pp.q[k];
+        if ((rc = qalloc(pp, &q.o_time, capacity))) return rc;
+        if ((rc = qalloc(pp, &q.d_tmax, capacity))) return rc;
+        if ((rc = qalloc(pp, &q.hit0, capacity))) return rc;
+        if ((rc = qalloc(pp, &q.hit_face, capacity))) return rc;
+        if ((rc = qalloc(pp, &q.pixel, capacity))) return rc;
+        if ((rc = qalloc(pp, &q.weight_n, capacity))) return rc;
+        if ((rc = qalloc(pp, &q.thr_beer, capacity))) return rc;
+        if ((rc = qalloc(pp, &q.misc, capacity))) return rc;
+        q.sort_key = nullptr;
+        pp.miss[k] = nullptr;
+        if (s->has_env) { if ((rc = qalloc(pp, &pp.miss[k], capacity))) return rc; }
+    }
+    for (int k = 0; k < 2; k++) {
+        DtShadowQueue& sq = pp.sq[k];
+        if ((rc = qalloc(pp, &sq.o_time, shadow_capacity))) return rc;
+        if ((rc = qalloc(pp, &sq.d_tmax, shadow_capacity))) return rc;
+        if ((rc = qalloc(pp, &sq.contrib_pix, shadow_capacity))) return rc;
+        sq.defer = nullptr;
+        if (need_defer && k == 0) { if ((rc = qalloc(pp, &sq.defer, shadow_capacity))) return rc; }
+    }
+    pp.capacity = capacity; pp.shadow_capacity = shadow_capacity; pp.has_miss = s->has_env; pp.has_defer = need_defer;
     return DT_OK;
 }
 
@@ -215,6 +230,20 @@ int tonemap_device(dt_scene* s, const float* hdr, int W, int H, float key, float
 
 struct RenderOut { float* hdr_dev; };
 
+// valid primary rays of this rank: every in-image pixel of the owned tiles
+long long count_valid_pixels(const dt_render_params& P, int W, int H) {
+    const int tiles_x = (W + 7) / 8, tiles_y = (H + 3) / 4;
+    const long long n_tiles = (long long)tiles_x * tiles_y;
+    if (P.tile_world == 1 && W % 8 == 0 && H % 4 == 0) return (long long)W * H;
+    long long valid = 0;
+    for (long long tile = P.tile_rank; tile < n_tiles; tile += P.tile_world) {
+        int tx = (int)(tile % tiles_x), ty = (int)(tile / tiles_x);
+        int w = std::min(8, W - tx * 8), h = std::min(4, H - ty * 4);
+        if (w > 0 && h > 0) valid += (long long)w * h;
+    }
+    return valid;
+}
+
 int render_core(dt_scene* s, const dt_camera_desc* cam, const dt_render_params* params, dt_stats* stats, bool primary_only) {
     int rc = check_cam(cam);
     if (rc) return rc;
@@ -243,94 +272,122 @@ int render_core(dt_scene* s, const dt_camera_desc* cam, const dt_render_params* 
     wave_max = (int)std::min<long long>(wave_max, std::max<long long>(total, 32));
     wave_max = (wave_max + 31) & ~31;
     const int fan = s->fanout_hint + (pt ? 1 : 0);
+    const int shadows_per_hit = std::max(1, s->lights_shadowed);
     uint32_t retries = 0;
 
     cudaStream_t st = s->stream;
     dt_stats S; memset(&S, 0, sizeof S);
+    const auto t_host0 = std::chrono::steady_clock::now();
     s->t_total.start(st);
 
 retry:
-    {
-        const int capacity = primary_only ? wave_max : (fan <= 1 ? wave_max : (int)std::min<long long>((long long)wave_max * 4, 1ll << 28));
-        const long long shcap = primary_only ? 32 : std::max<long long>(32, (long long)wave_max * std::max(1, s->lights_shadowed));
-        if (shcap > (1ll << 29)) { g_err = "shadow queue too large; lower max_wave_rays"; return DT_ERR_INVALID; }
-        if ((rc = ensure_queues(s, capacity, (int)shcap))) return rc;
-    }
     CK(cudaMemsetAsync(s->accum, 0, n_pix * sizeof(float4), st));
-    CK(cudaMemsetAsync(s->counters, 0, DT_CNT_COUNT * sizeof(int), st));
+    CK(cudaMemsetAsync(s->counters, 0, DT_MAX_PIPES * DT_CNT_COUNT * sizeof(int), st));
     // ---- sync-free wave loop: every ray of the frame fits one batch and the ray tree has a known depth bound, so all
-    // waves are enqueued back to back (wave sizes live in device memory) and shadow(k) runs on a second stream while
-    // closest(k+1) / shade(k+1) proceed.  One host synchronisation per frame.
+    // waves are enqueued back to back (wave sizes live in device memory), shadow(k) runs on a second stream while
+    // closest(k+1) / shade(k+1) proceed, and the frame is dealt to several such pipelines.  One host sync per frame.
     const bool bounded = !(pt && dc.russian_roulette) && s->dev.max_recursion_depth <= 16;
     if (!primary_only && !defer_mode && bounded && total <= (long long)wave_max && !s->sync_waves) {
         const int n_waves = s->dev.max_recursion_depth + 1;
-        cudaStream_t A = s->stream, B = s->stream2;
-        int* c = s->counters;
-        const int n0 = (int)total;
+        int NP = s->n_pipes_env > 0 ? s->n_pipes_env : (int)1;
+        NP = (int)std::min<long long>(std::min(NP, DT_MAX_PIPES), std::max<long long>(1, my_tiles));
         size_t ev_i = 0;
         auto ev = [&]() -> cudaEvent_t { if (ev_i >= s->ev_pool.size()) { cudaEvent_t e; cudaEventCreate(&e); s->ev_pool.push_back(e); } return s->ev_pool[ev_i++]; };
         std::vector<cudaEvent_t> tg, tc, th, ts;      // (start, stop) pairs per stage
-        { cudaEvent_t a = ev(), b = ev(); cudaEventRecord(a, A);
-          k_generate<<<(n0 + 255) / 256, 256, 0, A>>>(dc, wp, s->q[0], 0, 0, n0, s->accum);
-          cudaEventRecord(b, A); tg.push_back(a); tg.push_back(b); }
-        s->h_counters[DT_CNT_COUNT] = n0;              // pinned scratch slot past the readback area
-        CK(cudaMemcpyAsync(c + DT_CNT_CUR, s->h_counters + DT_CNT_COUNT, sizeof(int), cudaMemcpyHostToDevice, A));
-        int cur = 0;
-        for (int k = 0; k < n_waves; k++) {
-            const int slot = k & 1;
-            DtShadowQueue& sq = slot ? s->sq2 : s->sq;
-            { cudaEvent_t a = ev(), b = ev(); cudaEventRecord(a, A);
-              launch_traverse<false>(s, s->q[cur], sq, c + DT_CNT_CUR, 0, c + DT_CNT_FETCH_A, s->accum, A);
-              cudaEventRecord(b, A); tc.push_back(a); tc.push_back(b); }
-            if (k >= 2) CK(cudaStreamWaitEvent(A, s->ev_shadow[slot], 0));       // shadow(k-2) must have drained this queue
-            { cudaEvent_t a = ev(), b = ev(); cudaEventRecord(a, A);
-              DtShadeCounters sc = {c + DT_CNT_NEXT, c + (slot ? DT_CNT_SHADOW2 : DT_CNT_SHADOW), c + DT_CNT_OVERFLOW};
-              k_shade<<<s->grid_shade, 128, 0, A>>>(s->dev, dc, s->q[cur], s->miss[cur], c + DT_CNT_CUR, 0, s->q[1 - cur], s->miss[1 - cur], s->capacity,
-                                                    sq, s->shadow_capacity, sc, s->accum);
-              cudaEventRecord(b, A); th.push_back(a); th.push_back(b); }
-            CK(cudaEventRecord(s->ev_shade[slot], A));
-            CK(cudaStreamWaitEvent(B, s->ev_shade[slot], 0));
-            { cudaEvent_t a = ev(), b = ev(); cudaEventRecord(a, B);
-              launch_traverse<true>(s, s->q[cur], sq, c + (slot ? DT_CNT_SHADOW2 : DT_CNT_SHADOW), 0, c + (slot ? DT_CNT_FETCH_B2 : DT_CNT_FETCH_B), s->accum, B);
-              cudaEventRecord(b, B); ts.push_back(a); ts.push_back(b); }
-            CK(cudaEventRecord(s->ev_shadow[slot], B));
-            if (k >= 1) CK(cudaStreamWaitEvent(A, s->ev_shadow[1 - slot], 0));    // the other queue's counters are about to be reset
-            k_wave_advance<<<1, 1, 0, A>>>(c, 1 - slot, 1 - slot);
-            S.kernel_launches += 4; S.launches_traverse_closest++;
-            cur = 1 - cur;
+        auto timed = [&](std::vector<cudaEvent_t>& v, cudaStream_t q, auto&& launch) {
+            cudaEvent_t a = ev(), b = ev(); cudaEventRecord(a, q); launch(); cudaEventRecord(b, q); v.push_back(a); v.push_back(b);
+        };
+        DtWaveParams wps[DT_MAX_PIPES]; int n0[DT_MAX_PIPES];
+        for (int p = 0; p < NP; p++) {
+            DtPipe& pp = s->pipes[p];
+            wps[p] = wp;
+            wps[p].tile_world = P.tile_world * NP;
+            wps[p].tile_rank = P.tile_rank + p * P.tile_world;
+            const long long tiles_p = (n_tiles - wps[p].tile_rank + wps[p].tile_world - 1) / wps[p].tile_world;
+            wps[p].per_sample = tiles_p * 32;
+            const long long total_p = wps[p].per_sample * dc.spp;
+            n0[p] = (int)total_p;
+            const long long cap = std::max<long long>(32, fan <= 1 ? total_p : std::min<long long>(total_p * 4, 1ll << 28));
+            const long long shcap = std::max<long long>(32, total_p * shadows_per_hit);
+            if (shcap > (1ll << 29)) { g_err = "shadow queue too large; lower max_wave_rays"; return DT_ERR_INVALID; }
+            if ((rc = ensure_queues(s, pp, (int)cap, (int)shcap, false))) return rc;
         }
-        S.kernel_launches++;
-        CK(cudaStreamWaitEvent(A, s->ev_shadow[0], 0));
-        if (n_waves > 1) CK(cudaStreamWaitEvent(A, s->ev_shadow[1], 0));
-        CK(cudaMemcpyAsync(s->h_counters, c, DT_CNT_COUNT * sizeof(int), cudaMemcpyDeviceToHost, A));
-        CK(cudaStreamSynchronize(A));
+        CK(cudaEventRecord(s->ev_fork, st));
+        for (int p = 0; p < NP; p++) {
+            DtPipe& pp = s->pipes[p];
+            if (p > 0) CK(cudaStreamWaitEvent(pp.A, s->ev_fork, 0));
+            CK(cudaStreamWaitEvent(pp.B, s->ev_fork, 0));
+            timed(tg, pp.A, [&] { k_generate<<<(n0[p] + 255) / 256, 256, 0, pp.A>>>(dc, wps[p], pp.q[0], 0, 0, n0[p], s->accum); });
+            s->h_counters[DT_MAX_PIPES * DT_CNT_COUNT + p] = n0[p];          // pinned scratch past the readback area
+            CK(cudaMemcpyAsync(pp.counters + DT_CNT_CUR, s->h_counters + DT_MAX_PIPES * DT_CNT_COUNT + p, sizeof(int), cudaMemcpyHostToDevice, pp.A));
+            S.kernel_launches++;
+        }
+        for (int k = 0; k < n_waves; k++) {
+            const int slot = k & 1, cur = k & 1;
+            for (int p = 0; p < NP; p++) {
+                DtPipe& pp = s->pipes[p];
+                int* c = pp.counters;
+                DtShadowQueue& sq = pp.sq[slot];
+                timed(tc, pp.A, [&] { launch_traverse<false>(s, pp.q[cur], sq, c + DT_CNT_CUR, 0, c + DT_CNT_FETCH_A, s->accum, pp.A); });
+                if (k >= 2) CK(cudaStreamWaitEvent(pp.A, pp.ev_shadow[slot], 0));       // shadow(k-2) must have drained this queue
+                timed(th, pp.A, [&] {
+                    DtShadeCounters sc = {c + DT_CNT_NEXT, c + (slot ? DT_CNT_SHADOW2 : DT_CNT_SHADOW), c + DT_CNT_OVERFLOW};
+                    k_shade<<<s->grid_shade, 128, 0, pp.A>>>(s->dev, dc, pp.q[cur], pp.miss[cur], c + DT_CNT_CUR, 0, pp.q[1 - cur], pp.miss[1 - cur], pp.capacity,
+                                                            sq, pp.shadow_capacity, sc, s->accum); });
+                CK(cudaEventRecord(pp.ev_shade[slot], pp.A));
+                CK(cudaStreamWaitEvent(pp.B, pp.ev_shade[slot], 0));
+                timed(ts, pp.B, [&] { launch_traverse<true>(s, pp.q[cur], sq, c + (slot ? DT_CNT_SHADOW2 : DT_CNT_SHADOW), 0, c + (slot ? DT_CNT_FETCH_B2 : DT_CNT_FETCH_B), s->accum, pp.B); });
+                CK(cudaEventRecord(pp.ev_shadow[slot], pp.B));
+                if (k >= 1) CK(cudaStreamWaitEvent(pp.A, pp.ev_shadow[1 - slot], 0));    // the other queue's counters are about to be reset
+                k_wave_advance<<<1, 1, 0, pp.A>>>(c, 1 - slot, 1 - slot);
+                S.kernel_launches += 4; S.launches_traverse_closest++;
+            }
+        }
+        for (int p = 0; p < NP; p++) {
+            DtPipe& pp = s->pipes[p];
+            CK(cudaStreamWaitEvent(pp.A, pp.ev_shadow[0], 0));
+            if (n_waves > 1) CK(cudaStreamWaitEvent(pp.A, pp.ev_shadow[1], 0));
+            if (p > 0) { CK(cudaEventRecord(pp.ev_done, pp.A)); CK(cudaStreamWaitEvent(st, pp.ev_done, 0)); }
+        }
+        CK(cudaMemcpyAsync(s->h_counters, s->counters, DT_MAX_PIPES * DT_CNT_COUNT * sizeof(int), cudaMemcpyDeviceToHost, st));
+        if (s->debug_timing) fprintf(stderr, "[dt] enqueue of %d pipes x %d waves took %.3f ms on the host\n", NP, n_waves,
+                                     1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t_host0).count());
+        CK(cudaStreamSynchronize(st));
         CK(cudaGetLastError());
         auto sum = [&](std::vector<cudaEvent_t>& v) { float t = 0.f; for (size_t i = 0; i + 1 < v.size(); i += 2) { float ms = 0.f; cudaEventElapsedTime(&ms, v[i], v[i + 1]); t += ms; } return t; };
         S.ms_generate = sum(tg); S.ms_traverse_closest = sum(tc); S.ms_shade = sum(th); S.ms_traverse_shadow = sum(ts);
         S.waves = (uint32_t)n_waves;
-        if (s->h_counters[DT_CNT_OVERFLOW] != 0) {
+        bool overflow = false;
+        unsigned long long tot_c = 0, tot_s = 0;
+        for (int p = 0; p < NP; p++) {
+            const int* hc = s->h_counters + p * DT_CNT_COUNT;
+            if (hc[DT_CNT_OVERFLOW] != 0) overflow = true;
+            unsigned long long c8 = 0, s8 = 0;
+            memcpy(&c8, hc + DT_CNT_TOT_CLOSEST, 8); memcpy(&s8, hc + DT_CNT_TOT_SHADOW, 8);
+            tot_c += c8; tot_s += s8 + (unsigned long long)hc[((n_waves - 1) & 1) ? DT_CNT_SHADOW2 : DT_CNT_SHADOW];     // + last wave's queue
+        }
+        if (overflow) {
             if (retries >= 6 || wave_max <= 4096) { g_err = "wavefront queue overflow (ray-tree fan-out too large even for small waves)"; return DT_ERR_OVERFLOW; }
             retries++;
             wave_max = std::max(4096, (wave_max / 4 + 31) & ~31);      // smaller batches -> falls back to the synchronised loop
             goto retry;
         }
-        unsigned long long tot_c = 0, tot_s = 0;
-        memcpy(&tot_c, s->h_counters + DT_CNT_TOT_CLOSEST, 8); memcpy(&tot_s, s->h_counters + DT_CNT_TOT_SHADOW, 8);
-        tot_s += (unsigned long long)s->h_counters[((n_waves - 1) & 1) ? DT_CNT_SHADOW2 : DT_CNT_SHADOW];     // last wave's queue
-        S.rays_closest = tot_c; S.rays_shadow = tot_s;
-        long long valid = 0;
-        for (long long j = 0; j < my_tiles; j++) {
-            long long tile = j * P.tile_world + P.tile_rank;
-            int tx = (int)(tile % wp.tiles_x), ty = (int)(tile / wp.tiles_x);
-            int w = std::min(8, W - tx * 8), h = std::min(4, H - ty * 4);
-            if (w > 0 && h > 0) valid += (long long)w * h;
-        }
-        S.rays_closest += (uint64_t)(valid * dc.spp);
+        S.rays_closest = tot_c + (uint64_t)(count_valid_pixels(P, W, H) * dc.spp);
+        S.rays_shadow = tot_s;
         S.retries = retries;
         if (stats) *stats = S;
         return DT_OK;
     }
     {
+        DtPipe& pp = s->pipes[0];
+        {
+            const int capacity = primary_only ? wave_max : (fan <= 1 ? wave_max : (int)std::min<long long>((long long)wave_max * 4, 1ll << 28));
+            const long long shcap = primary_only ? 32 : std::max<long long>(32, (long long)wave_max * shadows_per_hit);
+            if (shcap > (1ll << 29)) { g_err = "shadow queue too large; lower max_wave_rays"; return DT_ERR_INVALID; }
+            if ((rc = ensure_queues(s, pp, capacity, (int)shcap, defer_mode))) return rc;
+        }
+        int* c = pp.counters;
+        DtShadowQueue& sq = pp.sq[0];
         long long next_primary = 0;
         int count = 0, cur = 0;
         int prev_shadow = 0;
@@ -342,44 +399,44 @@ retry:
             if (count < wave_max && next_primary < total) {
                 n_new = (int)std::min<long long>(wave_max - count, total - next_primary);
                 s->t_gen.start(st);
-                k_generate<<<(n_new + 255) / 256, 256, 0, st>>>(dc, wp, s->q[cur], count, next_primary, n_new, s->accum);
+                k_generate<<<(n_new + 255) / 256, 256, 0, st>>>(dc, wp, pp.q[cur], count, next_primary, n_new, s->accum);
                 s->t_gen.stop(st);
                 S.kernel_launches++;
                 count += n_new; next_primary += n_new;
             }
-            CK(cudaMemsetAsync(s->counters + DT_CNT_NEXT, 0, sizeof(int), st));
-            CK(cudaMemsetAsync(s->counters + DT_CNT_FETCH_A, 0, 2 * sizeof(int), st));
+            CK(cudaMemsetAsync(c + DT_CNT_NEXT, 0, sizeof(int), st));
+            CK(cudaMemsetAsync(c + DT_CNT_FETCH_A, 0, 2 * sizeof(int), st));
             s->t_closest.start(st);
-            launch_traverse<false>(s, s->q[cur], s->sq, nullptr, count, s->counters + DT_CNT_FETCH_A, s->accum);
+            launch_traverse<false>(s, pp.q[cur], sq, nullptr, count, c + DT_CNT_FETCH_A, s->accum);
             s->t_closest.stop(st);
             S.kernel_launches++; S.launches_traverse_closest++;
             if (primary_only) { CK(cudaStreamSynchronize(st)); S.ms_traverse_closest += s->t_closest.take(); S.ms_generate += s->t_gen.take(); S.waves++; break; }
             bool shadow_timed = false;
             if (defer_mode && prev_shadow > 0) {
-                k_filter_deferred<<<(prev_shadow + 255) / 256, 256, 0, st>>>(s->dev, s->sq, prev_shadow, s->q[cur]);
+                k_filter_deferred<<<(prev_shadow + 255) / 256, 256, 0, st>>>(s->dev, sq, prev_shadow, pp.q[cur]);
                 s->t_shadow.start(st);
-                launch_traverse<true>(s, s->q[cur], s->sq, nullptr, prev_shadow, s->counters + DT_CNT_FETCH_B, s->accum);
+                launch_traverse<true>(s, pp.q[cur], sq, nullptr, prev_shadow, c + DT_CNT_FETCH_B, s->accum);
                 s->t_shadow.stop(st);
                 shadow_timed = true;
                 S.kernel_launches += 2;
             }
-            CK(cudaMemsetAsync(s->counters + DT_CNT_SHADOW, 0, sizeof(int), st));
+            CK(cudaMemsetAsync(c + DT_CNT_SHADOW, 0, sizeof(int), st));
             s->t_shade.start(st);
             {
-                DtShadeCounters sc = {s->counters + DT_CNT_NEXT, s->counters + DT_CNT_SHADOW, s->counters + DT_CNT_OVERFLOW};
-                k_shade<<<(count + 127) / 128, 128, 0, st>>>(s->dev, dc, s->q[cur], s->miss[cur], nullptr, count, s->q[1 - cur], s->miss[1 - cur], s->capacity,
-                                                             s->sq, s->shadow_capacity, sc, s->accum);
+                DtShadeCounters sc = {c + DT_CNT_NEXT, c + DT_CNT_SHADOW, c + DT_CNT_OVERFLOW};
+                k_shade<<<(count + 127) / 128, 128, 0, st>>>(s->dev, dc, pp.q[cur], pp.miss[cur], nullptr, count, pp.q[1 - cur], pp.miss[1 - cur], pp.capacity,
+                                                             sq, pp.shadow_capacity, sc, s->accum);
             }
             s->t_shade.stop(st);
             S.kernel_launches++;
             if (!defer_mode) {
                 s->t_shadow.start(st);
-                launch_traverse<true>(s, s->q[cur], s->sq, s->counters + DT_CNT_SHADOW, 0, s->counters + DT_CNT_FETCH_B, s->accum);
+                launch_traverse<true>(s, pp.q[cur], sq, c + DT_CNT_SHADOW, 0, c + DT_CNT_FETCH_B, s->accum);
                 s->t_shadow.stop(st);
                 shadow_timed = true;
                 S.kernel_launches++;
             }
-            CK(cudaMemcpyAsync(s->h_counters, s->counters, DT_CNT_COUNT * sizeof(int), cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(s->h_counters, c, DT_CNT_COUNT * sizeof(int), cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
             CK(cudaGetLastError());
             S.ms_generate += s->t_gen.take();
@@ -389,7 +446,7 @@ retry:
             S.waves++;
             if (s->h_counters[DT_CNT_OVERFLOW] != 0) { overflow = true; break; }
             const int next_count = s->h_counters[DT_CNT_NEXT];
-            const int shadow_count = std::min(s->h_counters[DT_CNT_SHADOW], s->shadow_capacity);
+            const int shadow_count = std::min(s->h_counters[DT_CNT_SHADOW], pp.shadow_capacity);
             S.rays_closest += (uint64_t)next_count;
             S.rays_shadow += (uint64_t)shadow_count;
             prev_shadow = defer_mode ? shadow_count : 0;
@@ -397,8 +454,8 @@ retry:
             cur = 1 - cur;
         }
         if (!overflow && defer_mode && prev_shadow > 0) {
-            CK(cudaMemsetAsync(s->counters + DT_CNT_FETCH_B, 0, sizeof(int), st));
-            launch_traverse<true>(s, s->q[cur], s->sq, nullptr, prev_shadow, s->counters + DT_CNT_FETCH_B, s->accum);
+            CK(cudaMemsetAsync(c + DT_CNT_FETCH_B, 0, sizeof(int), st));
+            launch_traverse<true>(s, pp.q[cur], sq, nullptr, prev_shadow, c + DT_CNT_FETCH_B, s->accum);
             S.kernel_launches++;
         }
         if (overflow) {
@@ -408,15 +465,7 @@ retry:
             CK(cudaStreamSynchronize(st));
             goto retry;
         }
-        // valid primary rays: every in-image pixel of the owned tiles, spp times
-        long long valid = 0;
-        for (long long j = 0; j < my_tiles; j++) {
-            long long tile = j * P.tile_world + P.tile_rank;
-            int tx = (int)(tile % wp.tiles_x), ty = (int)(tile / wp.tiles_x);
-            int w = std::min(8, W - tx * 8), h = std::min(4, H - ty * 4);
-            if (w > 0 && h > 0) valid += (long long)w * h;
-        }
-        S.rays_closest += (uint64_t)(valid * (primary_only ? 1 : dc.spp));
+        S.rays_closest += (uint64_t)(count_valid_pixels(P, W, H) * (primary_only ? 1 : dc.spp));
     }
     S.retries = retries;
     if (stats) *stats = S;
@@ -473,15 +522,19 @@ int dt_scene_create(const dt_scene_desc* desc, dt_scene** out) {
     dt_scene* s = new dt_scene();
     s->device = g_device;
     memset(&s->dev, 0, sizeof s->dev);
-    memset(&s->q, 0, sizeof s->q);
-    memset(&s->sq, 0, sizeof s->sq);
-    memset(&s->sq2, 0, sizeof s->sq2);
     auto fail = [&](int code) { dt_scene_destroy(s); return code; };
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, s->device) != cudaSuccess) { g_err = "cudaGetDeviceProperties failed"; return fail(DT_ERR_CUDA); }
     s->num_sms = prop.multiProcessorCount;
-    if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&s->stream2, cudaStreamNonBlocking) != cudaSuccess) { g_err = "cudaStreamCreate failed"; return fail(DT_ERR_CUDA); }
-    for (int k = 0; k < 2; k++) if (cudaEventCreateWithFlags(&s->ev_shade[k], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&s->ev_shadow[k], cudaEventDisableTiming) != cudaSuccess) { g_err = "cudaEventCreate failed"; return fail(DT_ERR_CUDA); }
+    if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming) != cudaSuccess) { g_err = "cudaStreamCreate failed"; return fail(DT_ERR_CUDA); }
+    for (int p = 0; p < DT_MAX_PIPES; p++) {
+        DtPipe& pp = s->pipes[p];
+        bool ok = true;
+        if (p == 0) pp.A = s->stream; else ok = cudaStreamCreateWithFlags(&pp.A, cudaStreamNonBlocking) == cudaSuccess;
+        ok = ok && cudaStreamCreateWithFlags(&pp.B, cudaStreamNonBlocking) == cudaSuccess && cudaEventCreateWithFlags(&pp.ev_done, cudaEventDisableTiming) == cudaSuccess;
+        for (int k = 0; k < 2 && ok; k++) ok = cudaEventCreateWithFlags(&pp.ev_shade[k], cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&pp.ev_shadow[k], cudaEventDisableTiming) == cudaSuccess;
+        if (!ok) { g_err = "cudaStreamCreate / cudaEventCreate failed"; return fail(DT_ERR_CUDA); }
+    }
     DtSceneDev& D = s->dev;
     {
         const uint4* p = nullptr;
@@ -514,6 +567,9 @@ int dt_scene_create(const dt_scene_desc* desc, dt_scene** out) {
     D.n_point_lights = desc->n_point_lights; D.n_area_lights = desc->n_area_lights; D.n_directional_lights = desc->n_directional_lights;
     D.n_spot_lights = desc->n_spot_lights; D.n_env_lights = desc->n_env_lights; D.n_mesh_lights = desc->n_mesh_lights;
     D.bg_texture = desc->bg_texture; D.max_recursion_depth = desc->max_recursion_depth;
+    D.tlas_direct = 0;
+    D.one_bits = 0x3F800000u;
+    if (hs.tlas_nodes.size() == 1 && hs.tlas_prims.size() <= 4 && hs.tlas_nodes[0].imask == 0 && !getenv("DT_NO_TLAS_DIRECT")) D.tlas_direct = (int)hs.tlas_prims.size();
     memcpy(D.background_color, desc->background_color, 12);
     D.shadow_ray_epsilon = desc->shadow_ray_epsilon;
     memcpy(D.ambient_light, desc->ambient_light, 12);
@@ -527,15 +583,18 @@ int dt_scene_create(const dt_scene_desc* desc, dt_scene** out) {
     }
     s->fanout_hint = desc->max_recursion_depth > 0 ? (any_diel ? 2 : (any_refl ? 1 : 0)) : 0;
 
-    if (cudaMalloc(&s->counters, DT_CNT_COUNT * sizeof(int)) != cudaSuccess || cudaMallocHost(&s->h_counters, (DT_CNT_COUNT + 4) * sizeof(int)) != cudaSuccess ||
+    if (cudaMalloc(&s->counters, DT_MAX_PIPES * DT_CNT_COUNT * sizeof(int)) != cudaSuccess || cudaMallocHost(&s->h_counters, (DT_MAX_PIPES * DT_CNT_COUNT + DT_MAX_PIPES) * sizeof(int)) != cudaSuccess ||
         cudaMalloc(&s->tm_logsum, sizeof(double)) != cudaSuccess || cudaMalloc(&s->tm_hist, 256 * sizeof(unsigned int)) != cudaSuccess ||
         cudaMalloc(&s->tm_rank, sizeof(unsigned long long)) != cudaSuccess || cudaMalloc(&s->tm_prefix, sizeof(uint32_t)) != cudaSuccess) {
         g_err = "cudaMalloc of control buffers failed"; return fail(DT_ERR_CUDA);
     }
+    for (int p = 0; p < DT_MAX_PIPES; p++) s->pipes[p].counters = s->counters + p * DT_CNT_COUNT;
     for (Timer* t : {&s->t_total, &s->t_gen, &s->t_closest, &s->t_shadow, &s->t_shade, &s->t_resolve, &s->t_tm}) if (t->init()) return fail(DT_ERR_CUDA);
     // traversal variant (A/B measurement): 0 static if-if, 1 static while-while, 2 dynamic if-if, 3 dynamic while-while
     if (const char* e = getenv("DT_TRAVERSE_MODE")) s->trav_mode = std::min(3, std::max(0, atoi(e)));
     if (const char* e = getenv("DT_SYNC_WAVES")) s->sync_waves = atoi(e);
+    if (const char* e = getenv("DT_DEBUG_TIMING")) s->debug_timing = atoi(e);
+    if (const char* e = getenv("DT_PIPES")) s->n_pipes_env = std::min(DT_MAX_PIPES, std::max(0, atoi(e)));
     if (const char* e = getenv("DT_REFILL_THRESHOLD")) s->refill_threshold = std::min(32, std::max(1, atoi(e)));
     {
         int bps = 0;
@@ -571,8 +630,14 @@ void dt_scene_destroy(dt_scene* s) {
     if (s->tm_prefix) cudaFree(s->tm_prefix);
     for (Timer* t : {&s->t_total, &s->t_gen, &s->t_closest, &s->t_shadow, &s->t_shade, &s->t_resolve, &s->t_tm}) t->destroy();
     for (cudaEvent_t e : s->ev_pool) cudaEventDestroy(e);
-    for (int k = 0; k < 2; k++) { if (s->ev_shade[k]) cudaEventDestroy(s->ev_shade[k]); if (s->ev_shadow[k]) cudaEventDestroy(s->ev_shadow[k]); }
-    if (s->stream2) cudaStreamDestroy(s->stream2);
+    for (int p = 0; p < DT_MAX_PIPES; p++) {
+        DtPipe& pp = s->pipes[p];
+        for (int k = 0; k < 2; k++) { if (pp.ev_shade[k]) cudaEventDestroy(pp.ev_shade[k]); if (pp.ev_shadow[k]) cudaEventDestroy(pp.ev_shadow[k]); }
+        if (pp.ev_done) cudaEventDestroy(pp.ev_done);
+        if (pp.B) cudaStreamDestroy(pp.B);
+        if (p > 0 && pp.A) cudaStreamDestroy(pp.A);
+    }
+    if (s->ev_fork) cudaEventDestroy(s->ev_fork);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
@@ -657,7 +722,7 @@ int dt_primary_hits(dt_scene* s, const dt_camera_desc* cam, int32_t* shape, int3
     int32_t *d_shape = nullptr, *d_face = nullptr; float* d_t = nullptr;
     CK(cudaMalloc(&d_shape, (size_t)n_pix * 4)); CK(cudaMalloc(&d_face, (size_t)n_pix * 4)); CK(cudaMalloc(&d_t, (size_t)n_pix * 4));
     cudaStream_t st = s->stream;
-    k_unpack_hits<<<((int)n_slots + 255) / 256, 256, 0, st>>>(s->q[0].hit0, s->q[0].hit_face, s->q[0].pixel, (int)n_slots, d_shape, d_face, d_t, 1);
+    k_unpack_hits<<<((int)n_slots + 255) / 256, 256, 0, st>>>(s->pipes[0].q[0].hit0, s->pipes[0].q[0].hit_face, s->pipes[0].q[0].pixel, (int)n_slots, d_shape, d_face, d_t, 1);
     cudaMemcpyAsync(shape, d_shape, (size_t)n_pix * 4, cudaMemcpyDeviceToHost, st);
     cudaMemcpyAsync(face, d_face, (size_t)n_pix * 4, cudaMemcpyDeviceToHost, st);
     cudaMemcpyAsync(t, d_t, (size_t)n_pix * 4, cudaMemcpyDeviceToHost, st);
@@ -753,6 +818,25 @@ void dt_debug_stats(unsigned long long* out, int reset) {
     cudaDeviceSynchronize();
     cudaMemcpyFromSymbol(out, g_dt_stats, sizeof(unsigned long long) * 8);
     if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_dt_stats, z, sizeof z); }
+}
+#endif
+
+#ifdef DT_TIMELINE
+// debug build only: copy out (and reset) the per-warp timeline records; returns the number of records
+int dt_debug_timeline(unsigned long long* out, int max_records) {
+    cudaDeviceSynchronize();
+    unsigned int n = 0;
+    cudaMemcpyFromSymbol(&n, g_dt_tl_count, sizeof n);
+    if (n > (unsigned)max_records) n = (unsigned)max_records;
+    if (n > DT_TL_MAX) n = DT_TL_MAX;
+    if (out && n) cudaMemcpyFromSymbol(out, g_dt_tl, (size_t)n * 32);
+    unsigned int z = 0; cudaMemcpyToSymbol(g_dt_tl_count, &z, sizeof z);
+    return (int)n;
+}
+void dt_debug_steps_hist(unsigned int* out, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, g_dt_steps_hist, sizeof(unsigned int) * 128);
+    if (reset) { unsigned int z[128] = {0}; cudaMemcpyToSymbol(g_dt_steps_hist, z, sizeof z); }
 }
 #endif
 

@@ -96,6 +96,8 @@ struct DtSceneDev {
     int32_t n_shapes, n_mesh_shapes, n_materials;
     int32_t n_point_lights, n_area_lights, n_directional_lights, n_spot_lights, n_env_lights, n_mesh_lights;
     int32_t bg_texture, max_recursion_depth;
+    uint32_t one_bits;            // 0x3F800000, see dt_byte_m (dt_traverse.cuh)
+    int32_t tlas_direct;          // > 0: the TLAS is one leaf-only node over this many (<= 4) shapes -> rays start with the shape list itself
     int32_t background_color[3];
     float shadow_ray_epsilon;
     float ambient_light[3];

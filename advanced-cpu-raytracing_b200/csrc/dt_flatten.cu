@@ -81,41 +81,48 @@ bool dt_collapse_bvh8(const std::vector<DtB2Node>& b2, DtWideBvh& out, std::stri
             }
             slot_of[bk] = bs; child_in_slot[bs] = bk;
         }
-        // quantisation frame
+        // quantisation frame.  Child boxes are rounded OUTWARD with a 1/128-step margin on both sides: the kernel's node
+        // test evaluates plane distances with an absolute error of up to 2^-9 quantisation steps (dt_traverse.cuh,
+        // dt_byte_m).  The frame origin sits a margin below the node minimum so the margin also holds at q = 0.
         DtNode8 node; memset(&node, 0, sizeof node);
-        node.px = mn[0]; node.py = mn[1]; node.pz = mn[2];
+        const double margin = 1.0 / 128.0;
         int e[3];
         for (int a = 0; a < 3; a++) {
             double ext = (double)mx[a] - (double)mn[a];
             int ea = -120;
-            if (ext > 0) { ea = (int)std::ceil(std::log2(ext / 255.0)); }
+            if (ext > 0) { ea = (int)std::ceil(std::log2(ext / 254.0)); }
             if (ea < -120) ea = -120;
-            if (ea > 120) ea = 120;
+            if (ea > 100) ea = 100;
             e[a] = ea;
         }
         uint8_t qlo[3][8], qhi[3][8];
+        float origin[3];
         for (int a = 0; a < 3; a++) {
             for (;;) {
                 bool ok = true;
-                double sc = std::ldexp(1.0, e[a]);
-                double p = (double)mn[a];
+                const double sc = std::ldexp(1.0, e[a]);
+                float pf = (float)((double)mn[a] - 1.5 * margin * sc);
+                if ((double)pf > (double)mn[a] - margin * sc) pf = std::nextafterf(pf, -FLT_MAX);
+                if (!(pf == pf) || std::isinf(pf)) pf = mn[a];
+                const double p = (double)pf;
                 for (int s = 0; s < 8 && ok; s++) {
                     int k = child_in_slot[s];
                     if (k < 0) { qlo[a][s] = 0; qhi[a][s] = 0; continue; }
                     double lo = b2[ch[k]].mn[a], hi = b2[ch[k]].mx[a];
                     if (!(lo <= hi)) { lo = p; hi = p; }
-                    double ql = std::floor((lo - p) / sc), qh2 = std::ceil((hi - p) / sc);
+                    double ql = std::floor((lo - p) / sc - margin), qh2 = std::ceil((hi - p) / sc + margin);
                     if (ql < 0) ql = 0;
-                    while (p + ql * sc > lo && ql > 0) ql -= 1;
-                    while (p + qh2 * sc < hi) qh2 += 1;
+                    while (p + (ql + margin) * sc > lo && ql > 0) ql -= 1;
+                    while (p + (qh2 - margin) * sc < hi) qh2 += 1;
                     if (qh2 > 255 || ql > 255) { ok = false; break; }
                     qlo[a][s] = (uint8_t)ql; qhi[a][s] = (uint8_t)qh2;
                 }
-                if (ok) break;
+                if (ok) { origin[a] = pf; break; }
                 e[a]++;
-                if (e[a] > 126) { err = "BVH8 quantisation exponent overflow"; return false; }
+                if (e[a] > 100) { err = "BVH8 quantisation exponent overflow (scene extent beyond 2^100)"; return false; }
             }
         }
+        node.px = origin[0]; node.py = origin[1]; node.pz = origin[2];
         node.ex = (uint8_t)(e[0] + 127); node.ey = (uint8_t)(e[1] + 127); node.ez = (uint8_t)(e[2] + 127);
         // children: internal ones get consecutive node indices in slot order; leaves get consecutive primitives
         int n_internal = 0;

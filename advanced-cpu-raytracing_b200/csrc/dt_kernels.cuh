@@ -133,9 +133,12 @@ __device__ __forceinline__ void dt_store_shadow(const DtShadowQueue& sq, int i, 
     }
 }
 
+#ifndef DT_TRAV_MINBLOCKS
+#define DT_TRAV_MINBLOCKS 6       // resident blocks per SM the register allocator must allow (measured: 6 beats 7-9, which spill)
+#endif
 // Static variant: a warp fetches 32 consecutive rays and runs them to completion.
 template <bool ANY, bool WW>
-__global__ void __launch_bounds__(128) k_traverse(DtSceneDev S, DtRayQueue q, DtShadowQueue sq, const int* n_ptr, int n_fixed, int* fetch_counter, float4* accum) {
+__global__ void __launch_bounds__(128, DT_TRAV_MINBLOCKS) k_traverse(DtSceneDev S, DtRayQueue q, DtShadowQueue sq, const int* n_ptr, int n_fixed, int* fetch_counter, float4* accum) {
     const int n = n_ptr ? *n_ptr : n_fixed;
     const int lane = threadIdx.x & 31;
     for (;;) {
@@ -149,8 +152,9 @@ __global__ void __launch_bounds__(128) k_traverse(DtSceneDev S, DtRayQueue q, Dt
             const float4 o = ANY ? sq.o_time[i] : q.o_time[i];
             const float4 d = ANY ? sq.d_tmax[i] : q.d_tmax[i];
             DtTrav T;
+            uint2 stack[DT_STACK_SIZE];
             dt_trav_init<ANY>(T, S, V(o.x, o.y, o.z), V(d.x, d.y, d.z), o.w, ANY ? d.w : CUDART_INF_F);
-            while (!dt_trav_step<ANY, WW>(T, S)) {}
+            while (!dt_trav_step<ANY, WW>(T, stack, S)) {}
             if (ANY) dt_store_shadow(sq, i, T.best, accum); else dt_store_closest(q, i, T.best);
         }
     }
@@ -159,15 +163,29 @@ __global__ void __launch_bounds__(128) k_traverse(DtSceneDev S, DtRayQueue q, Dt
 // Dynamic variant: every lane is a resumable traversal state machine; when fewer than `refill_threshold`
 // lanes of the warp still hold a ray, the idle lanes fetch new rays with ONE warp-aggregated atomic
 // (Aila-Laine style persistent threads).  Keeps SIMT lanes busy on incoherent secondary / shadow rays.
+#ifdef DT_TIMELINE
+// debug build only: per-warp (kind|n, t_start, t_drained, t_exit) records in nanoseconds of %globaltimer
+#define DT_TL_MAX (1 << 20)
+__device__ unsigned long long g_dt_tl[DT_TL_MAX * 4];
+__device__ unsigned int g_dt_tl_count;
+__device__ unsigned int g_dt_steps_hist[2][64];      // [ANY][min(63, steps / 8)] per-ray state-machine steps
+__device__ __forceinline__ unsigned long long dt_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#endif
+
 template <bool ANY, bool WW>
-__global__ void __launch_bounds__(128) k_traverse_dyn(DtSceneDev S, DtRayQueue q, DtShadowQueue sq, const int* n_ptr, int n_fixed, int* fetch_counter,
+__global__ void __launch_bounds__(128, DT_TRAV_MINBLOCKS) k_traverse_dyn(DtSceneDev S, DtRayQueue q, DtShadowQueue sq, const int* n_ptr, int n_fixed, int* fetch_counter,
                                                       float4* accum, int refill_threshold) {
     const int n = n_ptr ? *n_ptr : n_fixed;
     const int lane = threadIdx.x & 31;
     const unsigned FULL = 0xFFFFFFFFu;
+    const unsigned lanes_lt = (1u << lane) - 1u;
     DtTrav T;
+    uint2 stack[DT_STACK_SIZE];
     int ray = -1;
     bool drained = false;
+#ifdef DT_TIMELINE
+    const unsigned long long tl_t0 = dt_now(); unsigned long long tl_td = 0; int tl_steps = 0;
+#endif
     for (;;) {
         if (!drained) {
             const unsigned idle = __ballot_sync(FULL, ray < 0);
@@ -177,7 +195,7 @@ __global__ void __launch_bounds__(128) k_traverse_dyn(DtSceneDev S, DtRayQueue q
                 if (lane == leader) base = atomicAdd(fetch_counter, __popc(idle));
                 base = __shfl_sync(FULL, base, leader);
                 if (ray < 0) {
-                    const int i = base + __popc(idle & ((1u << lane) - 1u));
+                    const int i = base + __popc(idle & lanes_lt);
                     if (i < n && (ANY || !q.pixel || q.pixel[i] != DT_DEAD_PIXEL)) {
                         const float4 o = ANY ? sq.o_time[i] : q.o_time[i];
                         const float4 d = ANY ? sq.d_tmax[i] : q.d_tmax[i];
@@ -185,14 +203,25 @@ __global__ void __launch_bounds__(128) k_traverse_dyn(DtSceneDev S, DtRayQueue q
                         ray = i;
                     }
                 }
-                if (base + __popc(idle) >= n) drained = true;
+                if (base + __popc(idle) >= n) {
+                    drained = true;
+#ifdef DT_TIMELINE
+                    tl_td = dt_now();
+#endif
+                }
             }
         }
         unsigned act = __ballot_sync(FULL, ray >= 0);
         if (act == 0u) { if (drained) break; else continue; }
         for (;;) {
             if (ray >= 0) {
-                if (dt_trav_step<ANY, WW>(T, S)) {
+#ifdef DT_TIMELINE
+                tl_steps++;
+#endif
+                if (dt_trav_step<ANY, WW>(T, stack, S)) {
+#ifdef DT_TIMELINE
+                    atomicAdd(&g_dt_steps_hist[ANY ? 1 : 0][min(63, tl_steps / 8)], 1u); tl_steps = 0;
+#endif
                     if (ANY) dt_store_shadow(sq, ray, T.best, accum); else dt_store_closest(q, ray, T.best);
                     ray = -1;
                 }
@@ -202,6 +231,12 @@ __global__ void __launch_bounds__(128) k_traverse_dyn(DtSceneDev S, DtRayQueue q
             if (!drained && __popc(act) < refill_threshold) break;
         }
     }
+#ifdef DT_TIMELINE
+    if (lane == 0) {
+        const unsigned int k = atomicAdd(&g_dt_tl_count, 1u);
+        if (k < DT_TL_MAX) { g_dt_tl[k * 4] = ((unsigned long long)(ANY ? 1 : 0) << 32) | (unsigned int)n; g_dt_tl[k * 4 + 1] = tl_t0; g_dt_tl[k * 4 + 2] = tl_td; g_dt_tl[k * 4 + 3] = dt_now(); }
+    }
+#endif
 }
 
 // occlusion query with an explicit result array (dt_trace_occluded)

@@ -29,17 +29,35 @@ __device__ __forceinline__ float det3(v3 a, v3 b, v3 c) {
     return __fadd_rn(__fadd_rn(first, second), third);
 }
 
+__device__ __forceinline__ float dt_rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
 // Mesh::IntersectFace hit test (mesh.cpp:203-236).  e1 = v0-v1, e2 = v0-v2 are stored precomputed (they are
-// the same single float subtractions the reference performs per test).
-__device__ __forceinline__ bool tri_test_exact(v3 o, v3 d, v3 v0, v3 e1, v3 e2, float& t, float& beta, float& gamma) {
-    float detA = det3(e1, e2, d);
+// the same single float subtractions the reference performs per test).  `t_reject_above`: callers pass the
+// distance beyond which a hit can no longer matter (best.t).
+//
+// Every accept decision is made on the reference's exact values (IEEE divisions, same association).  The early
+// REJECTS use one approximate reciprocal (relative error < 2^-20): a quotient whose approximation is negative
+// by more than a denormal is negative exactly; a barycentric sum or distance that exceeds its bound by a 1e-5
+// relative margin exceeds it exactly.  Rejected candidates therefore never pay for the three IEEE divisions.
+__device__ __forceinline__ bool tri_test_exact(v3 o, v3 d, v3 v0, v3 e1, v3 e2, float t_reject_above, float& t, float& beta, float& gamma) {
+    const float detA = det3(e1, e2, d);
     if (detA == 0) return false;
-    v3 s = vsub(v0, o);
-    beta = __fdiv_rn(det3(s, e2, d), detA);
+    const float inv = dt_rcp_approx(detA);
+    const v3 s = vsub(v0, o);
+    const float detB = det3(s, e2, d);
+    const float b_apx = __fmul_rn(detB, inv);
+    if (b_apx < -1e-30f || b_apx > 1.00001f) return false;
+    const float detG = det3(e1, s, d);
+    const float g_apx = __fmul_rn(detG, inv);
+    if (g_apx < -1e-30f || __fadd_rn(b_apx, g_apx) > 1.00001f) return false;
+    const float detT = det3(e1, e2, s);
+    const float t_apx = __fmul_rn(detT, inv);
+    if (t_apx < -1e-30f || t_apx > __fmul_rn(t_reject_above, 1.00001f)) return false;
+    beta = __fdiv_rn(detB, detA);
     if (beta < 0) return false;
-    gamma = __fdiv_rn(det3(e1, s, d), detA);
+    gamma = __fdiv_rn(detG, detA);
     if (gamma < 0 || __fadd_rn(gamma, beta) > 1) return false;
-    t = __fdiv_rn(det3(e1, e2, s), detA);
+    t = __fdiv_rn(detT, detA);
     return true;      // caller applies: t > 0 && t < minT
 }
 
@@ -89,18 +107,46 @@ __device__ __forceinline__ float dt_byte_f(uint32_t w, int j) {
 
 #define DT_SLACK_HI 1.0000019f     // 1 + 2^-19: conservative inflation of the slab interval against FMA/rcp rounding
 #define DT_SLACK_LO 0.9999981f
+#define DT_SLACK_BOTH 1.0000039f   // HI / LO folded onto the far side (tn >= 0, so tn*LO <= tf*HI <=> tn <= tf*HI/LO)
+
+#ifndef DT_NODE_V1
+// byte j of w placed in mantissa bits 8..15 of 1.0f: 0x3F80qq00 = 1 + q * 2^-15, ONE PRMT and no int->float conversion.
+// The plane distance q*a + b is then evaluated as m*A + B with A = 2^15 * a (exponent bump, exact) and B = b - A
+// (one rounding of magnitude <= 2^-24 * 2^15 |a| = 2^-9 quantisation steps, absorbed by the 1/128-step margin the
+// flattener adds when it rounds child boxes outward).
+// `one` is 0x3F800000 read from the scene constants (DtSceneDev::one_bits) so that neither nvcc nor ptxas can fold it:
+// PRMT takes a single immediate, and with a literal the compilers spend it on the constant and re-materialise the
+// selector in a register before every one of the 48 PRMTs of a node test.
+template <int J>
+__device__ __forceinline__ float dt_byte_m(uint32_t w, uint32_t one) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(one), "n"(0x7604 | (J << 4)));
+    return __uint_as_float(r);
+}
+#endif
 
 // Test the 8 quantised child boxes of a node; returns the hit mask (top 8 bits: internal children in
 // traversal-priority order, low 24 bits: primitives of hit leaf children).
 __device__ __forceinline__ uint32_t dt_node_hits(const uint4 n0, const uint4 n1, const uint4 n2, const uint4 n3, const uint4 n4,
-                                                 const DtRayPrep& r, float tmax) {
+                                                 const DtRayPrep& r, float tmax, const uint32_t one) {
     const uint32_t e_imask = n0.w;
+#ifdef DT_NODE_V1
     const float ax = __fmul_rn(__uint_as_float((e_imask & 0xFFu) << 23), r.idx);
     const float ay = __fmul_rn(__uint_as_float(((e_imask >> 8) & 0xFFu) << 23), r.idy);
     const float az = __fmul_rn(__uint_as_float(((e_imask >> 16) & 0xFFu) << 23), r.idz);
     const float bx = __fmul_rn(__fsub_rn(__uint_as_float(n0.x), r.o.x), r.idx);
     const float by = __fmul_rn(__fsub_rn(__uint_as_float(n0.y), r.o.y), r.idy);
     const float bz = __fmul_rn(__fsub_rn(__uint_as_float(n0.z), r.o.z), r.idz);
+#define DT_QF(w, j) dt_byte_f(w, j)
+#else
+    const float ax = __fmul_rn(__uint_as_float(((e_imask & 0xFFu) + 15u) << 23), r.idx);
+    const float ay = __fmul_rn(__uint_as_float((((e_imask >> 8) & 0xFFu) + 15u) << 23), r.idy);
+    const float az = __fmul_rn(__uint_as_float((((e_imask >> 16) & 0xFFu) + 15u) << 23), r.idz);
+    const float bx = __fmaf_rn(__fsub_rn(__uint_as_float(n0.x), r.o.x), r.idx, -ax);
+    const float by = __fmaf_rn(__fsub_rn(__uint_as_float(n0.y), r.o.y), r.idy, -ay);
+    const float bz = __fmaf_rn(__fsub_rn(__uint_as_float(n0.z), r.o.z), r.idz, -az);
+#define DT_QF(w, j) dt_byte_m<j>(w, one)
+#endif
     uint32_t hitmask = 0;
 #pragma unroll
     for (int half = 0; half < 2; half++) {
@@ -114,21 +160,43 @@ __device__ __forceinline__ uint32_t dt_node_hits(const uint4 n0, const uint4 n1,
         const uint32_t nx = r.idx < 0.f ? qhix : qlox, fx = r.idx < 0.f ? qlox : qhix;
         const uint32_t ny = r.idy < 0.f ? qhiy : qloy, fy = r.idy < 0.f ? qloy : qhiy;
         const uint32_t nz = r.idz < 0.f ? qhiz : qloz, fz = r.idz < 0.f ? qloz : qhiz;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const float tnx = __fmaf_rn(dt_byte_f(nx, j), ax, bx);
-            const float tny = __fmaf_rn(dt_byte_f(ny, j), ay, by);
-            const float tnz = __fmaf_rn(dt_byte_f(nz, j), az, bz);
-            const float tfx = __fmaf_rn(dt_byte_f(fx, j), ax, bx);
-            const float tfy = __fmaf_rn(dt_byte_f(fy, j), ay, by);
-            const float tfz = __fmaf_rn(dt_byte_f(fz, j), az, bz);
-            // fminf/fmaxf drop NaNs (0*inf on axis-parallel rays): a NaN constraint is ignored = conservative
-            const float tn = __fmul_rn(fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f)), DT_SLACK_LO);
-            const float tf = __fmul_rn(fminf(fminf(tfx, tfy), fminf(tfz, tmax)), DT_SLACK_HI);
-            if (tn <= tf) hitmask |= dt_byte(child_bits4, j) << dt_byte(bit_index4, j);
-        }
+#ifdef DT_NODE_V1
+#define DT_CHILD(j) { \
+            const float tnx = __fmaf_rn(DT_QF(nx, j), ax, bx), tny = __fmaf_rn(DT_QF(ny, j), ay, by), tnz = __fmaf_rn(DT_QF(nz, j), az, bz); \
+            const float tfx = __fmaf_rn(DT_QF(fx, j), ax, bx), tfy = __fmaf_rn(DT_QF(fy, j), ay, by), tfz = __fmaf_rn(DT_QF(fz, j), az, bz); \
+            const float tn = __fmul_rn(fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f)), DT_SLACK_LO); \
+            const float tf = __fmul_rn(fminf(fminf(tfx, tfy), fminf(tfz, tmax)), DT_SLACK_HI); \
+            if (tn <= tf) hitmask |= dt_byte(child_bits4, j) << dt_byte(bit_index4, j); }
+#else
+        // fminf/fmaxf drop NaNs (0*inf on axis-parallel rays): a NaN constraint is ignored = conservative
+#define DT_CHILD(j) { \
+            const float tnx = __fmaf_rn(DT_QF(nx, j), ax, bx), tny = __fmaf_rn(DT_QF(ny, j), ay, by), tnz = __fmaf_rn(DT_QF(nz, j), az, bz); \
+            const float tfx = __fmaf_rn(DT_QF(fx, j), ax, bx), tfy = __fmaf_rn(DT_QF(fy, j), ay, by), tfz = __fmaf_rn(DT_QF(fz, j), az, bz); \
+            const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f)); \
+            const float tf = __fmul_rn(fminf(fminf(tfx, tfy), fminf(tfz, tmax)), DT_SLACK_BOTH); \
+            if (tn <= tf) hitmask |= dt_byte(child_bits4, j) << dt_byte(bit_index4, j); }
+#endif
+        DT_CHILD(0) DT_CHILD(1) DT_CHILD(2) DT_CHILD(3)
+#undef DT_CHILD
     }
+#undef DT_QF
     return hitmask;
+}
+
+// Certificate for the accept-time leaf-box confirmation: true only when BoundingBox::doesIntersectWith (shape.hpp:78-100)
+// is CERTAIN to pass.  The slab distances are formed with the ray's reciprocal direction (<= 1.5 ulp from the reference's
+// IEEE quotients); the three conditions tmax > 0, tmax >= tmin, tmin < minT must hold with a 2^-19 relative margin.  Rays
+// with a clamped reciprocal (|d| < 1e-30 on some axis), flat boxes and grazing hits fail the certificate and take the
+// exact path (box_intersect_exact), so the decision is always the reference's.
+__device__ __forceinline__ bool dt_leaf_box_certain(const float4 mn, const float4 mx, const DtRayPrep& r, float minT) {
+    if (fabsf(r.idx) >= 1e30f || fabsf(r.idy) >= 1e30f || fabsf(r.idz) >= 1e30f) return false;
+    const float x1 = __fmul_rn(__fsub_rn(mn.x, r.o.x), r.idx), x2 = __fmul_rn(__fsub_rn(mx.x, r.o.x), r.idx);
+    const float y1 = __fmul_rn(__fsub_rn(mn.y, r.o.y), r.idy), y2 = __fmul_rn(__fsub_rn(mx.y, r.o.y), r.idy);
+    const float z1 = __fmul_rn(__fsub_rn(mn.z, r.o.z), r.idz), z2 = __fmul_rn(__fsub_rn(mx.z, r.o.z), r.idz);
+    const float tmin = fmaxf(fmaxf(fminf(x1, x2), fminf(y1, y2)), fminf(z1, z2));
+    const float tmax = fminf(fminf(fmaxf(x1, x2), fmaxf(y1, y2)), fmaxf(z1, z2));
+    const float m = __fmul_rn(fmaxf(fabsf(tmin), fabsf(tmax)), 1.9073486e-6f);
+    return tmax > 1e-30f && tmax > m && __fsub_rn(tmax, tmin) > __fadd_rn(m, m) && __fadd_rn(tmin, m) < minT;
 }
 
 // (t, shape, face) lexicographic "strictly better" — the reference's scan order with strict `<`.
@@ -159,8 +227,9 @@ struct DtTrav {
     const uint4* nodes;
     int sp, blas_sp, cur_shape;
     bool in_blas;
-    uint2 stack[DT_STACK_SIZE];
 };
+// The traversal stack is a SEPARATE local array (uint2 stack[DT_STACK_SIZE] in the kernel): with the dynamically indexed
+// array inside DtTrav the whole struct lives in local memory; on its own, the scalar state above stays in registers.
 
 template <bool ANY>
 __device__ __forceinline__ void dt_trav_init(DtTrav& T, const DtSceneDev& S, v3 wo, v3 wd, float mb_time, float tmax_in) {
@@ -172,24 +241,26 @@ __device__ __forceinline__ void dt_trav_init(DtTrav& T, const DtSceneDev& S, v3 
     DT_STAT(6);
     T.in_blas = false; T.blas_sp = 0; T.cur_shape = -1; T.sp = 0;
     T.nodes = S.tlas_nodes;
-    T.ng = make_uint2(0u, 0x80000000u);         // root as the single "child" of a virtual group
+    // root as the single "child" of a virtual group; a scene of a few shapes skips the TLAS node test and starts with the
+    // shape list (a primitive group), which is what the reference's linear scan does (raytracer.cpp:625-643)
+    T.ng = S.tlas_direct > 0 ? make_uint2(0u, (1u << S.tlas_direct) - 1u) : make_uint2(0u, 0x80000000u);
     T.tg = make_uint2(0u, 0u);
 }
 
 // Visit the nearest pending child node of the current group: load 80 B, test 8 boxes, refill ng / tg.
-__device__ __forceinline__ void dt_trav_node(DtTrav& T) {
+__device__ __forceinline__ void dt_trav_node(DtTrav& T, uint2* __restrict__ stack, const uint32_t one) {
     DT_STAT(0);
     const uint32_t hits = T.ng.y;
     const uint32_t imask = T.ng.y & 0xFFu;
     const int child_bit = 31 - __clz(hits);
     T.ng.y &= ~(1u << child_bit);
-    if (T.ng.y > 0x00FFFFFFu) { if (T.sp < DT_STACK_SIZE) T.stack[T.sp++] = T.ng; }
+    if (T.ng.y > 0x00FFFFFFu) { if (T.sp < DT_STACK_SIZE) stack[T.sp++] = T.ng; }
     const uint32_t slot = (uint32_t)(child_bit - 24) ^ (T.r.oct_inv4 & 0xFFu);
     const uint32_t rel = __popc(imask & ~(0xFFFFFFFFu << slot));
     const uint32_t ni = T.ng.x + rel;
     const uint4* np = T.nodes + (size_t)ni * 5;
     const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
-    const uint32_t hm = dt_node_hits(n0, n1, n2, n3, n4, T.r, T.best.t);
+    const uint32_t hm = dt_node_hits(n0, n1, n2, n3, n4, T.r, T.best.t, one);
     T.ng.x = n1.x;
     // a group without node hits must read as empty (a remnant imask would look like a primitive group)
     T.ng.y = (hm & 0xFF000000u) ? ((hm & 0xFF000000u) | (n0.w >> 24)) : 0u;
@@ -213,7 +284,7 @@ __device__ __forceinline__ void dt_to_local(const DtShapeDev* sh, v3 wo, v3 wd, 
 
 // One primitive of the current primitive group.  Returns true when an ANY query is decided (occluded).
 template <bool ANY>
-__device__ __forceinline__ bool dt_trav_prim(DtTrav& T, const DtSceneDev& S, bool& entered_blas) {
+__device__ __forceinline__ bool dt_trav_prim(DtTrav& T, uint2* __restrict__ stack, const DtSceneDev& S, bool& entered_blas) {
     DtHit& best = T.best;
     const int bit = __ffs(T.tg.y) - 1;
     T.tg.y &= ~(1u << bit);
@@ -223,21 +294,25 @@ __device__ __forceinline__ bool dt_trav_prim(DtTrav& T, const DtSceneDev& S, boo
         const float4* tp = S.tris + (size_t)prim * 3;
         const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
         float t, beta, gamma;
-        if (tri_test_exact(T.r.o, T.r.d, V(a.x, a.y, a.z), V(a.w, b.x, b.y), V(b.z, b.w, c.x), t, beta, gamma)) {
+        if (tri_test_exact(T.r.o, T.r.d, V(a.x, a.y, a.z), V(a.w, b.x, b.y), V(b.z, b.w, c.x), best.t, t, beta, gamma)) {
             const int face = __float_as_int(c.y);
             const bool cand = ANY ? (t > 0.0f && t < best.t) : (t > 0.0f && dt_better(t, T.cur_shape, face, best));
             if (cand) {
                 // The reference only reaches this face if the float slab test of its BVH2 leaf passes (bvh.cpp:7-10);
                 // every ancestor box contains the leaf box and the float slab interval is monotone in the box, so the
-                // leaf test implies the ancestors'.  Rare path: runs only for would-be winners.
+                // leaf test implies the ancestors'.  Runs only for would-be winners.
                 DT_STAT(4);
                 const float4 lb0 = __ldg(S.leaf_boxes + (size_t)prim * 2), lb1 = __ldg(S.leaf_boxes + (size_t)prim * 2 + 1);
-                const float lmn[3] = {lb0.x, lb0.y, lb0.z}, lmx[3] = {lb1.x, lb1.y, lb1.z};
                 // minT the reference would hold when it reaches this face: it scans in (shape, face) order, so a
                 // candidate that precedes the current best was tested BEFORE that best existed.
                 const bool after_best = best.shape >= 0 && (T.cur_shape > best.shape || (T.cur_shape == best.shape && face > best.face));
                 const float ref_min_t = ANY ? T.any_min_t : (after_best ? best.t : CUDART_INF_F);
-                if (box_intersect_exact(lmn, lmx, T.r.o, T.r.d, ref_min_t)) {
+                bool ok = dt_leaf_box_certain(lb0, lb1, T.r, ref_min_t);
+                if (!ok) {
+                    const float lmn[3] = {lb0.x, lb0.y, lb0.z}, lmx[3] = {lb1.x, lb1.y, lb1.z};
+                    ok = box_intersect_exact(lmn, lmx, T.r.o, T.r.d, ref_min_t);
+                }
+                if (ok) {
                     best.t = t; best.beta = beta; best.gamma = gamma; best.shape = T.cur_shape; best.face = face;
                     if (ANY) return true;
                 }
@@ -276,8 +351,8 @@ __device__ __forceinline__ bool dt_trav_prim(DtTrav& T, const DtSceneDev& S, boo
     const DtMeshDev* m = S.meshes + sh->mesh;
     // mesh.cpp:172 (Mesh::bbox) and the root node of BVH::IntersectBVH (same box) in local space
     if (!box_intersect_exact(m->bbox_min, m->bbox_max, lo, ld, shape_min_t)) return false;
-    if (T.ng.y > 0x00FFFFFFu) { if (T.sp < DT_STACK_SIZE) T.stack[T.sp++] = T.ng; }
-    if (T.tg.y != 0u) { if (T.sp < DT_STACK_SIZE) T.stack[T.sp++] = T.tg; }
+    if (T.ng.y > 0x00FFFFFFu) { if (T.sp < DT_STACK_SIZE) stack[T.sp++] = T.ng; }
+    if (T.tg.y != 0u) { if (T.sp < DT_STACK_SIZE) stack[T.sp++] = T.tg; }
     DT_STAT(3);
     T.blas_sp = T.sp;
     T.in_blas = true;
@@ -294,18 +369,18 @@ __device__ __forceinline__ bool dt_trav_prim(DtTrav& T, const DtSceneDev& S, boo
 // WW = true: descend nodes until some primitive group is pending, then drain it ("while-while").
 // Returns true when the ray is finished (ANY: best.shape >= 0 <=> occluded).
 template <bool ANY, bool WW>
-__device__ __forceinline__ bool dt_trav_step(DtTrav& T, const DtSceneDev& S) {
+__device__ __forceinline__ bool dt_trav_step(DtTrav& T, uint2* __restrict__ stack, const DtSceneDev& S) {
     DT_STAT(5);
     if (WW) {
-        while (T.ng.y > 0x00FFFFFFu && T.tg.y == 0u) dt_trav_node(T);
+        while (T.ng.y > 0x00FFFFFFu && T.tg.y == 0u) dt_trav_node(T, stack, S.one_bits);
         if (T.tg.y == 0u && T.ng.y != 0u && T.ng.y <= 0x00FFFFFFu) { T.tg = T.ng; T.ng = make_uint2(0u, 0u); }
     } else {
-        if (T.ng.y > 0x00FFFFFFu) dt_trav_node(T);
+        if (T.ng.y > 0x00FFFFFFu) dt_trav_node(T, stack, S.one_bits);
         else { T.tg = T.ng; T.ng = make_uint2(0u, 0u); }
     }
     while (T.tg.y != 0u) {
         bool entered = false;
-        if (dt_trav_prim<ANY>(T, S, entered)) return true;
+        if (dt_trav_prim<ANY>(T, stack, S, entered)) return true;
         if (entered) break;
     }
     if (T.ng.y <= 0x00FFFFFFu && T.tg.y == 0u) {
@@ -315,7 +390,7 @@ __device__ __forceinline__ bool dt_trav_step(DtTrav& T, const DtSceneDev& S) {
             T.nodes = S.tlas_nodes;
         }
         if (T.sp == 0) { if (ANY) T.best.shape = -1; return true; }
-        T.ng = T.stack[--T.sp];
+        T.ng = stack[--T.sp];
     }
     return false;
 }
@@ -325,7 +400,8 @@ __device__ __forceinline__ bool dt_trav_step(DtTrav& T, const DtSceneDev& S) {
 template <bool ANY>
 __device__ __forceinline__ void dt_trace(const DtSceneDev& S, v3 wo, v3 wd, float mb_time, float tmax_in, DtHit& best) {
     DtTrav T;
+    uint2 stack[DT_STACK_SIZE];
     dt_trav_init<ANY>(T, S, wo, wd, mb_time, tmax_in);
-    while (!dt_trav_step<ANY, true>(T, S)) {}
+    while (!dt_trav_step<ANY, true>(T, stack, S)) {}
     best = T.best;
 }
