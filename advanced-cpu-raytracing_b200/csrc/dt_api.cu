@@ -68,6 +68,8 @@ struct DtPipe {
     cudaStream_t A = nullptr, B = nullptr;
     cudaEvent_t ev_shade[2] = {nullptr, nullptr}, ev_shadow[2] = {nullptr, nullptr}, ev_done = nullptr;
     int* counters = nullptr;      // this pipe's block of dt_scene::counters
+    int* sort_perm = nullptr;     // material-sorted order of the current wave (sort stage)
+    int* sort_hist = nullptr;     // DT_SORT_BINS bin counts / cursors
     DtPipe() { memset(q, 0, sizeof q); memset(sq, 0, sizeof sq); }
     void free_queues() { for (void* p : allocs) cudaFree(p); allocs.clear(); capacity = shadow_capacity = 0; }
 };
@@ -99,9 +101,10 @@ struct dt_scene {
     float4* accum = nullptr; size_t accum_pix = 0;
     float* hdr = nullptr; uint8_t* ldr = nullptr; size_t out_pix = 0;
     double* tm_logsum = nullptr; unsigned int* tm_hist = nullptr; unsigned long long* tm_rank = nullptr; uint32_t* tm_prefix = nullptr;
-    Timer t_total, t_gen, t_closest, t_shadow, t_shade, t_resolve, t_tm;
+    Timer t_total, t_gen, t_closest, t_shadow, t_shade, t_sort, t_resolve, t_tm;
     int grid_trav[4][2] = {};
     int trav_mode = 2, refill_threshold = 16;
+    int sort_mode = 1;            // sort-by-material stage: 0 off, 1 auto (scenes with >= 3 materials), 2 always (DT_SORT)
 
     void free_queues() { for (DtPipe& p : pipes) p.free_queues(); }
 };
@@ -143,7 +146,7 @@ int ensure_queues(dt_scene* s, DtPipe& pp, int capacity, int shadow_capacity, bo
         if ((rc = qalloc(pp, &q.weight_n, capacity))) return rc;
         if ((rc = qalloc(pp, &q.thr_beer, capacity))) return rc;
         if ((rc = qalloc(pp, &q.misc, capacity))) return rc;
-        q.sort_key = nullptr;
+        if ((rc = qalloc(pp, &q.sort_key, capacity))) return rc;
         pp.miss[k] = nullptr;
         if (s->has_env) { if ((rc = qalloc(pp, &pp.miss[k], capacity))) return rc; }
     }
@@ -155,6 +158,8 @@ int ensure_queues(dt_scene* s, DtPipe& pp, int capacity, int shadow_capacity, bo
         sq.defer = nullptr;
         if (need_defer && k == 0) { if ((rc = qalloc(pp, &sq.defer, shadow_capacity))) return rc; }
     }
+    if ((rc = qalloc(pp, &pp.sort_perm, capacity))) return rc;
+    if ((rc = qalloc(pp, &pp.sort_hist, DT_SORT_BINS))) return rc;
     pp.capacity = capacity; pp.shadow_capacity = shadow_capacity; pp.has_miss = s->has_env; pp.has_defer = need_defer;
     return DT_OK;
 }
@@ -230,6 +235,16 @@ int tonemap_device(dt_scene* s, const float* hdr, int W, int H, float key, float
 
 struct RenderOut { float* hdr_dev; };
 
+// Sort stage (k_sort_*): fills pp.sort_perm with the material-sorted order of wave queue `q`; returns launches.
+int launch_sort(dt_scene* s, DtPipe& pp, const DtRayQueue& q, const int* n_ptr, int n_fixed, cudaStream_t st) {
+    cudaMemsetAsync(pp.sort_hist, 0, DT_SORT_BINS * sizeof(int), st);
+    const int grid = s->num_sms * 4;
+    k_sort_hist<<<grid, 256, 0, st>>>(s->dev, q, n_ptr, n_fixed, pp.sort_hist);
+    k_sort_scan<<<1, DT_SORT_BINS, 0, st>>>(pp.sort_hist);
+    k_sort_scatter<<<grid, 256, 0, st>>>(q, n_ptr, n_fixed, pp.sort_hist, pp.sort_perm);
+    return 3;
+}
+
 // valid primary rays of this rank: every in-image pixel of the owned tiles
 long long count_valid_pixels(const dt_render_params& P, int W, int H) {
     const int tiles_x = (W + 7) / 8, tiles_y = (H + 3) / 4;
@@ -273,6 +288,7 @@ int render_core(dt_scene* s, const dt_camera_desc* cam, const dt_render_params* 
     wave_max = (wave_max + 31) & ~31;
     const int fan = s->fanout_hint + (pt ? 1 : 0);
     const int shadows_per_hit = std::max(1, s->lights_shadowed);
+    const bool do_sort = !primary_only && !(P.flags & DT_FLAG_NO_SORT) && (s->sort_mode == 2 || (s->sort_mode == 1 && s->dev.n_materials >= 3));
     uint32_t retries = 0;
 
     cudaStream_t st = s->stream;
@@ -287,13 +303,13 @@ retry:
     // waves are enqueued back to back (wave sizes live in device memory), shadow(k) runs on a second stream while
     // closest(k+1) / shade(k+1) proceed, and the frame is dealt to several such pipelines.  One host sync per frame.
     const bool bounded = !(pt && dc.russian_roulette) && s->dev.max_recursion_depth <= 16;
-    if (!primary_only && !defer_mode && bounded && total <= (long long)wave_max && !s->sync_waves) {
+    if (!primary_only && !defer_mode && bounded && total <= (long long)wave_max && !s->sync_waves && !(P.flags & DT_FLAG_SERIAL_WAVES)) {
         const int n_waves = s->dev.max_recursion_depth + 1;
         int NP = s->n_pipes_env > 0 ? s->n_pipes_env : (int)1;
         NP = (int)std::min<long long>(std::min(NP, DT_MAX_PIPES), std::max<long long>(1, my_tiles));
         size_t ev_i = 0;
         auto ev = [&]() -> cudaEvent_t { if (ev_i >= s->ev_pool.size()) { cudaEvent_t e; cudaEventCreate(&e); s->ev_pool.push_back(e); } return s->ev_pool[ev_i++]; };
-        std::vector<cudaEvent_t> tg, tc, th, ts;      // (start, stop) pairs per stage
+        std::vector<cudaEvent_t> tg, tc, th, ts, tsort;      // (start, stop) pairs per stage
         auto timed = [&](std::vector<cudaEvent_t>& v, cudaStream_t q, auto&& launch) {
             cudaEvent_t a = ev(), b = ev(); cudaEventRecord(a, q); launch(); cudaEventRecord(b, q); v.push_back(a); v.push_back(b);
         };
@@ -330,9 +346,10 @@ retry:
                 DtShadowQueue& sq = pp.sq[slot];
                 timed(tc, pp.A, [&] { launch_traverse<false>(s, pp.q[cur], sq, c + DT_CNT_CUR, 0, c + DT_CNT_FETCH_A, s->accum, pp.A); });
                 if (k >= 2) CK(cudaStreamWaitEvent(pp.A, pp.ev_shadow[slot], 0));       // shadow(k-2) must have drained this queue
+                if (do_sort) timed(tsort, pp.A, [&] { S.kernel_launches += launch_sort(s, pp, pp.q[cur], c + DT_CNT_CUR, 0, pp.A); });
                 timed(th, pp.A, [&] {
                     DtShadeCounters sc = {c + DT_CNT_NEXT, c + (slot ? DT_CNT_SHADOW2 : DT_CNT_SHADOW), c + DT_CNT_OVERFLOW};
-                    k_shade<<<s->grid_shade, 128, 0, pp.A>>>(s->dev, dc, pp.q[cur], pp.miss[cur], c + DT_CNT_CUR, 0, pp.q[1 - cur], pp.miss[1 - cur], pp.capacity,
+                    k_shade<<<s->grid_shade, 128, 0, pp.A>>>(s->dev, dc, pp.q[cur], pp.miss[cur], c + DT_CNT_CUR, 0, do_sort ? pp.sort_perm : nullptr, pp.q[1 - cur], pp.miss[1 - cur], pp.capacity,
                                                             sq, pp.shadow_capacity, sc, s->accum); });
                 CK(cudaEventRecord(pp.ev_shade[slot], pp.A));
                 CK(cudaStreamWaitEvent(pp.B, pp.ev_shade[slot], 0));
@@ -355,7 +372,7 @@ retry:
         CK(cudaStreamSynchronize(st));
         CK(cudaGetLastError());
         auto sum = [&](std::vector<cudaEvent_t>& v) { float t = 0.f; for (size_t i = 0; i + 1 < v.size(); i += 2) { float ms = 0.f; cudaEventElapsedTime(&ms, v[i], v[i + 1]); t += ms; } return t; };
-        S.ms_generate = sum(tg); S.ms_traverse_closest = sum(tc); S.ms_shade = sum(th); S.ms_traverse_shadow = sum(ts);
+        S.ms_generate = sum(tg); S.ms_traverse_closest = sum(tc); S.ms_shade = sum(th); S.ms_traverse_shadow = sum(ts); S.ms_sort = sum(tsort);
         S.waves = (uint32_t)n_waves;
         bool overflow = false;
         unsigned long long tot_c = 0, tot_s = 0;
@@ -421,10 +438,11 @@ retry:
                 S.kernel_launches += 2;
             }
             CK(cudaMemsetAsync(c + DT_CNT_SHADOW, 0, sizeof(int), st));
+            if (do_sort) { s->t_sort.start(st); S.kernel_launches += launch_sort(s, pp, pp.q[cur], nullptr, count, st); s->t_sort.stop(st); }
             s->t_shade.start(st);
             {
                 DtShadeCounters sc = {c + DT_CNT_NEXT, c + DT_CNT_SHADOW, c + DT_CNT_OVERFLOW};
-                k_shade<<<(count + 127) / 128, 128, 0, st>>>(s->dev, dc, pp.q[cur], pp.miss[cur], nullptr, count, pp.q[1 - cur], pp.miss[1 - cur], pp.capacity,
+                k_shade<<<(count + 127) / 128, 128, 0, st>>>(s->dev, dc, pp.q[cur], pp.miss[cur], nullptr, count, do_sort ? pp.sort_perm : nullptr, pp.q[1 - cur], pp.miss[1 - cur], pp.capacity,
                                                              sq, pp.shadow_capacity, sc, s->accum);
             }
             s->t_shade.stop(st);
@@ -442,6 +460,7 @@ retry:
             S.ms_generate += s->t_gen.take();
             S.ms_traverse_closest += s->t_closest.take();
             S.ms_shade += s->t_shade.take();
+            S.ms_sort += s->t_sort.take();
             if (shadow_timed) S.ms_traverse_shadow += s->t_shadow.take();
             S.waves++;
             if (s->h_counters[DT_CNT_OVERFLOW] != 0) { overflow = true; break; }
@@ -589,10 +608,11 @@ int dt_scene_create(const dt_scene_desc* desc, dt_scene** out) {
         g_err = "cudaMalloc of control buffers failed"; return fail(DT_ERR_CUDA);
     }
     for (int p = 0; p < DT_MAX_PIPES; p++) s->pipes[p].counters = s->counters + p * DT_CNT_COUNT;
-    for (Timer* t : {&s->t_total, &s->t_gen, &s->t_closest, &s->t_shadow, &s->t_shade, &s->t_resolve, &s->t_tm}) if (t->init()) return fail(DT_ERR_CUDA);
+    for (Timer* t : {&s->t_total, &s->t_gen, &s->t_closest, &s->t_shadow, &s->t_shade, &s->t_sort, &s->t_resolve, &s->t_tm}) if (t->init()) return fail(DT_ERR_CUDA);
     // traversal variant (A/B measurement): 0 static if-if, 1 static while-while, 2 dynamic if-if, 3 dynamic while-while
     if (const char* e = getenv("DT_TRAVERSE_MODE")) s->trav_mode = std::min(3, std::max(0, atoi(e)));
     if (const char* e = getenv("DT_SYNC_WAVES")) s->sync_waves = atoi(e);
+    if (const char* e = getenv("DT_SORT")) s->sort_mode = std::min(2, std::max(0, atoi(e)));
     if (const char* e = getenv("DT_DEBUG_TIMING")) s->debug_timing = atoi(e);
     if (const char* e = getenv("DT_PIPES")) s->n_pipes_env = std::min(DT_MAX_PIPES, std::max(0, atoi(e)));
     if (const char* e = getenv("DT_REFILL_THRESHOLD")) s->refill_threshold = std::min(32, std::max(1, atoi(e)));
@@ -628,7 +648,7 @@ void dt_scene_destroy(dt_scene* s) {
     if (s->tm_hist) cudaFree(s->tm_hist);
     if (s->tm_rank) cudaFree(s->tm_rank);
     if (s->tm_prefix) cudaFree(s->tm_prefix);
-    for (Timer* t : {&s->t_total, &s->t_gen, &s->t_closest, &s->t_shadow, &s->t_shade, &s->t_resolve, &s->t_tm}) t->destroy();
+    for (Timer* t : {&s->t_total, &s->t_gen, &s->t_closest, &s->t_shadow, &s->t_shade, &s->t_sort, &s->t_resolve, &s->t_tm}) t->destroy();
     for (cudaEvent_t e : s->ev_pool) cudaEventDestroy(e);
     for (int p = 0; p < DT_MAX_PIPES; p++) {
         DtPipe& pp = s->pipes[p];

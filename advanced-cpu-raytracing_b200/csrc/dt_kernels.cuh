@@ -566,12 +566,78 @@ __device__ __forceinline__ void dt_shade_ray(const int i, const DtSceneDev& S, c
 }
 
 // Grid-stride launch: the wave size lives in device memory (n_ptr) so consecutive waves need no host round trip.
-__global__ void __launch_bounds__(128) k_shade(DtSceneDev S, DtCamDev cam, DtRayQueue in, const float4* in_miss, const int* n_ptr, int n_fixed,
+// `perm` (optional) is the material-sorted order of the wave produced by the sort stage below.
+__global__ void __launch_bounds__(128) k_shade(DtSceneDev S, DtCamDev cam, DtRayQueue in, const float4* in_miss, const int* n_ptr, int n_fixed, const int* perm,
                                                DtRayQueue out, float4* out_miss, int out_capacity,
                                                DtShadowQueue sq, int shadow_capacity, DtShadeCounters counters, float4* accum) {
     const int n = n_ptr ? *n_ptr : n_fixed;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-        dt_shade_ray(i, S, cam, in, in_miss, out, out_miss, out_capacity, sq, shadow_capacity, counters, accum);
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x)
+        dt_shade_ray(perm ? perm[j] : j, S, cam, in, in_miss, out, out_miss, out_capacity, sq, shadow_capacity, counters, accum);
+}
+
+// ------------------------------------------------------------------ sort / compact by material
+// Between closest-hit and shade: a counting sort of the wave by shading key (0 = dead slot or miss, 1 + material id of
+// the hit shape otherwise), so that the lanes of a shading warp run the same material / BRDF / texture branches
+// (PerformShading's switch over Material::type and BRDF, raytracer.cpp:65-134).  Three small launches: histogram,
+// exclusive scan of the (<= 256) bins, stable-per-block scatter of ray indices into `perm`.
+#define DT_SORT_BINS 256
+__device__ __forceinline__ int dt_sort_key(const DtSceneDev& S, const DtRayQueue& q, int i) {
+    if (q.pixel[i] == DT_DEAD_PIXEL) return 0;
+    const int shape = __float_as_int(q.hit0[i].w);
+    if (shape < 0) return 0;
+    const int m = S.shapes[shape].material;
+    return 1 + (m < 0 ? 0 : m % (DT_SORT_BINS - 1));
+}
+__global__ void __launch_bounds__(256) k_sort_hist(DtSceneDev S, DtRayQueue q, const int* n_ptr, int n_fixed, int* hist) {
+    __shared__ int h[DT_SORT_BINS];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const int n = n_ptr ? *n_ptr : n_fixed;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int k = dt_sort_key(S, q, i);
+        q.sort_key[i] = (uint32_t)k;
+        atomicAdd(&h[k], 1);
+    }
+    __syncthreads();
+    if (h[threadIdx.x]) atomicAdd(&hist[threadIdx.x], h[threadIdx.x]);
+}
+// one block of DT_SORT_BINS threads: hist -> exclusive offsets (in place, used as running cursors by the scatter)
+__global__ void __launch_bounds__(DT_SORT_BINS) k_sort_scan(int* hist) {
+    __shared__ int sc[DT_SORT_BINS];
+    const int t = threadIdx.x;
+    const int v = hist[t];
+    sc[t] = v;
+    __syncthreads();
+    for (int d = 1; d < DT_SORT_BINS; d <<= 1) {
+        const int x = t >= d ? sc[t - d] : 0;
+        __syncthreads();
+        sc[t] += x;
+        __syncthreads();
+    }
+    hist[t] = sc[t] - v;
+}
+// each block takes a contiguous chunk of the wave, reserves one range per bin, and writes its rays in chunk order
+__global__ void __launch_bounds__(256) k_sort_scatter(DtRayQueue q, const int* n_ptr, int n_fixed, int* cursors, int* perm) {
+    __shared__ int cnt[DT_SORT_BINS], base[DT_SORT_BINS];
+    const int n = n_ptr ? *n_ptr : n_fixed;
+    const int chunk = 256 * 8;
+    for (int c0 = blockIdx.x * chunk; c0 < n; c0 += gridDim.x * chunk) {
+        cnt[threadIdx.x] = 0;
+        __syncthreads();
+        int key[8], rank[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int i = c0 + k * 256 + threadIdx.x;
+            key[k] = i < n ? (int)q.sort_key[i] : -1;
+            rank[k] = key[k] >= 0 ? atomicAdd(&cnt[key[k]], 1) : 0;
+        }
+        __syncthreads();
+        if (cnt[threadIdx.x]) base[threadIdx.x] = atomicAdd(&cursors[threadIdx.x], cnt[threadIdx.x]);
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 8; k++) if (key[k] >= 0) perm[base[key[k]] + rank[k]] = c0 + k * 256 + threadIdx.x;
+        __syncthreads();
+    }
 }
 
 // Device-side bookkeeping between two waves of the sync-free loop (one thread).

@@ -21,6 +21,7 @@ DT_SHAPE_MESH, DT_SHAPE_INSTANCE, DT_SHAPE_SPHERE = 0, 1, 2
 DT_MAT_MIRROR, DT_MAT_DIELECTRIC, DT_MAT_CONDUCTOR, DT_MAT_EMISSIVE, DT_MAT_DEFAULT = range(5)
 DT_FLAG_SKIP_TONEMAP = 1
 DT_FLAG_NO_SORT = 2
+DT_FLAG_SERIAL_WAVES = 4
 
 
 class dt_material(C.Structure):

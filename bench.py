@@ -14,7 +14,9 @@ A *step* is one frame of the workload through the hot path:
   e2e        the public C-ABI call dt_render() with a pinned HOST LDR buffer: D2H of the frame inside the
              timed region, wall clock between device synchronisations
   roofline   closest-hit traversal kernel: algorithmic bytes/ray (736 B for config 2) x rays
-             / its CUDA-event time, against the measured HBM peak (MEASURED_PEAKS.json)
+             / its CUDA-event time (measured live in a separate DT_FLAG_SERIAL_WAVES pass, each kernel alone on
+             the GPU), against the measured HBM peak (MEASURED_PEAKS.json); `traffic` and the issue-slot / SIMT
+             figures come from the committed ncu capture (profiles/ncu_traverse_summary.json)
   cpu_baseline  the compiled reference (oracle/_ref/raytracer) on this box's host cores, same frame
 
 `--impl reference` times the reference's own CPU renderer on the same workload (rank 0 only).
@@ -68,6 +70,10 @@ def best_threads(height, cores):
 
 
 class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU DURING the timed region (NVML, ~10 ms period; nvidia-smi
+    subprocess as a fallback)."""
+    HW_SLOWDOWN, SW_THERMAL, HW_THERMAL, SW_POWER = 0x8, 0x20, 0x40, 0x4
+
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index = index
@@ -75,29 +81,64 @@ class ClockSampler(threading.Thread):
         self.reasons = set()
         self.max_mhz = None
         self._halt = threading.Event()
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(index))
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
+
+    @staticmethod
+    def _physical_index(i):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[i])
+            except Exception:
+                return i
+        return i
+
+    def _sample_nvml(self):
+        n = self.nvml
+        self.samples.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+        r = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") \
+            else int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+        for name, bit in (("hw_slowdown", self.HW_SLOWDOWN), ("hw_thermal_slowdown", self.HW_THERMAL), ("sw_thermal_slowdown", self.SW_THERMAL), ("sw_power_cap", self.SW_POWER)):
+            if r & bit:
+                self.reasons.add(name)
+
+    def _sample_smi(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                             stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, timeout=5).stdout.decode().strip()
+        f = [x.strip() for x in out.split(",")]
+        if len(f) >= 6:
+            self.samples.append(float(f[0]))
+            self.max_mhz = float(f[1])
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
+                if v.lower().startswith("active"):
+                    self.reasons.add(name)
 
     def run(self):
-        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         while not self._halt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
-                                     stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, timeout=5).stdout.decode().strip()
-                f = [x.strip() for x in out.split(",")]
-                if len(f) >= 6:
-                    self.samples.append(float(f[0]))
-                    self.max_mhz = float(f[1])
-                    for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
-                        if v.lower().startswith("active"):
-                            self.reasons.add(name)
+                if self.nvml:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            self._halt.wait(0.2)
+            self._halt.wait(0.01 if self.nvml else 0.2)
 
     def stop(self):
         self._halt.set()
         self.join(timeout=3)
         s = sorted(self.samples)
-        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s),
+                "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
 def run_reference_frame(xml_path, threads, probe=False):
@@ -168,7 +209,7 @@ def reference_arm(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -263,15 +304,13 @@ def main():
     t_wall0 = time.perf_counter()
     ms_sum, launches = 0.0, 0
     rays_c = rays_s = 0
-    ms_closest = ms_shadow = ms_shade = ms_gen = 0.0
-    n_closest_launches = 0
+    ov_closest = ov_shadow = ov_shade = 0.0
     for _ in range(args.steps):
         ms, st = device_step(True)
         ms_sum += ms
         launches += int(st.kernel_launches)
         rays_c += int(st.rays_closest); rays_s += int(st.rays_shadow)
-        ms_closest += st.ms_traverse_closest; ms_shadow += st.ms_traverse_shadow; ms_shade += st.ms_shade; ms_gen += st.ms_generate
-        n_closest_launches += int(st.launches_traverse_closest)
+        ov_closest += st.ms_traverse_closest; ov_shadow += st.ms_traverse_shadow; ov_shade += st.ms_shade
     barrier()
     t_wall = time.perf_counter() - t_wall0
     clocks = sampler.stop()
@@ -285,6 +324,21 @@ def main():
         e2e_step()
     barrier()
     e2e_s = time.perf_counter() - t0
+
+    # roofline pass (untimed for `value`): the same frame with DT_FLAG_SERIAL_WAVES, so that the CUDA-event time of each
+    # traversal launch is that of the kernel running alone (in the default mode shadow(k) overlaps closest(k+1))
+    n_roof = max(3, min(10, args.steps))
+    ms_closest = ms_shadow = ms_shade = ms_gen = 0.0
+    rays_c_roof = rays_s_roof = 0
+    n_closest_launches = 0
+    for _ in range(n_roof):
+        flush_buf.fill_(rank + 1)
+        torch.cuda.synchronize()
+        _, st = gs.render_device(cam, tile_rank=rank, tile_world=world, flags=capi.DT_FLAG_SERIAL_WAVES)
+        ms_closest += st.ms_traverse_closest; ms_shadow += st.ms_traverse_shadow; ms_shade += st.ms_shade; ms_gen += st.ms_generate
+        rays_c_roof += int(st.rays_closest); rays_s_roof += int(st.rays_shadow)
+        n_closest_launches += int(st.launches_traverse_closest)
+    barrier()
 
     # max over ranks of the times, sum over ranks of the rays
     vals = torch.tensor([ms_sum, e2e_s, ms_closest, ms_shadow], dtype=torch.float64, device="cuda")
@@ -308,10 +362,15 @@ def main():
             except Exception:
                 pass
         # roofline of the dominant kernel (closest-hit traversal): rank-0-local figures
-        gb_closest = B_RAY_CLOSEST * rays_c / 1e9
+        gb_closest = B_RAY_CLOSEST * rays_c_roof / 1e9
         achieved = gb_closest / (ms_closest / 1e3) if ms_closest > 0 else 0.0
-        gb_shadow = B_RAY_SHADOW * rays_s / 1e9
+        gb_shadow = B_RAY_SHADOW * rays_s_roof / 1e9
         achieved_shadow = gb_shadow / (ms_shadow / 1e3) if ms_shadow > 0 else 0.0
+        ncu = {}
+        try:
+            ncu = json.load(open(os.path.join(REPO, "profiles", "ncu_traverse_summary.json")))
+        except Exception:
+            pass
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -321,13 +380,19 @@ def main():
                 "rays_per_step": rays_per_step, "closest_rays_per_step": rays_c_all / args.steps, "shadow_rays_per_step": rays_s_all / args.steps,
                 "l2": "flushed between timed iterations (256 MiB write)", "timing": "CUDA events on the library stream (+ reduce), max over ranks",
                 "scene_load_s": t_load, "scene_upload_s": t_upload,
-                "stage_ms_per_step_rank0": {"generate": ms_gen / args.steps, "traverse_closest": ms_closest / args.steps, "shade": ms_shade / args.steps, "traverse_shadow": ms_shadow / args.steps},
+                "stage_ms_per_step_rank0_kernels_alone": {"generate": ms_gen / n_roof, "traverse_closest": ms_closest / n_roof, "shade": ms_shade / n_roof, "traverse_shadow": ms_shadow / n_roof,
+                                                          "note": "DT_FLAG_SERIAL_WAVES pass of %d frames after the timed region" % n_roof},
+                "stage_ms_per_step_rank0_overlapped": {"traverse_closest": ov_closest / args.steps, "shade": ov_shade / args.steps, "traverse_shadow": ov_shadow / args.steps,
+                                                       "note": "timed region; shadow(k) runs concurrently with closest(k+1)/shade(k+1), so these sum to more than ms_per_step"},
                 "wall_s_timed_region": t_wall,
             },
             "roofline": {"bound": "hbm", "kernel": "k_traverse<false> (closest-hit, persistent warps)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                         "algorithmic_bytes_per_ray": B_RAY_CLOSEST, "rays_per_launch": rays_c / max(1, n_closest_launches),
+                         "frac": achieved / peak, "traffic": ncu.get("traffic_bytes_per_launch"), "peak_source": peak_src,
+                         "algorithmic_bytes_per_ray": B_RAY_CLOSEST, "rays_per_launch": rays_c_roof / max(1, n_closest_launches),
+                         "algorithmic_bytes_per_launch": B_RAY_CLOSEST * rays_c_roof / max(1, n_closest_launches),
                          "avg_launch_ms": ms_closest / max(1, n_closest_launches),
+                         "how": "CUDA events around each of the %d closest-hit launches of %d frames rendered with DT_FLAG_SERIAL_WAVES (kernel alone on the GPU), L2 flushed before each frame" % (n_closest_launches, n_roof),
+                         "ncu": ncu.get("ncu"), "ncu_source": ncu.get("source"),
                          "shadow_kernel": {"achieved": achieved_shadow, "frac": achieved_shadow / peak, "algorithmic_bytes_per_ray": B_RAY_SHADOW}},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": C.sizeof(capi.dt_camera_desc) + C.sizeof(capi.dt_render_params),
                     "d2h_bytes_per_step": n_pix * 3, "ms_per_step": 1e3 * e2e_s_max / args.steps},

@@ -225,7 +225,11 @@ typedef struct dt_render_params {
 } dt_render_params;
 
 enum { DT_FLAG_SKIP_TONEMAP = 1,        /* leave hdr untouched, do not write ldr from the tonemapper               */
-       DT_FLAG_NO_SORT = 2 };           /* disable the sort-by-material stage (A/B measurement)                    */
+       DT_FLAG_NO_SORT = 2,             /* disable the sort-by-material stage (A/B measurement)                    */
+       DT_FLAG_SERIAL_WAVES = 4 };      /* measurement mode: one kernel at a time, host sync per wave, so that the
+                                           per-stage CUDA-event times in dt_stats are those of each kernel running
+                                           ALONE (default: waves enqueued back to back, shadow(k) overlapping
+                                           closest(k+1), stage times overlap)                                       */
 
 typedef struct dt_stats {
     uint64_t rays_closest;              /* closest-hit queries  (== Raytracer::IntersectObjects calls)  */
