@@ -24,3 +24,41 @@ def golden_scene(name):
         with open(path, "wb") as f:
             f.write(g["xml"].tobytes())
     return HostScene(path), g
+
+
+BRDF_SCENE_XML = """<Scene><MaxRecursionDepth>2</MaxRecursionDepth><BackgroundColor>10 10 20</BackgroundColor><ShadowRayEpsilon>1e-3</ShadowRayEpsilon>
+<Cameras><Camera id="1"><Position>0 3 14</Position><Gaze>0 -0.15 -1</Gaze><Up>0 1 0</Up><NearPlane>-1 1 -0.5 0.5</NearPlane>
+<NearDistance>1.6</NearDistance><ImageResolution>%d %d</ImageResolution><ImageName>brdf.png</ImageName></Camera></Cameras>
+<Lights><AmbientLight>15 15 15</AmbientLight><PointLight id="1"><Position>4 9 9</Position><Intensity>22000 21000 20000</Intensity></PointLight>
+<PointLight id="2"><Position>-7 4 6</Position><Intensity>9000 10000 12000</Intensity></PointLight></Lights>
+<BRDFs><OriginalPhong id="1"><Exponent>25</Exponent></OriginalPhong><OriginalBlinnPhong id="2"><Exponent>40</Exponent></OriginalBlinnPhong>
+<ModifiedPhong id="3"><Exponent>25</Exponent></ModifiedPhong><ModifiedPhong id="4" normalized="true"><Exponent>25</Exponent></ModifiedPhong>
+<ModifiedBlinnPhong id="5"><Exponent>40</Exponent></ModifiedBlinnPhong><ModifiedBlinnPhong id="6" normalized="true"><Exponent>40</Exponent></ModifiedBlinnPhong>
+<TorranceSparrow id="7"><Exponent>50</Exponent></TorranceSparrow><TorranceSparrow id="8" kdfresnel="true"><Exponent>50</Exponent></TorranceSparrow></BRDFs>
+<Materials>
+<Material id="1"><AmbientReflectance>1 1 1</AmbientReflectance><DiffuseReflectance>0.5 0.5 0.5</DiffuseReflectance><SpecularReflectance>0.1 0.1 0.1</SpecularReflectance><PhongExponent>5</PhongExponent></Material>
+%s</Materials>
+<VertexData>-12 0 -8
+12 0 -8
+12 0 8
+-12 0 8
+%s</VertexData>
+<Objects><Mesh id="1"><Material>1</Material><Faces>1 3 2
+1 4 3</Faces></Mesh>
+%s</Objects></Scene>"""
+
+
+def brdf_scene(path, width=480, height=240):
+    """Eight spheres, one per BRDF variant (brdf*.cpp: Phong, Blinn-Phong, modified Phong / Blinn-Phong with and
+    without normalisation, Torrance-Sparrow with and without kdfresnel), two point lights, no sampling."""
+    mats, verts, objs = "", "", ""
+    for k in range(8):
+        mats += ('<Material id="%d" BRDF="%d"><AmbientReflectance>1 1 1</AmbientReflectance><DiffuseReflectance>%g %g %g</DiffuseReflectance>'
+                 '<SpecularReflectance>0.5 0.5 0.5</SpecularReflectance><PhongExponent>30</PhongExponent><RefractionIndex>1.7</RefractionIndex></Material>\n'
+                 % (k + 2, k + 1, 0.25 + 0.05 * k, 0.45 - 0.03 * k, 0.2 + 0.04 * (k % 3)))
+        x, z, y = -7.5 + 2.15 * k, (-1.5 if k % 2 else 1.5), 1.0
+        verts += "%g %g %g\n" % (x, y, z)
+        objs += '<Sphere id="%d"><Material>%d</Material><Center>%d</Center><Radius>1</Radius></Sphere>\n' % (k + 1, k + 2, k + 5)
+    with open(path, "w") as f:
+        f.write(BRDF_SCENE_XML % (width, height, mats, verts, objs))
+    return path

@@ -92,6 +92,19 @@ def test_generated_config4_oracle_vs_reference_statistics(tmp_path):
     assert 10 * np.log10(255.0 ** 2 / mse) >= 20.0
 
 
+@needs_ref
+def test_all_brdfs_oracle_bit_exact_vs_reference(tmp_path):
+    """The five BRDF classes (eight variants) under point lights: deterministic, so the C restatement must reproduce
+    the compiled reference's PNG byte for byte."""
+    from scenes_util import brdf_scene
+    p = brdf_scene(str(tmp_path / "brdf.xml"), 240, 120)
+    hs = HostScene(p)
+    ldr, _, st = oracle_render(hs, hs.camera(0))
+    ref = run_reference(p)
+    assert np.array_equal(ldr, ref["png"])
+    assert (int(st.rays_closest), int(st.rays_shadow)) == (ref["closest"], ref["shadow"])
+
+
 # ------------------------------------------------------------------ host mirror
 def test_bvh2_invariants():
     hs, _ = golden_scene("scienceTree")
