@@ -100,6 +100,8 @@ struct dt_scene {
     int* h_counters = nullptr;    // pinned mirror (+ scratch)
     float4* accum = nullptr; size_t accum_pix = 0;
     float* hdr = nullptr; uint8_t* ldr = nullptr; size_t out_pix = 0;
+    float* peer_hdr = nullptr; uint8_t* peer_ldr = nullptr;     // another rank's frame buffers (dt_frame_import)
+    int peer_w = 0, peer_h = 0;
     double* tm_logsum = nullptr; unsigned int* tm_hist = nullptr; unsigned long long* tm_rank = nullptr; uint32_t* tm_prefix = nullptr;
     Timer t_total, t_gen, t_closest, t_shadow, t_shade, t_sort, t_resolve, t_tm;
     int grid_trav[4][2] = {};
@@ -545,12 +547,16 @@ int dt_scene_create(const dt_scene_desc* desc, dt_scene** out) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, s->device) != cudaSuccess) { g_err = "cudaGetDeviceProperties failed"; return fail(DT_ERR_CUDA); }
     s->num_sms = prop.multiProcessorCount;
-    if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming) != cudaSuccess) { g_err = "cudaStreamCreate failed"; return fail(DT_ERR_CUDA); }
+    // the closest-hit -> shade chain is the frame's critical path: its stream gets the high priority, the any-hit (shadow) stream the low one
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (const char* e = getenv("DT_STREAM_PRIO")) { if (atoi(e) == 0) prio_lo = prio_hi = 0; }
+    if (cudaStreamCreateWithPriority(&s->stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess || cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming) != cudaSuccess) { g_err = "cudaStreamCreate failed"; return fail(DT_ERR_CUDA); }
     for (int p = 0; p < DT_MAX_PIPES; p++) {
         DtPipe& pp = s->pipes[p];
         bool ok = true;
-        if (p == 0) pp.A = s->stream; else ok = cudaStreamCreateWithFlags(&pp.A, cudaStreamNonBlocking) == cudaSuccess;
-        ok = ok && cudaStreamCreateWithFlags(&pp.B, cudaStreamNonBlocking) == cudaSuccess && cudaEventCreateWithFlags(&pp.ev_done, cudaEventDisableTiming) == cudaSuccess;
+        if (p == 0) pp.A = s->stream; else ok = cudaStreamCreateWithPriority(&pp.A, cudaStreamNonBlocking, prio_hi) == cudaSuccess;
+        ok = ok && cudaStreamCreateWithPriority(&pp.B, cudaStreamNonBlocking, prio_lo) == cudaSuccess && cudaEventCreateWithFlags(&pp.ev_done, cudaEventDisableTiming) == cudaSuccess;
         for (int k = 0; k < 2 && ok; k++) ok = cudaEventCreateWithFlags(&pp.ev_shade[k], cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&pp.ev_shadow[k], cudaEventDisableTiming) == cudaSuccess;
         if (!ok) { g_err = "cudaStreamCreate / cudaEventCreate failed"; return fail(DT_ERR_CUDA); }
     }
@@ -637,6 +643,7 @@ void dt_scene_destroy(dt_scene* s) {
     if (!s) return;
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
+    dt_frame_release(s);
     s->free_queues();
     for (void* p : s->allocs) cudaFree(p);
     if (s->counters) cudaFree(s->counters);
@@ -671,7 +678,22 @@ int dt_render_device(dt_scene* s, const dt_camera_desc* cam, const dt_render_par
     const int n_pix = cam->width * cam->height;
     const int spp = cam->samples_per_pixel < 1 ? 1 : cam->samples_per_pixel;
     s->t_resolve.start(st);
-    k_resolve<<<(n_pix + 255) / 256, 256, 0, st>>>(s->accum, n_pix, spp, s->hdr, s->ldr, s->counters);
+    if (params && (params->flags & DT_FLAG_PEER_FRAME)) {
+        float* dst_hdr = s->hdr; uint8_t* dst_ldr = s->ldr;
+        if (s->peer_hdr) {
+            if (s->peer_w != cam->width || s->peer_h != cam->height) { g_err = "imported peer frame has a different resolution"; return DT_ERR_INVALID; }
+            dst_hdr = cam->has_tonemapper ? s->peer_hdr : nullptr;        // the destination tonemaps the whole frame from radiance ...
+            dst_ldr = cam->has_tonemapper ? nullptr : s->peer_ldr;        // ... or only needs the clamped bytes (main.cpp:118-125)
+        }
+        const int tiles_x = (cam->width + 7) / 8, tiles_y = (cam->height + 3) / 4;
+        const int world = params->tile_world < 1 ? 1 : params->tile_world;
+        const long long n_tiles = (long long)tiles_x * tiles_y;
+        const long long my_tiles = (n_tiles - params->tile_rank + world - 1) / world;
+        const long long threads = my_tiles * 32;
+        k_resolve_tiles<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(s->accum, cam->width, cam->height, tiles_x, my_tiles, params->tile_rank, world, spp, dst_hdr, dst_ldr, s->counters);
+    } else {
+        k_resolve<<<(n_pix + 255) / 256, 256, 0, st>>>(s->accum, n_pix, spp, s->hdr, s->ldr, s->counters);
+    }
     s->t_resolve.stop(st);
     S.kernel_launches++;
     s->t_total.stop(st);
@@ -703,6 +725,60 @@ int dt_finish_device(dt_scene* s, const dt_camera_desc* cam, const float* hdr_de
         k_clamp_hdr<<<((int)n_pix + 255) / 256, 256, 0, st>>>(s->hdr, (int)n_pix, s->ldr);
         S.kernel_launches++;
     }
+    rc = finish_core(s, cam, s->hdr, 0, ldr_rgb, &S);
+    if (rc) return rc;
+    s->t_total.stop(st);
+    CK(cudaStreamSynchronize(st));
+    S.ms_total = s->t_total.take();
+    if (stats) *stats = S;
+    return DT_OK;
+}
+
+int dt_frame_export(dt_scene* s, int32_t width, int32_t height, dt_frame_handle* out) {
+    if (!s || !out || width <= 0 || height <= 0) { g_err = "bad argument"; return DT_ERR_INVALID; }
+    CK(cudaSetDevice(s->device));
+    int rc = ensure_outputs(s, (size_t)width * height);
+    if (rc) return rc;
+    memset(out, 0, sizeof *out);
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "dt_frame_handle stores cudaIpcMemHandle_t as 64 bytes");
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, s->hdr)); memcpy(out->hdr, &h, 64);
+    CK(cudaIpcGetMemHandle(&h, s->ldr)); memcpy(out->ldr, &h, 64);
+    out->width = width; out->height = height;
+    return DT_OK;
+}
+
+int dt_frame_release(dt_scene* s) {
+    if (!s) return DT_OK;
+    cudaSetDevice(s->device);
+    if (s->peer_hdr) cudaIpcCloseMemHandle(s->peer_hdr);
+    if (s->peer_ldr) cudaIpcCloseMemHandle(s->peer_ldr);
+    s->peer_hdr = nullptr; s->peer_ldr = nullptr; s->peer_w = s->peer_h = 0;
+    return DT_OK;
+}
+
+int dt_frame_import(dt_scene* s, const dt_frame_handle* in) {
+    if (!s || !in) { g_err = "null argument"; return DT_ERR_INVALID; }
+    CK(cudaSetDevice(s->device));
+    dt_frame_release(s);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, in->hdr, 64);
+    CK(cudaIpcOpenMemHandle((void**)&s->peer_hdr, h, cudaIpcMemLazyEnablePeerAccess));
+    memcpy(&h, in->ldr, 64);
+    CK(cudaIpcOpenMemHandle((void**)&s->peer_ldr, h, cudaIpcMemLazyEnablePeerAccess));
+    s->peer_w = in->width; s->peer_h = in->height;
+    return DT_OK;
+}
+
+int dt_frame_finish(dt_scene* s, const dt_camera_desc* cam, uint8_t* ldr_rgb, dt_stats* stats) {
+    if (!s || !cam || !ldr_rgb) { g_err = "null argument"; return DT_ERR_INVALID; }
+    int rc = check_cam(cam);
+    if (rc) return rc;
+    CK(cudaSetDevice(s->device));
+    if (s->accum_pix < (size_t)cam->width * cam->height) { g_err = "no frame of this size has been rendered or exported"; return DT_ERR_INVALID; }
+    dt_stats S; memset(&S, 0, sizeof S);
+    cudaStream_t st = s->stream;
+    s->t_total.start(st);
     rc = finish_core(s, cam, s->hdr, 0, ldr_rgb, &S);
     if (rc) return rc;
     s->t_total.stop(st);

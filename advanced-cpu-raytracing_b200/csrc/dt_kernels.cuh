@@ -692,6 +692,29 @@ __global__ void k_resolve(const float4* accum, int n_pix, int spp, float* hdr, u
     }
 }
 
+// Resolve + gather fused (DT_FLAG_PEER_FRAME): one warp per OWNED 8x4 tile; hdr / ldr may point into another GPU's memory
+// (CUDA IPC mapping, stores travel over NVLink), so only owned pixels are written and nothing is read back from them.
+__global__ void k_resolve_tiles(const float4* accum, int width, int height, int tiles_x, long long my_tiles, int tile_rank, int tile_world,
+                                int spp, float* hdr, uint8_t* ldr, int* counters) {
+    const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= my_tiles) return;
+    const int lane = threadIdx.x & 31;
+    const long long tile = w * tile_world + tile_rank;
+    const int x = (int)(tile % tiles_x) * 8 + (lane & 7), y = (int)(tile / tiles_x) * 4 + (lane >> 3);
+    if (x >= width || y >= height) return;
+    const size_t i = (size_t)y * width + x;
+    const float4 a = accum[i];
+    float r = a.x, g = a.y, b = a.z;
+    if (spp > 1 && a.w > 0.f) { r = r / a.w; g = g / a.w; b = b / a.w; }
+    if (isnan(r) || isnan(g) || isnan(b)) atomicAdd(counters + DT_CNT_NAN, 1);
+    if (hdr) { hdr[3 * i] = r; hdr[3 * i + 1] = g; hdr[3 * i + 2] = b; }
+    if (ldr) {
+        ldr[3 * i] = (uint8_t)dt_clamp_channel(r);
+        ldr[3 * i + 1] = (uint8_t)dt_clamp_channel(g);
+        ldr[3 * i + 2] = (uint8_t)dt_clamp_channel(b);
+    }
+}
+
 // LDR clamp of an already resolved radiance buffer (main.cpp:118-125)
 __global__ void k_clamp_hdr(const float* hdr, int n_pix, uint8_t* ldr) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;

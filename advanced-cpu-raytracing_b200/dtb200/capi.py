@@ -22,6 +22,7 @@ DT_MAT_MIRROR, DT_MAT_DIELECTRIC, DT_MAT_CONDUCTOR, DT_MAT_EMISSIVE, DT_MAT_DEFA
 DT_FLAG_SKIP_TONEMAP = 1
 DT_FLAG_NO_SORT = 2
 DT_FLAG_SERIAL_WAVES = 4
+DT_FLAG_PEER_FRAME = 8
 
 
 class dt_material(C.Structure):
@@ -142,10 +143,15 @@ class dt_stats(C.Structure):
 
 
 # Every symbol include/dorktracer.h declares (tests check that the library exports all of them).
+class dt_frame_handle(C.Structure):
+    _fields_ = [("hdr", C.c_ubyte * 64), ("ldr", C.c_ubyte * 64), ("width", C.c_int32), ("height", C.c_int32)]
+
+
 DORKTRACER_SYMBOLS = [
     "dt_gpu_init", "dt_device_count", "dt_scene_create", "dt_scene_destroy", "dt_render", "dt_render_device",
     "dt_finish_device", "dt_primary_hits", "dt_trace_closest", "dt_trace_occluded", "dt_tonemap",
     "dt_scene_stream", "dt_last_error", "dt_version",
+    "dt_frame_export", "dt_frame_import", "dt_frame_release", "dt_frame_finish",
 ]
 DTHOST_SYMBOLS = [
     "dth_scene_load_xml", "dth_scene_free", "dth_scene_desc", "dth_scene_num_cameras", "dth_scene_camera",
@@ -224,6 +230,14 @@ def load_dorktracer():
     lib.dt_trace_occluded.restype = C.c_int
     lib.dt_tonemap.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]
     lib.dt_tonemap.restype = C.c_int
+    lib.dt_frame_export.argtypes = [vp, C.c_int32, C.c_int32, C.POINTER(dt_frame_handle)]
+    lib.dt_frame_export.restype = C.c_int
+    lib.dt_frame_import.argtypes = [vp, C.POINTER(dt_frame_handle)]
+    lib.dt_frame_import.restype = C.c_int
+    lib.dt_frame_release.argtypes = [vp]
+    lib.dt_frame_release.restype = C.c_int
+    lib.dt_frame_finish.argtypes = [vp, C.POINTER(dt_camera_desc), C.c_void_p, C.POINTER(dt_stats)]
+    lib.dt_frame_finish.restype = C.c_int
     lib.dt_scene_stream.argtypes = [vp]
     lib.dt_scene_stream.restype = C.c_void_p
     lib.dt_last_error.argtypes = []

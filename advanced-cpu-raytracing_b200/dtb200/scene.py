@@ -130,6 +130,32 @@ class GpuScene:
             self._err("dt_finish_device", rc)
         return ldr, stats
 
+    # ---- multi-GPU gather over peer memory (dt_frame_*): handles are plain bytes, ship them with any transport
+    def frame_export(self, width, height):
+        h = capi.dt_frame_handle()
+        rc = self.lib.dt_frame_export(self.handle, int(width), int(height), C.byref(h))
+        if rc != 0:
+            self._err("dt_frame_export", rc)
+        return bytes(bytearray(h))
+
+    def frame_import(self, handle_bytes):
+        h = capi.dt_frame_handle.from_buffer_copy(handle_bytes)
+        rc = self.lib.dt_frame_import(self.handle, C.byref(h))
+        if rc != 0:
+            self._err("dt_frame_import", rc)
+
+    def frame_release(self):
+        self.lib.dt_frame_release(self.handle)
+
+    def frame_finish(self, cam, ldr=None):
+        if ldr is None:
+            ldr = np.zeros((cam.height, cam.width, 3), np.uint8)
+        stats = capi.dt_stats()
+        rc = self.lib.dt_frame_finish(self.handle, C.byref(cam), ldr.ctypes.data_as(C.c_void_p), C.byref(stats))
+        if rc != 0:
+            self._err("dt_frame_finish", rc)
+        return ldr, stats
+
     def primary_hits(self, cam):
         n = cam.width * cam.height
         shape = np.empty(n, np.int32); face = np.empty(n, np.int32); t = np.empty(n, np.float32)

@@ -8,7 +8,9 @@ A *step* is one frame of the workload through the hot path:
   N > 1 : the same scene and view with sqrt(N) x the resolution per axis (per-GPU pixel count fixed -> weak
           scaling); the image is tile-sharded (8x4-pixel tiles, round-robin) across the ranks, each rank renders
           its tiles with the whole scene replicated, and the per-rank radiance frames are combined on rank 0
-          with ONE NCCL reduce (every pixel is non-zero on exactly one rank, so SUM == gather).
+          without a full-frame exchange: rank 0 exports its frame buffers (CUDA IPC) and every rank's resolve kernel
+          stores its tiles straight into them over NVLink (P2P stores), then one barrier.  Fallback when the IPC
+          mapping is unavailable: ONE NCCL reduce (every pixel is non-zero on exactly one rank, so SUM == gather).
 
   value      device time only: scene + camera resident, CUDA events on the library's stream (+ the reduce)
   e2e        the public C-ABI call dt_render() with a pinned HOST LDR buffer: D2H of the frame inside the
@@ -256,20 +258,48 @@ def main():
             __cuda_array_interface__ = {"shape": (n_pix * 3,), "typestr": "<f4", "data": (ptr, False), "version": 2}
         return torch.as_tensor(_Wrap(), device="cuda")
 
+    # Multi-GPU gather: rank 0 exports its frame buffers (CUDA IPC), the others import them and their resolve kernel
+    # stores the owned tiles straight into rank 0's memory over NVLink (DT_FLAG_PEER_FRAME); one barrier orders
+    # "all tiles written" before "rank 0 reads".  If the IPC mapping is unavailable the ranks fall back, together, to
+    # the NCCL reduce of the per-rank radiance frames.
+    peer = False
+    if world > 1 and not os.environ.get("DT_BENCH_NO_PEER"):
+        ok = 1
+        obj = [None]
+        try:
+            if rank == 0:
+                obj[0] = gs.frame_export(W, H)
+        except Exception as e:
+            sys.stderr.write("frame_export failed: %s\n" % e); ok = 0
+        dist.broadcast_object_list(obj, src=0)
+        try:
+            if rank != 0 and obj[0] is not None:
+                gs.frame_import(obj[0])
+            elif rank != 0:
+                ok = 0
+        except Exception as e:
+            sys.stderr.write("rank %d: frame_import failed: %s\n" % (rank, e)); ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        peer = bool(flag.item())
+    peer_flags = capi.DT_FLAG_PEER_FRAME if peer else 0
+
     def device_step(timed):
         """value path: inputs resident, no host copies.  Returns (ms, stats)."""
         flush_buf.fill_(rank + 1)                                              # L2 flush between iterations
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(lib_stream)
-        ptr, st = gs.render_device(cam, tile_rank=rank, tile_world=world)
+        ptr, st = gs.render_device(cam, tile_rank=rank, tile_world=world, flags=peer_flags)
         e1.record(lib_stream)
         ms = None
         if world > 1:
             r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            t = hdr_tensor(ptr)
             r0.record()
-            dist.reduce(t, dst=0, op=dist.ReduceOp.SUM)
+            if peer:
+                dist.barrier()
+            else:
+                dist.reduce(hdr_tensor(ptr), dst=0, op=dist.ReduceOp.SUM)
             r1.record()
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) + r0.elapsed_time(r1)
@@ -282,6 +312,13 @@ def main():
         """public API with host buffers: D2H of the finished frame inside the timed region."""
         if world == 1:
             _, _, st = gs.render(cam, ldr=ldr_np, want_hdr=False)
+        elif peer:
+            ptr, st = gs.render_device(cam, tile_rank=rank, tile_world=world, flags=peer_flags)
+            dist.barrier()
+            torch.cuda.synchronize()
+            if rank == 0:
+                gs.frame_finish(cam, ldr=ldr_np)
+            dist.barrier()                      # nobody overwrites rank 0's frame before it has been read out
         else:
             ptr, st = gs.render_device(cam, tile_rank=rank, tile_world=world)
             t = hdr_tensor(ptr)
@@ -334,7 +371,7 @@ def main():
     for _ in range(n_roof):
         flush_buf.fill_(rank + 1)
         torch.cuda.synchronize()
-        _, st = gs.render_device(cam, tile_rank=rank, tile_world=world, flags=capi.DT_FLAG_SERIAL_WAVES)
+        _, st = gs.render_device(cam, tile_rank=rank, tile_world=world, flags=capi.DT_FLAG_SERIAL_WAVES | peer_flags)
         ms_closest += st.ms_traverse_closest; ms_shadow += st.ms_traverse_shadow; ms_shade += st.ms_shade; ms_gen += st.ms_generate
         rays_c_roof += int(st.rays_closest); rays_s_roof += int(st.rays_shadow)
         n_closest_launches += int(st.launches_traverse_closest)
@@ -376,9 +413,9 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {
                 "workload": "config2: %d-triangle procedural mesh + ground + dielectric sphere, mirror/dielectric depth 6, 2 point lights, %dx%d, 1 spp%s"
-                            % (hs.n_triangles(), W, H, "" if world == 1 else " (1920x1080 x %d pixels, tile-sharded over %d GPUs, NCCL reduce to rank 0)" % (world, world)),
+                            % (hs.n_triangles(), W, H, "" if world == 1 else " (1920x1080 x %d pixels, tile-sharded over %d GPUs, %s)" % (world, world, "tiles stored into rank 0's frame over NVLink by the resolve kernel (CUDA IPC peer memory) + one barrier" if peer else "NCCL reduce to rank 0")),
                 "rays_per_step": rays_per_step, "closest_rays_per_step": rays_c_all / args.steps, "shadow_rays_per_step": rays_s_all / args.steps,
-                "l2": "flushed between timed iterations (256 MiB write)", "timing": "CUDA events on the library stream (+ reduce), max over ranks",
+                "l2": "flushed between timed iterations (256 MiB write)", "timing": "CUDA events on the library stream (+ barrier / reduce), max over ranks", "gather": ("peer-memory stores" if peer else "nccl-reduce") if world > 1 else "none",
                 "scene_load_s": t_load, "scene_upload_s": t_upload,
                 "stage_ms_per_step_rank0_kernels_alone": {"generate": ms_gen / n_roof, "traverse_closest": ms_closest / n_roof, "shade": ms_shade / n_roof, "traverse_shadow": ms_shadow / n_roof,
                                                           "note": "DT_FLAG_SERIAL_WAVES pass of %d frames after the timed region" % n_roof},

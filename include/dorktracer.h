@@ -226,7 +226,11 @@ typedef struct dt_render_params {
 
 enum { DT_FLAG_SKIP_TONEMAP = 1,        /* leave hdr untouched, do not write ldr from the tonemapper               */
        DT_FLAG_NO_SORT = 2,             /* disable the sort-by-material stage (A/B measurement)                    */
-       DT_FLAG_SERIAL_WAVES = 4 };      /* measurement mode: one kernel at a time, host sync per wave, so that the
+       DT_FLAG_SERIAL_WAVES = 4,
+       DT_FLAG_PEER_FRAME = 8 };        /* multi-GPU: resolve ONLY the owned tiles, straight into the frame buffers of
+                                           the rank that called dt_frame_export (this rank's own buffers if it did
+                                           not dt_frame_import): the gather is fused into the resolve kernel as P2P
+                                           stores over NVLink, no collective and no full-frame exchange             */      /* measurement mode: one kernel at a time, host sync per wave, so that the
                                            per-stage CUDA-event times in dt_stats are those of each kernel running
                                            ALONE (default: waves enqueued back to back, shadow(k) overlapping
                                            closest(k+1), stage times overlap)                                       */
@@ -268,6 +272,21 @@ int dt_render_device(dt_scene* scene, const dt_camera_desc* cam, const dt_render
  * full-frame radiance buffer hdr_dev (device pointer, W*H*3 floats) into host ldr_rgb. */
 int dt_finish_device(dt_scene* scene, const dt_camera_desc* cam, const float* hdr_dev,
                      uint8_t* ldr_rgb, dt_stats* stats);
+
+/* Multi-GPU gather over peer memory (one process per GPU on one box).  The destination rank exports its
+ * frame buffers as CUDA IPC handles (plain bytes: ship them with any host-side transport), the other ranks import them;
+ * renders issued with DT_FLAG_PEER_FRAME then store their tiles directly into the destination's memory.  The caller
+ * orders "all ranks finished rendering" before "destination reads the frame" (one barrier); dt_frame_finish then
+ * tonemaps (if the camera has a tonemapper) and copies the complete LDR frame to the host. */
+typedef struct dt_frame_handle {
+    unsigned char hdr[64];              /* cudaIpcMemHandle_t of the float W*H*3 radiance frame */
+    unsigned char ldr[64];              /* cudaIpcMemHandle_t of the uint8 W*H*3 LDR frame      */
+    int32_t width, height;
+} dt_frame_handle;
+int dt_frame_export(dt_scene* scene, int32_t width, int32_t height, dt_frame_handle* out);
+int dt_frame_import(dt_scene* scene, const dt_frame_handle* in);
+int dt_frame_release(dt_scene* scene);
+int dt_frame_finish(dt_scene* scene, const dt_camera_desc* cam, uint8_t* ldr_rgb, dt_stats* stats);
 
 /* Parity/debug: primary-ray closest hits.  shape = index into desc.shapes (-1 miss), face = canonical
  * (post-build) face index of the (base) mesh or -1 for spheres, t = hit distance (INFINITY on miss). */

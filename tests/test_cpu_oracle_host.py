@@ -244,7 +244,7 @@ def test_struct_sizes_match_the_header(tmp_path):
     """ctypes mirrors must have the C layout: compile a tiny program printing sizeof() of every ABI struct."""
     names = ["dt_material", "dt_brdf", "dt_point_light", "dt_area_light", "dt_directional_light", "dt_spot_light", "dt_env_light",
              "dt_mesh_light", "dt_image", "dt_texture", "dt_face", "dt_bvh2_node", "dt_mesh", "dt_shape", "dt_scene_desc",
-             "dt_camera_desc", "dt_render_params", "dt_stats"]
+             "dt_camera_desc", "dt_render_params", "dt_stats", "dt_frame_handle"]
     src = tmp_path / "sz.c"
     src.write_text('#include <stdio.h>\n#include "dorktracer.h"\nint main(){' + "".join('printf("%s %%zu\\n", sizeof(%s));' % (n, n) for n in names) + "return 0;}")
     exe = tmp_path / "sz"

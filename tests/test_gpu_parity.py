@@ -256,6 +256,30 @@ def test_sort_stage_is_a_pure_reordering():
             assert (int(st.rays_closest), int(st.rays_shadow)) == base[1:]
 
 
+def test_peer_frame_gather_two_processes(tmp_path):
+    """Multi-GPU gather fused into the resolve kernel (dt_frame_export / dt_frame_import / DT_FLAG_PEER_FRAME): a second
+    PROCESS renders the odd tiles and stores them straight into this process's frame buffers through a CUDA IPC mapping
+    (two ranks on the one GPU of the test box; on a multi-GPU box the same stores cross NVLink).  The assembled frame must
+    equal the single-rank frame byte for byte, and the ray counts must add up."""
+    import subprocess, sys
+    name = "cornellbox_recursive_conductors"
+    hs, _ = golden_scene(name)
+    cam = hs.camera(0)
+    cam.width, cam.height = 404, 302                       # ragged: 50.5 x 75.5 tiles
+    gs = GpuScene(hs)
+    full, _, st_full = gs.render(cam, want_hdr=False)
+    hfile = tmp_path / "handle.bin"
+    hfile.write_bytes(gs.frame_export(cam.width, cam.height))
+    _, st0 = gs.render_device(cam, tile_rank=0, tile_world=2, flags=capi.DT_FLAG_PEER_FRAME)
+    worker = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_peer_worker.py")
+    out = subprocess.run([sys.executable, worker, name, str(hfile), str(cam.width), str(cam.height)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=300)
+    assert out.returncode == 0, out.stdout.decode()[-2000:]
+    c1, s1 = (int(x) for x in out.stdout.decode().strip().splitlines()[-1].split()[2:4])
+    ldr, _ = gs.frame_finish(cam)
+    assert np.array_equal(ldr, full)
+    assert int(st0.rays_closest) + c1 == int(st_full.rays_closest) and int(st0.rays_shadow) + s1 == int(st_full.rays_shadow)
+
+
 # ------------------------------------------------------------------ generic queries and tonemapper
 def test_trace_queries_vs_oracle():
     hs, _ = golden_scene("scienceTree")
