@@ -568,7 +568,7 @@ __device__ __forceinline__ void dt_shade_ray(const int i, const DtSceneDev& S, c
 // Grid-stride launch: the wave size lives in device memory (n_ptr) so consecutive waves need no host round trip.
 // `perm` (optional) is the material-sorted order of the wave produced by the sort stage below.
 #ifndef DT_SHADE_MINBLOCKS
-#define DT_SHADE_MINBLOCKS 1
+#define DT_SHADE_MINBLOCKS 4       // 128 registers: measured best on config 4 (shade 162 ms at 193 regs, 133 at 170, 124 at 128, 125 at 102)
 #endif
 __global__ void __launch_bounds__(128, DT_SHADE_MINBLOCKS) k_shade(DtSceneDev S, DtCamDev cam, DtRayQueue in, const float4* in_miss, const int* n_ptr, int n_fixed, const int* perm,
                                                DtRayQueue out, float4* out_miss, int out_capacity,
