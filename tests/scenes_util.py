@@ -62,3 +62,37 @@ def brdf_scene(path, width=480, height=240):
     with open(path, "w") as f:
         f.write(BRDF_SCENE_XML % (width, height, mats, verts, objs))
     return path
+
+
+def blur_dof_scene(path, width=240, height=160, spp=100):
+    """Motion-blurred sphere and mesh (Shape::motionBlurVector), a rough mirror (Material::roughness), and a thin-lens
+    camera (ApertureSize / FocusDistance): the sampling paths of GenerateRay / Reflect that the deterministic scenes do
+    not reach.  Point lights only; the randomness is the per-sample time / lens / roughness."""
+    xml = """<Scene><MaxRecursionDepth>2</MaxRecursionDepth><BackgroundColor>20 30 50</BackgroundColor><ShadowRayEpsilon>1e-3</ShadowRayEpsilon>
+<Cameras><Camera id="1"><Position>0 2.5 12</Position><Gaze>0 -0.12 -1</Gaze><Up>0 1 0</Up><NearPlane>-1 1 -0.6667 0.6667</NearPlane>
+<NearDistance>2</NearDistance><ImageResolution>%d %d</ImageResolution><NumSamples>%d</NumSamples><FocusDistance>11</FocusDistance><ApertureSize>0.35</ApertureSize>
+<ImageName>blur.png</ImageName></Camera></Cameras>
+<Lights><AmbientLight>25 25 25</AmbientLight><PointLight id="1"><Position>5 9 8</Position><Intensity>20000 20000 19000</Intensity></PointLight></Lights>
+<Materials><Material id="1"><AmbientReflectance>1 1 1</AmbientReflectance><DiffuseReflectance>0.55 0.5 0.45</DiffuseReflectance><SpecularReflectance>0.2 0.2 0.2</SpecularReflectance><PhongExponent>20</PhongExponent></Material>
+<Material id="2"><AmbientReflectance>1 1 1</AmbientReflectance><DiffuseReflectance>0.7 0.2 0.15</DiffuseReflectance><SpecularReflectance>0.4 0.4 0.4</SpecularReflectance><PhongExponent>40</PhongExponent></Material>
+<Material id="3" type="mirror"><AmbientReflectance>0 0 0</AmbientReflectance><DiffuseReflectance>0.05 0.05 0.05</DiffuseReflectance><SpecularReflectance>0 0 0</SpecularReflectance><MirrorReflectance>0.85 0.85 0.9</MirrorReflectance><Roughness>0.15</Roughness></Material>
+<Material id="4"><AmbientReflectance>1 1 1</AmbientReflectance><DiffuseReflectance>0.15 0.5 0.25</DiffuseReflectance><SpecularReflectance>0.1 0.1 0.1</SpecularReflectance><PhongExponent>8</PhongExponent></Material></Materials>
+<VertexData>-10 0 -10
+10 0 -10
+10 0 10
+-10 0 10
+-3 1.2 0
+0.3 1.2 1.5
+3.2 1.4 -1
+1 0.01 3
+3 0.01 3
+2 2.2 3</VertexData>
+<Objects><Mesh id="1"><Material>1</Material><Faces>1 3 2
+1 4 3</Faces></Mesh>
+<Mesh id="2"><Material>4</Material><MotionBlur>0.8 0 0</MotionBlur><Faces>8 9 10</Faces></Mesh>
+<Sphere id="1"><Material>2</Material><Center>5</Center><Radius>1.2</Radius><MotionBlur>0 0.9 0.4</MotionBlur></Sphere>
+<Sphere id="2"><Material>3</Material><Center>6</Center><Radius>1.2</Radius></Sphere>
+<Sphere id="3"><Material>2</Material><Center>7</Center><Radius>1.4</Radius></Sphere></Objects></Scene>""" % (width, height, spp)
+    with open(path, "w") as f:
+        f.write(xml)
+    return path
