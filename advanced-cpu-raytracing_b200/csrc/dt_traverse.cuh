@@ -85,8 +85,10 @@ struct DtRayPrep {
     uint32_t oct_inv4;
 };
 
+// Reciprocal direction for the CONSERVATIVE tests only (node boxes, certificates): one MUFU, <= 1 ulp off the exact
+// quotient, which the 2^-18 slack of those tests covers; every exact decision divides by the direction itself.
 __device__ __forceinline__ float dt_safe_rcp(float d) {
-    return fabsf(d) < 1e-30f ? copysignf(1e30f, d) : __frcp_rn(d);
+    return fabsf(d) < 1e-30f ? copysignf(1e30f, d) : dt_rcp_approx(d);
 }
 __device__ __forceinline__ void dt_prep(DtRayPrep& r, v3 o, v3 d) {
     r.o = o; r.d = d;
@@ -197,6 +199,26 @@ __device__ __forceinline__ bool dt_leaf_box_certain(const float4 mn, const float
     const float tmax = fminf(fminf(fmaxf(x1, x2), fmaxf(y1, y2)), fmaxf(z1, z2));
     const float m = __fmul_rn(fmaxf(fabsf(tmin), fabsf(tmax)), 1.9073486e-6f);
     return tmax > 1e-30f && tmax > m && __fsub_rn(tmax, tmin) > __fadd_rn(m, m) && __fadd_rn(tmin, m) < minT;
+}
+
+// Three-way certificate for the per-shape slab tests (Mesh::bbox, InstancedMesh::bbox): +1 the reference's test certainly
+// passes, -1 it certainly fails, 0 too close to call (the caller then runs box_intersect_exact).  Same error model as above.
+__device__ __forceinline__ int dt_box_certificate(const float* mn, const float* mx, v3 o, const DtRayPrep& r, float minT) {
+    if (fabsf(r.idx) >= 1e30f || fabsf(r.idy) >= 1e30f || fabsf(r.idz) >= 1e30f) return 0;
+    const float x1 = __fmul_rn(__fsub_rn(mn[0], o.x), r.idx), x2 = __fmul_rn(__fsub_rn(mx[0], o.x), r.idx);
+    const float y1 = __fmul_rn(__fsub_rn(mn[1], o.y), r.idy), y2 = __fmul_rn(__fsub_rn(mx[1], o.y), r.idy);
+    const float z1 = __fmul_rn(__fsub_rn(mn[2], o.z), r.idz), z2 = __fmul_rn(__fsub_rn(mx[2], o.z), r.idz);
+    const float tmin = fmaxf(fmaxf(fminf(x1, x2), fminf(y1, y2)), fminf(z1, z2));
+    const float tmax = fminf(fminf(fmaxf(x1, x2), fmaxf(y1, y2)), fmaxf(z1, z2));
+    const float m = __fadd_rn(__fmul_rn(fmaxf(fabsf(tmin), fabsf(tmax)), 1.9073486e-6f), 1e-30f);
+    if (!(m < 1e30f)) return 0;                                                        // NaN / overflow: undecided
+    if (tmax > m && __fsub_rn(tmax, tmin) > __fadd_rn(m, m) && __fadd_rn(tmin, m) < minT) return 1;
+    if (tmax < -m || __fsub_rn(tmin, tmax) > __fadd_rn(m, m) || __fsub_rn(tmin, m) > minT) return -1;
+    return 0;
+}
+__device__ __forceinline__ bool dt_box_test(const float* mn, const float* mx, v3 o, v3 d, const DtRayPrep& r, float minT) {
+    const int c = dt_box_certificate(mn, mx, o, r, minT);
+    return c != 0 ? c > 0 : box_intersect_exact(mn, mx, o, d, minT);
 }
 
 // (t, shape, face) lexicographic "strictly better" — the reference's scan order with strict `<`.
@@ -344,20 +366,22 @@ __device__ __forceinline__ bool dt_trav_prim(DtTrav& T, uint2* __restrict__ stac
     if (kind == DT_SHAPE_INSTANCE) {
         v3 so = T.wo;
         if (sh->has_motion_blur) so = vadd(so, vscale(F3(sh->motion_blur), T.mb_time));
-        if (!box_intersect_exact(sh->bbox_min, sh->bbox_max, so, T.wd, shape_min_t)) return false;   // instancedMesh.cpp:29
+        if (!dt_box_test(sh->bbox_min, sh->bbox_max, so, T.wd, T.r, shape_min_t)) return false;       // instancedMesh.cpp:29 (T.r: world ray)
     }
     v3 lo, ld;
     dt_to_local(sh, T.wo, T.wd, T.mb_time, lo, ld);
     const DtMeshDev* m = S.meshes + sh->mesh;
     // mesh.cpp:172 (Mesh::bbox) and the root node of BVH::IntersectBVH (same box) in local space
-    if (!box_intersect_exact(m->bbox_min, m->bbox_max, lo, ld, shape_min_t)) return false;
+    DtRayPrep lr;
+    dt_prep(lr, lo, ld);
+    if (!dt_box_test(m->bbox_min, m->bbox_max, lo, ld, lr, shape_min_t)) return false;
     if (T.ng.y > 0x00FFFFFFu) { if (T.sp < DT_STACK_SIZE) stack[T.sp++] = T.ng; }
     if (T.tg.y != 0u) { if (T.sp < DT_STACK_SIZE) stack[T.sp++] = T.tg; }
     DT_STAT(3);
     T.blas_sp = T.sp;
     T.in_blas = true;
     T.cur_shape = si;
-    dt_prep(T.r, lo, ld);
+    T.r = lr;
     T.nodes = S.blas_nodes;
     T.ng = make_uint2(m->node_root, 0x80000000u);
     T.tg = make_uint2(0u, 0u);
