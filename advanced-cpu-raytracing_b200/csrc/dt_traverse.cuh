@@ -53,6 +53,8 @@ __device__ __forceinline__ bool tri_test_exact(v3 o, v3 d, v3 v0, v3 e1, v3 e2, 
     const float detT = det3(e1, e2, s);
     const float t_apx = __fmul_rn(detT, inv);
     if (t_apx < -1e-30f || t_apx > __fmul_rn(t_reject_above, 1.00001f)) return false;
+    // clearly inside the triangle (both quotients positive, their sum below 1 by more than the approximation error):
+    // beta >= 0, gamma >= 0, beta + gamma <= 1 hold for the exact quotients as well.  Near an edge: the reference's own test.
     beta = __fdiv_rn(detB, detA);
     if (beta < 0) return false;
     gamma = __fdiv_rn(detG, detA);
@@ -242,11 +244,9 @@ __device__ unsigned long long g_dt_stats[8];     // 0 nodes, 1 tri tests, 2 shap
 struct DtTrav {
     v3 wo, wd;                  // world-space ray
     float mb_time;
-    float any_min_t;            // ANY: shadowRay.hitInfo.minT = lightT + 0.01 (raytracer.cpp:580)
     DtRayPrep r;                // ray of the current level (world in the TLAS, local inside a BLAS)
     DtHit best;
     uint2 ng, tg;               // current node group / primitive group
-    const uint4* nodes;
     int sp, blas_sp, cur_shape;
     bool in_blas;
 };
@@ -257,12 +257,10 @@ template <bool ANY>
 __device__ __forceinline__ void dt_trav_init(DtTrav& T, const DtSceneDev& S, v3 wo, v3 wd, float mb_time, float tmax_in) {
     T.wo = wo; T.wd = wd; T.mb_time = mb_time;
     T.best.t = ANY ? tmax_in : CUDART_INF_F;
-    T.any_min_t = __fadd_rn(tmax_in, 0.01f);
     T.best.shape = -1; T.best.face = -1; T.best.beta = 0.f; T.best.gamma = 0.f;
     dt_prep(T.r, wo, wd);
     DT_STAT(6);
     T.in_blas = false; T.blas_sp = 0; T.cur_shape = -1; T.sp = 0;
-    T.nodes = S.tlas_nodes;
     // root as the single "child" of a virtual group; a scene of a few shapes skips the TLAS node test and starts with the
     // shape list (a primitive group), which is what the reference's linear scan does (raytracer.cpp:625-643)
     T.ng = S.tlas_direct > 0 ? make_uint2(0u, (1u << S.tlas_direct) - 1u) : make_uint2(0u, 0x80000000u);
@@ -270,7 +268,8 @@ __device__ __forceinline__ void dt_trav_init(DtTrav& T, const DtSceneDev& S, v3 
 }
 
 // Visit the nearest pending child node of the current group: load 80 B, test 8 boxes, refill ng / tg.
-__device__ __forceinline__ void dt_trav_node(DtTrav& T, uint2* __restrict__ stack, const uint32_t one) {
+__device__ __forceinline__ void dt_trav_node(DtTrav& T, uint2* __restrict__ stack, const DtSceneDev& S) {
+    const uint32_t one = S.one_bits;
     DT_STAT(0);
     const uint32_t hits = T.ng.y;
     const uint32_t imask = T.ng.y & 0xFFu;
@@ -280,7 +279,7 @@ __device__ __forceinline__ void dt_trav_node(DtTrav& T, uint2* __restrict__ stac
     const uint32_t slot = (uint32_t)(child_bit - 24) ^ (T.r.oct_inv4 & 0xFFu);
     const uint32_t rel = __popc(imask & ~(0xFFFFFFFFu << slot));
     const uint32_t ni = T.ng.x + rel;
-    const uint4* np = T.nodes + (size_t)ni * 5;
+    const uint4* np = (T.in_blas ? S.blas_nodes : S.tlas_nodes) + (size_t)ni * 5;
     const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
     const uint32_t hm = dt_node_hits(n0, n1, n2, n3, n4, T.r, T.best.t, one);
     T.ng.x = n1.x;
@@ -328,7 +327,7 @@ __device__ __forceinline__ bool dt_trav_prim(DtTrav& T, uint2* __restrict__ stac
                 // minT the reference would hold when it reaches this face: it scans in (shape, face) order, so a
                 // candidate that precedes the current best was tested BEFORE that best existed.
                 const bool after_best = best.shape >= 0 && (T.cur_shape > best.shape || (T.cur_shape == best.shape && face > best.face));
-                const float ref_min_t = ANY ? T.any_min_t : (after_best ? best.t : CUDART_INF_F);
+                const float ref_min_t = ANY ? __fadd_rn(best.t, 0.01f) : (after_best ? best.t : CUDART_INF_F);     // ANY: minT = lightT + 0.01 (raytracer.cpp:580); best.t is still lightT
                 bool ok = dt_leaf_box_certain(lb0, lb1, T.r, ref_min_t);
                 if (!ok) {
                     const float lmn[3] = {lb0.x, lb0.y, lb0.z}, lmx[3] = {lb1.x, lb1.y, lb1.z};
@@ -362,7 +361,7 @@ __device__ __forceinline__ bool dt_trav_prim(DtTrav& T, uint2* __restrict__ stac
     }
     // Mesh / InstancedMesh: the reference's exact per-shape pre-tests, then descend into the BLAS.
     // ray.hitInfo.minT at the time the reference scans shape si: only hits of lower-index shapes exist.
-    const float shape_min_t = ANY ? T.any_min_t : ((best.shape >= 0 && si > best.shape) ? best.t : CUDART_INF_F);
+    const float shape_min_t = ANY ? __fadd_rn(best.t, 0.01f) : ((best.shape >= 0 && si > best.shape) ? best.t : CUDART_INF_F);
     if (kind == DT_SHAPE_INSTANCE) {
         v3 so = T.wo;
         if (sh->has_motion_blur) so = vadd(so, vscale(F3(sh->motion_blur), T.mb_time));
@@ -382,7 +381,6 @@ __device__ __forceinline__ bool dt_trav_prim(DtTrav& T, uint2* __restrict__ stac
     T.in_blas = true;
     T.cur_shape = si;
     T.r = lr;
-    T.nodes = S.blas_nodes;
     T.ng = make_uint2(m->node_root, 0x80000000u);
     T.tg = make_uint2(0u, 0u);
     entered_blas = true;
@@ -396,10 +394,10 @@ template <bool ANY, bool WW>
 __device__ __forceinline__ bool dt_trav_step(DtTrav& T, uint2* __restrict__ stack, const DtSceneDev& S) {
     DT_STAT(5);
     if (WW) {
-        while (T.ng.y > 0x00FFFFFFu && T.tg.y == 0u) dt_trav_node(T, stack, S.one_bits);
+        while (T.ng.y > 0x00FFFFFFu && T.tg.y == 0u) dt_trav_node(T, stack, S);
         if (T.tg.y == 0u && T.ng.y != 0u && T.ng.y <= 0x00FFFFFFu) { T.tg = T.ng; T.ng = make_uint2(0u, 0u); }
     } else {
-        if (T.ng.y > 0x00FFFFFFu) dt_trav_node(T, stack, S.one_bits);
+        if (T.ng.y > 0x00FFFFFFu) dt_trav_node(T, stack, S);
         else { T.tg = T.ng; T.ng = make_uint2(0u, 0u); }
     }
     while (T.tg.y != 0u) {
@@ -411,7 +409,6 @@ __device__ __forceinline__ bool dt_trav_step(DtTrav& T, uint2* __restrict__ stac
         if (T.in_blas && T.sp == T.blas_sp) {
             T.in_blas = false;
             dt_prep(T.r, T.wo, T.wd);
-            T.nodes = S.tlas_nodes;
         }
         if (T.sp == 0) { if (ANY) T.best.shape = -1; return true; }
         T.ng = stack[--T.sp];
