@@ -134,11 +134,14 @@ __device__ __forceinline__ void dt_store_shadow(const DtShadowQueue& sq, int i, 
 }
 
 #ifndef DT_TRAV_MINBLOCKS
-#define DT_TRAV_MINBLOCKS 6       // resident blocks per SM the register allocator must allow (measured: 6 beats 7-9, which spill)
+#define DT_TRAV_MINBLOCKS 7       // closest-hit kernel: resident blocks per SM the register allocator must allow (72 registers)
+#endif
+#ifndef DT_TRAV_MINBLOCKS_ANY
+#define DT_TRAV_MINBLOCKS_ANY 8   // any-hit kernel (less state: no barycentrics, no tie-breaking): 64 registers, no spills
 #endif
 // Static variant: a warp fetches 32 consecutive rays and runs them to completion.
 template <bool ANY, bool WW>
-__global__ void __launch_bounds__(128, DT_TRAV_MINBLOCKS) k_traverse(DtSceneDev S, DtRayQueue q, DtShadowQueue sq, const int* n_ptr, int n_fixed, int* fetch_counter, float4* accum) {
+__global__ void __launch_bounds__(128, ANY ? DT_TRAV_MINBLOCKS_ANY : DT_TRAV_MINBLOCKS) k_traverse(DtSceneDev S, DtRayQueue q, DtShadowQueue sq, const int* n_ptr, int n_fixed, int* fetch_counter, float4* accum) {
     const int n = n_ptr ? *n_ptr : n_fixed;
     const int lane = threadIdx.x & 31;
     for (;;) {
@@ -154,7 +157,7 @@ __global__ void __launch_bounds__(128, DT_TRAV_MINBLOCKS) k_traverse(DtSceneDev 
             DtTrav T;
             uint2 stack[DT_STACK_SIZE];
             dt_trav_init<ANY>(T, S, V(o.x, o.y, o.z), V(d.x, d.y, d.z), o.w, ANY ? d.w : CUDART_INF_F);
-            while (!dt_trav_step<ANY, WW>(T, stack, S)) {}
+            while (!dt_trav_step<ANY, WW>(T, stack, S, (ANY ? sq.o_time : q.o_time) + i, (ANY ? sq.d_tmax : q.d_tmax) + i)) {}
             if (ANY) dt_store_shadow(sq, i, T.best, accum); else dt_store_closest(q, i, T.best);
         }
     }
@@ -173,7 +176,7 @@ __device__ __forceinline__ unsigned long long dt_now() { unsigned long long t; a
 #endif
 
 template <bool ANY, bool WW>
-__global__ void __launch_bounds__(128, DT_TRAV_MINBLOCKS) k_traverse_dyn(DtSceneDev S, DtRayQueue q, DtShadowQueue sq, const int* n_ptr, int n_fixed, int* fetch_counter,
+__global__ void __launch_bounds__(128, ANY ? DT_TRAV_MINBLOCKS_ANY : DT_TRAV_MINBLOCKS) k_traverse_dyn(DtSceneDev S, DtRayQueue q, DtShadowQueue sq, const int* n_ptr, int n_fixed, int* fetch_counter,
                                                       float4* accum, int refill_threshold) {
     const int n = n_ptr ? *n_ptr : n_fixed;
     const int lane = threadIdx.x & 31;
@@ -218,7 +221,7 @@ __global__ void __launch_bounds__(128, DT_TRAV_MINBLOCKS) k_traverse_dyn(DtScene
 #ifdef DT_TIMELINE
                 tl_steps++;
 #endif
-                if (dt_trav_step<ANY, WW>(T, stack, S)) {
+                if (dt_trav_step<ANY, WW>(T, stack, S, (ANY ? sq.o_time : q.o_time) + ray, (ANY ? sq.d_tmax : q.d_tmax) + ray)) {
 #ifdef DT_TIMELINE
                     atomicAdd(&g_dt_steps_hist[ANY ? 1 : 0][min(63, tl_steps / 8)], 1u); tl_steps = 0;
 #endif

@@ -242,25 +242,25 @@ __device__ unsigned long long g_dt_stats[8];     // 0 nodes, 1 tri tests, 2 shap
 // Per-ray traversal state: a resumable state machine so that persistent warps can refill finished lanes
 // (dynamic fetch) instead of idling until the slowest ray of the warp is done.
 struct DtTrav {
-    v3 wo, wd;                  // world-space ray
-    float mb_time;
+    // The world-space ray and its motion-blur time are NOT kept: the ray equals r while in the TLAS and is re-read from the
+    // wave queue (one 32-byte load) when a BLAS is left; the time (queue o.w) is read only by motion-blurred shapes.
+    // Seven registers that buy the kernel one more resident block per SM.
     DtRayPrep r;                // ray of the current level (world in the TLAS, local inside a BLAS)
     DtHit best;
     uint2 ng, tg;               // current node group / primitive group
-    int sp, blas_sp, cur_shape;
-    bool in_blas;
+    int sp, blas_sp;
+    int cur_shape;              // shape whose BLAS is being traversed, -1 while in the TLAS
 };
 // The traversal stack is a SEPARATE local array (uint2 stack[DT_STACK_SIZE] in the kernel): with the dynamically indexed
 // array inside DtTrav the whole struct lives in local memory; on its own, the scalar state above stays in registers.
 
 template <bool ANY>
 __device__ __forceinline__ void dt_trav_init(DtTrav& T, const DtSceneDev& S, v3 wo, v3 wd, float mb_time, float tmax_in) {
-    T.wo = wo; T.wd = wd; T.mb_time = mb_time;
     T.best.t = ANY ? tmax_in : CUDART_INF_F;
     T.best.shape = -1; T.best.face = -1; T.best.beta = 0.f; T.best.gamma = 0.f;
     dt_prep(T.r, wo, wd);
     DT_STAT(6);
-    T.in_blas = false; T.blas_sp = 0; T.cur_shape = -1; T.sp = 0;
+    T.blas_sp = 0; T.cur_shape = -1; T.sp = 0;
     // root as the single "child" of a virtual group; a scene of a few shapes skips the TLAS node test and starts with the
     // shape list (a primitive group), which is what the reference's linear scan does (raytracer.cpp:625-643)
     T.ng = S.tlas_direct > 0 ? make_uint2(0u, (1u << S.tlas_direct) - 1u) : make_uint2(0u, 0x80000000u);
@@ -279,7 +279,7 @@ __device__ __forceinline__ void dt_trav_node(DtTrav& T, uint2* __restrict__ stac
     const uint32_t slot = (uint32_t)(child_bit - 24) ^ (T.r.oct_inv4 & 0xFFu);
     const uint32_t rel = __popc(imask & ~(0xFFFFFFFFu << slot));
     const uint32_t ni = T.ng.x + rel;
-    const uint4* np = (T.in_blas ? S.blas_nodes : S.tlas_nodes) + (size_t)ni * 5;
+    const uint4* np = (T.cur_shape >= 0 ? S.blas_nodes : S.tlas_nodes) + (size_t)ni * 5;
     const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
     const uint32_t hm = dt_node_hits(n0, n1, n2, n3, n4, T.r, T.best.t, one);
     T.ng.x = n1.x;
@@ -292,7 +292,7 @@ __device__ __forceinline__ void dt_trav_node(DtTrav& T, uint2* __restrict__ stac
 // World -> local ray (mesh.cpp:164-170, sphere.cpp:23-30, instancedMesh.cpp:33-39).  For an identity inverseTransform the
 // double-precision product reduces to x*1 + 0 + 0 + 0: the value is unchanged except that -0 becomes +0, which `x + 0.0f`
 // reproduces exactly, so the 24 DMUL/DADD are skipped (the common case: untransformed meshes and spheres).
-__device__ __forceinline__ void dt_to_local(const DtShapeDev* sh, v3 wo, v3 wd, float mb_time, v3& lo, v3& ld) {
+__device__ __forceinline__ void dt_to_local(const DtShapeDev* sh, v3 wo, v3 wd, const float4* __restrict__ ray_o, v3& lo, v3& ld) {
     if (sh->inv_is_identity) {
         lo = V(__fadd_rn(wo.x, 0.0f), __fadd_rn(wo.y, 0.0f), __fadd_rn(wo.z, 0.0f));
         ld = V(__fadd_rn(wd.x, 0.0f), __fadd_rn(wd.y, 0.0f), __fadd_rn(wd.z, 0.0f));
@@ -300,17 +300,17 @@ __device__ __forceinline__ void dt_to_local(const DtShapeDev* sh, v3 wo, v3 wd, 
         lo = apply_transform(sh->inv, wo, 1.0f);
         ld = apply_transform(sh->inv, wd, 0.0f);
     }
-    if (sh->has_motion_blur) lo = vadd(lo, vscale(F3(sh->motion_blur), mb_time));
+    if (sh->has_motion_blur) lo = vadd(lo, vscale(F3(sh->motion_blur), ray_o->w));       // motionBlurTime of this ray
 }
 
 // One primitive of the current primitive group.  Returns true when an ANY query is decided (occluded).
 template <bool ANY>
-__device__ __forceinline__ bool dt_trav_prim(DtTrav& T, uint2* __restrict__ stack, const DtSceneDev& S, bool& entered_blas) {
+__device__ __forceinline__ bool dt_trav_prim(DtTrav& T, uint2* __restrict__ stack, const DtSceneDev& S, const float4* __restrict__ ray_o, bool& entered_blas) {
     DtHit& best = T.best;
     const int bit = __ffs(T.tg.y) - 1;
     T.tg.y &= ~(1u << bit);
     const uint32_t prim = T.tg.x + (uint32_t)bit;
-    if (T.in_blas) {
+    if (T.cur_shape >= 0) {
         DT_STAT(1);
         const float4* tp = S.tris + (size_t)prim * 3;
         const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
@@ -348,7 +348,7 @@ __device__ __forceinline__ bool dt_trav_prim(DtTrav& T, uint2* __restrict__ stac
     const int kind = sh->kind;
     if (kind == DT_SHAPE_SPHERE) {
         v3 lo, ld;
-        dt_to_local(sh, T.wo, T.wd, T.mb_time, lo, ld);
+        dt_to_local(sh, T.r.o, T.r.d, ray_o, lo, ld);       // TLAS level: T.r is the world ray
         float t;
         if (sphere_test_exact(lo, ld, F3(sh->center), sh->radius, t)) {
             if (ANY) {
@@ -363,12 +363,12 @@ __device__ __forceinline__ bool dt_trav_prim(DtTrav& T, uint2* __restrict__ stac
     // ray.hitInfo.minT at the time the reference scans shape si: only hits of lower-index shapes exist.
     const float shape_min_t = ANY ? __fadd_rn(best.t, 0.01f) : ((best.shape >= 0 && si > best.shape) ? best.t : CUDART_INF_F);
     if (kind == DT_SHAPE_INSTANCE) {
-        v3 so = T.wo;
-        if (sh->has_motion_blur) so = vadd(so, vscale(F3(sh->motion_blur), T.mb_time));
-        if (!dt_box_test(sh->bbox_min, sh->bbox_max, so, T.wd, T.r, shape_min_t)) return false;       // instancedMesh.cpp:29 (T.r: world ray)
+        v3 so = T.r.o;
+        if (sh->has_motion_blur) so = vadd(so, vscale(F3(sh->motion_blur), ray_o->w));
+        if (!dt_box_test(sh->bbox_min, sh->bbox_max, so, T.r.d, T.r, shape_min_t)) return false;       // instancedMesh.cpp:29 (T.r: world ray)
     }
     v3 lo, ld;
-    dt_to_local(sh, T.wo, T.wd, T.mb_time, lo, ld);
+    dt_to_local(sh, T.r.o, T.r.d, ray_o, lo, ld);
     const DtMeshDev* m = S.meshes + sh->mesh;
     // mesh.cpp:172 (Mesh::bbox) and the root node of BVH::IntersectBVH (same box) in local space
     DtRayPrep lr;
@@ -378,7 +378,6 @@ __device__ __forceinline__ bool dt_trav_prim(DtTrav& T, uint2* __restrict__ stac
     if (T.tg.y != 0u) { if (T.sp < DT_STACK_SIZE) stack[T.sp++] = T.tg; }
     DT_STAT(3);
     T.blas_sp = T.sp;
-    T.in_blas = true;
     T.cur_shape = si;
     T.r = lr;
     T.ng = make_uint2(m->node_root, 0x80000000u);
@@ -390,8 +389,9 @@ __device__ __forceinline__ bool dt_trav_prim(DtTrav& T, uint2* __restrict__ stac
 // One step of the state machine.  WW = false: one node visit + its primitives ("if-if");
 // WW = true: descend nodes until some primitive group is pending, then drain it ("while-while").
 // Returns true when the ray is finished (ANY: best.shape >= 0 <=> occluded).
+// ray_o / ray_d: where the world-space ray of this traversal can be re-read (queue entry or caller's copy).
 template <bool ANY, bool WW>
-__device__ __forceinline__ bool dt_trav_step(DtTrav& T, uint2* __restrict__ stack, const DtSceneDev& S) {
+__device__ __forceinline__ bool dt_trav_step(DtTrav& T, uint2* __restrict__ stack, const DtSceneDev& S, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d) {
     DT_STAT(5);
     if (WW) {
         while (T.ng.y > 0x00FFFFFFu && T.tg.y == 0u) dt_trav_node(T, stack, S);
@@ -402,13 +402,14 @@ __device__ __forceinline__ bool dt_trav_step(DtTrav& T, uint2* __restrict__ stac
     }
     while (T.tg.y != 0u) {
         bool entered = false;
-        if (dt_trav_prim<ANY>(T, stack, S, entered)) return true;
+        if (dt_trav_prim<ANY>(T, stack, S, ray_o, entered)) return true;
         if (entered) break;
     }
     if (T.ng.y <= 0x00FFFFFFu && T.tg.y == 0u) {
-        if (T.in_blas && T.sp == T.blas_sp) {
-            T.in_blas = false;
-            dt_prep(T.r, T.wo, T.wd);
+        if (T.cur_shape >= 0 && T.sp == T.blas_sp) {
+            T.cur_shape = -1;
+            const float4 wo = *ray_o, wd = *ray_d;
+            dt_prep(T.r, V(wo.x, wo.y, wo.z), V(wd.x, wd.y, wd.z));
         }
         if (T.sp == 0) { if (ANY) T.best.shape = -1; return true; }
         T.ng = stack[--T.sp];
@@ -423,6 +424,7 @@ __device__ __forceinline__ void dt_trace(const DtSceneDev& S, v3 wo, v3 wd, floa
     DtTrav T;
     uint2 stack[DT_STACK_SIZE];
     dt_trav_init<ANY>(T, S, wo, wd, mb_time, tmax_in);
-    while (!dt_trav_step<ANY, true>(T, stack, S)) {}
+    const float4 ro = make_float4(wo.x, wo.y, wo.z, mb_time), rd = make_float4(wd.x, wd.y, wd.z, tmax_in);
+    while (!dt_trav_step<ANY, true>(T, stack, S, &ro, &rd)) {}
     best = T.best;
 }
