@@ -105,7 +105,7 @@ struct dt_scene {
     double* tm_logsum = nullptr; unsigned int* tm_hist = nullptr; unsigned long long* tm_rank = nullptr; uint32_t* tm_prefix = nullptr;
     Timer t_total, t_gen, t_closest, t_shadow, t_shade, t_sort, t_resolve, t_tm;
     int grid_trav[4][2] = {};
-    int trav_mode = 2, refill_threshold = 16;
+    int trav_mode = 2, refill_threshold = 12;
     int sort_mode = 1;            // sort-by-material stage: 0 off, 1 auto (scenes with >= 3 materials), 2 always (DT_SORT)
 
     void free_queues() { for (DtPipe& p : pipes) p.free_queues(); }
