@@ -287,6 +287,8 @@ def main():
     def device_step(timed):
         """value path: inputs resident, no host copies.  Returns (ms, stats)."""
         flush_buf.fill_(rank + 1)                                              # L2 flush between iterations
+        if world > 1:
+            dist.barrier()                                                     # untimed: the ranks start the step together (the flush skews them)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(lib_stream)
