@@ -102,6 +102,7 @@ struct dt_scene {
     float* hdr = nullptr; uint8_t* ldr = nullptr; size_t out_pix = 0;
     float* peer_hdr = nullptr; uint8_t* peer_ldr = nullptr;     // another rank's frame buffers (dt_frame_import)
     int peer_w = 0, peer_h = 0;
+    bool frame_exported = false;  // other processes hold IPC mappings of hdr / ldr: they must not be reallocated
     double* tm_logsum = nullptr; unsigned int* tm_hist = nullptr; unsigned long long* tm_rank = nullptr; uint32_t* tm_prefix = nullptr;
     Timer t_total, t_gen, t_closest, t_shadow, t_shade, t_sort, t_resolve, t_tm;
     int grid_trav[4][2] = {};
@@ -168,6 +169,7 @@ int ensure_queues(dt_scene* s, DtPipe& pp, int capacity, int shadow_capacity, bo
 
 int ensure_outputs(dt_scene* s, size_t n_pix) {
     if (s->accum_pix < n_pix) {
+        if (s->frame_exported) { g_err = "the frame buffers are exported to other processes (dt_frame_export) and cannot grow; export a frame of the largest resolution first"; return DT_ERR_INVALID; }
         if (s->accum) cudaFree(s->accum);
         if (s->hdr) cudaFree(s->hdr);
         if (s->ldr) cudaFree(s->ldr);
@@ -745,6 +747,7 @@ int dt_frame_export(dt_scene* s, int32_t width, int32_t height, dt_frame_handle*
     CK(cudaIpcGetMemHandle(&h, s->hdr)); memcpy(out->hdr, &h, 64);
     CK(cudaIpcGetMemHandle(&h, s->ldr)); memcpy(out->ldr, &h, 64);
     out->width = width; out->height = height;
+    s->frame_exported = true;
     return DT_OK;
 }
 
