@@ -92,6 +92,12 @@ struct dt_scene {
     DtPipe pipes[DT_MAX_PIPES];
     cudaEvent_t ev_fork = nullptr;
     std::vector<cudaEvent_t> ev_pool;    // timing events of the sync-free loop
+    int use_graph = 1;            // replay the sync-free frame as a CUDA graph (DT_GRAPH=0: enqueue every launch, A/B)
+    bool capturing = false;
+    cudaGraphExec_t frame_graph = nullptr;
+    std::string frame_key;        // everything baked into frame_graph
+    std::vector<cudaEvent_t> g_tg, g_tc, g_th, g_ts, g_tsort;
+    uint32_t g_launches = 0, g_closest = 0;
     int grid_shade = 0;
     int sync_waves = 0;           // DT_SYNC_WAVES=1 forces the host-synchronised wave loop (A/B)
     int n_pipes_env = 0;          // DT_PIPES=n forces the pipeline count (0 = auto)
@@ -315,7 +321,9 @@ retry:
         auto ev = [&]() -> cudaEvent_t { if (ev_i >= s->ev_pool.size()) { cudaEvent_t e; cudaEventCreate(&e); s->ev_pool.push_back(e); } return s->ev_pool[ev_i++]; };
         std::vector<cudaEvent_t> tg, tc, th, ts, tsort;      // (start, stop) pairs per stage
         auto timed = [&](std::vector<cudaEvent_t>& v, cudaStream_t q, auto&& launch) {
-            cudaEvent_t a = ev(), b = ev(); cudaEventRecord(a, q); launch(); cudaEventRecord(b, q); v.push_back(a); v.push_back(b);
+            cudaEvent_t a = ev(), b = ev();
+            const unsigned int fl = s->capturing ? cudaEventRecordExternal : cudaEventRecordDefault;      // inside a capture: real event-record nodes
+            cudaEventRecordWithFlags(a, q, fl); launch(); cudaEventRecordWithFlags(b, q, fl); v.push_back(a); v.push_back(b);
         };
         DtWaveParams wps[DT_MAX_PIPES]; int n0[DT_MAX_PIPES];
         for (int p = 0; p < NP; p++) {
@@ -332,45 +340,87 @@ retry:
             if (shcap > (1ll << 29)) { g_err = "shadow queue too large; lower max_wave_rays"; return DT_ERR_INVALID; }
             if ((rc = ensure_queues(s, pp, (int)cap, (int)shcap, false))) return rc;
         }
+        // The whole frame -- generate, 7 x (closest, sort, shade, shadow, advance) on two streams, counter read-back -- is
+        // captured ONCE into a CUDA graph and replayed while camera, seed, resolution and queue allocations stay the same
+        // (the kernel parameters are baked into the graph): one cudaGraphLaunch per frame instead of ~50 launches and
+        // ~150 event operations.  DT_GRAPH=0 enqueues directly (A/B).
+        uint32_t n_launches = 0, n_closest = 0;
+        auto enqueue_frame = [&]() -> int {
         CK(cudaEventRecord(s->ev_fork, st));
-        for (int p = 0; p < NP; p++) {
-            DtPipe& pp = s->pipes[p];
-            if (p > 0) CK(cudaStreamWaitEvent(pp.A, s->ev_fork, 0));
-            CK(cudaStreamWaitEvent(pp.B, s->ev_fork, 0));
-            timed(tg, pp.A, [&] { k_generate<<<(n0[p] + 255) / 256, 256, 0, pp.A>>>(dc, wps[p], pp.q[0], 0, 0, n0[p], s->accum); });
-            s->h_counters[DT_MAX_PIPES * DT_CNT_COUNT + p] = n0[p];          // pinned scratch past the readback area
-            CK(cudaMemcpyAsync(pp.counters + DT_CNT_CUR, s->h_counters + DT_MAX_PIPES * DT_CNT_COUNT + p, sizeof(int), cudaMemcpyHostToDevice, pp.A));
-            S.kernel_launches++;
-        }
-        for (int k = 0; k < n_waves; k++) {
-            const int slot = k & 1, cur = k & 1;
             for (int p = 0; p < NP; p++) {
                 DtPipe& pp = s->pipes[p];
-                int* c = pp.counters;
-                DtShadowQueue& sq = pp.sq[slot];
-                timed(tc, pp.A, [&] { launch_traverse<false>(s, pp.q[cur], sq, c + DT_CNT_CUR, 0, c + DT_CNT_FETCH_A, s->accum, pp.A); });
-                if (k >= 2) CK(cudaStreamWaitEvent(pp.A, pp.ev_shadow[slot], 0));       // shadow(k-2) must have drained this queue
-                if (do_sort) timed(tsort, pp.A, [&] { S.kernel_launches += launch_sort(s, pp, pp.q[cur], c + DT_CNT_CUR, 0, pp.A); });
-                timed(th, pp.A, [&] {
-                    DtShadeCounters sc = {c + DT_CNT_NEXT, c + (slot ? DT_CNT_SHADOW2 : DT_CNT_SHADOW), c + DT_CNT_OVERFLOW};
-                    k_shade<<<s->grid_shade, 128, 0, pp.A>>>(s->dev, dc, pp.q[cur], pp.miss[cur], c + DT_CNT_CUR, 0, do_sort ? pp.sort_perm : nullptr, pp.q[1 - cur], pp.miss[1 - cur], pp.capacity,
-                                                            sq, pp.shadow_capacity, sc, s->accum); });
-                CK(cudaEventRecord(pp.ev_shade[slot], pp.A));
-                CK(cudaStreamWaitEvent(pp.B, pp.ev_shade[slot], 0));
-                timed(ts, pp.B, [&] { launch_traverse<true>(s, pp.q[cur], sq, c + (slot ? DT_CNT_SHADOW2 : DT_CNT_SHADOW), 0, c + (slot ? DT_CNT_FETCH_B2 : DT_CNT_FETCH_B), s->accum, pp.B); });
-                CK(cudaEventRecord(pp.ev_shadow[slot], pp.B));
-                if (k >= 1) CK(cudaStreamWaitEvent(pp.A, pp.ev_shadow[1 - slot], 0));    // the other queue's counters are about to be reset
-                k_wave_advance<<<1, 1, 0, pp.A>>>(c, 1 - slot, 1 - slot);
-                S.kernel_launches += 4; S.launches_traverse_closest++;
+                if (p > 0) CK(cudaStreamWaitEvent(pp.A, s->ev_fork, 0));
+                CK(cudaStreamWaitEvent(pp.B, s->ev_fork, 0));
+                timed(tg, pp.A, [&] { k_generate<<<(n0[p] + 255) / 256, 256, 0, pp.A>>>(dc, wps[p], pp.q[0], 0, 0, n0[p], s->accum); });
+                s->h_counters[DT_MAX_PIPES * DT_CNT_COUNT + p] = n0[p];          // pinned scratch past the readback area
+                CK(cudaMemcpyAsync(pp.counters + DT_CNT_CUR, s->h_counters + DT_MAX_PIPES * DT_CNT_COUNT + p, sizeof(int), cudaMemcpyHostToDevice, pp.A));
+                n_launches++;
             }
+            for (int k = 0; k < n_waves; k++) {
+                const int slot = k & 1, cur = k & 1;
+                for (int p = 0; p < NP; p++) {
+                    DtPipe& pp = s->pipes[p];
+                    int* c = pp.counters;
+                    DtShadowQueue& sq = pp.sq[slot];
+                    timed(tc, pp.A, [&] { launch_traverse<false>(s, pp.q[cur], sq, c + DT_CNT_CUR, 0, c + DT_CNT_FETCH_A, s->accum, pp.A); });
+                    if (k >= 2) CK(cudaStreamWaitEvent(pp.A, pp.ev_shadow[slot], 0));       // shadow(k-2) must have drained this queue
+                    if (do_sort) timed(tsort, pp.A, [&] { n_launches += launch_sort(s, pp, pp.q[cur], c + DT_CNT_CUR, 0, pp.A); });
+                    timed(th, pp.A, [&] {
+                        DtShadeCounters sc = {c + DT_CNT_NEXT, c + (slot ? DT_CNT_SHADOW2 : DT_CNT_SHADOW), c + DT_CNT_OVERFLOW};
+                        k_shade<<<s->grid_shade, 128, 0, pp.A>>>(s->dev, dc, pp.q[cur], pp.miss[cur], c + DT_CNT_CUR, 0, do_sort ? pp.sort_perm : nullptr, pp.q[1 - cur], pp.miss[1 - cur], pp.capacity,
+                                                                sq, pp.shadow_capacity, sc, s->accum); });
+                    CK(cudaEventRecord(pp.ev_shade[slot], pp.A));
+                    CK(cudaStreamWaitEvent(pp.B, pp.ev_shade[slot], 0));
+                    timed(ts, pp.B, [&] { launch_traverse<true>(s, pp.q[cur], sq, c + (slot ? DT_CNT_SHADOW2 : DT_CNT_SHADOW), 0, c + (slot ? DT_CNT_FETCH_B2 : DT_CNT_FETCH_B), s->accum, pp.B); });
+                    CK(cudaEventRecord(pp.ev_shadow[slot], pp.B));
+                    if (k >= 1) CK(cudaStreamWaitEvent(pp.A, pp.ev_shadow[1 - slot], 0));    // the other queue's counters are about to be reset
+                    k_wave_advance<<<1, 1, 0, pp.A>>>(c, 1 - slot, 1 - slot);
+                    n_launches += 4; n_closest++;
+                }
+            }
+            for (int p = 0; p < NP; p++) {
+                DtPipe& pp = s->pipes[p];
+                CK(cudaStreamWaitEvent(pp.A, pp.ev_shadow[0], 0));
+                if (n_waves > 1) CK(cudaStreamWaitEvent(pp.A, pp.ev_shadow[1], 0));
+                if (p > 0) { CK(cudaEventRecord(pp.ev_done, pp.A)); CK(cudaStreamWaitEvent(st, pp.ev_done, 0)); }
+            }
+            CK(cudaMemcpyAsync(s->h_counters, s->counters, DT_MAX_PIPES * DT_CNT_COUNT * sizeof(int), cudaMemcpyDeviceToHost, st));
+    return DT_OK;
+        };
+        std::string key;
+        if (s->use_graph) {
+            key.append((const char*)&dc, sizeof dc); key.append((const char*)wps, sizeof(DtWaveParams) * NP); key.append((const char*)n0, sizeof(int) * NP);
+            const int misc[6] = {NP, n_waves, do_sort ? 1 : 0, s->trav_mode, s->refill_threshold, (int)s->dev.n_shapes};
+            key.append((const char*)misc, sizeof misc);
+            const void* ptrs[2] = {s->accum, s->counters};
+            key.append((const char*)ptrs, sizeof ptrs);
+            for (int p = 0; p < NP; p++) { const void* qp[3] = {s->pipes[p].q[0].o_time, s->pipes[p].sq[0].o_time, s->pipes[p].sort_perm}; key.append((const char*)qp, sizeof qp); }
         }
-        for (int p = 0; p < NP; p++) {
-            DtPipe& pp = s->pipes[p];
-            CK(cudaStreamWaitEvent(pp.A, pp.ev_shadow[0], 0));
-            if (n_waves > 1) CK(cudaStreamWaitEvent(pp.A, pp.ev_shadow[1], 0));
-            if (p > 0) { CK(cudaEventRecord(pp.ev_done, pp.A)); CK(cudaStreamWaitEvent(st, pp.ev_done, 0)); }
+        if (s->use_graph && s->frame_graph && key == s->frame_key) {
+            tg = s->g_tg; tc = s->g_tc; th = s->g_th; ts = s->g_ts; tsort = s->g_tsort;
+            n_launches = s->g_launches; n_closest = s->g_closest;
+            CK(cudaGraphLaunch(s->frame_graph, st));
+        } else if (s->use_graph) {
+            if (s->frame_graph) { cudaGraphExecDestroy(s->frame_graph); s->frame_graph = nullptr; s->frame_key.clear(); }
+            while (s->ev_pool.size() < (size_t)(2 * NP * (1 + 4 * n_waves))) { cudaEvent_t e; CK(cudaEventCreate(&e)); s->ev_pool.push_back(e); }   // none created inside the capture
+            s->capturing = true;
+            cudaGraph_t g = nullptr;
+            CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            const int erc = enqueue_frame();
+            const cudaError_t ce = cudaStreamEndCapture(st, &g);
+            s->capturing = false;
+            if (erc) { if (g) cudaGraphDestroy(g); return erc; }
+            if (ce != cudaSuccess || !g) { g_err = std::string("CUDA graph capture of the frame failed: ") + cudaGetErrorString(ce); return DT_ERR_CUDA; }
+            const cudaError_t ie = cudaGraphInstantiate(&s->frame_graph, g, 0);
+            cudaGraphDestroy(g);
+            if (ie != cudaSuccess) { s->frame_graph = nullptr; g_err = std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ie); return DT_ERR_CUDA; }
+            s->frame_key = key;
+            s->g_tg = tg; s->g_tc = tc; s->g_th = th; s->g_ts = ts; s->g_tsort = tsort; s->g_launches = n_launches; s->g_closest = n_closest;
+            CK(cudaGraphLaunch(s->frame_graph, st));
+        } else {
+            if ((rc = enqueue_frame())) return rc;
         }
-        CK(cudaMemcpyAsync(s->h_counters, s->counters, DT_MAX_PIPES * DT_CNT_COUNT * sizeof(int), cudaMemcpyDeviceToHost, st));
+        S.kernel_launches += n_launches; S.launches_traverse_closest += n_closest;
         if (s->debug_timing) fprintf(stderr, "[dt] enqueue of %d pipes x %d waves took %.3f ms on the host\n", NP, n_waves,
                                      1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t_host0).count());
         CK(cudaStreamSynchronize(st));
@@ -621,6 +671,7 @@ int dt_scene_create(const dt_scene_desc* desc, dt_scene** out) {
     if (const char* e = getenv("DT_TRAVERSE_MODE")) s->trav_mode = std::min(3, std::max(0, atoi(e)));
     if (const char* e = getenv("DT_SYNC_WAVES")) s->sync_waves = atoi(e);
     if (const char* e = getenv("DT_SORT")) s->sort_mode = std::min(2, std::max(0, atoi(e)));
+    if (const char* e = getenv("DT_GRAPH")) s->use_graph = atoi(e);
     if (const char* e = getenv("DT_DEBUG_TIMING")) s->debug_timing = atoi(e);
     if (const char* e = getenv("DT_PIPES")) s->n_pipes_env = std::min(DT_MAX_PIPES, std::max(0, atoi(e)));
     if (const char* e = getenv("DT_REFILL_THRESHOLD")) s->refill_threshold = std::min(32, std::max(1, atoi(e)));
@@ -658,6 +709,7 @@ void dt_scene_destroy(dt_scene* s) {
     if (s->tm_rank) cudaFree(s->tm_rank);
     if (s->tm_prefix) cudaFree(s->tm_prefix);
     for (Timer* t : {&s->t_total, &s->t_gen, &s->t_closest, &s->t_shadow, &s->t_shade, &s->t_sort, &s->t_resolve, &s->t_tm}) t->destroy();
+    if (s->frame_graph) cudaGraphExecDestroy(s->frame_graph);
     for (cudaEvent_t e : s->ev_pool) cudaEventDestroy(e);
     for (int p = 0; p < DT_MAX_PIPES; p++) {
         DtPipe& pp = s->pipes[p];
