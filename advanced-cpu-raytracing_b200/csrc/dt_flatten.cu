@@ -23,7 +23,9 @@ struct Child { int node; float mn[3], mx[3]; bool leaf; uint32_t first, count; }
 
 }  // namespace
 
-bool dt_collapse_bvh8(const std::vector<DtB2Node>& b2, DtWideBvh& out, std::string& err) {
+bool dt_collapse_bvh8(const std::vector<DtB2Node>& b2, DtWideBvh& out, std::string& err, int max_leaf) {
+    if (max_leaf < 1) max_leaf = 1;
+    if (max_leaf > 3) max_leaf = 3;
     out.nodes.clear(); out.prim_order.clear(); out.max_depth = 0;
     if (b2.empty()) { err = "empty tree"; return false; }
     struct Work { int b2node; uint32_t out_index; int depth; };
@@ -31,7 +33,7 @@ bool dt_collapse_bvh8(const std::vector<DtB2Node>& b2, DtWideBvh& out, std::stri
     out.nodes.emplace_back();
     queue.push_back({0, 0u, 1});
     size_t qh = 0;
-    auto is_leaf = [&](int n) { return b2[n].left < 0 || b2[n].count <= 3; };
+    auto is_leaf = [&](int n) { return b2[n].left < 0 || (int)b2[n].count <= max_leaf; };
     while (qh < queue.size()) {
         Work w = queue[qh++];
         out.max_depth = std::max(out.max_depth, w.depth);
@@ -222,6 +224,10 @@ bool dt_flatten_scene(const dt_scene_desc* d, DtHostScene& out, std::string& err
     std::map<const float*, uint32_t> vert_off, uv_off;
     out.meshes.resize((size_t)d->n_meshes);
     int blas_depth = 0;
+    // triangles per BVH8 leaf child (1..3): smaller leaves = one quantised box per triangle = fewer exact triangle tests per ray,
+    // at the price of more nodes (measured in profiles/r1_ab_leaf_size.log)
+    int blas_leaf = DT_BLAS_LEAF_TRIS;
+    if (const char* e = getenv("DT_LEAF_TRIS")) blas_leaf = atoi(e);
     for (int mi = 0; mi < d->n_meshes; mi++) {
         const dt_mesh& m = d->meshes[mi];
         if (m.n_faces <= 0 || !m.faces || !m.bvh || m.n_bvh_nodes <= 0 || !m.vertices) { err = "mesh " + std::to_string(mi) + " is empty"; return false; }
@@ -300,7 +306,7 @@ bool dt_flatten_scene(const dt_scene_desc* d, DtHostScene& out, std::string& err
         };
         split_big_leaves(b2, tri_box);
         DtWideBvh wide;
-        if (!dt_collapse_bvh8(b2, wide, err)) return false;
+        if (!dt_collapse_bvh8(b2, wide, err, blas_leaf)) return false;
         blas_depth = std::max(blas_depth, wide.max_depth);
         md.node_root = (uint32_t)out.blas_nodes.size();
         uint32_t node_off = md.node_root, prim_off = (uint32_t)(out.tris.size() / 3);
@@ -400,7 +406,9 @@ bool dt_flatten_scene(const dt_scene_desc* d, DtHostScene& out, std::string& err
             b2[(size_t)t.node] = nd;
         }
         DtWideBvh wide;
-        if (!dt_collapse_bvh8(b2, wide, err)) return false;
+        int tlas_leaf = DT_TLAS_LEAF_SHAPES;
+        if (const char* e = getenv("DT_TLAS_LEAF")) tlas_leaf = atoi(e);
+        if (!dt_collapse_bvh8(b2, wide, err, tlas_leaf)) return false;
         out.tlas_nodes = wide.nodes;
         out.tlas_prims.resize(wide.prim_order.size());
         for (size_t k = 0; k < wide.prim_order.size(); k++) out.tlas_prims[k] = (int32_t)order[wide.prim_order[k]];

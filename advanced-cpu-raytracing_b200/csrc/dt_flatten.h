@@ -19,7 +19,9 @@ struct DtB2Node {
 
 // Collapse a binary tree (root = node 0, leaves of <= 3 primitives) into a BVH8 with 8-bit quantised child
 // boxes rounded outward.  Returns false (err filled) if the tree is malformed.
-bool dt_collapse_bvh8(const std::vector<DtB2Node>& b2, DtWideBvh& out, std::string& err);
+#define DT_BLAS_LEAF_TRIS 1        // triangles per BVH8 leaf child (measured: 1 beats 2 and 3 on configs 2, 3 and 5)
+#define DT_TLAS_LEAF_SHAPES 3      // shapes per TLAS leaf child
+bool dt_collapse_bvh8(const std::vector<DtB2Node>& b2, DtWideBvh& out, std::string& err, int max_leaf = 3);
 
 struct DtHostScene {
     // everything that gets uploaded, in upload layout
