@@ -623,6 +623,7 @@ int dt_scene_create(const dt_scene_desc* desc, dt_scene** out) {
     if ((rc = upload<int32_t>(s->allocs, hs.tlas_prims.data(), hs.tlas_prims.size(), &D.tlas_prims))) return fail(rc);
     if ((rc = upload<float4>(s->allocs, hs.tris.data(), hs.tris.size(), &D.tris))) return fail(rc);
     if ((rc = upload<float4>(s->allocs, hs.leaf_boxes.data(), hs.leaf_boxes.size(), &D.leaf_boxes))) return fail(rc);
+    if ((rc = upload<uint32_t>(s->allocs, hs.face_prim.data(), hs.face_prim.size(), &D.face_prim))) return fail(rc);
     if ((rc = upload<DtShapeDev>(s->allocs, hs.shapes.data(), hs.shapes.size(), &D.shapes))) return fail(rc);
     if ((rc = upload<DtMeshDev>(s->allocs, hs.meshes.data(), hs.meshes.size(), &D.meshes))) return fail(rc);
     if ((rc = upload<DtFaceDev>(s->allocs, hs.faces.data(), hs.faces.size(), &D.faces))) return fail(rc);

@@ -17,13 +17,15 @@
 
 #define DT_STACK_SIZE 48          // traversal stack entries (uint2) per ray; build verifies the trees fit
 
-// 80-byte compressed wide-BVH node, five 16-byte words (Ylitie, Karras, Laine 2017 layout).
+// 80-byte compressed wide-BVH node, five 16-byte words (after Ylitie, Karras, Laine 2017; every leaf child is one primitive,
+// so the per-slot meta bytes of that layout shrink to one leaf mask and the node test returns a plain 8-bit slot mask).
 struct DtNode8 {
     float px, py, pz;             // quantisation origin
     uint8_t ex, ey, ez, imask;    // per-axis exponent (biased, as float exponent bits), internal-child mask
     uint32_t child_base;          // index of first internal child (children are stored compactly)
     uint32_t prim_base;           // index of first primitive referenced by this node's leaf children
-    uint8_t meta[8];              // per child slot: internal: 0b001_11sss, leaf: (unary count)<<5 | offset, empty 0
+    uint8_t lmask;                // leaf-child mask: slot s holds exactly ONE primitive, prim_base + popc(lmask & ((1 << s) - 1))
+    uint8_t pad[7];
     uint8_t qlox[8], qloy[8], qloz[8], qhix[8], qhiy[8], qhiz[8];
 };
 static_assert(sizeof(DtNode8) == 80, "DtNode8 must be 80 bytes");
@@ -75,6 +77,7 @@ struct DtSceneDev {
     const uint4* blas_nodes;
     const float4* tris;           // 3 x float4 per triangle, BVH8 leaf order
     const float4* leaf_boxes;     // 2 x float4 per triangle (same order): bbox of the reference BVH2 leaf that holds it
+    const uint32_t* face_prim;    // canonical face -> index into tris / leaf_boxes (rare path: dt_best_survives)
     // shading data
     const DtShapeDev* shapes;
     const DtMeshDev* meshes;

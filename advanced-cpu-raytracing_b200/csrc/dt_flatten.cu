@@ -23,9 +23,7 @@ struct Child { int node; float mn[3], mx[3]; bool leaf; uint32_t first, count; }
 
 }  // namespace
 
-bool dt_collapse_bvh8(const std::vector<DtB2Node>& b2, DtWideBvh& out, std::string& err, int max_leaf) {
-    if (max_leaf < 1) max_leaf = 1;
-    if (max_leaf > 3) max_leaf = 3;
+bool dt_collapse_bvh8(const std::vector<DtB2Node>& b2, DtWideBvh& out, std::string& err) {
     out.nodes.clear(); out.prim_order.clear(); out.max_depth = 0;
     if (b2.empty()) { err = "empty tree"; return false; }
     struct Work { int b2node; uint32_t out_index; int depth; };
@@ -33,7 +31,7 @@ bool dt_collapse_bvh8(const std::vector<DtB2Node>& b2, DtWideBvh& out, std::stri
     out.nodes.emplace_back();
     queue.push_back({0, 0u, 1});
     size_t qh = 0;
-    auto is_leaf = [&](int n) { return b2[n].left < 0 || (int)b2[n].count <= max_leaf; };
+    auto is_leaf = [&](int n) { return b2[n].left < 0 || b2[n].count <= 1; };       // every leaf child is ONE primitive
     while (qh < queue.size()) {
         Work w = queue[qh++];
         out.max_depth = std::max(out.max_depth, w.depth);
@@ -133,20 +131,16 @@ bool dt_collapse_bvh8(const std::vector<DtB2Node>& b2, DtWideBvh& out, std::stri
         node.prim_base = (uint32_t)out.prim_order.size();
         out.nodes.resize(out.nodes.size() + (size_t)n_internal);
         uint32_t next_child = node.child_base;
-        uint32_t prim_off = 0;
         for (int s = 0; s < 8; s++) {
             int k = child_in_slot[s];
-            if (k < 0) { node.meta[s] = 0; continue; }
+            if (k < 0) continue;
             int c = ch[k];
             if (is_leaf(c)) {
-                uint32_t cnt = b2[c].count;
-                if (cnt == 0 || cnt > 3) { err = "leaf with unsupported primitive count"; return false; }
-                node.meta[s] = (uint8_t)((((1u << cnt) - 1u) << 5) | prim_off);
-                for (uint32_t i = 0; i < cnt; i++) out.prim_order.push_back(b2[c].first + i);
-                prim_off += cnt;
+                if (b2[c].count != 1) { err = "leaf with unsupported primitive count (the binary tree must be split down to single primitives)"; return false; }
+                node.lmask |= (uint8_t)(1u << s);
+                out.prim_order.push_back(b2[c].first);                  // slot order == primitive order within the node
             } else {
                 node.imask |= (uint8_t)(1u << s);
-                node.meta[s] = (uint8_t)((1u << 5) | (24u + (uint32_t)s));
                 queue.push_back({c, next_child++, w.depth + 1});
             }
             node.qlox[s] = qlo[0][s]; node.qloy[s] = qlo[1][s]; node.qloz[s] = qlo[2][s];
@@ -159,13 +153,13 @@ bool dt_collapse_bvh8(const std::vector<DtB2Node>& b2, DtWideBvh& out, std::stri
 
 namespace {
 
-// Make sure every leaf of a binary tree holds <= 3 primitives by splitting large leaf ranges in halves
+// Make sure every leaf of a binary tree holds ONE primitive by splitting larger leaf ranges in halves
 // (the reference build leaves a multi-face leaf when a midpoint split puts every centroid on one side,
 // mesh.cpp:104-106).  prim_box(i, mn, mx) yields the box of primitive i.
 template <class BoxFn>
 void split_big_leaves(std::vector<DtB2Node>& b2, BoxFn prim_box) {
     for (size_t i = 0; i < b2.size(); i++) {
-        if (b2[i].left >= 0 || b2[i].count <= 3) continue;
+        if (b2[i].left >= 0 || b2[i].count <= 1) continue;
         uint32_t first = b2[i].first, count = b2[i].count;
         uint32_t lc = count / 2;
         DtB2Node l, r;
@@ -224,10 +218,6 @@ bool dt_flatten_scene(const dt_scene_desc* d, DtHostScene& out, std::string& err
     std::map<const float*, uint32_t> vert_off, uv_off;
     out.meshes.resize((size_t)d->n_meshes);
     int blas_depth = 0;
-    // triangles per BVH8 leaf child (1..3): smaller leaves = one quantised box per triangle = fewer exact triangle tests per ray,
-    // at the price of more nodes (measured in profiles/r1_ab_leaf_size.log)
-    int blas_leaf = DT_BLAS_LEAF_TRIS;
-    if (const char* e = getenv("DT_LEAF_TRIS")) blas_leaf = atoi(e);
     for (int mi = 0; mi < d->n_meshes; mi++) {
         const dt_mesh& m = d->meshes[mi];
         if (m.n_faces <= 0 || !m.faces || !m.bvh || m.n_bvh_nodes <= 0 || !m.vertices) { err = "mesh " + std::to_string(mi) + " is empty"; return false; }
@@ -306,12 +296,14 @@ bool dt_flatten_scene(const dt_scene_desc* d, DtHostScene& out, std::string& err
         };
         split_big_leaves(b2, tri_box);
         DtWideBvh wide;
-        if (!dt_collapse_bvh8(b2, wide, err, blas_leaf)) return false;
+        if (!dt_collapse_bvh8(b2, wide, err)) return false;
         blas_depth = std::max(blas_depth, wide.max_depth);
         md.node_root = (uint32_t)out.blas_nodes.size();
         uint32_t node_off = md.node_root, prim_off = (uint32_t)(out.tris.size() / 3);
         for (DtNode8 n : wide.nodes) { n.child_base += node_off; n.prim_base += prim_off; out.blas_nodes.push_back(n); }
+        out.face_prim.resize(out.faces.size(), 0);
         for (uint32_t f : wide.prim_order) {
+            out.face_prim[md.face_base + f] = (uint32_t)(out.tris.size() / 3);         // canonical face -> leaf-order slot
             const DtFaceDev& fd = out.faces[md.face_base + f];
             const float* a = &V[(size_t)fd.v0 * 3]; const float* b = &V[(size_t)fd.v1 * 3]; const float* c = &V[(size_t)fd.v2 * 3];
             // e1 = v0 - v1, e2 = v0 - v2: the float subtractions of mesh.cpp:208-210 (host compiled without FMA)
@@ -392,7 +384,7 @@ bool dt_flatten_scene(const dt_scene_desc* d, DtHostScene& out, std::string& err
                     cmn[a] = std::min(cmn[a], c); cmx[a] = std::max(cmx[a], c);
                 }
             }
-            if (t.count > 3) {
+            if (t.count > 1) {
                 int axis = 0; float best = cmx[0] - cmn[0];
                 for (int a = 1; a < 3; a++) if (cmx[a] - cmn[a] > best) { best = cmx[a] - cmn[a]; axis = a; }
                 uint32_t half = t.count / 2;
@@ -406,9 +398,7 @@ bool dt_flatten_scene(const dt_scene_desc* d, DtHostScene& out, std::string& err
             b2[(size_t)t.node] = nd;
         }
         DtWideBvh wide;
-        int tlas_leaf = DT_TLAS_LEAF_SHAPES;
-        if (const char* e = getenv("DT_TLAS_LEAF")) tlas_leaf = atoi(e);
-        if (!dt_collapse_bvh8(b2, wide, err, tlas_leaf)) return false;
+        if (!dt_collapse_bvh8(b2, wide, err)) return false;
         out.tlas_nodes = wide.nodes;
         out.tlas_prims.resize(wide.prim_order.size());
         for (size_t k = 0; k < wide.prim_order.size(); k++) out.tlas_prims[k] = (int32_t)order[wide.prim_order[k]];

@@ -19,9 +19,7 @@ struct DtB2Node {
 
 // Collapse a binary tree (root = node 0, leaves of <= 3 primitives) into a BVH8 with 8-bit quantised child
 // boxes rounded outward.  Returns false (err filled) if the tree is malformed.
-#define DT_BLAS_LEAF_TRIS 1        // triangles per BVH8 leaf child (measured: 1 beats 2 and 3 on configs 2, 3 and 5)
-#define DT_TLAS_LEAF_SHAPES 3      // shapes per TLAS leaf child
-bool dt_collapse_bvh8(const std::vector<DtB2Node>& b2, DtWideBvh& out, std::string& err, int max_leaf = 3);
+bool dt_collapse_bvh8(const std::vector<DtB2Node>& b2, DtWideBvh& out, std::string& err);
 
 struct DtHostScene {
     // everything that gets uploaded, in upload layout
@@ -30,6 +28,7 @@ struct DtHostScene {
     std::vector<DtNode8> blas_nodes;
     std::vector<float4> tris;
     std::vector<float4> leaf_boxes;
+    std::vector<uint32_t> face_prim;      // canonical face (DtMeshDev::face_base + f) -> index into tris / leaf_boxes
     std::vector<DtShapeDev> shapes;
     std::vector<DtMeshDev> meshes;
     std::vector<DtFaceDev> faces;

@@ -99,22 +99,10 @@ __device__ __forceinline__ void dt_prep(DtRayPrep& r, v3 o, v3 d) {
     r.oct_inv4 = oct * 0x01010101u;
 }
 
-__device__ __forceinline__ uint32_t dt_sign_extend_s8x4(uint32_t x) {
-    // each byte's top bit replicated over the byte
-    return ((x >> 7) & 0x01010101u) * 0xFFu;
-}
-__device__ __forceinline__ uint32_t dt_byte(uint32_t w, int j) { return (w >> (j * 8)) & 0xFFu; }
-// byte j of w as an exact float without the slow I2F pipe: PRMT builds 0x4B0000qq = 2^23 + q, one FADD removes 2^23.
-__device__ __forceinline__ float dt_byte_f(uint32_t w, int j) {
-    return __fadd_rn(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440u | (uint32_t)j)), -8388608.0f);
-}
+#define DT_SLACK_BOTH 1.0000039f   // (1 + 2^-19) / (1 - 2^-19): conservative inflation of the slab interval against FMA / rcp rounding,
+                                   // folded onto the far side (tn >= 0, so tn*LO <= tf*HI <=> tn <= tf*HI/LO)
 
-#define DT_SLACK_HI 1.0000019f     // 1 + 2^-19: conservative inflation of the slab interval against FMA/rcp rounding
-#define DT_SLACK_LO 0.9999981f
-#define DT_SLACK_BOTH 1.0000039f   // HI / LO folded onto the far side (tn >= 0, so tn*LO <= tf*HI <=> tn <= tf*HI/LO)
-
-#ifndef DT_NODE_V1
-// byte j of w placed in mantissa bits 8..15 of 1.0f: 0x3F80qq00 = 1 + q * 2^-15, ONE PRMT and no int->float conversion.
+// byte J of w placed in mantissa bits 8..15 of 1.0f: 0x3F80qq00 = 1 + q * 2^-15, ONE PRMT and no int->float conversion.
 // The plane distance q*a + b is then evaluated as m*A + B with A = 2^15 * a (exponent bump, exact) and B = b - A
 // (one rounding of magnitude <= 2^-24 * 2^15 |a| = 2^-9 quantisation steps, absorbed by the 1/128-step margin the
 // flattener adds when it rounds child boxes outward).
@@ -127,10 +115,9 @@ __device__ __forceinline__ float dt_byte_m(uint32_t w, uint32_t one) {
     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(one), "n"(0x7604 | (J << 4)));
     return __uint_as_float(r);
 }
-#endif
 
 // Blackwell packed FP32: one FFMA2 evaluates the near and the far plane distance of an axis, (qn, qf) * a + b, with the same
-// round-to-nearest as two FFMAs -- the node test is issue-bound, and its 48 plane evaluations become 24 instructions.
+// round-to-nearest as two FFMAs.
 __device__ __forceinline__ void dt_fma2(float qn, float qf, float a, float b, float& tn, float& tf) {
     unsigned long long q, aa, bb, r;
     asm("mov.b64 %0, {%1, %2};" : "=l"(q) : "f"(qn), "f"(qf));
@@ -140,64 +127,48 @@ __device__ __forceinline__ void dt_fma2(float qn, float qf, float a, float b, fl
     asm("mov.b64 {%0, %1}, %2;" : "=f"(tn), "=f"(tf) : "l"(r));
 }
 
-// Test the 8 quantised child boxes of a node; returns the hit mask (top 8 bits: internal children in
-// traversal-priority order, low 24 bits: primitives of hit leaf children).
-__device__ __forceinline__ uint32_t dt_node_hits(const uint4 n0, const uint4 n1, const uint4 n2, const uint4 n3, const uint4 n4,
-                                                 const DtRayPrep& r, float tmax, const uint32_t one) {
+// Test the 8 quantised child boxes of a node against the ray: bit s of the result = the box in child slot s is hit within
+// [0, tmax] (conservatively).  The ALU pipe (PRMT, min/max, logic) is what this routine saturates, so the result is a plain
+// slot mask -- one predicated OR per child -- and the caller derives visiting order and primitive indices from two masks.
+__device__ __forceinline__ uint32_t dt_node_hits(const uint4 n0, const uint4 n2, const uint4 n3, const uint4 n4, const DtRayPrep& r, float tmax, const uint32_t one) {
     const uint32_t e_imask = n0.w;
-#ifdef DT_NODE_V1
-    const float ax = __fmul_rn(__uint_as_float((e_imask & 0xFFu) << 23), r.idx);
-    const float ay = __fmul_rn(__uint_as_float(((e_imask >> 8) & 0xFFu) << 23), r.idy);
-    const float az = __fmul_rn(__uint_as_float(((e_imask >> 16) & 0xFFu) << 23), r.idz);
-    const float bx = __fmul_rn(__fsub_rn(__uint_as_float(n0.x), r.o.x), r.idx);
-    const float by = __fmul_rn(__fsub_rn(__uint_as_float(n0.y), r.o.y), r.idy);
-    const float bz = __fmul_rn(__fsub_rn(__uint_as_float(n0.z), r.o.z), r.idz);
-#define DT_QF(w, j) dt_byte_f(w, j)
-#else
     const float ax = __fmul_rn(__uint_as_float(((e_imask & 0xFFu) + 15u) << 23), r.idx);
     const float ay = __fmul_rn(__uint_as_float((((e_imask >> 8) & 0xFFu) + 15u) << 23), r.idy);
     const float az = __fmul_rn(__uint_as_float((((e_imask >> 16) & 0xFFu) + 15u) << 23), r.idz);
     const float bx = __fmaf_rn(__fsub_rn(__uint_as_float(n0.x), r.o.x), r.idx, -ax);
     const float by = __fmaf_rn(__fsub_rn(__uint_as_float(n0.y), r.o.y), r.idy, -ay);
     const float bz = __fmaf_rn(__fsub_rn(__uint_as_float(n0.z), r.o.z), r.idz, -az);
-#define DT_QF(w, j) dt_byte_m<j>(w, one)
-#endif
-    uint32_t hitmask = 0;
+    uint32_t h = 0;
 #pragma unroll
     for (int half = 0; half < 2; half++) {
-        const uint32_t meta4 = half ? n1.w : n1.z;
-        const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
-        const uint32_t inner_mask4 = dt_sign_extend_s8x4(is_inner4 << 3);
-        const uint32_t bit_index4 = (meta4 ^ (r.oct_inv4 & inner_mask4)) & 0x1F1F1F1Fu;
-        const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
         const uint32_t qlox = half ? n2.y : n2.x, qloy = half ? n2.w : n2.z, qloz = half ? n3.y : n3.x;
         const uint32_t qhix = half ? n3.w : n3.z, qhiy = half ? n4.y : n4.x, qhiz = half ? n4.w : n4.z;
         const uint32_t nx = r.idx < 0.f ? qhix : qlox, fx = r.idx < 0.f ? qlox : qhix;
         const uint32_t ny = r.idy < 0.f ? qhiy : qloy, fy = r.idy < 0.f ? qloy : qhiy;
         const uint32_t nz = r.idz < 0.f ? qhiz : qloz, fz = r.idz < 0.f ? qloz : qhiz;
-#ifdef DT_NODE_V1
-#define DT_CHILD(j) { \
-            const float tnx = __fmaf_rn(DT_QF(nx, j), ax, bx), tny = __fmaf_rn(DT_QF(ny, j), ay, by), tnz = __fmaf_rn(DT_QF(nz, j), az, bz); \
-            const float tfx = __fmaf_rn(DT_QF(fx, j), ax, bx), tfy = __fmaf_rn(DT_QF(fy, j), ay, by), tfz = __fmaf_rn(DT_QF(fz, j), az, bz); \
-            const float tn = __fmul_rn(fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f)), DT_SLACK_LO); \
-            const float tf = __fmul_rn(fminf(fminf(tfx, tfy), fminf(tfz, tmax)), DT_SLACK_HI); \
-            if (tn <= tf) hitmask |= dt_byte(child_bits4, j) << dt_byte(bit_index4, j); }
-#else
         // fminf/fmaxf drop NaNs (0*inf on axis-parallel rays): a NaN constraint is ignored = conservative
 #define DT_CHILD(j) { \
             float tnx, tny, tnz, tfx, tfy, tfz; \
-            dt_fma2(DT_QF(nx, j), DT_QF(fx, j), ax, bx, tnx, tfx); \
-            dt_fma2(DT_QF(ny, j), DT_QF(fy, j), ay, by, tny, tfy); \
-            dt_fma2(DT_QF(nz, j), DT_QF(fz, j), az, bz, tnz, tfz); \
+            dt_fma2(dt_byte_m<j>(nx, one), dt_byte_m<j>(fx, one), ax, bx, tnx, tfx); \
+            dt_fma2(dt_byte_m<j>(ny, one), dt_byte_m<j>(fy, one), ay, by, tny, tfy); \
+            dt_fma2(dt_byte_m<j>(nz, one), dt_byte_m<j>(fz, one), az, bz, tnz, tfz); \
             const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f)); \
             const float tf = __fmul_rn(fminf(fminf(tfx, tfy), fminf(tfz, tmax)), DT_SLACK_BOTH); \
-            if (tn <= tf) hitmask |= dt_byte(child_bits4, j) << dt_byte(bit_index4, j); }
-#endif
+            if (tn <= tf) h |= 1u << (half * 4 + j); }
         DT_CHILD(0) DT_CHILD(1) DT_CHILD(2) DT_CHILD(3)
 #undef DT_CHILD
     }
-#undef DT_QF
-    return hitmask;
+    return h;
+}
+
+// Visiting order of the inner children: the child in slot s gets priority (s ^ oct) -- slots are assigned along the octant
+// corners by the flattener, so this is front-to-back for the ray's direction octant (oct = 7 - octant).  XOR with a constant
+// permutes the 8 mask bits: three conditional swaps (adjacent bits, bit pairs, nibbles).
+__device__ __forceinline__ uint32_t dt_perm8(uint32_t x, uint32_t oct) {
+    if (oct & 1u) x = ((x & 0x55u) << 1) | ((x >> 1) & 0x55u);
+    if (oct & 2u) x = ((x & 0x33u) << 2) | ((x >> 2) & 0x33u);
+    if (oct & 4u) x = ((x & 0x0Fu) << 4) | ((x >> 4) & 0x0Fu);
+    return x;
 }
 
 // Certificate for the accept-time leaf-box confirmation: true only when BoundingBox::doesIntersectWith (shape.hpp:78-100)
@@ -276,7 +247,7 @@ __device__ __forceinline__ void dt_trav_init(DtTrav& T, const DtSceneDev& S, v3 
     T.blas_sp = 0; T.cur_shape = -1; T.sp = 0;
     // root as the single "child" of a virtual group; a scene of a few shapes skips the TLAS node test and starts with the
     // shape list (a primitive group), which is what the reference's linear scan does (raytracer.cpp:625-643)
-    T.ng = S.tlas_direct > 0 ? make_uint2(0u, (1u << S.tlas_direct) - 1u) : make_uint2(0u, 0x80000000u);
+    T.ng = S.tlas_direct > 0 ? make_uint2(0u, ((1u << S.tlas_direct) - 1u) * 0x101u) : make_uint2(0u, 0x80000000u);       // hit slots | leaf mask << 8
     T.tg = make_uint2(0u, 0u);
 }
 
@@ -294,12 +265,15 @@ __device__ __forceinline__ void dt_trav_node(DtTrav& T, uint2* __restrict__ stac
     const uint32_t ni = T.ng.x + rel;
     const uint4* np = (T.cur_shape >= 0 ? S.blas_nodes : S.tlas_nodes) + (size_t)ni * 5;
     const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
-    const uint32_t hm = dt_node_hits(n0, n1, n2, n3, n4, T.r, T.best.t, one);
+    const uint32_t h = dt_node_hits(n0, n2, n3, n4, T.r, T.best.t, one);
+    const uint32_t im = n0.w >> 24, lm = n1.z & 0xFFu;
+    const uint32_t hi = h & im, hl = h & lm;
+    // node group: inner hits in visiting priority at bits 24..31 + the node's inner mask (a group without hits reads as empty);
+    // primitive group: hit leaf slots at bits 0..7 + the node's leaf mask at bits 8..15 (slot -> primitive index by popcount)
     T.ng.x = n1.x;
-    // a group without node hits must read as empty (a remnant imask would look like a primitive group)
-    T.ng.y = (hm & 0xFF000000u) ? ((hm & 0xFF000000u) | (n0.w >> 24)) : 0u;
+    T.ng.y = hi ? ((dt_perm8(hi, T.r.oct_inv4 & 7u) << 24) | im) : 0u;
     T.tg.x = n1.y;
-    T.tg.y = hm & 0x00FFFFFFu;
+    T.tg.y = hl ? (hl | (lm << 8)) : 0u;
 }
 
 // World -> local ray (mesh.cpp:164-170, sphere.cpp:23-30, instancedMesh.cpp:33-39).  For an identity inverseTransform the
@@ -316,13 +290,43 @@ __device__ __forceinline__ void dt_to_local(const DtShapeDev* sh, v3 wo, v3 wd, 
     if (sh->has_motion_blur) lo = vadd(lo, vscale(F3(sh->motion_blur), ray_o->w));       // motionBlurTime of this ray
 }
 
+// Scan-order exactness when the visiting order differs from the reference's.  The reference scans (shape, face) in ascending
+// order and tests every box with the minT it holds at that moment.  If a candidate c that PRECEDES the current best b in scan
+// order arrives later with t_c a few ulps ABOVE t_b (two surfaces meeting at an edge or corner), the reference would have held
+// minT = t_c when it reached b, and b's own box tests (shape box, mesh box, BVH2 leaf box: `tmin < minT`) may have rejected b
+// -- flat boxes put tmin within an ulp of t_b.  This re-runs b's box tests exactly with minT = t_c.  Rare path (~1e-6 of rays).
+__device__ __noinline__ bool dt_best_survives(const DtSceneDev& S, const DtHit& b, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d, float minT) {
+    const DtShapeDev* sh = S.shapes + b.shape;
+    if (sh->kind == DT_SHAPE_SPHERE) return true;                          // Sphere::Intersect has no box test
+    const float4 o4 = *ray_o, d4 = *ray_d;
+    const v3 wo = V(o4.x, o4.y, o4.z), wd = V(d4.x, d4.y, d4.z);
+    if (sh->kind == DT_SHAPE_INSTANCE) {
+        v3 so = wo;
+        if (sh->has_motion_blur) so = vadd(so, vscale(F3(sh->motion_blur), o4.w));
+        if (!box_intersect_exact(sh->bbox_min, sh->bbox_max, so, wd, minT)) return false;
+    }
+    v3 lo, ld;
+    dt_to_local(sh, wo, wd, ray_o, lo, ld);
+    const DtMeshDev* m = S.meshes + sh->mesh;
+    if (!box_intersect_exact(m->bbox_min, m->bbox_max, lo, ld, minT)) return false;
+    const uint32_t prim = __ldg(S.face_prim + m->face_base + (uint32_t)b.face);
+    const float4 lb0 = __ldg(S.leaf_boxes + (size_t)prim * 2), lb1 = __ldg(S.leaf_boxes + (size_t)prim * 2 + 1);
+    const float lmn[3] = {lb0.x, lb0.y, lb0.z}, lmx[3] = {lb1.x, lb1.y, lb1.z};
+    return box_intersect_exact(lmn, lmx, lo, ld, minT);
+}
+// c = (shape, face) precedes the best hit in the reference's scan order and lies within a few ulps behind it
+__device__ __forceinline__ bool dt_close_behind(float t, int shape, int face, const DtHit& best) {
+    return best.shape >= 0 && t > best.t && t <= __fmul_rn(best.t, 1.000001f) && (shape < best.shape || (shape == best.shape && face < best.face));
+}
+
 // One primitive of the current primitive group.  Returns true when an ANY query is decided (occluded).
 template <bool ANY>
-__device__ __forceinline__ bool dt_trav_prim(DtTrav& T, uint2* __restrict__ stack, const DtSceneDev& S, const float4* __restrict__ ray_o, bool& entered_blas) {
+__device__ __forceinline__ bool dt_trav_prim(DtTrav& T, uint2* __restrict__ stack, const DtSceneDev& S, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d, bool& entered_blas) {
     DtHit& best = T.best;
-    const int bit = __ffs(T.tg.y) - 1;
+    const int bit = __ffs(T.tg.y & 0xFFu) - 1;                                   // next hit leaf slot of the group
+    const uint32_t prim = T.tg.x + (uint32_t)__popc((T.tg.y >> 8) & ((1u << bit) - 1u));
     T.tg.y &= ~(1u << bit);
-    const uint32_t prim = T.tg.x + (uint32_t)bit;
+    if ((T.tg.y & 0xFFu) == 0u) T.tg.y = 0u;
     if (T.cur_shape >= 0) {
         DT_STAT(1);
         const float4* tp = S.tris + (size_t)prim * 3;
@@ -350,6 +354,13 @@ __device__ __forceinline__ bool dt_trav_prim(DtTrav& T, uint2* __restrict__ stac
                     best.t = t; best.beta = beta; best.gamma = gamma; best.shape = T.cur_shape; best.face = face;
                     if (ANY) return true;
                 }
+            } else if (!ANY && t > 0.0f && dt_close_behind(t, T.cur_shape, face, best)) {
+                // scanned BEFORE the best hit by the reference: valid on its own (minT = infinity)?  then the best hit must survive minT = t
+                const float4 lb0 = __ldg(S.leaf_boxes + (size_t)prim * 2), lb1 = __ldg(S.leaf_boxes + (size_t)prim * 2 + 1);
+                const float lmn[3] = {lb0.x, lb0.y, lb0.z}, lmx[3] = {lb1.x, lb1.y, lb1.z};
+                if (box_intersect_exact(lmn, lmx, T.r.o, T.r.d, CUDART_INF_F) && !dt_best_survives(S, best, ray_o, ray_d, t)) {
+                    best.t = t; best.beta = beta; best.gamma = gamma; best.shape = T.cur_shape; best.face = face;
+                }
             }
         }
         return false;
@@ -367,6 +378,8 @@ __device__ __forceinline__ bool dt_trav_prim(DtTrav& T, uint2* __restrict__ stac
             if (ANY) {
                 if (t > 0.0f && t < best.t) { best.shape = si; best.face = -1; best.t = t; return true; }
             } else if (t > 0.0f && dt_better(t, si, -1, best)) {
+                best.t = t; best.beta = 0.f; best.gamma = 0.f; best.shape = si; best.face = -1;
+            } else if (t > 0.0f && dt_close_behind(t, si, -1, best) && !dt_best_survives(S, best, ray_o, ray_d, t)) {
                 best.t = t; best.beta = 0.f; best.gamma = 0.f; best.shape = si; best.face = -1;
             }
         }
@@ -415,7 +428,7 @@ __device__ __forceinline__ bool dt_trav_step(DtTrav& T, uint2* __restrict__ stac
     }
     while (T.tg.y != 0u) {
         bool entered = false;
-        if (dt_trav_prim<ANY>(T, stack, S, ray_o, entered)) return true;
+        if (dt_trav_prim<ANY>(T, stack, S, ray_o, ray_d, entered)) return true;
         if (entered) break;
     }
     if (T.ng.y <= 0x00FFFFFFu && T.tg.y == 0u) {
