@@ -12,12 +12,12 @@ from dtb200 import scenegen
 cfg = sys.argv[1]
 t0 = time.time()
 if cfg == 'c3': p = scenegen.gen_config3('/tmp/gen/c3')
-elif cfg == 'c4': p = scenegen.gen_config4('/tmp/gen/c4', spp=16)
-elif cfg == 'c5': p = scenegen.gen_config5('/tmp/gen/c5', spp=4)
+elif cfg == 'c4': p = scenegen.gen_config4('/tmp/gen/c4', spp=int(os.environ.get('DT_AB_SPP', '16')))
+elif cfg == 'c5': p = scenegen.gen_config5('/tmp/gen/c5', spp=int(os.environ.get('DT_AB_SPP', '4')))
 else: raise SystemExit('unknown config')
 hs = HostScene(p); cam = hs.camera(0); t1 = time.time()
 gs = GpuScene(hs); t2 = time.time()
-gs.render(cam, want_hdr=False)
+if os.environ.get('DT_AB_WARM', '1') == '1': gs.render(cam, want_hdr=False)
 n = int(os.environ.get('DT_AB_N', '3')); acc = np.zeros(7)
 for _ in range(n):
     ldr, hdr, st = gs.render(cam, want_hdr=False)
@@ -34,6 +34,6 @@ for spec in sys.argv[2:] or ['']:
     for kv in filter(None, spec.split(',')):
         k, v = kv.split('=')
         env[k] = v
-    out = subprocess.run([sys.executable, '-c', CHILD, cfg], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=1500).stdout.decode()
+    out = subprocess.run([sys.executable, '-c', CHILD, cfg], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=3000).stdout.decode()
     lines = out.strip().splitlines()
     print('[%s] %s' % (spec, lines[-1] if lines else 'NO OUTPUT'), flush=True)
