@@ -264,9 +264,74 @@ __device__ inline void sphere_surface(const DtSceneDev& S, const DtShapeDev& sh,
 }
 
 // ---------------------------------------------------------------- BRDFs (brdf*.cpp)
+// The reference evaluates its lobes in double through degrees: cos(rad(deg(acos(c)))) and pow(., exponent).  Two algebraic
+// shortcuts keep the double results to ~1e-15 relative (the LDR tolerance is 4e-3) and remove the bulk of the shading
+// kernel's double-precision transcendental work on path-traced frames (three BRDF evaluations per hit):
+//  * cos_deg(angle_between_unit(a, b)) is the clamped dot product itself (the degree <-> radian factors are exact inverses in double);
+//  * pow(x, e) with an integer exponent (every shipped scene; <Exponent> is parsed as a number) is repeated squaring in double.
+// The `theta_i >= 90` cut-off is taken on the cosine: (float)(acos(c) * 180/pi) >= 90.0f  <=>  c <= 6.657903e-08f (computed
+// by bisection over all floats).  The two "Original" variants still divide by the cosine of the float-rounded angle: kept as is.
+#define DT_COS_90_CUTOFF 6.657903e-08f
+__device__ __forceinline__ double dt_cos_between(v3 a, v3 b) { return (double)fminf(1.0f, fmaxf(-1.0f, vdot(a, b))); }
+__device__ __forceinline__ double dt_pow_lobe(double x, double e) {
+    if (e >= 0.0 && e <= 65536.0 && e == floor(e)) {
+        unsigned n = (unsigned)e;
+        double r = 1.0, p = x;
+        while (n) { if (n & 1u) r *= p; p *= p; n >>= 1; }
+        return r;
+    }
+    return pow(x, e);
+}
+
 __device__ inline v3 brdf_apply(const DtSceneDev& S, const dt_material& mat, v3 kd, v3 ks, v3 w_i, v3 w_o, v3 n) {
     const dt_brdf b = S.brdfs[mat.brdf];
     const float exponent = b.exponent;
+    if (b.kind == DT_BRDF_MODIFIED_PHONG || b.kind == DT_BRDF_MODIFIED_BLINN_PHONG || b.kind == DT_BRDF_TORRANCE_SPARROW) {
+        if (fminf(1.0f, fmaxf(-1.0f, vdot(w_i, n))) <= DT_COS_90_CUTOFF) return V(0, 0, 0);          // angleTheta_i >= 90.0f
+    }
+    switch (b.kind) {
+        case DT_BRDF_MODIFIED_PHONG: {                                         // brdfModifiedPhong.cpp:14-33
+            v3 pr = vunit(vsub(vscale(vscale(n, 2.0f), vdot(n, w_i)), w_i));
+            const double cosTerm = dt_pow_lobe(dt_cos_between(pr, w_o), (double)exponent);
+            if (b.flag) {
+                v3 kdTerm = vscale(kd, (float)(1.0f / DT_PI));
+                double cons = (exponent + 2) / (2 * DT_PI);
+                return vadd(kdTerm, vscale(ks, (float)(cons * cosTerm)));
+            }
+            return vadd(kd, vscale(ks, (float)cosTerm));
+        }
+        case DT_BRDF_MODIFIED_BLINN_PHONG: {                                   // brdfModifiedBlinnPhong.cpp:11-29
+            v3 s = vadd(w_i, w_o);
+            v3 half = vdiv(s, vlen(s));
+            const double cosTerm = dt_pow_lobe(dt_cos_between(half, n), (double)exponent);
+            if (b.flag) {
+                v3 kdTerm = vscale(kd, (float)(1.0f / DT_PI));
+                double cons = (exponent + 8) / (8 * DT_PI);
+                return vadd(kdTerm, vscale(ks, (float)(cons * cosTerm)));
+            }
+            return vadd(kd, vscale(ks, (float)cosTerm));
+        }
+        case DT_BRDF_TORRANCE_SPARROW: {                                       // brdfTorranceSparrow.cpp:15-59
+            v3 s = vadd(w_i, w_o);
+            v3 half = vdiv(s, vlen(s));
+            double e = exponent;
+            double d = (e + 2) * dt_pow_lobe((double)vdot(half, n), e) / (2 * DT_PI);
+            double ri = mat.refractive_index;
+            double r0 = ((ri - 1) * (ri - 1)) / ((ri + 1) * (ri + 1));                                // pow(x, 2.0) is x*x, correctly rounded
+            const double om = 1.0 - (double)vdot(half, w_o), om2 = om * om;
+            double f = r0 + (1.0 - r0) * (om2 * om2 * om);                                            // pow(., 5.0)
+            double ndoth = vdot(n, half), ndotwo = vdot(n, w_o), ndotwi = vdot(n, w_i), wodoth = vdot(w_o, half);
+            double g = fmin(1.0, fmin(2.0f * ndoth * ndotwo / wodoth, 2.0 * ndoth * ndotwi / wodoth));
+            double kdCoeff = (1.0f / DT_PI);
+            if (b.flag) kdCoeff *= (1 - f);
+            v3 kdTerm = vscale(kd, (float)kdCoeff);
+            double costheta = vdot(n, w_i);
+            double cosphi = vdot(n, w_o);
+            v3 ksTerm = vscale(ks, (float)((d * f * g) / (4 * costheta * cosphi)));
+            return vadd(kdTerm, ksTerm);
+        }
+        default: break;
+    }
     const float angleTheta_i = (float)angle_between_unit(w_i, n);
     switch (b.kind) {
         case DT_BRDF_PHONG: {                                                  // brdfPhong.cpp:11-20
@@ -282,52 +347,7 @@ __device__ inline v3 brdf_apply(const DtSceneDev& S, const dt_material& mat, v3 
             double a = angle_between_unit(half, n);
             return vadd(kd, vscale(ks, (float)(pow(cos_deg(a), (double)exponent) / cos_deg((double)angleTheta_i))));
         }
-        case DT_BRDF_MODIFIED_PHONG: {                                         // brdfModifiedPhong.cpp:14-33
-            if (angleTheta_i >= 90.0f || angleTheta_i < 0) return V(0, 0, 0);
-            v3 pr = vunit(vsub(vscale(vscale(n, 2.0f), vdot(n, w_i)), w_i));
-            double angleR = angle_between_unit(pr, w_o);
-            if (b.flag) {
-                v3 kdTerm = vscale(kd, (float)(1.0f / DT_PI));
-                double cons = (exponent + 2) / (2 * DT_PI);
-                double cosTerm = pow(cos_deg(angleR), (double)exponent);
-                v3 ksTerm = vscale(ks, (float)(cons * cosTerm));
-                return vadd(kdTerm, ksTerm);
-            }
-            return vadd(kd, vscale(ks, (float)pow(cos_deg(angleR), (double)exponent)));
-        }
-        case DT_BRDF_MODIFIED_BLINN_PHONG: {                                   // brdfModifiedBlinnPhong.cpp:11-29
-            if (angleTheta_i >= 90.0f) return V(0, 0, 0);
-            v3 s = vadd(w_i, w_o);
-            v3 half = vdiv(s, vlen(s));
-            double a = angle_between_unit(half, n);
-            if (b.flag) {
-                v3 kdTerm = vscale(kd, (float)(1.0f / DT_PI));
-                double cons = (exponent + 8) / (8 * DT_PI);
-                double cosTerm = pow(cos_deg(a), (double)exponent);
-                v3 ksTerm = vscale(ks, (float)(cons * cosTerm));
-                return vadd(kdTerm, ksTerm);
-            }
-            return vadd(kd, vscale(ks, (float)pow(cos_deg(a), (double)exponent)));
-        }
-        default: {                                                             // brdfTorranceSparrow.cpp:15-59
-            if (angleTheta_i >= 90.0f) return V(0, 0, 0);
-            v3 s = vadd(w_i, w_o);
-            v3 half = vdiv(s, vlen(s));
-            double e = exponent;
-            double d = (e + 2) * pow((double)vdot(half, n), e) / (2 * DT_PI);
-            double ri = mat.refractive_index;
-            double r0 = pow(ri - 1, 2.0) / pow(ri + 1, 2.0);
-            double f = r0 + (1.0 - r0) * pow((1.0 - (double)vdot(half, w_o)), 5.0);
-            double ndoth = vdot(n, half), ndotwo = vdot(n, w_o), ndotwi = vdot(n, w_i), wodoth = vdot(w_o, half);
-            double g = fmin(1.0, fmin(2.0f * ndoth * ndotwo / wodoth, 2.0 * ndoth * ndotwi / wodoth));
-            double kdCoeff = (1.0f / DT_PI);
-            if (b.flag) kdCoeff *= (1 - f);
-            v3 kdTerm = vscale(kd, (float)kdCoeff);
-            double costheta = vdot(n, w_i);
-            double cosphi = vdot(n, w_o);
-            v3 ksTerm = vscale(ks, (float)((d * f * g) / (4 * costheta * cosphi)));
-            return vadd(kdTerm, ksTerm);
-        }
+        default: return V(0, 0, 0);
     }
 }
 
