@@ -318,6 +318,32 @@ def test_trace_queries_vs_oracle():
     assert gs.trace_closest(o[:0], d[:0])[0].size == 0          # empty input
 
 
+def test_degenerate_rays_do_not_poison_the_batch():
+    """NaN / infinite / zero directions and far-away origins mixed into a batch: the call must return (no hang, no CUDA
+    error), and every ordinary ray of the same batch must still match the oracle bit for bit."""
+    hs, _ = golden_scene("scienceTree")
+    gs = GpuScene(hs)
+    rng = np.random.RandomState(3)
+    n = 8192
+    o = (rng.rand(n, 3).astype(np.float32) - 0.5) * np.array([8, 4, 4], np.float32) + np.array([0, 2, 6], np.float32)
+    d = rng.randn(n, 3).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True).astype(np.float32)
+    bad = np.zeros(n, bool)
+    bad[::16] = True
+    k = np.nonzero(bad)[0]
+    d[k[0::6]] = np.float32(np.nan)
+    d[k[1::6]] = 0.0
+    d[k[2::6], 0] = np.float32(np.inf)
+    o[k[3::6]] = np.float32(1e30)
+    o[k[4::6], 1] = np.float32(np.nan)
+    d[k[5::6]] *= np.float32(1e-38)                 # denormal direction
+    s, f, t = gs.trace_closest(o, d)
+    rs, rf, rt = oracle_trace_closest(hs, o[~bad], d[~bad])
+    _assert_hits_equal((s[~bad], f[~bad], t[~bad]), (rs, rf, rt))
+    occ = gs.trace_occluded(o, d, np.full(n, np.inf, np.float32))
+    assert occ.shape == (n,)
+
+
 def test_tonemap_vs_oracle():
     rng = np.random.RandomState(2)
     hdr = (rng.rand(270, 480, 3).astype(np.float32) ** 4) * 300
