@@ -252,6 +252,7 @@ __device__ __forceinline__ void dt_trav_init(DtTrav& T, const DtSceneDev& S, v3 
 }
 
 // Visit the nearest pending child node of the current group: load 80 B, test 8 boxes, refill ng / tg.
+template <bool ANY>
 __device__ __forceinline__ void dt_trav_node(DtTrav& T, uint2* __restrict__ stack, const DtSceneDev& S) {
     const uint32_t one = S.one_bits;
     DT_STAT(0);
@@ -260,7 +261,8 @@ __device__ __forceinline__ void dt_trav_node(DtTrav& T, uint2* __restrict__ stac
     const int child_bit = 31 - __clz(hits);
     T.ng.y &= ~(1u << child_bit);
     if (T.ng.y > 0x00FFFFFFu) { if (T.sp < DT_STACK_SIZE) stack[T.sp++] = T.ng; }
-    const uint32_t slot = (uint32_t)(child_bit - 24) ^ (T.r.oct_inv4 & 0xFFu);
+    // occlusion queries visit the children in plain slot order (any hit will do): no octant permutation
+    const uint32_t slot = ANY ? (uint32_t)(child_bit - 24) : ((uint32_t)(child_bit - 24) ^ (T.r.oct_inv4 & 0xFFu));
     const uint32_t rel = __popc(imask & ~(0xFFFFFFFFu << slot));
     const uint32_t ni = T.ng.x + rel;
     const uint4* np = (T.cur_shape >= 0 ? S.blas_nodes : S.tlas_nodes) + (size_t)ni * 5;
@@ -271,7 +273,7 @@ __device__ __forceinline__ void dt_trav_node(DtTrav& T, uint2* __restrict__ stac
     // node group: inner hits in visiting priority at bits 24..31 + the node's inner mask (a group without hits reads as empty);
     // primitive group: hit leaf slots at bits 0..7 + the node's leaf mask at bits 8..15 (slot -> primitive index by popcount)
     T.ng.x = n1.x;
-    T.ng.y = hi ? ((dt_perm8(hi, T.r.oct_inv4 & 7u) << 24) | im) : 0u;
+    T.ng.y = hi ? (((ANY ? hi : dt_perm8(hi, T.r.oct_inv4 & 7u)) << 24) | im) : 0u;
     T.tg.x = n1.y;
     T.tg.y = hl ? (hl | (lm << 8)) : 0u;
 }
@@ -420,10 +422,10 @@ template <bool ANY, bool WW>
 __device__ __forceinline__ bool dt_trav_step(DtTrav& T, uint2* __restrict__ stack, const DtSceneDev& S, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d) {
     DT_STAT(5);
     if (WW) {
-        while (T.ng.y > 0x00FFFFFFu && T.tg.y == 0u) dt_trav_node(T, stack, S);
+        while (T.ng.y > 0x00FFFFFFu && T.tg.y == 0u) dt_trav_node<ANY>(T, stack, S);
         if (T.tg.y == 0u && T.ng.y != 0u && T.ng.y <= 0x00FFFFFFu) { T.tg = T.ng; T.ng = make_uint2(0u, 0u); }
     } else {
-        if (T.ng.y > 0x00FFFFFFu) dt_trav_node(T, stack, S);
+        if (T.ng.y > 0x00FFFFFFu) dt_trav_node<ANY>(T, stack, S);
         else { T.tg = T.ng; T.ng = make_uint2(0u, 0u); }
     }
     while (T.tg.y != 0u) {
