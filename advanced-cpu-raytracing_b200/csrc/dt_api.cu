@@ -61,12 +61,12 @@ struct Timer {
 struct DtPipe {
     DtRayQueue q[2];
     float4* miss[2] = {nullptr, nullptr};
-    DtShadowQueue sq[2];          // shadow(k) on stream B overlaps closest(k+1) / shade(k+1) on stream A
+    DtShadowQueue sq[3];          // wave k fills sq[k % 3]; shadow(k) on stream B overlaps closest(k+1) / shade(k+1) on stream A
     int capacity = 0, shadow_capacity = 0;
     bool has_miss = false, has_defer = false;
     std::vector<void*> allocs;
     cudaStream_t A = nullptr, B = nullptr;
-    cudaEvent_t ev_shade[2] = {nullptr, nullptr}, ev_shadow[2] = {nullptr, nullptr}, ev_done = nullptr;
+    cudaEvent_t ev_shade[3] = {nullptr, nullptr, nullptr}, ev_shadow[3] = {nullptr, nullptr, nullptr}, ev_done = nullptr;
     int* counters = nullptr;      // this pipe's block of dt_scene::counters
     int* sort_perm = nullptr;     // material-sorted order of the current wave (sort stage)
     int* sort_hist = nullptr;     // DT_SORT_BINS bin counts / cursors
@@ -92,7 +92,7 @@ struct dt_scene {
     DtPipe pipes[DT_MAX_PIPES];
     cudaEvent_t ev_fork = nullptr;
     std::vector<cudaEvent_t> ev_pool;    // timing events of the sync-free loop
-    int use_graph = 1;            // replay the sync-free frame as a CUDA graph (DT_GRAPH=0: enqueue every launch, A/B)
+    int use_graph = 0;            // DT_GRAPH=1: replay the sync-free frame as a CUDA graph instead of enqueueing every launch (see the wave loop)
     bool capturing = false;
     cudaGraphExec_t frame_graph = nullptr;
     std::string frame_key;        // everything baked into frame_graph
@@ -113,6 +113,7 @@ struct dt_scene {
     Timer t_total, t_gen, t_closest, t_shadow, t_shade, t_sort, t_resolve, t_tm;
     int grid_trav[4][2] = {};
     int trav_mode = 2, refill_threshold = 12;
+    int shadow_order = 1;         // 1: shadow(k) released together with closest(k+1) (see the wave loop); 0: right after shade(k)
     int sort_mode = 1;            // sort-by-material stage: 0 off, 1 auto (scenes with >= 3 materials), 2 always (DT_SORT)
 
     void free_queues() { for (DtPipe& p : pipes) p.free_queues(); }
@@ -159,7 +160,7 @@ int ensure_queues(dt_scene* s, DtPipe& pp, int capacity, int shadow_capacity, bo
         pp.miss[k] = nullptr;
         if (s->has_env) { if ((rc = qalloc(pp, &pp.miss[k], capacity))) return rc; }
     }
-    for (int k = 0; k < 2; k++) {
+    for (int k = 0; k < 3; k++) {
         DtShadowQueue& sq = pp.sq[k];
         if ((rc = qalloc(pp, &sq.o_time, shadow_capacity))) return rc;
         if ((rc = qalloc(pp, &sq.d_tmax, shadow_capacity))) return rc;
@@ -356,32 +357,49 @@ retry:
                 CK(cudaMemcpyAsync(pp.counters + DT_CNT_CUR, s->h_counters + DT_MAX_PIPES * DT_CNT_COUNT + p, sizeof(int), cudaMemcpyHostToDevice, pp.A));
                 n_launches++;
             }
+            // Schedule per pipe (A = high-priority stream, B = low):
+            //   A: closest(k) -> sort(k) -> shade(k) [fills shadow queue k % 3] -> advance(k) -> closest(k+1) ...
+            //   B: shadow(k) is RELEASED BY advance(k), i.e. together with closest(k+1), and enqueued after it.  Both kernels are
+            //      persistent and each can fill the GPU alone; released together, the high-priority closest(k+1) (the frame's
+            //      critical path) gets the SM slots first and shadow(k) takes what it frees while it drains, then drains itself
+            //      under shade(k+1) / closest(k+2).  With three shadow queues shadow(k) only has to finish before advance(k+2)
+            //      recycles its queue.  Measured on config 2 (profiles/r1e_ab_shadow_order.log): 4.00 ms against 4.18 ms for
+            //      DT_SHADOW_ORDER=0 (release shadow(k) right after shade(k), where it grabs every SM before closest(k+1) exists).
+            //      Enforcing "closest first" strictly (a programmatic launch event fired once all closest blocks are resident)
+            //      was slower, 4.3 ms, and a graph replay does not keep the order between its branches (4.1-4.2 ms), which is
+            //      why enqueueing the launches is the default and the graph the option.
+            auto launch_shadow = [&](DtPipe& pp, int k) {
+                const int q = k % 3, cur = k & 1;
+                int* c = pp.counters;
+                timed(ts, pp.B, [&] { launch_traverse<true>(s, pp.q[cur], pp.sq[q], c + dt_cnt_shadow(q), 0, c + dt_cnt_fetch_b(q), s->accum, pp.B); });
+                cudaEventRecord(pp.ev_shadow[q], pp.B);
+                n_launches++;
+            };
             for (int k = 0; k < n_waves; k++) {
-                const int slot = k & 1, cur = k & 1;
+                const int q = k % 3, cur = k & 1;
                 for (int p = 0; p < NP; p++) {
                     DtPipe& pp = s->pipes[p];
                     int* c = pp.counters;
-                    DtShadowQueue& sq = pp.sq[slot];
+                    DtShadowQueue& sq = pp.sq[q];
                     timed(tc, pp.A, [&] { launch_traverse<false>(s, pp.q[cur], sq, c + DT_CNT_CUR, 0, c + DT_CNT_FETCH_A, s->accum, pp.A); });
-                    if (k >= 2) CK(cudaStreamWaitEvent(pp.A, pp.ev_shadow[slot], 0));       // shadow(k-2) must have drained this queue
+                    if (s->shadow_order && k >= 1) { CK(cudaStreamWaitEvent(pp.B, pp.ev_shade[(k - 1) % 3], 0)); launch_shadow(pp, k - 1); }
+                    if (k >= 3) CK(cudaStreamWaitEvent(pp.A, pp.ev_shadow[q], 0));           // shadow(k-3) must have drained this queue
                     if (do_sort) timed(tsort, pp.A, [&] { n_launches += launch_sort(s, pp, pp.q[cur], c + DT_CNT_CUR, 0, pp.A); });
                     timed(th, pp.A, [&] {
-                        DtShadeCounters sc = {c + DT_CNT_NEXT, c + (slot ? DT_CNT_SHADOW2 : DT_CNT_SHADOW), c + DT_CNT_OVERFLOW};
+                        DtShadeCounters sc = {c + DT_CNT_NEXT, c + dt_cnt_shadow(q), c + DT_CNT_OVERFLOW};
                         k_shade<<<s->grid_shade, 128, 0, pp.A>>>(s->dev, dc, pp.q[cur], pp.miss[cur], c + DT_CNT_CUR, 0, do_sort ? pp.sort_perm : nullptr, pp.q[1 - cur], pp.miss[1 - cur], pp.capacity,
                                                                 sq, pp.shadow_capacity, sc, s->accum); });
-                    CK(cudaEventRecord(pp.ev_shade[slot], pp.A));
-                    CK(cudaStreamWaitEvent(pp.B, pp.ev_shade[slot], 0));
-                    timed(ts, pp.B, [&] { launch_traverse<true>(s, pp.q[cur], sq, c + (slot ? DT_CNT_SHADOW2 : DT_CNT_SHADOW), 0, c + (slot ? DT_CNT_FETCH_B2 : DT_CNT_FETCH_B), s->accum, pp.B); });
-                    CK(cudaEventRecord(pp.ev_shadow[slot], pp.B));
-                    if (k >= 1) CK(cudaStreamWaitEvent(pp.A, pp.ev_shadow[1 - slot], 0));    // the other queue's counters are about to be reset
-                    k_wave_advance<<<1, 1, 0, pp.A>>>(c, 1 - slot, 1 - slot);
-                    n_launches += 4; n_closest++;
+                    if (!s->shadow_order) { CK(cudaEventRecord(pp.ev_shade[q], pp.A)); CK(cudaStreamWaitEvent(pp.B, pp.ev_shade[q], 0)); launch_shadow(pp, k); }
+                    if (k >= 2) CK(cudaStreamWaitEvent(pp.A, pp.ev_shadow[(k + 1) % 3], 0));  // shadow(k-2): its queue is recycled for wave k+1
+                    k_wave_advance<<<1, 1, 0, pp.A>>>(c, (k + 1) % 3);
+                    if (s->shadow_order) CK(cudaEventRecord(pp.ev_shade[q], pp.A));
+                    n_launches += 3; n_closest++;
                 }
             }
             for (int p = 0; p < NP; p++) {
                 DtPipe& pp = s->pipes[p];
-                CK(cudaStreamWaitEvent(pp.A, pp.ev_shadow[0], 0));
-                if (n_waves > 1) CK(cudaStreamWaitEvent(pp.A, pp.ev_shadow[1], 0));
+                if (s->shadow_order) { CK(cudaStreamWaitEvent(pp.B, pp.ev_shade[(n_waves - 1) % 3], 0)); launch_shadow(pp, n_waves - 1); }
+                for (int q = 0; q < 3 && q < n_waves; q++) CK(cudaStreamWaitEvent(pp.A, pp.ev_shadow[q], 0));
                 if (p > 0) { CK(cudaEventRecord(pp.ev_done, pp.A)); CK(cudaStreamWaitEvent(st, pp.ev_done, 0)); }
             }
             CK(cudaMemcpyAsync(s->h_counters, s->counters, DT_MAX_PIPES * DT_CNT_COUNT * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -390,7 +408,7 @@ retry:
         std::string key;
         if (s->use_graph) {
             key.append((const char*)&dc, sizeof dc); key.append((const char*)wps, sizeof(DtWaveParams) * NP); key.append((const char*)n0, sizeof(int) * NP);
-            const int misc[6] = {NP, n_waves, do_sort ? 1 : 0, s->trav_mode, s->refill_threshold, (int)s->dev.n_shapes};
+            const int misc[7] = {NP, n_waves, do_sort ? 1 : 0, s->trav_mode, s->refill_threshold, (int)s->dev.n_shapes, s->shadow_order};
             key.append((const char*)misc, sizeof misc);
             const void* ptrs[2] = {s->accum, s->counters};
             key.append((const char*)ptrs, sizeof ptrs);
@@ -435,7 +453,9 @@ retry:
             if (hc[DT_CNT_OVERFLOW] != 0) overflow = true;
             unsigned long long c8 = 0, s8 = 0;
             memcpy(&c8, hc + DT_CNT_TOT_CLOSEST, 8); memcpy(&s8, hc + DT_CNT_TOT_SHADOW, 8);
-            tot_c += c8; tot_s += s8 + (unsigned long long)hc[((n_waves - 1) & 1) ? DT_CNT_SHADOW2 : DT_CNT_SHADOW];     // + last wave's queue
+            tot_c += c8; tot_s += s8;
+            for (int k = std::max(0, n_waves - 2); k < n_waves; k++)                          // the last two waves' queues were not recycled
+                tot_s += (unsigned long long)std::min(hc[dt_cnt_shadow(k % 3)], s->pipes[p].shadow_capacity);
         }
         if (overflow) {
             if (retries >= 6 || wave_max <= 4096) { g_err = "wavefront queue overflow (ray-tree fan-out too large even for small waves)"; return DT_ERR_OVERFLOW; }
@@ -609,7 +629,7 @@ int dt_scene_create(const dt_scene_desc* desc, dt_scene** out) {
         bool ok = true;
         if (p == 0) pp.A = s->stream; else ok = cudaStreamCreateWithPriority(&pp.A, cudaStreamNonBlocking, prio_hi) == cudaSuccess;
         ok = ok && cudaStreamCreateWithPriority(&pp.B, cudaStreamNonBlocking, prio_lo) == cudaSuccess && cudaEventCreateWithFlags(&pp.ev_done, cudaEventDisableTiming) == cudaSuccess;
-        for (int k = 0; k < 2 && ok; k++) ok = cudaEventCreateWithFlags(&pp.ev_shade[k], cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&pp.ev_shadow[k], cudaEventDisableTiming) == cudaSuccess;
+        for (int k = 0; k < 3 && ok; k++) ok = cudaEventCreateWithFlags(&pp.ev_shade[k], cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&pp.ev_shadow[k], cudaEventDisableTiming) == cudaSuccess;
         if (!ok) { g_err = "cudaStreamCreate / cudaEventCreate failed"; return fail(DT_ERR_CUDA); }
     }
     DtSceneDev& D = s->dev;
@@ -672,6 +692,7 @@ int dt_scene_create(const dt_scene_desc* desc, dt_scene** out) {
     if (const char* e = getenv("DT_TRAVERSE_MODE")) s->trav_mode = std::min(3, std::max(0, atoi(e)));
     if (const char* e = getenv("DT_SYNC_WAVES")) s->sync_waves = atoi(e);
     if (const char* e = getenv("DT_SORT")) s->sort_mode = std::min(2, std::max(0, atoi(e)));
+    if (const char* e = getenv("DT_SHADOW_ORDER")) s->shadow_order = atoi(e);
     if (const char* e = getenv("DT_GRAPH")) s->use_graph = atoi(e);
     if (const char* e = getenv("DT_DEBUG_TIMING")) s->debug_timing = atoi(e);
     if (const char* e = getenv("DT_PIPES")) s->n_pipes_env = std::min(DT_MAX_PIPES, std::max(0, atoi(e)));
@@ -684,6 +705,7 @@ int dt_scene_create(const dt_scene_desc* desc, dt_scene** out) {
                                  {(const void*)k_traverse_dyn<false, true>, (const void*)k_traverse_dyn<true, true>}};
         for (int m = 0; m < 4; m++) for (int a = 0; a < 2; a++) {
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, fns[m][a], 128, 0);
+            if (const char* e = getenv(a ? "DT_BPS_ANY" : "DT_BPS_CLOSEST")) bps = std::min(bps, std::max(1, atoi(e)));      // experiment knob: blocks per SM
             s->grid_trav[m][a] = s->num_sms * std::max(1, bps);
         }
     }
@@ -714,7 +736,7 @@ void dt_scene_destroy(dt_scene* s) {
     for (cudaEvent_t e : s->ev_pool) cudaEventDestroy(e);
     for (int p = 0; p < DT_MAX_PIPES; p++) {
         DtPipe& pp = s->pipes[p];
-        for (int k = 0; k < 2; k++) { if (pp.ev_shade[k]) cudaEventDestroy(pp.ev_shade[k]); if (pp.ev_shadow[k]) cudaEventDestroy(pp.ev_shadow[k]); }
+        for (int k = 0; k < 3; k++) { if (pp.ev_shade[k]) cudaEventDestroy(pp.ev_shade[k]); if (pp.ev_shadow[k]) cudaEventDestroy(pp.ev_shadow[k]); }
         if (pp.ev_done) cudaEventDestroy(pp.ev_done);
         if (pp.B) cudaStreamDestroy(pp.B);
         if (p > 0 && pp.A) cudaStreamDestroy(pp.A);

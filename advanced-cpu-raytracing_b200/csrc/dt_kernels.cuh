@@ -29,6 +29,7 @@ struct DtWaveParams {
 enum { DT_CNT_NEXT = 0, DT_CNT_SHADOW = 1, DT_CNT_FETCH_A = 2, DT_CNT_FETCH_B = 3, DT_CNT_NAN = 4, DT_CNT_OVERFLOW = 5, DT_CNT_DEFER = 6,
        DT_CNT_CUR = 7,            // rays in the current wave (device-resident loop)
        DT_CNT_SHADOW2 = 8, DT_CNT_FETCH_B2 = 9,   // second shadow queue (shadow(k) overlaps closest(k+1))
+       DT_CNT_SHADOW3 = 14, DT_CNT_FETCH_B3 = 15, // third shadow queue (shadow(k) may run until advance(k+2))
        DT_CNT_TOT_CLOSEST = 10, DT_CNT_TOT_SHADOW = 12,   // 64-bit totals (two ints each)
        DT_CNT_COUNT = 16 };
 struct DtShadeCounters { int* next; int* shadow; int* overflow; };
@@ -646,17 +647,22 @@ __global__ void __launch_bounds__(256) k_sort_scatter(DtRayQueue q, const int* n
     }
 }
 
-// Device-side bookkeeping between two waves of the sync-free loop (one thread).
-__global__ void k_wave_advance(int* c, int shadow_slot_done, int shadow_slot_next) {
+// Shadow queue q of the sync-free loop (three of them, wave k uses k % 3): its ray counter and its fetch counter.
+__host__ __device__ __forceinline__ int dt_cnt_shadow(int q) { return q == 0 ? DT_CNT_SHADOW : (q == 1 ? DT_CNT_SHADOW2 : DT_CNT_SHADOW3); }
+__host__ __device__ __forceinline__ int dt_cnt_fetch_b(int q) { return q == 0 ? DT_CNT_FETCH_B : (q == 1 ? DT_CNT_FETCH_B2 : DT_CNT_FETCH_B3); }
+
+// Device-side bookkeeping between two waves of the sync-free loop (one thread), after shade(k): the next wave's size, and the
+// recycling of shadow queue `q_recycle` (= the queue wave k+1 will fill; last used by wave k-2, whose shadow pass is complete).
+__global__ void k_wave_advance(int* c, int q_recycle) {
     unsigned long long* tot_c = reinterpret_cast<unsigned long long*>(c + DT_CNT_TOT_CLOSEST);
     unsigned long long* tot_s = reinterpret_cast<unsigned long long*>(c + DT_CNT_TOT_SHADOW);
     *tot_c += (unsigned long long)c[DT_CNT_NEXT];
-    *tot_s += (unsigned long long)c[shadow_slot_done ? DT_CNT_SHADOW2 : DT_CNT_SHADOW];
+    *tot_s += (unsigned long long)c[dt_cnt_shadow(q_recycle)];
     c[DT_CNT_CUR] = c[DT_CNT_NEXT];
     c[DT_CNT_NEXT] = 0;
     c[DT_CNT_FETCH_A] = 0;
-    c[shadow_slot_next ? DT_CNT_SHADOW2 : DT_CNT_SHADOW] = 0;
-    c[shadow_slot_next ? DT_CNT_FETCH_B2 : DT_CNT_FETCH_B] = 0;
+    c[dt_cnt_shadow(q_recycle)] = 0;
+    c[dt_cnt_fetch_b(q_recycle)] = 0;
 }
 
 // Deferred mesh-light NEE (see k_shade): after the next wave's closest-hit pass, drop the entries whose GI
