@@ -56,6 +56,11 @@ struct Timer {
 
 }  // namespace
 
+// for the other translation units of the library (dt_build.cu)
+void dt_internal_set_error(const std::string& msg) { g_err = msg; }
+int dt_internal_ensure_device() { return ensure_device(); }
+
+
 #define DT_MAX_PIPES 8
 
 struct DtPipe {

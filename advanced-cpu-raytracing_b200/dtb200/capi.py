@@ -17,6 +17,7 @@ c_d16 = C.c_double * 16
 c_i3 = C.c_int32 * 3
 
 DT_OK = 0
+DT_ERR_INVALID, DT_ERR_NO_DEVICE, DT_ERR_CUDA, DT_ERR_OVERFLOW, DT_ERR_UNSUPPORTED = -1, -2, -3, -4, -5
 DT_SHAPE_MESH, DT_SHAPE_INSTANCE, DT_SHAPE_SPHERE = 0, 1, 2
 DT_MAT_MIRROR, DT_MAT_DIELECTRIC, DT_MAT_CONDUCTOR, DT_MAT_EMISSIVE, DT_MAT_DEFAULT = range(5)
 DT_FLAG_SKIP_TONEMAP = 1
@@ -151,12 +152,13 @@ DORKTRACER_SYMBOLS = [
     "dt_gpu_init", "dt_device_count", "dt_scene_create", "dt_scene_destroy", "dt_render", "dt_render_device",
     "dt_finish_device", "dt_primary_hits", "dt_trace_closest", "dt_trace_occluded", "dt_tonemap",
     "dt_scene_stream", "dt_last_error", "dt_version",
-    "dt_frame_export", "dt_frame_import", "dt_frame_release", "dt_frame_finish",
+    "dt_frame_export", "dt_frame_import", "dt_frame_release", "dt_frame_finish", "dt_bvh2_build",
 ]
 DTHOST_SYMBOLS = [
     "dth_scene_load_xml", "dth_scene_free", "dth_scene_desc", "dth_scene_num_cameras", "dth_scene_camera",
     "dth_scene_camera_image_name", "dth_scene_set_image", "dth_scene_image_path", "dth_scene_image_loaded",
     "dth_camera_look_at", "dth_camera_default", "dth_write_png", "dth_last_error",
+    "dth_set_bvh_builder", "dth_last_bvh_build_seconds",
 ]
 
 _libs = {}
@@ -201,6 +203,10 @@ def load_dthost():
     lib.dth_write_png.restype = C.c_int
     lib.dth_last_error.argtypes = []
     lib.dth_last_error.restype = C.c_char_p
+    lib.dth_set_bvh_builder.argtypes = [C.c_void_p, C.c_int32]
+    lib.dth_set_bvh_builder.restype = None
+    lib.dth_last_bvh_build_seconds.argtypes = []
+    lib.dth_last_bvh_build_seconds.restype = C.c_double
     return lib
 
 
@@ -238,6 +244,9 @@ def load_dorktracer():
     lib.dt_frame_release.restype = C.c_int
     lib.dt_frame_finish.argtypes = [vp, C.POINTER(dt_camera_desc), C.c_void_p, C.POINTER(dt_stats)]
     lib.dt_frame_finish.restype = C.c_int
+    lib.dt_bvh2_build.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
+                                  C.POINTER(C.c_uint32), C.POINTER(C.c_float)]
+    lib.dt_bvh2_build.restype = C.c_int
     lib.dt_scene_stream.argtypes = [vp]
     lib.dt_scene_stream.restype = C.c_void_p
     lib.dt_last_error.argtypes = []

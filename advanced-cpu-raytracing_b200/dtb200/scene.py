@@ -10,12 +10,24 @@ from . import capi
 class HostScene:
     """dth_scene handle: Scene::loadFromXml equivalent (include/dorktracer_host.h)."""
 
-    def __init__(self, xml_path):
+    def __init__(self, xml_path, gpu_build=False, gpu_build_min_faces=4096):
+        """gpu_build: Mesh::ConstructBVH runs on the GPU (dt_bvh2_build) for meshes of at least gpu_build_min_faces faces."""
         self.lib = capi.load_dthost()
         self.handle = C.c_void_p()
-        rc = self.lib.dth_scene_load_xml(os.fsencode(xml_path), C.byref(self.handle))
+        if gpu_build:
+            dt = capi.load_dorktracer()
+            self.lib.dth_set_bvh_builder(C.cast(dt.dt_bvh2_build, C.c_void_p), int(gpu_build_min_faces))
+        try:
+            rc = self.lib.dth_scene_load_xml(os.fsencode(xml_path), C.byref(self.handle))
+        finally:
+            if gpu_build:
+                self.lib.dth_set_bvh_builder(None, 0)
         if rc != 0:
-            raise RuntimeError("dth_scene_load_xml(%s) failed: %s" % (xml_path, self.lib.dth_last_error().decode()))
+            msg = self.lib.dth_last_error().decode()
+            if gpu_build:
+                msg += " / " + capi.load_dorktracer().dt_last_error().decode()
+            raise RuntimeError("dth_scene_load_xml(%s) failed: %s" % (xml_path, msg))
+        self.bvh_build_seconds = float(self.lib.dth_last_bvh_build_seconds())
         self.xml_path = xml_path
         self._fill_missing_images()
 

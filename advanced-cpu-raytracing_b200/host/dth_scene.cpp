@@ -10,6 +10,7 @@
 #include <array>
 #include <algorithm>
 #include <cfloat>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -213,9 +214,39 @@ void bvh_recompute_box(MeshStore& m, dt_bvh2_node& node) {
     }
     memcpy(node.bmin, mn, 12); memcpy(node.bmax, mx, 12);
 }
-void bvh_build(MeshStore& m) {
+dth_bvh_builder g_bvh_builder = nullptr;
+int32_t g_bvh_builder_min_faces = 0;
+thread_local double g_bvh_seconds = 0.0;
+
+bool bvh_build_host(MeshStore& m);
+// Mesh::ConstructBVH through the registered builder (dt_bvh2_build): the builder returns the tree and the face order, the
+// host applies the order to the per-face arrays.
+bool bvh_build(MeshStore& m) {
+    const auto t0 = std::chrono::steady_clock::now();
+    bool ok = true;
+    const int n = (int)m.faces.size();
+    if (!g_bvh_builder || n < g_bvh_builder_min_faces || n < 2) ok = bvh_build_host(m);
+    else {
+        static_assert(sizeof(V3) == 12 && sizeof(Box) == 24, "V3 / Box must be plain float triples");
+        std::vector<uint32_t> order((size_t)n);
+        m.bvh.assign((size_t)n * 2 - 1, dt_bvh2_node());
+        uint32_t n_nodes = 0;
+        float mn[3], mx[3]; put3(mn, m.bbox.mn); put3(mx, m.bbox.mx);
+        const int rc = g_bvh_builder(n, &m.centers[0].x, &m.fboxes[0].mn.x, mn, mx, order.data(), m.bvh.data(), (uint32_t)m.bvh.size(), &n_nodes, nullptr);
+        if (rc != 0) { g_err = "BVH builder failed with status " + std::to_string(rc); ok = false; }
+        else {
+            m.bvh.resize(n_nodes);
+            std::vector<dt_face> f((size_t)n); std::vector<V3> c((size_t)n); std::vector<Box> b((size_t)n);
+            for (int i = 0; i < n; i++) { f[i] = m.faces[order[i]]; c[i] = m.centers[order[i]]; b[i] = m.fboxes[order[i]]; }
+            m.faces.swap(f); m.centers.swap(c); m.fboxes.swap(b);
+        }
+    }
+    g_bvh_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return ok;
+}
+bool bvh_build_host(MeshStore& m) {
     int n = (int)m.faces.size();
-    if (n <= 0) { m.bvh.clear(); return; }
+    if (n <= 0) { m.bvh.clear(); return true; }
     m.bvh.assign((size_t)n * 2 - 1, dt_bvh2_node());
     for (auto& nd : m.bvh) { nd.left = nd.right = -1; nd.first_face = nd.face_count = 0; memset(nd.bmin, 0, 12); memset(nd.bmax, 0, 12); }
     dt_bvh2_node& root = m.bvh[0];
@@ -248,6 +279,7 @@ void bvh_build(MeshStore& m) {
         stack.push_back(ri); stack.push_back(li);
     }
     m.bvh.resize(next_free);   // unused tail of the 2n-1 allocation is never referenced
+    return true;
 }
 
 // ---- Scene::computeTransform (parser.cpp:651-723): raw-text indexing, single-digit ids ----
@@ -676,7 +708,7 @@ bool parse_scene(dth_scene& sc, const dth::XmlNode* root) {
             }
             if (ms.faces.empty()) { g_err = std::string(tag) + " has no faces"; return false; }
             ms.bbox = bbox;
-            bvh_build(ms);
+            if (!bvh_build(ms)) return false;
             sh.mesh = (int)sc.mesh_store.size() - 1;
             sc.mesh_shapes.push_back(sh);
             if (pass == 1) {
@@ -742,7 +774,7 @@ bool parse_scene(dth_scene& sc, const dth::XmlNode* root) {
         for (int k = 0; k < 3; k++) if (ids[k] < 1 || ids[k] > nverts) { g_err = "triangle vertex id out of range"; return false; }
         add_face(ms, ids[0], ids[1], ids[2], nullptr);
         ms.bbox = ms.fboxes[0];
-        bvh_build(ms);
+        if (!bvh_build(ms)) return false;
         sh.mesh = (int)sc.mesh_store.size() - 1;
         sc.mesh_shapes.push_back(sh);
     }
@@ -811,9 +843,13 @@ void dth_scene::finalize() {
 
 extern "C" {
 
+void dth_set_bvh_builder(dth_bvh_builder builder, int32_t min_faces) { g_bvh_builder = builder; g_bvh_builder_min_faces = min_faces; }
+double dth_last_bvh_build_seconds(void) { return g_bvh_seconds; }
+
 int dth_scene_load_xml(const char* xml_path, dth_scene** out) {
     if (!xml_path || !out) { g_err = "null argument"; return DT_ERR_INVALID; }
     *out = nullptr;
+    g_bvh_seconds = 0.0;
     std::ifstream f(xml_path, std::ios::binary);
     if (!f) { g_err = std::string("Error: The xml file cannot be loaded: ") + xml_path; return DT_ERR_INVALID; }
     std::stringstream ss; ss << f.rdbuf();

@@ -303,6 +303,17 @@ int dt_trace_occluded(dt_scene* scene, const float* origins, const float* dirs, 
 int dt_tonemap(const float* hdr_rgb, int32_t width, int32_t height, float key, float burn, float saturation,
                float gamma, uint8_t* ldr_rgb);
 
+/* Mesh::ConstructBVH / RecursiveBVHBuild / RecomputeBoundingBox (mesh.cpp:23-156) on the GPU: the
+ * reference's longest-axis spatial-midpoint build INCLUDING the face permutation of its in-place two-pointer partition
+ * (mesh.cpp:92-102), which defines the canonical face ids, and its node numbering (mesh.cpp:107-121).  Host arrays:
+ * centers = Face::center xyz per face, face_boxes = Face::bbox (min xyz, max xyz) per face, root_min / root_max = Mesh::bbox
+ * (the root box is not recomputed, mesh.cpp:31-35).  Out: face_order[new] = old face index, nodes[0 .. *n_nodes)
+ * (node_capacity >= 2 * n_faces - 1, mesh.cpp:29), device time of the build without the copies in *ms_device (may be NULL).
+ * Identical to the reference's build except for the sign of a zero box coordinate (min / max are order-independent here).
+ * Rejects non-finite inputs. */
+int dt_bvh2_build(int32_t n_faces, const float* centers, const float* face_boxes, const float* root_min, const float* root_max,
+                  uint32_t* face_order, dt_bvh2_node* nodes, uint32_t node_capacity, uint32_t* n_nodes, float* ms_device);
+
 /* The CUDA stream (cudaStream_t) all device work of this scene is enqueued on, so callers can bracket calls
  * with their own CUDA events / order collectives after a render without a device-wide sync. */
 void* dt_scene_stream(dt_scene* scene);

@@ -25,6 +25,15 @@ typedef struct dth_scene dth_scene;     /* opaque: owns every array the returned
 int dth_scene_load_xml(const char* xml_path, dth_scene** out);
 void dth_scene_free(dth_scene* scene);
 
+/* Optional replacement for the host's own Mesh::ConstructBVH (mesh.cpp:23-156) during dth_scene_load_xml: the signature of
+ * dt_bvh2_build (dorktracer.h).  Meshes with fewer than `min_faces` faces are still built on the host.  NULL restores the
+ * host build.  A builder error fails the load (no silent fallback). */
+typedef int (*dth_bvh_builder)(int32_t n_faces, const float* centers, const float* face_boxes, const float* root_min, const float* root_max,
+                               uint32_t* face_order, dt_bvh2_node* nodes, uint32_t node_capacity, uint32_t* n_nodes, float* ms_device);
+void dth_set_bvh_builder(dth_bvh_builder builder, int32_t min_faces);
+/* seconds spent in BVH construction (host or builder, including the face permutation) during the last load on this thread */
+double dth_last_bvh_build_seconds(void);
+
 const dt_scene_desc* dth_scene_desc(const dth_scene* scene);
 int dth_scene_num_cameras(const dth_scene* scene);
 const dt_camera_desc* dth_scene_camera(const dth_scene* scene, int index);

@@ -293,3 +293,62 @@ def test_product_path_never_touches_the_oracle():
                 assert "dtoracle" not in text and "oracle_util" not in text and "dto_" not in text, os.path.join(root, f)
     deps = subprocess.run(["ldd", os.path.join(pkg, "libdorktracer.so")], stdout=subprocess.PIPE).stdout.decode()
     assert "dtoracle" not in deps
+
+
+# ------------------------------------------------------------------ the closed form dt_build.cu relies on
+def test_two_pointer_partition_closed_form_is_exhaustively_exact():
+    """mesh.cpp:92-102's in-place partition loop against the closed form of csrc/dt_build.cu (header comment), for every
+    left/right pattern of up to 12 faces: the permutation is what defines the canonical face ids."""
+    def loop(a, left):
+        a = list(a); i, j = 0, len(a) - 1
+        while i <= j:
+            if left[a[i]]:
+                i += 1
+            else:
+                a[i], a[j] = a[j], a[i]; j -= 1
+        return a
+
+    def closed(a, left):
+        n = len(a); L = [left[x] for x in a]; m = sum(L)
+        cnt = [0] * (n + 1)
+        for p in range(n):
+            cnt[p + 1] = cnt[p] + L[p]
+        bad_left = [p for p in range(m) if not L[p]]
+        bad_right = [p for p in range(n - 1, m - 1, -1) if L[p]]
+        out = [None] * n
+        for p in range(n):
+            if p < m:
+                out[p] = a[p] if L[p] else a[bad_right[p - cnt[p]]]
+            elif p == n - 1 or L[p + 1]:
+                k = 1 + (m - cnt[p + 1])
+                out[p] = a[bad_left[k - 1]] if k <= len(bad_left) else a[m]
+            else:
+                out[p] = a[p + 1]
+        return out
+
+    for n in range(0, 13):
+        for bits in range(1 << n):
+            left = [(bits >> k) & 1 for k in range(n)]
+            a = list(range(n))
+            assert loop(a, left) == closed(a, left), (n, bits)
+
+
+def test_host_loader_reports_builder_failure_instead_of_falling_back(tmp_path):
+    """A registered BVH builder that fails must fail the load (no silent host fallback)."""
+    import ctypes as C
+    from dtb200 import capi, scenegen
+    lib = capi.load_dthost()
+    proto = C.CFUNCTYPE(C.c_int, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p)
+    calls = []
+    cb = proto(lambda *a: calls.append(a[0]) or -3)
+    p = scenegen.gen_config2(str(tmp_path / "c2s"), nlon=40, nlat=19, width=64, height=64)
+    lib.dth_set_bvh_builder(C.cast(cb, C.c_void_p), 100)
+    try:
+        h = C.c_void_p()
+        rc = lib.dth_scene_load_xml(os.fsencode(p), C.byref(h))
+    finally:
+        lib.dth_set_bvh_builder(None, 0)
+    assert rc != 0 and calls and b"builder" in lib.dth_last_error()
+    h2 = C.c_void_p()
+    assert lib.dth_scene_load_xml(os.fsencode(p), C.byref(h2)) == 0
+    lib.dth_scene_free(h2)

@@ -438,3 +438,130 @@ def _oracle_band(hs, cam, y0, y1):
                  + (d[..., 2] * d[..., 2]).astype(np.float32)).astype(np.float32)
     d = (d / ln[..., None]).astype(np.float32)
     return oracle_trace_closest(hs, np.broadcast_to(o, d.shape).reshape(-1, 3), d.reshape(-1, 3))
+
+
+# ------------------------------------------------------------------ Mesh::ConstructBVH on the GPU
+def _mesh_arrays(hs):
+    """(faces as raw bytes, BVH2 node fields) of every mesh of a loaded scene."""
+    out = []
+    d = hs.desc
+    for i in range(d.n_meshes):
+        m = d.meshes[i]
+        faces = np.frombuffer(C.string_at(m.faces, m.n_faces * C.sizeof(capi.dt_face)), np.uint8).copy()
+        nodes = np.frombuffer(C.string_at(m.bvh, m.n_bvh_nodes * C.sizeof(capi.dt_bvh2_node)), np.dtype(
+            [("bmin", "<f4", 3), ("bmax", "<f4", 3), ("left", "<i4"), ("right", "<i4"), ("first", "<u4"), ("count", "<u4")])).copy()
+        out.append((faces, nodes))
+    return out
+
+
+def _assert_same_build(a, b):
+    assert len(a) == len(b)
+    for (fa, na), (fb, nb) in zip(a, b):
+        assert fa.shape == fb.shape and (fa == fb).all(), "canonical face order differs"
+        assert na.shape == nb.shape, "node count differs: %d vs %d" % (na.size, nb.size)
+        for k in ("left", "right", "first", "count"):
+            assert (na[k] == nb[k]).all(), "node field %s differs" % k
+        assert (na["bmin"] == nb["bmin"]).all() and (na["bmax"] == nb["bmax"]).all(), "node boxes differ"     # float ==: -0 equals +0
+
+
+def _reference_build(centers, boxes, root_min, root_max):
+    """mesh.cpp:23-156 restated sequentially (the recursion as an explicit stack, left first): face order + nodes."""
+    n = len(centers)
+    order = list(range(n))
+    nodes = [dict(mn=np.array(root_min, np.float32), mx=np.array(root_max, np.float32), left=-1, right=-1, first=0, count=n)]
+    stack = [0]
+    while stack:
+        v = stack.pop()
+        nd = nodes[v]
+        if nd["count"] < 2:
+            continue
+        ln = nd["mx"] - nd["mn"]
+        if ln[0] > ln[1]:
+            axis = 0 if ln[0] > ln[2] else 2
+        else:
+            axis = 1 if ln[1] > ln[2] else 2
+        split = np.float32(nd["mn"][axis] + np.float32(ln[axis] * np.float32(0.5)))
+        i, j = nd["first"], nd["first"] + nd["count"] - 1
+        while i <= j:
+            if centers[order[i]][axis] < split:
+                i += 1
+            else:
+                order[i], order[j] = order[j], order[i]
+                j -= 1
+        lc = i - nd["first"]
+        if lc == 0 or lc == nd["count"]:
+            continue
+        kids = []
+        for first, count in ((nd["first"], lc), (i, nd["count"] - lc)):
+            ids = order[first:first + count]
+            kids.append(dict(mn=boxes[ids, :3].min(axis=0), mx=boxes[ids, 3:].max(axis=0), left=-1, right=-1, first=first, count=count))
+        nd["left"], nd["right"], nd["count"] = len(nodes), len(nodes) + 1, 0
+        nodes.extend(kids)
+        stack.append(nd["right"]); stack.append(nd["left"])
+    return np.array(order, np.uint32), nodes
+
+
+@pytest.mark.parametrize("case", ["random", "duplicates", "grid", "two", "line"])
+def test_gpu_bvh2_build_matches_sequential_reference_build(case):
+    rng = np.random.RandomState(7)
+    if case == "random":
+        c = rng.uniform(-10, 10, (3000, 3)).astype(np.float32)
+    elif case == "duplicates":                      # many coincident centres: rejected splits, multi-face leaves, rotations
+        c = rng.randint(0, 6, (2500, 3)).astype(np.float32)
+    elif case == "grid":
+        g = np.arange(12, dtype=np.float32)
+        c = np.stack(np.meshgrid(g, g * 0.5, g * 0.25, indexing="ij"), -1).reshape(-1, 3)
+    elif case == "two":
+        c = np.array([[0, 0, 0], [1, 0, 0]], np.float32)
+    else:
+        c = np.zeros((700, 3), np.float32); c[:, 1] = rng.permutation(700)
+    ext = rng.uniform(0.0, 0.4, c.shape).astype(np.float32)
+    boxes = np.concatenate([c - ext, c + ext], axis=1).astype(np.float32)
+    root_min, root_max = boxes[:, :3].min(axis=0), np.maximum(boxes[:, 3:].max(axis=0), np.float32(1.17549435e-38))   # parser.cpp:1393 quirk
+    lib = capi.load_dorktracer()
+    n = len(c)
+    order = np.zeros(n, np.uint32)
+    nodes = np.zeros(2 * n - 1, np.dtype([("bmin", "<f4", 3), ("bmax", "<f4", 3), ("left", "<i4"), ("right", "<i4"), ("first", "<u4"), ("count", "<u4")]))
+    n_nodes, ms = C.c_uint32(0), C.c_float(0)
+    c = np.ascontiguousarray(c)
+    rc = lib.dt_bvh2_build(n, c.ctypes.data, boxes.ctypes.data, root_min.ctypes.data, root_max.ctypes.data, order.ctypes.data, nodes.ctypes.data,
+                           len(nodes), C.byref(n_nodes), C.byref(ms))
+    assert rc == 0, lib.dt_last_error().decode()
+    want_order, want_nodes = _reference_build(c, boxes, root_min, root_max)
+    assert (order == want_order).all(), "face permutation differs from the sequential partition"
+    assert n_nodes.value == len(want_nodes)
+    for k, w in enumerate(want_nodes):
+        g = nodes[k]
+        assert (g["left"], g["right"], g["first"], g["count"]) == (w["left"], w["right"], w["first"], w["count"]), "node %d" % k
+        assert (g["bmin"] == w["mn"]).all() and (g["bmax"] == w["mx"]).all(), "box of node %d" % k
+
+
+def test_gpu_bvh2_build_rejects_bad_input():
+    lib = capi.load_dorktracer()
+    c = np.zeros((4, 3), np.float32); b = np.zeros((4, 6), np.float32); b[2, 1] = np.nan
+    order = np.zeros(4, np.uint32); nodes = np.zeros(7 * 10, np.uint32); n_nodes = C.c_uint32(0)
+    mn = np.zeros(3, np.float32)
+    assert lib.dt_bvh2_build(4, c.ctypes.data, b.ctypes.data, mn.ctypes.data, mn.ctypes.data, order.ctypes.data, nodes.ctypes.data, 7, C.byref(n_nodes), None) == capi.DT_ERR_INVALID
+    b[2, 1] = 0
+    assert lib.dt_bvh2_build(4, c.ctypes.data, b.ctypes.data, mn.ctypes.data, mn.ctypes.data, order.ctypes.data, nodes.ctypes.data, 6, C.byref(n_nodes), None) == capi.DT_ERR_INVALID
+    assert lib.dt_bvh2_build(0, c.ctypes.data, b.ctypes.data, mn.ctypes.data, mn.ctypes.data, order.ctypes.data, nodes.ctypes.data, 7, C.byref(n_nodes), None) == capi.DT_ERR_INVALID
+
+
+@pytest.mark.parametrize("name", ["scienceTree", "cornellbox_recursive_conductors"])
+def test_gpu_built_golden_scene_is_identical_and_renders_the_same(name):
+    hs, g = golden_scene(name)
+    hs_gpu = HostScene(hs.xml_path, gpu_build=True, gpu_build_min_faces=2)
+    _assert_same_build(_mesh_arrays(hs_gpu), _mesh_arrays(hs))
+    cam = hs_gpu.camera(0)
+    cam.width, cam.height = 200, 200
+    gs = GpuScene(hs_gpu)
+    _assert_hits_equal(gs.primary_hits(cam), oracle_primary_hits(hs, cam))
+    gs.close()
+
+
+def test_gpu_build_of_the_config2_mesh_matches_the_host_build(tmp_path):
+    p = scenegen.gen_config2(str(tmp_path / "c2"))                 # 996 002 triangles
+    host = HostScene(p)
+    gpu = HostScene(p, gpu_build=True)
+    _assert_same_build(_mesh_arrays(gpu), _mesh_arrays(host))
+    print("config 2 BVH2 build: host %.3f s, GPU path %.3f s (copies and face permutation included)" % (host.bvh_build_seconds, gpu.bvh_build_seconds))
