@@ -1,5 +1,6 @@
 // C ABI of the render hot path (include/dorktracer.h): scene upload, wavefront driver, outputs.
 #include "dt_flatten.h"
+#include "dt_flatten_gpu.h"
 #include "dt_kernels.cuh"
 
 #include <algorithm>
@@ -82,6 +83,7 @@ struct DtPipe {
 struct dt_scene {
     int device = 0;
     int num_sms = 148;
+    size_t n_blas_nodes = 0, n_prims = 0, n_faces = 0;     // sizes of the acceleration arrays (dt_scene_accel_checksum)
     cudaStream_t stream = nullptr;
     DtSceneDev dev;
     std::vector<void*> allocs;
@@ -627,7 +629,10 @@ int dt_scene_create(const dt_scene_desc* desc, dt_scene** out) {
     *out = nullptr;
     DtHostScene hs;
     std::string err;
-    if (!dt_flatten_scene(desc, hs, err)) { g_err = "scene description rejected: " + err; return DT_ERR_INVALID; }
+    // meshes of at least this many faces get their BLAS from the GPU flattener (dt_flatten_gpu.cu); smaller ones are not worth its launches
+    int gpu_min_faces = 32768;
+    if (const char* e = getenv("DT_GPU_FLATTEN_MIN_FACES")) gpu_min_faces = atoi(e) < 0 ? 0x7FFFFFFF : std::max(1, atoi(e));
+    if (!dt_flatten_scene(desc, hs, err, gpu_min_faces)) { g_err = "scene description rejected: " + err; return DT_ERR_INVALID; }
     int rc = ensure_device();
     if (rc) return rc;
     dt_scene* s = new dt_scene();
@@ -655,17 +660,53 @@ int dt_scene_create(const dt_scene_desc* desc, dt_scene** out) {
         const uint4* p = nullptr;
         if ((rc = upload<uint4>(s->allocs, (const uint4*)hs.tlas_nodes.data(), hs.tlas_nodes.size() * 5, &p))) return fail(rc);
         D.tlas_nodes = p;
-        if ((rc = upload<uint4>(s->allocs, (const uint4*)hs.blas_nodes.data(), hs.blas_nodes.size() * 5, &p))) return fail(rc);
-        D.blas_nodes = p;
     }
     if ((rc = upload<int32_t>(s->allocs, hs.tlas_prims.data(), hs.tlas_prims.size(), &D.tlas_prims))) return fail(rc);
-    if ((rc = upload<float4>(s->allocs, hs.tris.data(), hs.tris.size(), &D.tris))) return fail(rc);
-    if ((rc = upload<float4>(s->allocs, hs.leaf_boxes.data(), hs.leaf_boxes.size(), &D.leaf_boxes))) return fail(rc);
-    if ((rc = upload<uint32_t>(s->allocs, hs.face_prim.data(), hs.face_prim.size(), &D.face_prim))) return fail(rc);
-    if ((rc = upload<DtShapeDev>(s->allocs, hs.shapes.data(), hs.shapes.size(), &D.shapes))) return fail(rc);
-    if ((rc = upload<DtMeshDev>(s->allocs, hs.meshes.data(), hs.meshes.size(), &D.meshes))) return fail(rc);
     if ((rc = upload<DtFaceDev>(s->allocs, hs.faces.data(), hs.faces.size(), &D.faces))) return fail(rc);
     if ((rc = upload<float>(s->allocs, hs.verts.data(), hs.verts.size(), &D.verts))) return fail(rc);
+    {
+        // BLAS arrays: the host-flattened meshes first, then one slice per GPU-flattened mesh (in mesh order)
+        size_t gpu_faces = 0;
+        for (int mi : hs.gpu_meshes) gpu_faces += (size_t)desc->meshes[mi].n_faces;
+        const size_t host_nodes = hs.blas_nodes.size(), host_prims = hs.tris.size() / 3;
+        const size_t node_cap = host_nodes + gpu_faces, n_prims = host_prims + gpu_faces;      // a BVH8 over n single-face leaves has fewer than n nodes
+        if (n_prims > 0x7FFFFFF0ull || node_cap > 0x7FFFFFF0ull) { g_err = "scene too large for 32-bit primitive indices"; return fail(DT_ERR_INVALID); }
+        const uint4* nodes = nullptr;
+        if ((rc = upload<uint4>(s->allocs, (const uint4*)hs.blas_nodes.data(), host_nodes * 5, &nodes, (node_cap - host_nodes) * 5))) return fail(rc);
+        if ((rc = upload<float4>(s->allocs, hs.tris.data(), hs.tris.size(), &D.tris, gpu_faces * 3))) return fail(rc);
+        if ((rc = upload<float4>(s->allocs, hs.leaf_boxes.data(), hs.leaf_boxes.size(), &D.leaf_boxes, gpu_faces * 2))) return fail(rc);
+        if ((rc = upload<uint32_t>(s->allocs, hs.face_prim.data(), std::min(hs.face_prim.size(), hs.faces.size()), &D.face_prim, hs.faces.size() - std::min(hs.face_prim.size(), hs.faces.size())))) return fail(rc);
+        size_t n_nodes = host_nodes, prim_off = host_prims;
+        int blas_depth = hs.blas_depth;
+        for (int mi : hs.gpu_meshes) {
+            const dt_mesh& m = desc->meshes[mi];
+            DtMeshDev& md = hs.meshes[(size_t)mi];
+            uint32_t made = 0; int depth = 0;
+            md.node_root = (uint32_t)n_nodes;
+            if (!dt_flatten_mesh_gpu(m, D.faces + md.face_base, D.verts + (size_t)md.vert_base * 3, (DtNode8*)nodes, (uint32_t)n_nodes, (uint32_t)(node_cap - n_nodes),
+                                     (float4*)D.tris, (float4*)D.leaf_boxes, (uint32_t*)D.face_prim + md.face_base, (uint32_t)prim_off, &made, &depth, err)) {
+                g_err = "scene description rejected: " + err; return fail(DT_ERR_INVALID);
+            }
+            n_nodes += made; prim_off += (size_t)m.n_faces;
+            blas_depth = std::max(blas_depth, depth);
+        }
+        if (hs.tlas_depth + blas_depth + 4 > DT_STACK_SIZE) {
+            g_err = "scene description rejected: BVH too deep for the traversal stack (" + std::to_string(hs.tlas_depth + blas_depth + 4) + " > " + std::to_string(DT_STACK_SIZE) + ")";
+            return fail(DT_ERR_INVALID);
+        }
+        if (node_cap - n_nodes > (1u << 16)) {                     // give the unused tail of the node allocation back
+            const uint4* exact = nullptr;
+            if ((rc = upload<uint4>(s->allocs, (const uint4*)nullptr, 0, &exact, n_nodes * 5))) return fail(rc);
+            CK(cudaMemcpy((void*)exact, nodes, n_nodes * sizeof(DtNode8), cudaMemcpyDeviceToDevice));
+            for (auto it = s->allocs.begin(); it != s->allocs.end(); ++it) if (*it == (void*)nodes) { s->allocs.erase(it); break; }
+            cudaFree((void*)nodes);
+            nodes = exact;
+        }
+        D.blas_nodes = nodes;
+        s->n_blas_nodes = n_nodes; s->n_prims = n_prims; s->n_faces = hs.faces.size();
+    }
+    if ((rc = upload<DtShapeDev>(s->allocs, hs.shapes.data(), hs.shapes.size(), &D.shapes))) return fail(rc);
+    if ((rc = upload<DtMeshDev>(s->allocs, hs.meshes.data(), hs.meshes.size(), &D.meshes))) return fail(rc);
     if ((rc = upload<float>(s->allocs, hs.uvs.data(), hs.uvs.size(), &D.uvs))) return fail(rc);
     if ((rc = upload<dt_material>(s->allocs, desc->materials, (size_t)desc->n_materials, &D.materials))) return fail(rc);
     if ((rc = upload<dt_brdf>(s->allocs, desc->brdfs, (size_t)desc->n_brdfs, &D.brdfs))) return fail(rc);
@@ -1032,6 +1073,18 @@ void dt_debug_steps_hist(unsigned int* out, int reset) {
     if (reset) { unsigned int z[128] = {0}; cudaMemcpyToSymbol(g_dt_steps_hist, z, sizeof z); }
 }
 #endif
+
+int dt_scene_accel_checksum(dt_scene* s, uint64_t out[10]) {
+    if (!s || !out) { g_err = "null argument"; return DT_ERR_INVALID; }
+    CK(cudaSetDevice(s->device));
+    CK(cudaDeviceSynchronize());
+    std::string err;
+    const void* ptr[4] = {s->dev.blas_nodes, s->dev.tris, s->dev.leaf_boxes, s->dev.face_prim};
+    const size_t bytes[4] = {s->n_blas_nodes * sizeof(DtNode8), s->n_prims * 48, s->n_prims * 32, s->n_faces * 4};
+    for (int k = 0; k < 4; k++) if (!dt_device_checksum(ptr[k], bytes[k], out + 2 * k, err)) { g_err = err; return DT_ERR_CUDA; }
+    out[8] = s->n_blas_nodes; out[9] = s->n_prims;
+    return DT_OK;
+}
 
 void* dt_scene_stream(dt_scene* s) { return s ? (void*)s->stream : nullptr; }
 

@@ -11,18 +11,10 @@
 #include <map>
 #include <numeric>
 
-namespace {
+#include "dt_collapse_core.h"
 
-inline float area_of(const float* mn, const float* mx) {
-    float dx = mx[0] - mn[0], dy = mx[1] - mn[1], dz = mx[2] - mn[2];
-    if (!(dx >= 0) || !(dy >= 0) || !(dz >= 0)) return 0.f;
-    return dx * dy + dy * dz + dz * dx;
-}
-
-struct Child { int node; float mn[3], mx[3]; bool leaf; uint32_t first, count; };
-
-}  // namespace
-
+// BFS collapse; the per-node work (child selection, slot assignment, quantisation) is dt_collapse_node (dt_collapse_core.h),
+// shared with the GPU flattener (dt_flatten_gpu.cu) so that both produce the same bytes.
 bool dt_collapse_bvh8(const std::vector<DtB2Node>& b2, DtWideBvh& out, std::string& err) {
     out.nodes.clear(); out.prim_order.clear(); out.max_depth = 0;
     if (b2.empty()) { err = "empty tree"; return false; }
@@ -31,120 +23,21 @@ bool dt_collapse_bvh8(const std::vector<DtB2Node>& b2, DtWideBvh& out, std::stri
     out.nodes.emplace_back();
     queue.push_back({0, 0u, 1});
     size_t qh = 0;
-    auto is_leaf = [&](int n) { return b2[n].left < 0 || b2[n].count <= 1; };       // every leaf child is ONE primitive
     while (qh < queue.size()) {
         Work w = queue[qh++];
         out.max_depth = std::max(out.max_depth, w.depth);
-        const DtB2Node& root = b2[w.b2node];
-        std::vector<int> ch;
-        if (is_leaf(w.b2node)) ch.push_back(w.b2node);            // tiny tree: the root itself is the only (leaf) child
-        else { ch.push_back(root.left); ch.push_back(root.right); }
-        while (ch.size() < 8) {
-            int best = -1; float best_area = -1.f;
-            for (size_t k = 0; k < ch.size(); k++) {
-                if (is_leaf(ch[k])) continue;
-                float a = area_of(b2[ch[k]].mn, b2[ch[k]].mx);
-                if (a > best_area) { best_area = a; best = (int)k; }
-            }
-            if (best < 0) break;
-            int n = ch[best];
-            ch[best] = b2[n].left;
-            ch.push_back(b2[n].right);
-        }
-        // node bounds = union of children
-        float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
-        for (int c : ch) for (int a = 0; a < 3; a++) {
-            if (b2[c].mn[a] < mn[a]) mn[a] = b2[c].mn[a];
-            if (b2[c].mx[a] > mx[a]) mx[a] = b2[c].mx[a];
-        }
-        for (int a = 0; a < 3; a++) if (!(mn[a] <= mx[a])) { mn[a] = 0.f; mx[a] = 0.f; }   // NaN / empty guard
-        // slot assignment: slot s prefers the child towards corner (s&4 ? +x : -x, s&2 ? +y : -y, s&1 ? +z : -z)
-        float cen[3] = {0.5f * (mn[0] + mx[0]), 0.5f * (mn[1] + mx[1]), 0.5f * (mn[2] + mx[2])};
-        int slot_of[8]; for (int k = 0; k < 8; k++) slot_of[k] = -1;
-        int child_in_slot[8]; for (int s = 0; s < 8; s++) child_in_slot[s] = -1;
-        float cost[8][8];
-        for (size_t k = 0; k < ch.size(); k++) {
-            const DtB2Node& c = b2[ch[k]];
-            float d[3] = {0.5f * (c.mn[0] + c.mx[0]) - cen[0], 0.5f * (c.mn[1] + c.mx[1]) - cen[1], 0.5f * (c.mn[2] + c.mx[2]) - cen[2]};
-            for (int s = 0; s < 8; s++) cost[k][s] = ((s & 4) ? d[0] : -d[0]) + ((s & 2) ? d[1] : -d[1]) + ((s & 1) ? d[2] : -d[2]);
-        }
-        for (size_t it = 0; it < ch.size(); it++) {
-            float bc = -FLT_MAX; int bk = -1, bs = -1;
-            for (size_t k = 0; k < ch.size(); k++) {
-                if (slot_of[k] >= 0) continue;
-                for (int s = 0; s < 8; s++) {
-                    if (child_in_slot[s] >= 0) continue;
-                    float cst = cost[k][s];
-                    if (!(cst == cst)) cst = 0.f;
-                    if (cst > bc || bk < 0) { bc = cst; bk = (int)k; bs = s; }
-                }
-            }
-            slot_of[bk] = bs; child_in_slot[bs] = bk;
-        }
-        // quantisation frame.  Child boxes are rounded OUTWARD with a 1/128-step margin on both sides: the kernel's node
-        // test evaluates plane distances with an absolute error of up to 2^-9 quantisation steps (dt_traverse.cuh,
-        // dt_byte_m).  The frame origin sits a margin below the node minimum so the margin also holds at q = 0.
-        DtNode8 node; memset(&node, 0, sizeof node);
-        const double margin = 1.0 / 128.0;
-        int e[3];
-        for (int a = 0; a < 3; a++) {
-            double ext = (double)mx[a] - (double)mn[a];
-            int ea = -120;
-            if (ext > 0) { ea = (int)std::ceil(std::log2(ext / 254.0)); }
-            if (ea < -120) ea = -120;
-            if (ea > 100) ea = 100;
-            e[a] = ea;
-        }
-        uint8_t qlo[3][8], qhi[3][8];
-        float origin[3];
-        for (int a = 0; a < 3; a++) {
-            for (;;) {
-                bool ok = true;
-                const double sc = std::ldexp(1.0, e[a]);
-                float pf = (float)((double)mn[a] - 1.5 * margin * sc);
-                if ((double)pf > (double)mn[a] - margin * sc) pf = std::nextafterf(pf, -FLT_MAX);
-                if (!(pf == pf) || std::isinf(pf)) pf = mn[a];
-                const double p = (double)pf;
-                for (int s = 0; s < 8 && ok; s++) {
-                    int k = child_in_slot[s];
-                    if (k < 0) { qlo[a][s] = 0; qhi[a][s] = 0; continue; }
-                    double lo = b2[ch[k]].mn[a], hi = b2[ch[k]].mx[a];
-                    if (!(lo <= hi)) { lo = p; hi = p; }
-                    double ql = std::floor((lo - p) / sc - margin), qh2 = std::ceil((hi - p) / sc + margin);
-                    if (ql < 0) ql = 0;
-                    while (p + (ql + margin) * sc > lo && ql > 0) ql -= 1;
-                    while (p + (qh2 - margin) * sc < hi) qh2 += 1;
-                    if (qh2 > 255 || ql > 255) { ok = false; break; }
-                    qlo[a][s] = (uint8_t)ql; qhi[a][s] = (uint8_t)qh2;
-                }
-                if (ok) { origin[a] = pf; break; }
-                e[a]++;
-                if (e[a] > 100) { err = "BVH8 quantisation exponent overflow (scene extent beyond 2^100)"; return false; }
-            }
-        }
-        node.px = origin[0]; node.py = origin[1]; node.pz = origin[2];
-        node.ex = (uint8_t)(e[0] + 127); node.ey = (uint8_t)(e[1] + 127); node.ez = (uint8_t)(e[2] + 127);
+        DtNode8 node; int child_in_slot[8];
+        const int rc = dt_collapse_node(b2.data(), w.b2node, node, child_in_slot);
+        if (rc == DT_COLLAPSE_ERR_EXPONENT) { err = "BVH8 quantisation exponent overflow (scene extent beyond 2^100)"; return false; }
+        if (rc == DT_COLLAPSE_ERR_LEAF) { err = "leaf with unsupported primitive count (the binary tree must be split down to single primitives)"; return false; }
         // children: internal ones get consecutive node indices in slot order; leaves get consecutive primitives
-        int n_internal = 0;
-        for (int s = 0; s < 8; s++) { int k = child_in_slot[s]; if (k >= 0 && !is_leaf(ch[k])) n_internal++; }
         node.child_base = (uint32_t)out.nodes.size();
         node.prim_base = (uint32_t)out.prim_order.size();
-        out.nodes.resize(out.nodes.size() + (size_t)n_internal);
-        uint32_t next_child = node.child_base;
         for (int s = 0; s < 8; s++) {
-            int k = child_in_slot[s];
-            if (k < 0) continue;
-            int c = ch[k];
-            if (is_leaf(c)) {
-                if (b2[c].count != 1) { err = "leaf with unsupported primitive count (the binary tree must be split down to single primitives)"; return false; }
-                node.lmask |= (uint8_t)(1u << s);
-                out.prim_order.push_back(b2[c].first);                  // slot order == primitive order within the node
-            } else {
-                node.imask |= (uint8_t)(1u << s);
-                queue.push_back({c, next_child++, w.depth + 1});
-            }
-            node.qlox[s] = qlo[0][s]; node.qloy[s] = qlo[1][s]; node.qloz[s] = qlo[2][s];
-            node.qhix[s] = qhi[0][s]; node.qhiy[s] = qhi[1][s]; node.qhiz[s] = qhi[2][s];
+            const int c = child_in_slot[s];
+            if (c < 0) continue;
+            if (node.lmask & (1u << s)) out.prim_order.push_back(b2[c].first);       // slot order == primitive order within the node
+            else { queue.push_back({c, (uint32_t)out.nodes.size(), w.depth + 1}); out.nodes.emplace_back(); }
         }
         out.nodes[w.out_index] = node;
     }
@@ -208,7 +101,7 @@ void rows012(double* dst, const double* src16) { memcpy(dst, src16, sizeof(doubl
 
 }  // namespace
 
-bool dt_flatten_scene(const dt_scene_desc* d, DtHostScene& out, std::string& err) {
+bool dt_flatten_scene(const dt_scene_desc* d, DtHostScene& out, std::string& err, int gpu_min_faces) {
     if (!d) { err = "null scene description"; return false; }
     if (d->abi_version != DT_ABI_VERSION) { err = "dt_scene_desc.abi_version mismatch"; return false; }
     if (d->n_shapes <= 0) { err = "scene has no shapes"; return false; }
@@ -245,6 +138,7 @@ bool dt_flatten_scene(const dt_scene_desc* d, DtHostScene& out, std::string& err
         md.face_base = (uint32_t)out.faces.size();
 
         // canonical faces
+        out.faces.reserve(out.faces.size() + (size_t)m.n_faces);
         for (int f = 0; f < m.n_faces; f++) {
             const dt_face& fc = m.faces[f];
             int ids[3] = {fc.v0_id - 1 + m.vertex_offset, fc.v1_id - 1 + m.vertex_offset, fc.v2_id - 1 + m.vertex_offset};
@@ -258,6 +152,13 @@ bool dt_flatten_scene(const dt_scene_desc* d, DtHostScene& out, std::string& err
             fd.light_weight = (float)(fc.area / m.surface_area);
             fd.pad = 0;
             out.faces.push_back(fd);
+        }
+
+        if (m.n_faces >= gpu_min_faces) {                       // BLAS of this mesh: dt_flatten_mesh_gpu, after the upload of faces / verts
+            out.gpu_meshes.push_back(mi);
+            out.n_triangles += (uint64_t)m.n_faces;
+            out.meshes[(size_t)mi] = md;
+            continue;
         }
 
         // ---- reference BVH2 -> generic binary tree with subtree ranges (children have larger indices than
@@ -402,6 +303,7 @@ bool dt_flatten_scene(const dt_scene_desc* d, DtHostScene& out, std::string& err
         out.tlas_nodes = wide.nodes;
         out.tlas_prims.resize(wide.prim_order.size());
         for (size_t k = 0; k < wide.prim_order.size(); k++) out.tlas_prims[k] = (int32_t)order[wide.prim_order[k]];
+        out.tlas_depth = wide.max_depth; out.blas_depth = blas_depth;
         out.max_stack_need = wide.max_depth + blas_depth + 4;
     }
     if (out.max_stack_need > DT_STACK_SIZE) {

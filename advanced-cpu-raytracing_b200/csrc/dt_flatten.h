@@ -38,7 +38,10 @@ struct DtHostScene {
     std::vector<uint8_t> image_u8;
     std::vector<float> image_f32;
     int max_stack_need = 0;
+    int tlas_depth = 0, blas_depth = 0;   // BVH8 depths (blas_depth: host-flattened meshes only)
     uint64_t n_triangles = 0;
+    std::vector<int> gpu_meshes;          // meshes left to the GPU flattener (dt_flatten_gpu.cu): faces / verts / DtMeshDev are filled, the BLAS is not
 };
 
-bool dt_flatten_scene(const dt_scene_desc* d, DtHostScene& out, std::string& err);
+// gpu_min_faces: meshes with at least this many faces are left to the GPU flattener (INT_MAX: flatten everything here).
+bool dt_flatten_scene(const dt_scene_desc* d, DtHostScene& out, std::string& err, int gpu_min_faces = 0x7FFFFFFF);

@@ -152,7 +152,7 @@ DORKTRACER_SYMBOLS = [
     "dt_gpu_init", "dt_device_count", "dt_scene_create", "dt_scene_destroy", "dt_render", "dt_render_device",
     "dt_finish_device", "dt_primary_hits", "dt_trace_closest", "dt_trace_occluded", "dt_tonemap",
     "dt_scene_stream", "dt_last_error", "dt_version",
-    "dt_frame_export", "dt_frame_import", "dt_frame_release", "dt_frame_finish", "dt_bvh2_build",
+    "dt_frame_export", "dt_frame_import", "dt_frame_release", "dt_frame_finish", "dt_bvh2_build", "dt_scene_accel_checksum",
 ]
 DTHOST_SYMBOLS = [
     "dth_scene_load_xml", "dth_scene_free", "dth_scene_desc", "dth_scene_num_cameras", "dth_scene_camera",
@@ -247,6 +247,8 @@ def load_dorktracer():
     lib.dt_bvh2_build.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
                                   C.POINTER(C.c_uint32), C.POINTER(C.c_float)]
     lib.dt_bvh2_build.restype = C.c_int
+    lib.dt_scene_accel_checksum.argtypes = [vp, C.POINTER(C.c_uint64 * 10)]
+    lib.dt_scene_accel_checksum.restype = C.c_int
     lib.dt_scene_stream.argtypes = [vp]
     lib.dt_scene_stream.restype = C.c_void_p
     lib.dt_last_error.argtypes = []

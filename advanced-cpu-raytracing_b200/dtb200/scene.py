@@ -168,6 +168,14 @@ class GpuScene:
             self._err("dt_frame_finish", rc)
         return ldr, stats
 
+    def accel_checksum(self):
+        """Ten integers identifying the device-resident acceleration arrays (dt_scene_accel_checksum)."""
+        out = (C.c_uint64 * 10)()
+        rc = self.lib.dt_scene_accel_checksum(self.handle, C.byref(out))
+        if rc != 0:
+            self._err("dt_scene_accel_checksum", rc)
+        return tuple(int(x) for x in out)
+
     def primary_hits(self, cam):
         n = cam.width * cam.height
         shape = np.empty(n, np.int32); face = np.empty(n, np.int32); t = np.empty(n, np.float32)

@@ -314,6 +314,11 @@ int dt_tonemap(const float* hdr_rgb, int32_t width, int32_t height, float key, f
 int dt_bvh2_build(int32_t n_faces, const float* centers, const float* face_boxes, const float* root_min, const float* root_max,
                   uint32_t* face_order, dt_bvh2_node* nodes, uint32_t node_capacity, uint32_t* n_nodes, float* ms_device);
 
+/* Parity/debug: checksums (sum of 32-bit words, position-weighted sum) of the scene's device-resident acceleration arrays
+ * -- BVH8 nodes, leaf-order triangles, reference leaf boxes, face -> primitive map -- then the node and primitive counts.
+ * The host flattener and the GPU flattener (DT_GPU_FLATTEN_MIN_FACES) must agree on all ten. */
+int dt_scene_accel_checksum(dt_scene* scene, uint64_t out[10]);
+
 /* The CUDA stream (cudaStream_t) all device work of this scene is enqueued on, so callers can bracket calls
  * with their own CUDA events / order collectives after a render without a device-wide sync. */
 void* dt_scene_stream(dt_scene* scene);

@@ -565,3 +565,74 @@ def test_gpu_build_of_the_config2_mesh_matches_the_host_build(tmp_path):
     gpu = HostScene(p, gpu_build=True)
     _assert_same_build(_mesh_arrays(gpu), _mesh_arrays(host))
     print("config 2 BVH2 build: host %.3f s, GPU path %.3f s (copies and face permutation included)" % (host.bvh_build_seconds, gpu.bvh_build_seconds))
+
+
+def _scene_with_flattener(hs, min_faces):
+    """GpuScene whose BLAS came from the host flattener (min_faces < 0) or the GPU flattener (meshes >= min_faces)."""
+    old = os.environ.get("DT_GPU_FLATTEN_MIN_FACES")
+    os.environ["DT_GPU_FLATTEN_MIN_FACES"] = str(min_faces)
+    try:
+        return GpuScene(hs)
+    finally:
+        if old is None:
+            del os.environ["DT_GPU_FLATTEN_MIN_FACES"]
+        else:
+            os.environ["DT_GPU_FLATTEN_MIN_FACES"] = old
+
+
+@pytest.mark.parametrize("name", ["scienceTree", "cornellbox_recursive_conductors", "simple"])
+def test_gpu_flattener_emits_the_host_flatteners_bytes_golden(name):
+    hs, _ = golden_scene(name)
+    a, b = _scene_with_flattener(hs, -1), _scene_with_flattener(hs, 1)
+    try:
+        assert a.accel_checksum() == b.accel_checksum()
+        cam = hs.camera(0)
+        cam.width, cam.height = 160, 160
+        _assert_hits_equal(b.primary_hits(cam), oracle_primary_hits(hs, cam))
+    finally:
+        a.close(); b.close()
+
+
+def test_gpu_flattener_emits_the_host_flatteners_bytes_config2_and_instances(tmp_path):
+    for p in (scenegen.gen_config2(str(tmp_path / "c2")),                                        # 996 002 triangles, one big mesh + a quad
+              scenegen.gen_config3(str(tmp_path / "c3"), grid=6, width=96, height=64, spp=1)):   # instanced base mesh, textures
+        hs = HostScene(p)
+        a, b = _scene_with_flattener(hs, -1), _scene_with_flattener(hs, 1)
+        try:
+            ca, cb = a.accel_checksum(), b.accel_checksum()
+            assert ca == cb, (ca, cb)
+            cam = hs.camera(0)
+            cam.width, cam.height = 320, 180
+            _assert_hits_equal(b.primary_hits(cam), a.primary_hits(cam))
+        finally:
+            a.close(); b.close()
+
+
+def test_gpu_flattener_splits_multi_face_leaves_like_the_host(tmp_path):
+    """Coincident centroids leave multi-face BVH2 leaves (mesh.cpp:104-106); both flatteners split them the same way."""
+    rng = np.random.RandomState(3)
+    verts, faces = [], []
+    for k in range(300):                              # stacks of identical triangles + a few distinct ones
+        base = rng.uniform(-5, 5, 3) if k % 7 else np.zeros(3)
+        tri = base + np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float64)
+        for _ in range(1 + (k % 5)):
+            i0 = len(verts)
+            verts.extend(tri.tolist()); faces.append((i0 + 1, i0 + 2, i0 + 3))
+    xml = ("<Scene><MaxRecursionDepth>0</MaxRecursionDepth><BackgroundColor>0 0 0</BackgroundColor><ShadowRayEpsilon>1e-3</ShadowRayEpsilon>"
+           "<Cameras><Camera id=\"1\"><Position>0 0 20</Position><Gaze>0 0 -1</Gaze><Up>0 1 0</Up><NearPlane>-1 1 -1 1</NearPlane><NearDistance>2</NearDistance>"
+           "<ImageResolution>64 64</ImageResolution><ImageName>s.png</ImageName></Camera></Cameras>"
+           "<Lights><AmbientLight>25 25 25</AmbientLight><PointLight id=\"1\"><Position>0 0 30</Position><Intensity>1000 1000 1000</Intensity></PointLight></Lights>"
+           "<Materials><Material id=\"1\"><AmbientReflectance>1 1 1</AmbientReflectance><DiffuseReflectance>1 1 1</DiffuseReflectance>"
+           "<SpecularReflectance>0 0 0</SpecularReflectance><PhongExponent>1</PhongExponent></Material></Materials>"
+           "<VertexData>%s</VertexData><Objects><Mesh id=\"1\"><Material>1</Material><Faces>%s</Faces></Mesh></Objects></Scene>"
+           % ("\n".join("%r %r %r" % tuple(v) for v in verts), "\n".join("%d %d %d" % f for f in faces)))
+    p = tmp_path / "stacks.xml"
+    p.write_text(xml)
+    hs = HostScene(str(p))
+    a, b = _scene_with_flattener(hs, -1), _scene_with_flattener(hs, 1)
+    try:
+        assert a.accel_checksum() == b.accel_checksum()
+        cam = hs.camera(0)
+        _assert_hits_equal(b.primary_hits(cam), oracle_primary_hits(hs, cam))
+    finally:
+        a.close(); b.close()
