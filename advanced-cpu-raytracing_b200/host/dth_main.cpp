@@ -38,10 +38,11 @@ int main(int argc, char* argv[]) {
         if (!strcmp(argv[i], "--seed")) seed = strtoull(argv[i + 1], nullptr, 10);
     }
     dth_scene* hs = nullptr;
-    if (dth_scene_load_xml(argv[1], &hs) != DT_OK) { fprintf(stderr, "%s\n", dth_last_error()); return 1; }
+    if (dt_gpu_init(device) < 0) { fprintf(stderr, "%s\n", dt_last_error()); return 1; }
+    dth_set_bvh_builder(dt_bvh2_build, 32768);        // Mesh::ConstructBVH of the large meshes on the GPU
+    if (dth_scene_load_xml(argv[1], &hs) != DT_OK) { fprintf(stderr, "%s / %s\n", dth_last_error(), dt_last_error()); return 1; }
     for (int i = 0; i < dth_scene_desc(hs)->n_images; i++)
         if (!dth_scene_image_loaded(hs, i)) { fprintf(stderr, "image '%s' could not be decoded (PNG/EXR only in the stand-alone driver)\n", dth_scene_image_path(hs, i)); return 1; }
-    if (dt_gpu_init(device) < 0) { fprintf(stderr, "%s\n", dt_last_error()); return 1; }
     dt_scene* gs = nullptr;
     if (dt_scene_create(dth_scene_desc(hs), &gs) != DT_OK) { fprintf(stderr, "%s\n", dt_last_error()); return 1; }
     auto start = std::chrono::steady_clock::now();

@@ -237,8 +237,10 @@ def main():
     nlon, nlat = (int(x) for x in args.tris.split("x"))
     tmp = tempfile.mkdtemp(prefix="dt_bench_r%d_" % rank)
     xml = make_workload(tmp, nlon, nlat)
+    if capi.load_dorktracer().dt_gpu_init(local_rank) < 0:
+        raise RuntimeError(capi.load_dorktracer().dt_last_error().decode())
     t0 = time.perf_counter()
-    hs = HostScene(xml)
+    hs = HostScene(xml, gpu_build=True)          # Mesh::ConstructBVH on the GPU (dt_bvh2_build), bit-identical to the host build
     t_load = time.perf_counter() - t0
     t0 = time.perf_counter()
     gs = GpuScene(hs, device=local_rank)
