@@ -46,6 +46,17 @@ __device__ __forceinline__ int dt_agg_inc(int* counter) {
     return base + __popc(active & ((1u << lane) - 1u));
 }
 
+// k consecutive slots for every active lane with ONE atomic per warp (k is warp-uniform)
+__device__ __forceinline__ int dt_agg_reserve(int* counter, int k) {
+    const unsigned active = __activemask();
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(active) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(counter, __popc(active) * k);
+    base = __shfl_sync(active, base, leader);
+    return base + __popc(active & ((1u << lane) - 1u)) * k;
+}
+
 __device__ __forceinline__ void dt_accum(float4* accum, uint32_t pix, v3 c) {
     float* p = reinterpret_cast<float*>(accum + pix);
     atomicAdd(p + 0, c.x); atomicAdd(p + 1, c.y); atomicAdd(p + 2, c.z);
@@ -262,8 +273,10 @@ struct DtChild {
     v3 miss;
 };
 
-__device__ __forceinline__ int dt_emit_child(const DtRayQueue& out, float4* out_miss, const DtShadeCounters& counters, int capacity, uint32_t pix, const DtChild& c) {
-    const int slot = dt_agg_inc(counters.next);
+// slot < 0: allocate one here; otherwise a slot obtained earlier (dt_agg_inc / dt_agg_reserve on counters.next), so that the
+// atomic's round trip overlaps the computation of the child
+__device__ __forceinline__ int dt_emit_child(const DtRayQueue& out, float4* out_miss, const DtShadeCounters& counters, int capacity, uint32_t pix, const DtChild& c, int slot = -1) {
+    if (slot < 0) slot = dt_agg_inc(counters.next);
     if (slot >= capacity) { atomicAdd(counters.overflow, 1); return -1; }
     out.o_time[slot] = make_float4(c.o.x, c.o.y, c.o.z, c.mb);
     out.d_tmax[slot] = make_float4(c.d.x, c.d.y, c.d.z, CUDART_INF_F);
@@ -275,9 +288,10 @@ __device__ __forceinline__ int dt_emit_child(const DtRayQueue& out, float4* out_
     return slot;
 }
 
+// slot < 0: allocate one here; otherwise a slot reserved with dt_agg_reserve
 __device__ __forceinline__ void dt_emit_shadow(const DtShadowQueue& sq, const DtShadeCounters& counters, int capacity, v3 o, v3 d, float mb, float tmax,
-                                               v3 contrib, uint32_t pix, int defer_slot, int defer_light) {
-    const int slot = dt_agg_inc(counters.shadow);
+                                               v3 contrib, uint32_t pix, int defer_slot, int defer_light, int slot = -1) {
+    if (slot < 0) slot = dt_agg_inc(counters.shadow);
     if (slot >= capacity) { atomicAdd(counters.overflow, 1); return; }
     sq.o_time[slot] = make_float4(o.x, o.y, o.z, mb);
     sq.d_tmax[slot] = make_float4(d.x, d.y, d.z, tmax);
@@ -396,6 +410,9 @@ __device__ __forceinline__ void dt_shade_ray(const int i, const DtSceneDev& S, c
     if (!inside && sampleDirect) {
         v3 local = vmul(F3(S.ambient_light), F3(mat.ambient));
         const v3 so = vadd(hitPoint, vscale(normal, S.shadow_ray_epsilon));
+        // every point light emits exactly one shadow ray: their slots come from one reservation whose round trip (the top stall
+        // of this kernel when each ray was allocated on its own) overlaps the first light's shading
+        const int point_slot0 = S.n_point_lights > 0 ? dt_agg_reserve(counters.shadow, S.n_point_lights) : 0;
         for (int l = 0; l < S.n_point_lights; l++) {
             const dt_point_light& L = S.point_lights[l];
             v3 lp = F3(L.position);
@@ -407,7 +424,7 @@ __device__ __forceinline__ void dt_shade_ray(const int i, const DtSceneDev& S, c
             v3 res = V(1.f, 1.f, 1.f);
             v3 c = shade_term(S, sh, mat, hitPoint, normal, sf.u, sf.v, w_i, w_o, E, &res);
             if (mat.brdf >= 0) thr = vmul(thr, res);
-            dt_emit_shadow(sq, counters, shadow_capacity, so, sdir, mb, lightT, vmul(W, c), pix, -1, -1);
+            dt_emit_shadow(sq, counters, shadow_capacity, so, sdir, mb, lightT, vmul(W, c), pix, -1, -1, point_slot0 + l);
         }
         for (int l = 0; l < S.n_area_lights; l++) {
             const dt_area_light& L = S.area_lights[l];
@@ -489,13 +506,14 @@ __device__ __forceinline__ void dt_shade_ray(const int i, const DtSceneDev& S, c
     if (depth <= 0) return;        // all three recursive helpers start with `if(recDepth <= 0) return 0`
 
     if (mat.type == DT_MAT_MIRROR) {                                              // raytracer.cpp:442-472
+        const int slot = dt_agg_inc(counters.next);
         DtChild c;
         c.d = reflect_dir(rng, normal, w_o, mat.roughness);
         c.o = vadd(hitPoint, vscale(normal, S.shadow_ray_epsilon)); c.mb = mb;
         c.W = vmul(W, F3(mat.mirror)); c.n_medium = 1.0f; c.thr = thr; c.beer_thr = 0.f;
         c.depth = depth - 1; c.beer_mat = 0; c.rng_key = dt_hash(rng.key, 0x1B873593u); c.flags = 0; c.miss = V(0, 0, 0);
         if (S.n_env_lights > 0) { c.flags |= DT_FLAG_ENV_ON_MISS; c.miss = env_sample(S, 0, c.d); }
-        dt_emit_child(out, out_miss, counters, out_capacity, pix, c);
+        dt_emit_child(out, out_miss, counters, out_capacity, pix, c, slot);
     } else if (mat.type == DT_MAT_CONDUCTOR) {                                    // raytracer.cpp:208-254
         v3 dd = vneg(w_o);
         float cosTheta = -vdot(dd, normal);
@@ -534,6 +552,7 @@ __device__ __forceinline__ void dt_shade_ray(const int i, const DtSceneDev& S, c
             c.depth = depth - 1; c.beer_mat = mat_id; c.rng_key = dt_hash(rng.key, 0x3D4D51CBu); c.flags = 0; c.miss = V(0, 0, 0);
             dt_emit_child(out, out_miss, counters, out_capacity, pix, c);
         } else {
+            const int slot2 = dt_agg_reserve(counters.next, 2);                   // reflected + refracted child
             float cosPhi = sqrtf(1 - criticalTerm);
             float n2cosTheta = n2 * cosTheta;
             float n1cosPhi = n1 * cosPhi;
@@ -550,7 +569,7 @@ __device__ __forceinline__ void dt_shade_ray(const int i, const DtSceneDev& S, c
             c.depth = depth - 1; c.beer_mat = mat_id; c.rng_key = dt_hash(rng.key, 0x4CF5AD43u); c.flags = 0; c.miss = V(0, 0, 0);
             v3 env = V(0, 0, 0);
             if (S.n_env_lights > 0) { env = env_sample(S, 0, refl_dir); c.flags |= DT_FLAG_ENV_ON_MISS; c.miss = env; }
-            dt_emit_child(out, out_miss, counters, out_capacity, pix, c);
+            dt_emit_child(out, out_miss, counters, out_capacity, pix, c, slot2);
 
             v3 w_t = vsub(vscale(vadd(dd, vscale(mn, cosTheta)), r), vscale(mn, cosPhi));
             if (mat.roughness > 0.001) {
@@ -564,7 +583,7 @@ __device__ __forceinline__ void dt_shade_ray(const int i, const DtSceneDev& S, c
             c.W = vscale(W, rRefract); c.beer_thr = 1.001f;
             c.rng_key = dt_hash(rng.key, 0x5A27B1E9u);
             // a refracted ray that misses reads the environment along the REFLECTED direction (raytracer.cpp:408)
-            dt_emit_child(out, out_miss, counters, out_capacity, pix, c);
+            dt_emit_child(out, out_miss, counters, out_capacity, pix, c, slot2 + 1);
         }
     }
 }
