@@ -410,9 +410,11 @@ __device__ __forceinline__ void dt_shade_ray(const int i, const DtSceneDev& S, c
     if (!inside && sampleDirect) {
         v3 local = vmul(F3(S.ambient_light), F3(mat.ambient));
         const v3 so = vadd(hitPoint, vscale(normal, S.shadow_ray_epsilon));
-        // every point light emits exactly one shadow ray: their slots come from one reservation whose round trip (the top stall
-        // of this kernel when each ray was allocated on its own) overlaps the first light's shading
-        const int point_slot0 = S.n_point_lights > 0 ? dt_agg_reserve(counters.shadow, S.n_point_lights) : 0;
+        // every point / area / directional / spot / mesh light emits exactly one shadow ray per shaded hit: all their slots come
+        // from one reservation whose round trip (the top stall of this kernel when each ray was allocated on its own)
+        // overlaps the first light's shading
+        const int n_shadow = S.n_point_lights + S.n_area_lights + S.n_directional_lights + S.n_spot_lights + S.n_mesh_lights;
+        int shadow_slot = n_shadow > 0 ? dt_agg_reserve(counters.shadow, n_shadow) : 0;
         for (int l = 0; l < S.n_point_lights; l++) {
             const dt_point_light& L = S.point_lights[l];
             v3 lp = F3(L.position);
@@ -424,7 +426,7 @@ __device__ __forceinline__ void dt_shade_ray(const int i, const DtSceneDev& S, c
             v3 res = V(1.f, 1.f, 1.f);
             v3 c = shade_term(S, sh, mat, hitPoint, normal, sf.u, sf.v, w_i, w_o, E, &res);
             if (mat.brdf >= 0) thr = vmul(thr, res);
-            dt_emit_shadow(sq, counters, shadow_capacity, so, sdir, mb, lightT, vmul(W, c), pix, -1, -1, point_slot0 + l);
+            dt_emit_shadow(sq, counters, shadow_capacity, so, sdir, mb, lightT, vmul(W, c), pix, -1, -1, shadow_slot++);
         }
         for (int l = 0; l < S.n_area_lights; l++) {
             const dt_area_light& L = S.area_lights[l];
@@ -441,7 +443,7 @@ __device__ __forceinline__ void dt_shade_ray(const int i, const DtSceneDev& S, c
             v3 res = V(1.f, 1.f, 1.f);
             v3 c = shade_term(S, sh, mat, hitPoint, normal, sf.u, sf.v, w_i, w_o, E, &res);
             if (mat.brdf >= 0) thr = vmul(thr, res);
-            dt_emit_shadow(sq, counters, shadow_capacity, so, w_i, mb, lightT, vmul(W, c), pix, -1, -1);
+            dt_emit_shadow(sq, counters, shadow_capacity, so, w_i, mb, lightT, vmul(W, c), pix, -1, -1, shadow_slot++);
         }
         for (int l = 0; l < S.n_env_lights; l++) {                                // no shadow ray (raytracer.cpp:741-755)
             v3 nn = vunit(normal);
@@ -462,7 +464,7 @@ __device__ __forceinline__ void dt_shade_ray(const int i, const DtSceneDev& S, c
             v3 res = V(1.f, 1.f, 1.f);
             v3 c = shade_term(S, sh, mat, hitPoint, normal, sf.u, sf.v, w_i, w_o, F3(L.radiance), &res);
             if (mat.brdf >= 0) thr = vmul(thr, res);
-            dt_emit_shadow(sq, counters, shadow_capacity, so, w_i, mb, CUDART_INF_F, vmul(W, c), pix, -1, -1);
+            dt_emit_shadow(sq, counters, shadow_capacity, so, w_i, mb, CUDART_INF_F, vmul(W, c), pix, -1, -1, shadow_slot++);
         }
         for (int l = 0; l < S.n_spot_lights; l++) {
             const dt_spot_light& L = S.spot_lights[l];
@@ -473,7 +475,7 @@ __device__ __forceinline__ void dt_shade_ray(const int i, const DtSceneDev& S, c
             v3 res = V(1.f, 1.f, 1.f);
             v3 c = shade_term(S, sh, mat, hitPoint, normal, sf.u, sf.v, w_i, w_o, E, &res);
             if (mat.brdf >= 0) thr = vmul(thr, res);
-            dt_emit_shadow(sq, counters, shadow_capacity, so, w_i, mb, lightT, vmul(W, c), pix, -1, -1);
+            dt_emit_shadow(sq, counters, shadow_capacity, so, w_i, mb, lightT, vmul(W, c), pix, -1, -1, shadow_slot++);
         }
         for (int l = 0; l < S.n_mesh_lights; l++) {
             const dt_mesh_light& L = S.mesh_lights[l];
@@ -498,7 +500,7 @@ __device__ __forceinline__ void dt_shade_ray(const int i, const DtSceneDev& S, c
             if (mat.brdf >= 0) thr = vmul(thr, res);
             // hitMeshLightId (raytracer.cpp:91-95,107,781): this light is skipped when the GI child of this very
             // hit lands on the emissive shape with the same id -> decided one wave later (deferred entry).
-            dt_emit_shadow(sq, counters, shadow_capacity, so, w_i, mb, lightT, vmul(W, c), pix, gi_slot, L.id);
+            dt_emit_shadow(sq, counters, shadow_capacity, so, w_i, mb, lightT, vmul(W, c), pix, gi_slot, L.id, shadow_slot++);
         }
         dt_accum(accum, pix, vmul(W, local));
     }
