@@ -46,15 +46,19 @@ __device__ __forceinline__ int dt_agg_inc(int* counter) {
     return base + __popc(active & ((1u << lane) - 1u));
 }
 
-// k consecutive slots for every active lane with ONE atomic per warp (k is warp-uniform)
-__device__ __forceinline__ int dt_agg_reserve(int* counter, int k) {
+// k slots for every active lane with ONE atomic per warp (k is warp-uniform).  The warp's block of slots is laid out
+// item-major: item j of the lane with rank r is slot  first + j * stride  (first = return value, stride = active lanes), so the
+// lanes' stores of one item are consecutive and the j-th items of neighbouring lanes (e.g. their shadow rays towards the same
+// light) stay neighbours in the queue.
+__device__ __forceinline__ int dt_agg_reserve(int* counter, int k, int& stride) {
     const unsigned active = __activemask();
     const int lane = threadIdx.x & 31;
     const int leader = __ffs(active) - 1;
+    stride = __popc(active);
     int base = 0;
-    if (lane == leader) base = atomicAdd(counter, __popc(active) * k);
+    if (lane == leader) base = atomicAdd(counter, stride * k);
     base = __shfl_sync(active, base, leader);
-    return base + __popc(active & ((1u << lane) - 1u)) * k;
+    return base + __popc(active & ((1u << lane) - 1u));
 }
 
 __device__ __forceinline__ void dt_accum(float4* accum, uint32_t pix, v3 c) {
@@ -414,7 +418,8 @@ __device__ __forceinline__ void dt_shade_ray(const int i, const DtSceneDev& S, c
         // from one reservation whose round trip (the top stall of this kernel when each ray was allocated on its own)
         // overlaps the first light's shading
         const int n_shadow = S.n_point_lights + S.n_area_lights + S.n_directional_lights + S.n_spot_lights + S.n_mesh_lights;
-        int shadow_slot = n_shadow > 0 ? dt_agg_reserve(counters.shadow, n_shadow) : 0;
+        int shadow_stride = 0;
+        int shadow_slot = n_shadow > 0 ? dt_agg_reserve(counters.shadow, n_shadow, shadow_stride) : 0;
         for (int l = 0; l < S.n_point_lights; l++) {
             const dt_point_light& L = S.point_lights[l];
             v3 lp = F3(L.position);
@@ -426,7 +431,7 @@ __device__ __forceinline__ void dt_shade_ray(const int i, const DtSceneDev& S, c
             v3 res = V(1.f, 1.f, 1.f);
             v3 c = shade_term(S, sh, mat, hitPoint, normal, sf.u, sf.v, w_i, w_o, E, &res);
             if (mat.brdf >= 0) thr = vmul(thr, res);
-            dt_emit_shadow(sq, counters, shadow_capacity, so, sdir, mb, lightT, vmul(W, c), pix, -1, -1, shadow_slot++);
+            dt_emit_shadow(sq, counters, shadow_capacity, so, sdir, mb, lightT, vmul(W, c), pix, -1, -1, shadow_slot); shadow_slot += shadow_stride;
         }
         for (int l = 0; l < S.n_area_lights; l++) {
             const dt_area_light& L = S.area_lights[l];
@@ -443,7 +448,7 @@ __device__ __forceinline__ void dt_shade_ray(const int i, const DtSceneDev& S, c
             v3 res = V(1.f, 1.f, 1.f);
             v3 c = shade_term(S, sh, mat, hitPoint, normal, sf.u, sf.v, w_i, w_o, E, &res);
             if (mat.brdf >= 0) thr = vmul(thr, res);
-            dt_emit_shadow(sq, counters, shadow_capacity, so, w_i, mb, lightT, vmul(W, c), pix, -1, -1, shadow_slot++);
+            dt_emit_shadow(sq, counters, shadow_capacity, so, w_i, mb, lightT, vmul(W, c), pix, -1, -1, shadow_slot); shadow_slot += shadow_stride;
         }
         for (int l = 0; l < S.n_env_lights; l++) {                                // no shadow ray (raytracer.cpp:741-755)
             v3 nn = vunit(normal);
@@ -464,7 +469,7 @@ __device__ __forceinline__ void dt_shade_ray(const int i, const DtSceneDev& S, c
             v3 res = V(1.f, 1.f, 1.f);
             v3 c = shade_term(S, sh, mat, hitPoint, normal, sf.u, sf.v, w_i, w_o, F3(L.radiance), &res);
             if (mat.brdf >= 0) thr = vmul(thr, res);
-            dt_emit_shadow(sq, counters, shadow_capacity, so, w_i, mb, CUDART_INF_F, vmul(W, c), pix, -1, -1, shadow_slot++);
+            dt_emit_shadow(sq, counters, shadow_capacity, so, w_i, mb, CUDART_INF_F, vmul(W, c), pix, -1, -1, shadow_slot); shadow_slot += shadow_stride;
         }
         for (int l = 0; l < S.n_spot_lights; l++) {
             const dt_spot_light& L = S.spot_lights[l];
@@ -475,7 +480,7 @@ __device__ __forceinline__ void dt_shade_ray(const int i, const DtSceneDev& S, c
             v3 res = V(1.f, 1.f, 1.f);
             v3 c = shade_term(S, sh, mat, hitPoint, normal, sf.u, sf.v, w_i, w_o, E, &res);
             if (mat.brdf >= 0) thr = vmul(thr, res);
-            dt_emit_shadow(sq, counters, shadow_capacity, so, w_i, mb, lightT, vmul(W, c), pix, -1, -1, shadow_slot++);
+            dt_emit_shadow(sq, counters, shadow_capacity, so, w_i, mb, lightT, vmul(W, c), pix, -1, -1, shadow_slot); shadow_slot += shadow_stride;
         }
         for (int l = 0; l < S.n_mesh_lights; l++) {
             const dt_mesh_light& L = S.mesh_lights[l];
@@ -500,7 +505,7 @@ __device__ __forceinline__ void dt_shade_ray(const int i, const DtSceneDev& S, c
             if (mat.brdf >= 0) thr = vmul(thr, res);
             // hitMeshLightId (raytracer.cpp:91-95,107,781): this light is skipped when the GI child of this very
             // hit lands on the emissive shape with the same id -> decided one wave later (deferred entry).
-            dt_emit_shadow(sq, counters, shadow_capacity, so, w_i, mb, lightT, vmul(W, c), pix, gi_slot, L.id, shadow_slot++);
+            dt_emit_shadow(sq, counters, shadow_capacity, so, w_i, mb, lightT, vmul(W, c), pix, gi_slot, L.id, shadow_slot); shadow_slot += shadow_stride;
         }
         dt_accum(accum, pix, vmul(W, local));
     }
@@ -554,7 +559,8 @@ __device__ __forceinline__ void dt_shade_ray(const int i, const DtSceneDev& S, c
             c.depth = depth - 1; c.beer_mat = mat_id; c.rng_key = dt_hash(rng.key, 0x3D4D51CBu); c.flags = 0; c.miss = V(0, 0, 0);
             dt_emit_child(out, out_miss, counters, out_capacity, pix, c);
         } else {
-            const int slot2 = dt_agg_reserve(counters.next, 2);                   // reflected + refracted child
+            int stride2 = 0;
+            const int slot2 = dt_agg_reserve(counters.next, 2, stride2);          // reflected + refracted child
             float cosPhi = sqrtf(1 - criticalTerm);
             float n2cosTheta = n2 * cosTheta;
             float n1cosPhi = n1 * cosPhi;
@@ -585,7 +591,7 @@ __device__ __forceinline__ void dt_shade_ray(const int i, const DtSceneDev& S, c
             c.W = vscale(W, rRefract); c.beer_thr = 1.001f;
             c.rng_key = dt_hash(rng.key, 0x5A27B1E9u);
             // a refracted ray that misses reads the environment along the REFLECTED direction (raytracer.cpp:408)
-            dt_emit_child(out, out_miss, counters, out_capacity, pix, c, slot2 + 1);
+            dt_emit_child(out, out_miss, counters, out_capacity, pix, c, slot2 + stride2);
         }
     }
 }
