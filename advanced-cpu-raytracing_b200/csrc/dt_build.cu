@@ -197,7 +197,8 @@ __global__ void k_iota(uint32_t* id, int32_t* seg, const float* xyz, float* cx, 
 
 struct DevBuf {
     std::vector<void*> ptrs;
-    ~DevBuf() { for (void* p : ptrs) cudaFree(p); }
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    ~DevBuf() { for (void* p : ptrs) cudaFree(p); if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); }
     template <class T> cudaError_t get(T** p, size_t n) { void* v = nullptr; cudaError_t e = cudaMalloc(&v, n * sizeof(T) + 16); if (e == cudaSuccess) { ptrs.push_back(v); *p = (T*)v; } return e; }
 };
 
@@ -222,7 +223,8 @@ extern "C" int dt_bvh2_build(int32_t n_faces, const float* centers, const float*
     BCK(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, flag, excl, (int)(n + 1)));
     void* scan_tmp; BCK(B.get((uint8_t**)&scan_tmp, scan_bytes));
     cudaStream_t st = nullptr;
-    cudaEvent_t e0, e1; BCK(cudaEventCreate(&e0)); BCK(cudaEventCreate(&e1));
+    BCK(cudaEventCreate(&B.e0)); BCK(cudaEventCreate(&B.e1));
+    const cudaEvent_t e0 = B.e0, e1 = B.e1;
     BCK(cudaMemcpy(fboxes, face_boxes, (size_t)n * 24, cudaMemcpyHostToDevice));
     BCK(cudaMemcpy(aos, centers, (size_t)n * 12, cudaMemcpyHostToDevice));
     BCK(cudaEventRecord(e0, st));
@@ -267,7 +269,6 @@ extern "C" int dt_bvh2_build(int32_t n_faces, const float* centers, const float*
     BCK(cudaStreamSynchronize(st));
     BCK(cudaGetLastError());
     if (ms_device) { float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1); *ms_device = ms; }
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
     *n_nodes_out = h_n_nodes;
     return DT_OK;
 }
