@@ -380,6 +380,14 @@ __device__ __forceinline__ void dt_shade_ray(const int i, const DtSceneDev& S, c
     v3 thr = V(tb.x, tb.y, tb.z);
     int gi_slot = -1;
 
+    // Queue slots are requested up front so that the atomics' round trips overlap the sampling / BRDF arithmetic below.
+    // Every point / area / directional / spot / mesh light emits exactly one shadow ray per shaded hit: one reservation.
+    const bool sampleDirect = !cam.path_tracing || cam.nee;
+    const bool direct = !inside && sampleDirect;
+    const int n_shadow = direct ? S.n_point_lights + S.n_area_lights + S.n_directional_lights + S.n_spot_lights + S.n_mesh_lights : 0;
+    int shadow_stride = 0;
+    int shadow_slot = n_shadow > 0 ? dt_agg_reserve(counters.shadow, n_shadow, shadow_stride) : 0;
+
     // ---- ComputeGlobalIllumination (raytracer.cpp:135-191) ----
     if (cam.path_tracing) {
         bool go = true;
@@ -390,6 +398,7 @@ __device__ __forceinline__ void dt_shade_ray(const int i, const DtSceneDev& S, c
             else thr = vdiv(thr, maxT);
         } else if (depth <= 0) go = false;
         if (go) {
+            gi_slot = dt_agg_inc(counters.next);
             float rand1 = rng01(rng), rand2 = rng01(rng);
             float phi = (float)(2 * DT_PI * rand1);
             float theta = cam.importance_sampling ? asinf(sqrtf(rand2)) : acosf(rand2);
@@ -404,22 +413,15 @@ __device__ __forceinline__ void dt_shade_ray(const int i, const DtSceneDev& S, c
             c.W = vmul(W, vscale(vscale(f, 2.0f), DT_PI_F));
             c.n_medium = n_medium; c.thr = thr; c.beer_thr = 0.f;
             c.depth = depth - 1; c.beer_mat = 0; c.rng_key = dt_hash(rng.key, 0xA511E9B3u); c.flags = 0; c.miss = V(0, 0, 0);
-            gi_slot = dt_emit_child(out, out_miss, counters, out_capacity, pix, c);
+            gi_slot = dt_emit_child(out, out_miss, counters, out_capacity, pix, c, gi_slot);
             if (mat.brdf >= 0) thr = vmul(thr, res);                              // Shade(): ray.throughput *= res
         }
     }
 
     // ---- ambient + SampleDirectLighting (raytracer.cpp:98-108, 701-806) ----
-    const bool sampleDirect = !cam.path_tracing || cam.nee;
-    if (!inside && sampleDirect) {
+    if (direct) {
         v3 local = vmul(F3(S.ambient_light), F3(mat.ambient));
         const v3 so = vadd(hitPoint, vscale(normal, S.shadow_ray_epsilon));
-        // every point / area / directional / spot / mesh light emits exactly one shadow ray per shaded hit: all their slots come
-        // from one reservation whose round trip (the top stall of this kernel when each ray was allocated on its own)
-        // overlaps the first light's shading
-        const int n_shadow = S.n_point_lights + S.n_area_lights + S.n_directional_lights + S.n_spot_lights + S.n_mesh_lights;
-        int shadow_stride = 0;
-        int shadow_slot = n_shadow > 0 ? dt_agg_reserve(counters.shadow, n_shadow, shadow_stride) : 0;
         for (int l = 0; l < S.n_point_lights; l++) {
             const dt_point_light& L = S.point_lights[l];
             v3 lp = F3(L.position);
