@@ -268,11 +268,12 @@ int launch_sort(dt_scene* s, DtPipe& pp, const DtRayQueue& q, const int* n_ptr, 
 // valid primary rays of this rank: every in-image pixel of the owned tiles
 long long count_valid_pixels(const dt_render_params& P, int W, int H) {
     const int tiles_x = (W + 7) / 8, tiles_y = (H + 3) / 4;
-    const long long n_tiles = (long long)tiles_x * tiles_y;
     if (P.tile_world == 1 && W % 8 == 0 && H % 4 == 0) return (long long)W * H;
     long long valid = 0;
-    for (long long tile = P.tile_rank; tile < n_tiles; tile += P.tile_world) {
-        int tx = (int)(tile % tiles_x), ty = (int)(tile / tiles_x);
+    const long long mine = dt_rank_tile_count(tiles_x, tiles_y, P.tile_rank, P.tile_world);
+    for (long long j = 0; j < mine; j++) {
+        int tx, ty;
+        if (!dt_rank_tile(j, P.tile_rank, P.tile_world, tiles_x, tiles_y, tx, ty)) continue;
         int w = std::min(8, W - tx * 8), h = std::min(4, H - ty * 4);
         if (w > 0 && h > 0) valid += (long long)w * h;
     }
@@ -296,8 +297,7 @@ int render_core(dt_scene* s, const dt_camera_desc* cam, const dt_render_params* 
     wp.seed_lo = (uint32_t)P.seed; wp.seed_hi = (uint32_t)(P.seed >> 32);
     wp.tile_rank = P.tile_rank; wp.tile_world = P.tile_world;
     wp.tiles_x = (W + 7) / 8; wp.tiles_y = (H + 3) / 4;
-    const long long n_tiles = (long long)wp.tiles_x * wp.tiles_y;
-    const long long my_tiles = (n_tiles - P.tile_rank + P.tile_world - 1) / P.tile_world;
+    const long long my_tiles = dt_rank_tile_count(wp.tiles_x, wp.tiles_y, P.tile_rank, P.tile_world);
     wp.per_sample = my_tiles * 32;
     const long long total = wp.per_sample * dc.spp;
 
@@ -341,7 +341,7 @@ retry:
             wps[p] = wp;
             wps[p].tile_world = P.tile_world * NP;
             wps[p].tile_rank = P.tile_rank + p * P.tile_world;
-            const long long tiles_p = (n_tiles - wps[p].tile_rank + wps[p].tile_world - 1) / wps[p].tile_world;
+            const long long tiles_p = dt_rank_tile_count(wp.tiles_x, wp.tiles_y, wps[p].tile_rank, wps[p].tile_world);
             wps[p].per_sample = tiles_p * 32;
             const long long total_p = wps[p].per_sample * dc.spp;
             n0[p] = (int)total_p;
@@ -824,10 +824,9 @@ int dt_render_device(dt_scene* s, const dt_camera_desc* cam, const dt_render_par
         }
         const int tiles_x = (cam->width + 7) / 8, tiles_y = (cam->height + 3) / 4;
         const int world = params->tile_world < 1 ? 1 : params->tile_world;
-        const long long n_tiles = (long long)tiles_x * tiles_y;
-        const long long my_tiles = (n_tiles - params->tile_rank + world - 1) / world;
-        const long long threads = my_tiles * 32;
-        k_resolve_tiles<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(s->accum, cam->width, cam->height, tiles_x, my_tiles, params->tile_rank, world, spp, dst_hdr, dst_ldr, s->counters);
+        const long long my_tiles = dt_rank_tile_count(tiles_x, tiles_y, params->tile_rank, world);
+        const long long threads = my_tiles / DT_TILE_GROUP * 32;     // one warp per strip
+        k_resolve_tiles<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(s->accum, cam->width, cam->height, tiles_x, tiles_y, my_tiles, params->tile_rank, world, spp, dst_hdr, dst_ldr, s->counters);
     } else {
         k_resolve<<<(n_pix + 255) / 256, 256, 0, st>>>(s->accum, n_pix, spp, s->hdr, s->ldr, s->counters);
     }
@@ -946,7 +945,7 @@ int dt_render(dt_scene* s, const dt_camera_desc* cam, const dt_render_params* pa
 int dt_primary_hits(dt_scene* s, const dt_camera_desc* cam, int32_t* shape, int32_t* face, float* t) {
     if (!s || !shape || !face || !t) { g_err = "null argument"; return DT_ERR_INVALID; }
     dt_render_params P; memset(&P, 0, sizeof P); P.seed = 1234; P.tile_world = 1;
-    const long long n_slots = (long long)((cam->width + 7) / 8) * ((cam->height + 3) / 4) * 32;
+    const long long n_slots = dt_rank_tile_count((cam->width + 7) / 8, (cam->height + 3) / 4, 0, 1) * 32;      // ray slots of the frame (whole strips)
     if (n_slots > (1ll << 28)) { g_err = "image too large for dt_primary_hits"; return DT_ERR_INVALID; }
     P.max_wave_rays = (int)n_slots;
     dt_stats S;

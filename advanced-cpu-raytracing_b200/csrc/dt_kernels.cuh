@@ -18,6 +18,24 @@ struct DtCamDev {
     int path_tracing, importance_sampling, nee, russian_roulette;
 };
 
+// Tile ownership across ranks.  Every row of 8x4-pixel tiles is
+// cut into STRIPS of DT_TILE_GROUP tiles (64x4 pixels; the last strip of a row may be shorter) and the strips are dealt out
+// round-robin in row-major strip order, so that a rank's resolve kernel writes 192 contiguous bytes per row segment into the
+// destination rank's frame over NVLink instead of 24.  j-th tile slot of a rank -> tile (tx, ty); false = dead slot.
+#define DT_TILE_GROUP 8
+__host__ __device__ __forceinline__ bool dt_rank_tile(long long j, int rank, int world, int tiles_x, int tiles_y, int& tx, int& ty) {
+    const int strips_x = (tiles_x + DT_TILE_GROUP - 1) / DT_TILE_GROUP;
+    const long long strip = (j / DT_TILE_GROUP) * world + rank;
+    ty = (int)(strip / strips_x);
+    tx = (int)(strip % strips_x) * DT_TILE_GROUP + (int)(j % DT_TILE_GROUP);
+    return ty < tiles_y && tx < tiles_x;
+}
+// tile slots of a rank (whole strips; slots past the end of a short strip are dead)
+__host__ __device__ __forceinline__ long long dt_rank_tile_count(int tiles_x, int tiles_y, int rank, int world) {
+    const long long strips = (long long)((tiles_x + DT_TILE_GROUP - 1) / DT_TILE_GROUP) * tiles_y;
+    return rank < strips ? ((strips - rank + world - 1) / world) * DT_TILE_GROUP : 0;
+}
+
 struct DtWaveParams {
     uint32_t seed_lo, seed_hi;
     int tile_rank, tile_world;
@@ -97,12 +115,13 @@ __global__ void k_generate(DtCamDev cam, DtWaveParams wp, DtRayQueue q, int base
     const long long k = k0 + idx;
     const int s = (int)(k / wp.per_sample);
     const long long rem = k % wp.per_sample;
-    const long long tile = (rem >> 5) * wp.tile_world + wp.tile_rank;
+    int tx, ty;
+    const bool live = dt_rank_tile(rem >> 5, wp.tile_rank, wp.tile_world, wp.tiles_x, wp.tiles_y, tx, ty);
     const int lane = (int)(rem & 31);
-    const int x = (int)(tile % wp.tiles_x) * 8 + (lane & 7);
-    const int y = (int)(tile / wp.tiles_x) * 4 + (lane >> 3);
+    const int x = tx * 8 + (lane & 7);
+    const int y = ty * 4 + (lane >> 3);
     const int slot = base + idx;
-    if (x >= cam.width || y >= cam.height) {
+    if (!live || x >= cam.width || y >= cam.height) {
         q.pixel[slot] = DT_DEAD_PIXEL;
         return;
     }
@@ -730,26 +749,50 @@ __global__ void k_resolve(const float4* accum, int n_pix, int spp, float* hdr, u
     }
 }
 
-// Resolve + gather fused (DT_FLAG_PEER_FRAME): one warp per OWNED 8x4 tile; hdr / ldr may point into another GPU's memory
-// (CUDA IPC mapping, stores travel over NVLink), so only owned pixels are written and nothing is read back from them.
-__global__ void k_resolve_tiles(const float4* accum, int width, int height, int tiles_x, long long my_tiles, int tile_rank, int tile_world,
+// Resolve + gather fused (DT_FLAG_PEER_FRAME): hdr / ldr may point into another GPU's memory (CUDA IPC mapping, stores travel
+// over NVLink), so only owned pixels are written and nothing is read back from them.  One warp per owned strip of
+// DT_TILE_GROUP tiles (64x4 pixels): a lane resolves 4 consecutive pixels of two rows; the 12 LDR bytes it produces are
+// exchanged by shuffles so that every store instruction writes whole 32-bit words, 64 contiguous bytes per row
+// (fast path: full strip, width a multiple of 4 so that rows are word-aligned; otherwise byte stores).
+__global__ void k_resolve_tiles(const float4* accum, int width, int height, int tiles_x, int tiles_y, long long my_tiles, int tile_rank, int tile_world,
                                 int spp, float* hdr, uint8_t* ldr, int* counters) {
-    const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (w >= my_tiles) return;
+    const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;      // strip slot of this rank
+    if (w * DT_TILE_GROUP >= my_tiles) return;
     const int lane = threadIdx.x & 31;
-    const long long tile = w * tile_world + tile_rank;
-    const int x = (int)(tile % tiles_x) * 8 + (lane & 7), y = (int)(tile / tiles_x) * 4 + (lane >> 3);
-    if (x >= width || y >= height) return;
-    const size_t i = (size_t)y * width + x;
-    const float4 a = accum[i];
-    float r = a.x, g = a.y, b = a.z;
-    if (spp > 1 && a.w > 0.f) { r = r / a.w; g = g / a.w; b = b / a.w; }
-    if (isnan(r) || isnan(g) || isnan(b)) atomicAdd(counters + DT_CNT_NAN, 1);
-    if (hdr) { hdr[3 * i] = r; hdr[3 * i + 1] = g; hdr[3 * i + 2] = b; }
-    if (ldr) {
-        ldr[3 * i] = (uint8_t)dt_clamp_channel(r);
-        ldr[3 * i + 1] = (uint8_t)dt_clamp_channel(g);
-        ldr[3 * i + 2] = (uint8_t)dt_clamp_channel(b);
+    int tx0, ty;
+    if (!dt_rank_tile(w * DT_TILE_GROUP, tile_rank, tile_world, tiles_x, tiles_y, tx0, ty)) return;
+    const int x0 = tx0 * 8, y0 = ty * 4;
+    const int strip_w = min(DT_TILE_GROUP * 8, min(tiles_x * 8, width) - x0);      // pixels of this strip inside the image
+    const bool fast = ldr && (width & 3) == 0 && strip_w == DT_TILE_GROUP * 8;
+    const int l16 = lane & 15;
+    for (int half = 0; half < 2; half++) {
+        const int y = y0 + half * 2 + (lane >> 4);
+        uint32_t words[3] = {0u, 0u, 0u};
+        uint8_t* bytes = reinterpret_cast<uint8_t*>(words);
+        for (int k = 0; k < 4; k++) {
+            const int x = x0 + l16 * 4 + k;
+            if (y >= height || x >= x0 + strip_w) continue;
+            const size_t i = (size_t)y * width + x;
+            const float4 a = accum[i];
+            float r = a.x, g = a.y, b = a.z;
+            if (spp > 1 && a.w > 0.f) { r = r / a.w; g = g / a.w; b = b / a.w; }
+            if (isnan(r) || isnan(g) || isnan(b)) atomicAdd(counters + DT_CNT_NAN, 1);
+            if (hdr) { hdr[3 * i] = r; hdr[3 * i + 1] = g; hdr[3 * i + 2] = b; }
+            if (ldr) {
+                const uint8_t cr = (uint8_t)dt_clamp_channel(r), cg = (uint8_t)dt_clamp_channel(g), cb = (uint8_t)dt_clamp_channel(b);
+                if (fast) { bytes[3 * k] = cr; bytes[3 * k + 1] = cg; bytes[3 * k + 2] = cb; }
+                else { ldr[3 * i] = cr; ldr[3 * i + 1] = cg; ldr[3 * i + 2] = cb; }
+            }
+        }
+        if (fast) {                                                                  // warp-uniform
+            // a row of the strip is 48 words; lane l16 holds words 3*l16 .. 3*l16+2 and stores words l16, 16 + l16, 32 + l16
+            uint32_t* row = reinterpret_cast<uint32_t*>(ldr + ((size_t)y * width + x0) * 3);
+            for (int k = 0; k < 3; k++) {
+                const int j = 16 * k + l16, src = (lane & 16) | (j / 3), slot = j % 3;
+                const uint32_t w0 = __shfl_sync(0xFFFFFFFFu, words[0], src), w1 = __shfl_sync(0xFFFFFFFFu, words[1], src), w2 = __shfl_sync(0xFFFFFFFFu, words[2], src);
+                if (y < height) row[j] = slot == 0 ? w0 : (slot == 1 ? w1 : w2);
+            }
+        }
     }
 }
 

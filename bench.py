@@ -286,6 +286,8 @@ def main():
         peer = bool(flag.item())
     peer_flags = capi.DT_FLAG_PEER_FRAME if peer else 0
 
+    split_ms = [0.0, 0.0]                                                      # this rank's render / wait-at-the-barrier parts of the timed steps
+
     def device_step(timed):
         """value path: inputs resident, no host copies.  Returns (ms, stats)."""
         flush_buf.fill_(rank + 1)                                              # L2 flush between iterations
@@ -307,6 +309,8 @@ def main():
             r1.record()
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) + r0.elapsed_time(r1)
+            if timed:
+                split_ms[0] += e0.elapsed_time(e1); split_ms[1] += r0.elapsed_time(r1)
         else:
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1)
@@ -353,6 +357,8 @@ def main():
         rays_c += int(st.rays_closest); rays_s += int(st.rays_shadow)
         ov_closest += st.ms_traverse_closest; ov_shadow += st.ms_traverse_shadow; ov_shade += st.ms_shade
     barrier()
+    if world > 1 and os.environ.get("DT_BENCH_VERBOSE"):
+        print("[bench] rank %d: render %.3f ms + barrier wait %.3f ms per step" % (rank, split_ms[0] / args.steps, split_ms[1] / args.steps), file=sys.stderr, flush=True)
     t_wall = time.perf_counter() - t_wall0
     clocks = sampler.stop()
 
