@@ -6,7 +6,7 @@ A *step* is one frame of the workload through the hot path:
   N = 1 : BASELINE.json configs[1] — ~1M-triangle mesh (procedural "blob": the named bunny/dragon assets are
           stripped from the reference mount), mirror + dielectric recursion depth 6, 2 point lights, 1920x1080.
   N > 1 : the same scene and view with sqrt(N) x the resolution per axis (per-GPU pixel count fixed -> weak
-          scaling); the image is tile-sharded (8x4-pixel tiles, round-robin) across the ranks, each rank renders
+          scaling); the image is tile-sharded (strips of eight 8x4-pixel tiles, round-robin) across the ranks, each rank renders
           its tiles with the whole scene replicated, and the per-rank radiance frames are combined on rank 0
           without a full-frame exchange: rank 0 exports its frame buffers (CUDA IPC) and every rank's resolve kernel
           stores its tiles straight into them over NVLink (P2P stores), then one barrier.  Fallback when the IPC
