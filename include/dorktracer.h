@@ -219,7 +219,8 @@ typedef struct dt_camera_desc {         /* src/camera.hpp:12-50, rendererParams.
 
 typedef struct dt_render_params {
     uint64_t seed;                      /* counter-based RNG key (the reference's RNG is unseeded + racy)        */
-    int32_t tile_rank, tile_world;      /* image tiles t with t % tile_world == tile_rank are rendered (1 GPU: 0,1) */
+    int32_t tile_rank, tile_world;      /* strips s (8 consecutive 8x4-pixel tiles of a tile row, row-major) with
+                                           s % tile_world == tile_rank are rendered (1 GPU: 0,1) */
     int32_t max_wave_rays;              /* primary rays per wave, 0 = default                                      */
     int32_t flags;                      /* DT_FLAG_*                                                               */
 } dt_render_params;
