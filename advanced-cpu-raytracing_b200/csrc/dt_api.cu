@@ -75,7 +75,7 @@ struct DtPipe {
     cudaEvent_t ev_shade[3] = {nullptr, nullptr, nullptr}, ev_shadow[3] = {nullptr, nullptr, nullptr}, ev_done = nullptr;
     int* counters = nullptr;      // this pipe's block of dt_scene::counters
     int* sort_perm = nullptr;     // material-sorted order of the current wave (sort stage)
-    int* sort_hist = nullptr;     // DT_SORT_BINS bin counts / cursors
+    int* sort_hist = nullptr;     // DT_SORT_BINS bin counts + DT_SORT_BINS running cursors
     DtPipe() { memset(q, 0, sizeof q); memset(sq, 0, sizeof sq); }
     void free_queues() { for (void* p : allocs) cudaFree(p); allocs.clear(); capacity = shadow_capacity = 0; }
 };
@@ -178,7 +178,7 @@ int ensure_queues(dt_scene* s, DtPipe& pp, int capacity, int shadow_capacity, bo
         if (need_defer && k == 0) { if ((rc = qalloc(pp, &sq.defer, shadow_capacity))) return rc; }
     }
     if ((rc = qalloc(pp, &pp.sort_perm, capacity))) return rc;
-    if ((rc = qalloc(pp, &pp.sort_hist, DT_SORT_BINS))) return rc;
+    if ((rc = qalloc(pp, &pp.sort_hist, 2 * DT_SORT_BINS))) return rc;
     pp.capacity = capacity; pp.shadow_capacity = shadow_capacity; pp.has_miss = s->has_env; pp.has_defer = need_defer;
     return DT_OK;
 }
@@ -257,12 +257,11 @@ struct RenderOut { float* hdr_dev; };
 
 // Sort stage (k_sort_*): fills pp.sort_perm with the material-sorted order of wave queue `q`; returns launches.
 int launch_sort(dt_scene* s, DtPipe& pp, const DtRayQueue& q, const int* n_ptr, int n_fixed, cudaStream_t st) {
-    cudaMemsetAsync(pp.sort_hist, 0, DT_SORT_BINS * sizeof(int), st);
+    cudaMemsetAsync(pp.sort_hist, 0, 2 * DT_SORT_BINS * sizeof(int), st);           // bin counts + running cursors
     const int grid = s->num_sms * 4;
     k_sort_hist<<<grid, 256, 0, st>>>(s->dev, q, n_ptr, n_fixed, pp.sort_hist);
-    k_sort_scan<<<1, DT_SORT_BINS, 0, st>>>(pp.sort_hist);
-    k_sort_scatter<<<grid, 256, 0, st>>>(q, n_ptr, n_fixed, pp.sort_hist, pp.sort_perm);
-    return 3;
+    k_sort_scatter<<<grid, 256, 0, st>>>(q, n_ptr, n_fixed, pp.sort_hist, pp.sort_hist + DT_SORT_BINS, pp.sort_perm);
+    return 2;
 }
 
 // valid primary rays of this rank: every in-image pixel of the owned tiles

@@ -633,8 +633,8 @@ __global__ void __launch_bounds__(128, DT_SHADE_MINBLOCKS) k_shade(DtSceneDev S,
 // ------------------------------------------------------------------ sort / compact by material
 // Between closest-hit and shade: a counting sort of the wave by shading key (0 = dead slot or miss, 1 + material id of
 // the hit shape otherwise), so that the lanes of a shading warp run the same material / BRDF / texture branches
-// (PerformShading's switch over Material::type and BRDF, raytracer.cpp:65-134).  Three small launches: histogram,
-// exclusive scan of the (<= 256) bins, stable-per-block scatter of ray indices into `perm`.
+// (PerformShading's switch over Material::type and BRDF, raytracer.cpp:65-134).  Two small launches: histogram,
+// stable-per-block scatter of ray indices into `perm` (each block scans the <= 256 bin counts itself).
 #define DT_SORT_BINS 256
 __device__ __forceinline__ int dt_sort_key(const DtSceneDev& S, const DtRayQueue& q, int i) {
     if (q.pixel[i] == DT_DEAD_PIXEL) return 0;
@@ -656,26 +656,27 @@ __global__ void __launch_bounds__(256) k_sort_hist(DtSceneDev S, DtRayQueue q, c
     __syncthreads();
     if (h[threadIdx.x]) atomicAdd(&hist[threadIdx.x], h[threadIdx.x]);
 }
-// one block of DT_SORT_BINS threads: hist -> exclusive offsets (in place, used as running cursors by the scatter)
-__global__ void __launch_bounds__(DT_SORT_BINS) k_sort_scan(int* hist) {
-    __shared__ int sc[DT_SORT_BINS];
-    const int t = threadIdx.x;
-    const int v = hist[t];
-    sc[t] = v;
-    __syncthreads();
-    for (int d = 1; d < DT_SORT_BINS; d <<= 1) {
-        const int x = t >= d ? sc[t - d] : 0;
-        __syncthreads();
-        sc[t] += x;
-        __syncthreads();
-    }
-    hist[t] = sc[t] - v;
-}
-// each block takes a contiguous chunk of the wave, reserves one range per bin, and writes its rays in chunk order
-__global__ void __launch_bounds__(256) k_sort_scatter(DtRayQueue q, const int* n_ptr, int n_fixed, int* cursors, int* perm) {
-    __shared__ int cnt[DT_SORT_BINS], base[DT_SORT_BINS];
+// Each block turns the bin counts into exclusive offsets itself (256 values: cheaper than a third launch between the
+// histogram and the scatter), takes contiguous chunks of the wave, reserves one range per bin through the running cursors
+// (zeroed with the histogram) and writes its rays in chunk order.
+__global__ void __launch_bounds__(256) k_sort_scatter(DtRayQueue q, const int* n_ptr, int n_fixed, const int* hist, int* cursors, int* perm) {
+    __shared__ int cnt[DT_SORT_BINS], base[DT_SORT_BINS], offs[DT_SORT_BINS];
+    static_assert(DT_SORT_BINS == 256, "one thread per bin");
     const int n = n_ptr ? *n_ptr : n_fixed;
     const int chunk = 256 * 8;
+    if (blockIdx.x * chunk >= n) return;
+    {
+        const int t = threadIdx.x, v = hist[t];
+        offs[t] = v;
+        __syncthreads();
+        for (int d = 1; d < DT_SORT_BINS; d <<= 1) {
+            const int x = t >= d ? offs[t - d] : 0;
+            __syncthreads();
+            offs[t] += x;
+            __syncthreads();
+        }
+        offs[t] -= v;                                                              // exclusive
+    }
     for (int c0 = blockIdx.x * chunk; c0 < n; c0 += gridDim.x * chunk) {
         cnt[threadIdx.x] = 0;
         __syncthreads();
@@ -687,7 +688,7 @@ __global__ void __launch_bounds__(256) k_sort_scatter(DtRayQueue q, const int* n
             rank[k] = key[k] >= 0 ? atomicAdd(&cnt[key[k]], 1) : 0;
         }
         __syncthreads();
-        if (cnt[threadIdx.x]) base[threadIdx.x] = atomicAdd(&cursors[threadIdx.x], cnt[threadIdx.x]);
+        if (cnt[threadIdx.x]) base[threadIdx.x] = offs[threadIdx.x] + atomicAdd(&cursors[threadIdx.x], cnt[threadIdx.x]);
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < 8; k++) if (key[k] >= 0) perm[base[key[k]] + rank[k]] = c0 + k * 256 + threadIdx.x;
