@@ -55,3 +55,17 @@ def test_two_rank_gloo_combine(tmp_path):
     mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
     combined, full = np.load(out)
     assert np.array_equal(combined, full)                 # SUM of disjoint shards == the unsharded frame, bit for bit
+
+
+def test_tiles_are_dealt_out_in_row_aligned_strips():
+    """dt_rank_tile (csrc/dt_kernels.cuh) / tiles.tile_owner: strips of TILE_GROUP tiles never wrap around a tile row, every
+    strip has one owner, and consecutive strips (row-major) go to consecutive ranks."""
+    for (w, h, world) in ((1920, 1080, 8), (2712, 1528, 2), (100, 52, 3), (64, 4, 4)):
+        own = tiles.tile_owner(w, h, world)
+        ty, tx = own.shape
+        strips_x = (tx + tiles.TILE_GROUP - 1) // tiles.TILE_GROUP
+        for y in range(0, ty, max(1, ty // 7)):
+            for sx in range(strips_x):
+                seg = own[y, sx * tiles.TILE_GROUP:(sx + 1) * tiles.TILE_GROUP]
+                assert (seg == seg[0]).all()
+                assert seg[0] == (y * strips_x + sx) % world
