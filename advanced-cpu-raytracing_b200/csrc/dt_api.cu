@@ -125,20 +125,36 @@ struct dt_scene {
     int shadow_order = 1;         // 1: shadow(k) released together with closest(k+1) (see the wave loop); 0: right after shade(k)
     int sort_mode = 1;            // sort-by-material stage: 0 off, 1 auto (scenes with >= 3 materials), 2 always (DT_SORT)
 
+    // device-resident wave loop (path tracing with Russian roulette, multi-batch frames): one CUDA graph per frame shape
+    int dev_loop = 1;             // DT_DEVLOOP=0: host-synchronised loop instead (A/B)
+    int tail_threshold = -2;      // rays alive at which the loop hands over to k_tail; -2 = auto (64 per k_tail block), -1 = never (DT_TAIL_THRESHOLD)
+    cudaGraph_t loop_graph = nullptr;
+    cudaGraphExec_t loop_exec = nullptr;
+    std::string loop_key;
+    uint32_t loop_launches_per_iter = 0;
+    DtTailMem tail; int tail_grid = 0; bool tail_has_miss = false, tail_has_defer = false;
+    std::vector<void*> tail_allocs;
+
     void free_queues() { for (DtPipe& p : pipes) p.free_queues(); }
+    void free_loop() {
+        if (loop_exec) cudaGraphExecDestroy(loop_exec);
+        if (loop_graph) cudaGraphDestroy(loop_graph);
+        loop_exec = nullptr; loop_graph = nullptr; loop_key.clear();
+    }
+    void free_tail() { for (void* p : tail_allocs) cudaFree(p); tail_allocs.clear(); tail_grid = 0; }
 };
 
 namespace {
 
 template <bool ANY>
-void launch_traverse(dt_scene* s, const DtRayQueue& q, const DtShadowQueue& sq, const int* n_ptr, int n_fixed, int* fetch, float4* accum, cudaStream_t st = nullptr, int spare_blocks_per_sm = 0) {
+void launch_traverse(dt_scene* s, const DtRayQueue& q, const DtShadowQueue& sq, const int* n_ptr, int n_fixed, int n_cap, int* fetch, float4* accum, cudaStream_t st = nullptr, int spare_blocks_per_sm = 0) {
     const int grid = std::max(s->num_sms, s->grid_trav[s->trav_mode][ANY ? 1 : 0] - spare_blocks_per_sm * s->num_sms);
     if (!st) st = s->stream;
     switch (s->trav_mode) {
-        case 0: k_traverse<ANY, false><<<grid, 128, 0, st>>>(s->dev, q, sq, n_ptr, n_fixed, fetch, accum); break;
-        case 1: k_traverse<ANY, true><<<grid, 128, 0, st>>>(s->dev, q, sq, n_ptr, n_fixed, fetch, accum); break;
-        case 2: k_traverse_dyn<ANY, false><<<grid, 128, 0, st>>>(s->dev, q, sq, n_ptr, n_fixed, fetch, accum, s->refill_threshold); break;
-        default: k_traverse_dyn<ANY, true><<<grid, 128, 0, st>>>(s->dev, q, sq, n_ptr, n_fixed, fetch, accum, s->refill_threshold); break;
+        case 0: k_traverse<ANY, false><<<grid, 128, 0, st>>>(s->dev, q, sq, n_ptr, n_fixed, n_cap, fetch, accum); break;
+        case 1: k_traverse<ANY, true><<<grid, 128, 0, st>>>(s->dev, q, sq, n_ptr, n_fixed, n_cap, fetch, accum); break;
+        case 2: k_traverse_dyn<ANY, false><<<grid, 128, 0, st>>>(s->dev, q, sq, n_ptr, n_fixed, n_cap, fetch, accum, s->refill_threshold); break;
+        default: k_traverse_dyn<ANY, true><<<grid, 128, 0, st>>>(s->dev, q, sq, n_ptr, n_fixed, n_cap, fetch, accum, s->refill_threshold); break;
     }
 }
 
@@ -198,13 +214,16 @@ int ensure_outputs(dt_scene* s, size_t n_pix) {
     return DT_OK;
 }
 
-DtCamDev make_cam(const dt_camera_desc* c) {
+DtCamDev make_cam(const dt_camera_desc* c, int flags) {
     DtCamDev d;
+    memset(&d, 0, sizeof d);                 // the struct is part of the graph cache keys: no indeterminate padding
     memcpy(d.position, c->position, 12); memcpy(d.gaze, c->gaze, 12); memcpy(d.up, c->up, 12); memcpy(d.right, c->right, 12); memcpy(d.q, c->q, 12);
     d.left = c->left; d.right_ = c->right_; d.bottom = c->bottom; d.top = c->top;
     d.width = c->width; d.height = c->height; d.spp = c->samples_per_pixel < 1 ? 1 : c->samples_per_pixel;
     d.focus_distance = c->focus_distance; d.aperture_size = c->aperture_size;
     d.path_tracing = c->path_tracing; d.importance_sampling = c->importance_sampling; d.nee = c->next_event_estimation; d.russian_roulette = c->russian_roulette;
+    d.jitter_aa = (flags & DT_FLAG_JITTER_AA) ? 1 : 0;
+    d.row_limit = (flags & DT_FLAG_REF_ROW_BANDS) ? (c->height / 8) * 8 : c->height;      // main.cpp:15,38-39: 8 bands of H / 8 rows
     return d;
 }
 
@@ -232,16 +251,12 @@ int tonemap_device(dt_scene* s, const float* hdr, int W, int H, float key, float
         if (bi > lastIdx) bi = lastIdx;
         if (bi < 0) bi = 0;
         unsigned long long rank = (unsigned long long)bi;
-        CK(cudaMemcpyAsync(s->tm_rank, &rank, sizeof rank, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(s->tm_rank, &rank, sizeof rank, cudaMemcpyHostToDevice, st));       // pageable source: staged before the call returns
         CK(cudaMemsetAsync(s->tm_hist, 0, 256 * sizeof(unsigned int), st));
         uint32_t mask = 0;
         for (int pass = 0; pass < 4; pass++) {
             const int shift = 24 - 8 * pass;
-            // prefix lives on the device; k_tm_hist needs it by value -> read it back (4 tiny syncs per frame)
-            uint32_t prefix = 0;
-            CK(cudaMemcpyAsync(&prefix, s->tm_prefix, 4, cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
-            k_tm_hist<<<s->num_sms * 8, 256, 0, st>>>(hdr, n_vals, prefix, mask, shift, s->tm_hist);
+            k_tm_hist<<<s->num_sms * 8, 256, 0, st>>>(hdr, n_vals, s->tm_prefix, mask, shift, s->tm_hist);
             k_tm_pick<<<1, 1, 0, st>>>(s->tm_hist, s->tm_rank, s->tm_prefix, shift);
             *launches += 2;
             mask |= 0xFFu << shift;
@@ -256,8 +271,8 @@ int tonemap_device(dt_scene* s, const float* hdr, int W, int H, float key, float
 struct RenderOut { float* hdr_dev; };
 
 // Sort stage (k_sort_*): fills pp.sort_perm with the material-sorted order of wave queue `q`; returns launches.
-int launch_sort(dt_scene* s, DtPipe& pp, const DtRayQueue& q, const int* n_ptr, int n_fixed, cudaStream_t st) {
-    cudaMemsetAsync(pp.sort_hist, 0, 2 * DT_SORT_BINS * sizeof(int), st);           // bin counts + running cursors
+int launch_sort(dt_scene* s, DtPipe& pp, const DtRayQueue& q, const int* n_ptr, int n_fixed, cudaStream_t st, bool zero_hist = true) {
+    if (zero_hist) cudaMemsetAsync(pp.sort_hist, 0, 2 * DT_SORT_BINS * sizeof(int), st);           // bin counts + running cursors (the device loop zeroes them in k_loop_begin)
     const int grid = s->num_sms * 4;
     k_sort_hist<<<grid, 256, 0, st>>>(s->dev, q, n_ptr, n_fixed, pp.sort_hist);
     k_sort_scatter<<<grid, 256, 0, st>>>(q, n_ptr, n_fixed, pp.sort_hist, pp.sort_hist + DT_SORT_BINS, pp.sort_perm);
@@ -265,8 +280,9 @@ int launch_sort(dt_scene* s, DtPipe& pp, const DtRayQueue& q, const int* n_ptr, 
 }
 
 // valid primary rays of this rank: every in-image pixel of the owned tiles
-long long count_valid_pixels(const dt_render_params& P, int W, int H) {
-    const int tiles_x = (W + 7) / 8, tiles_y = (H + 3) / 4;
+long long count_valid_pixels(const dt_render_params& P, int W, int H_image, int row_limit) {
+    const int tiles_x = (W + 7) / 8, tiles_y = (H_image + 3) / 4;
+    const int H = std::min(H_image, row_limit);                 // rows that get camera rays
     if (P.tile_world == 1 && W % 8 == 0 && H % 4 == 0) return (long long)W * H;
     long long valid = 0;
     const long long mine = dt_rank_tile_count(tiles_x, tiles_y, P.tile_rank, P.tile_world);
@@ -279,6 +295,131 @@ long long count_valid_pixels(const dt_render_params& P, int W, int H) {
     return valid;
 }
 
+
+template <class T>
+int talloc(std::vector<void*>& allocs, T** p, size_t n) {
+    void* v = nullptr;
+    CK(cudaMalloc(&v, std::max<size_t>(n * sizeof(T), 16)));
+    allocs.push_back(v);
+    *p = (T*)v;
+    return DT_OK;
+}
+
+// Block-private queues of k_tail: `grid` blocks x `cap` rays (+ cap x shadows_per_hit shadow rays).
+int ensure_tail(dt_scene* s, int shadows_per_hit, bool need_defer) {
+    if (s->tail_grid > 0 && s->tail_has_miss == s->has_env && (s->tail_has_defer || !need_defer) && s->tail.shadow_capacity >= s->tail.capacity * shadows_per_hit) return DT_OK;
+    s->free_tail();
+    s->free_loop();                      // the graph holds the old pointers
+    int bps = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_tail, 128, 0));
+    const int grid = s->num_sms * std::max(1, bps);
+    DtTailMem& M = s->tail;
+    memset(&M, 0, sizeof M);
+    M.capacity = 1024; M.shadow_capacity = M.capacity * shadows_per_hit;
+    const size_t nq = (size_t)grid * M.capacity, ns = (size_t)grid * M.shadow_capacity;
+    int rc;
+#define A(pp_, n_) talloc(s->tail_allocs, pp_, n_)
+    for (int k = 0; k < 2; k++) {
+        DtRayQueue& q = M.q[k];
+        if ((rc = A(&q.o_time, nq)) || (rc = A(&q.d_tmax, nq)) || (rc = A(&q.hit0, nq)) || (rc = A(&q.hit_face, nq)) || (rc = A(&q.pixel, nq)) ||
+            (rc = A(&q.weight_n, nq)) || (rc = A(&q.thr_beer, nq)) || (rc = A(&q.misc, nq))) return rc;
+        q.sort_key = nullptr;
+        if (s->has_env) { if ((rc = A(&M.miss[k], nq))) return rc; }
+    }
+    if ((rc = A(&M.sq.o_time, ns)) || (rc = A(&M.sq.d_tmax, ns)) || (rc = A(&M.sq.contrib_pix, ns))) return rc;
+    if (need_defer) { if ((rc = A(&M.sq.defer, ns))) return rc; }
+#undef A
+    s->tail_grid = grid; s->tail_has_miss = s->has_env; s->tail_has_defer = need_defer;
+    return DT_OK;
+}
+
+// Device-resident wave loop (see k_loop_begin in dt_kernels.cuh): the whole frame is one graph launch and one host sync.
+// *overflow: a queue overflowed on the device (the frame is incomplete; the caller retries with smaller waves).
+int render_devloop(dt_scene* s, const DtCamDev& dc, const DtWaveParams& wp, long long total, int wave_max, int capacity, int shadow_capacity,
+                   int shadows_per_hit, bool defer_mode, bool do_sort, dt_stats& S, bool* overflow) {
+    DtPipe& pp = s->pipes[0];
+    int rc;
+    if ((rc = ensure_queues(s, pp, capacity, shadow_capacity, defer_mode))) return rc;
+    const bool use_tail = s->tail_threshold != -1;
+    if (use_tail && (rc = ensure_tail(s, shadows_per_hit, defer_mode))) return rc;
+    const int tail_threshold = !use_tail ? -1 : (s->tail_threshold >= 0 ? std::min(s->tail_threshold, s->tail_grid * (s->tail.capacity / 4)) : s->tail_grid * 64);
+    cudaStream_t st = s->stream;
+    int* c = pp.counters;
+    DtShadowQueue& sq = pp.sq[0];
+
+    std::string key;
+    key.append((const char*)&dc, sizeof dc); key.append((const char*)&wp, sizeof wp);
+    const long long misc[12] = {total, wave_max, pp.capacity, pp.shadow_capacity, defer_mode, do_sort, tail_threshold, s->trav_mode, s->refill_threshold, s->dev.n_shapes, s->tail_grid, s->grid_shade};
+    key.append((const char*)misc, sizeof misc);
+    const void* ptrs[6] = {s->accum, c, pp.q[0].o_time, sq.o_time, pp.sort_perm, s->tail.q[0].o_time};
+    key.append((const char*)ptrs, sizeof ptrs);
+
+    if (!s->loop_exec || key != s->loop_key) {
+        s->free_loop();
+        cudaGraph_t g = nullptr;
+        CK(cudaGraphCreate(&g, 0));
+        s->loop_graph = g;
+        cudaGraphConditionalHandle handle;
+        CK(cudaGraphConditionalHandleCreate(&handle, g, 1, cudaGraphCondAssignDefault));       // every launch starts with "run the body"
+        cudaGraphNodeParams np = {};
+        np.type = cudaGraphNodeTypeConditional;
+        np.conditional.handle = handle; np.conditional.type = cudaGraphCondTypeWhile; np.conditional.size = 1;
+        cudaGraphNode_t wnode = nullptr;
+        CK(cudaGraphAddNode(&wnode, g, nullptr, 0, &np));
+        cudaGraph_t body = np.conditional.phGraph_out[0];
+        uint32_t launches = 0;
+        CK(cudaStreamBeginCaptureToGraph(st, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+        for (int cur = 0; cur < 2; cur++) {
+            k_loop_begin<<<1, 2 * DT_SORT_BINS, 0, st>>>(c, wave_max, total, do_sort ? pp.sort_hist : nullptr);
+            k_generate_dev<<<s->num_sms * 8, 256, 0, st>>>(dc, wp, pp.q[cur], c, s->accum);
+            launch_traverse<false>(s, pp.q[cur], sq, c + DT_CNT_CUR, 0, pp.capacity, c + DT_CNT_FETCH_A, s->accum, st);
+            launches += 3;
+            if (defer_mode) {
+                k_filter_deferred_dev<<<s->num_sms * 4, 256, 0, st>>>(s->dev, sq, c + DT_CNT_PREV_SHADOW, pp.shadow_capacity, pp.q[cur]);
+                launch_traverse<true>(s, pp.q[cur], sq, c + DT_CNT_PREV_SHADOW, 0, pp.shadow_capacity, c + DT_CNT_FETCH_B, s->accum, st);
+                launches += 2;
+            }
+            if (do_sort) launches += launch_sort(s, pp, pp.q[cur], c + DT_CNT_CUR, 0, st, false);
+            {
+                DtShadeCounters sc = {c + DT_CNT_NEXT, c + DT_CNT_SHADOW, c + DT_CNT_OVERFLOW};
+                k_shade<<<s->grid_shade, 128, 0, st>>>(s->dev, dc, pp.q[cur], pp.miss[cur], c + DT_CNT_CUR, 0, do_sort ? pp.sort_perm : nullptr, pp.q[1 - cur], pp.miss[1 - cur], pp.capacity,
+                                                        sq, pp.shadow_capacity, sc, s->accum);
+                launches++;
+            }
+            if (!defer_mode) { launch_traverse<true>(s, pp.q[cur], sq, c + DT_CNT_SHADOW, 0, pp.shadow_capacity, c + DT_CNT_FETCH_B, s->accum, st); launches++; }
+            k_loop_end<<<1, 1, 0, st>>>(c, pp.capacity, pp.shadow_capacity, defer_mode ? 1 : 0, total, tail_threshold, cur, handle);
+            launches++;
+        }
+        cudaGraph_t captured = nullptr;
+        cudaError_t ce = cudaStreamEndCapture(st, &captured);
+        if (ce != cudaSuccess) { g_err = std::string("capture of the wave-loop body failed: ") + cudaGetErrorString(ce); s->free_loop(); return DT_ERR_CUDA; }
+        if (use_tail) {
+            CK(cudaStreamBeginCaptureToGraph(st, g, &wnode, nullptr, 1, cudaStreamCaptureModeThreadLocal));
+            k_tail<<<s->tail_grid, 128, 0, st>>>(s->dev, dc, pp.q[0], pp.miss[0], sq, c, s->tail, defer_mode ? 1 : 0, s->accum);
+            ce = cudaStreamEndCapture(st, &captured);
+            if (ce != cudaSuccess) { g_err = std::string("capture of the tail kernel failed: ") + cudaGetErrorString(ce); s->free_loop(); return DT_ERR_CUDA; }
+        }
+        ce = cudaGraphInstantiate(&s->loop_exec, g, 0);
+        if (ce != cudaSuccess) { s->loop_exec = nullptr; g_err = std::string("cudaGraphInstantiate (wave loop): ") + cudaGetErrorString(ce); s->free_loop(); return DT_ERR_CUDA; }
+        s->loop_key = key;
+        s->loop_launches_per_iter = launches;
+    }
+    CK(cudaGraphLaunch(s->loop_exec, st));
+    CK(cudaMemcpyAsync(s->h_counters, c, DT_CNT_COUNT * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    const int* hc = s->h_counters;
+    *overflow = hc[DT_CNT_OVERFLOW] != 0;
+    unsigned long long c8 = 0, s8 = 0;
+    memcpy(&c8, hc + DT_CNT_TOT_CLOSEST, 8); memcpy(&s8, hc + DT_CNT_TOT_SHADOW, 8);
+    S.rays_closest = c8; S.rays_shadow = s8;
+    S.waves = (uint32_t)(hc[DT_CNT_WAVES] + hc[DT_CNT_TAIL_WAVES]);
+    S.kernel_launches = (uint32_t)hc[DT_CNT_ITERS] * s->loop_launches_per_iter + (use_tail ? 1u : 0u);
+    S.launches_traverse_closest = (uint32_t)hc[DT_CNT_ITERS] * 2u;
+    if (s->debug_timing) fprintf(stderr, "[dt] device loop: %d body iterations, %d waves + %d tail waves (%d rays handed to k_tail)\n", hc[DT_CNT_ITERS], hc[DT_CNT_WAVES], hc[DT_CNT_TAIL_WAVES], hc[DT_CNT_TAIL_RAYS]);
+    return DT_OK;
+}
+
 int render_core(dt_scene* s, const dt_camera_desc* cam, const dt_render_params* params, dt_stats* stats, bool primary_only) {
     int rc = check_cam(cam);
     if (rc) return rc;
@@ -286,7 +427,7 @@ int render_core(dt_scene* s, const dt_camera_desc* cam, const dt_render_params* 
     dt_render_params P; memset(&P, 0, sizeof P); P.seed = 1234; P.tile_world = 1;
     if (params) P = *params;
     if (P.tile_world < 1 || P.tile_rank < 0 || P.tile_rank >= P.tile_world) { g_err = "bad tile_rank/tile_world"; return DT_ERR_INVALID; }
-    DtCamDev dc = make_cam(cam);
+    DtCamDev dc = make_cam(cam, P.flags);
     if (primary_only) { dc.spp = 1; }
     const int W = cam->width, H = cam->height;
     const size_t n_pix = (size_t)W * H;
@@ -307,7 +448,9 @@ int render_core(dt_scene* s, const dt_camera_desc* cam, const dt_render_params* 
     wave_max = (wave_max + 31) & ~31;
     const int fan = s->fanout_hint + (pt ? 1 : 0);
     const int shadows_per_hit = std::max(1, s->lights_shadowed);
-    const bool do_sort = !primary_only && !(P.flags & DT_FLAG_NO_SORT) && (s->sort_mode == 2 || (s->sort_mode == 1 && s->dev.n_materials >= 3));
+    const bool do_sort = !primary_only && !(P.flags & DT_FLAG_NO_SORT) && s->sort_mode != 0 && (s->sort_mode == 2 || (P.flags & DT_FLAG_FORCE_SORT) || s->dev.n_materials >= 3);
+    const bool host_loop = s->sync_waves || (P.flags & (DT_FLAG_HOST_WAVE_LOOP | DT_FLAG_SERIAL_WAVES));
+    const bool frame_graph = s->use_graph || (P.flags & DT_FLAG_FRAME_GRAPH);
     uint32_t retries = 0;
 
     cudaStream_t st = s->stream;
@@ -315,14 +458,29 @@ int render_core(dt_scene* s, const dt_camera_desc* cam, const dt_render_params* 
     const auto t_host0 = std::chrono::steady_clock::now();
     s->t_total.start(st);
 
+    // Queue sizes for waves of `wave` rays.  A closest-hit wave can hold up to 4x its parents when the ray tree fans out (dielectric:
+    // two children per hit; path tracing: GI child + specular child), and every one of those hits may be lit, so the shadow queue
+    // follows the CLOSEST queue's capacity, not the wave size.  Every overflow retry shrinks the wave 4x and grows the ratio 4x.
+    // DT_FLAG_TEST_TIGHT_QUEUES sizes the first attempt for a fan-out of 1 (test hook for the overflow -> retry path).
+    auto queue_caps = [&](long long wave, long long& cap, long long& shcap) {
+        const bool tight = (P.flags & DT_FLAG_TEST_TIGHT_QUEUES) && retries == 0;
+        const long long mult = (fan <= 1 || tight) ? (retries == 0 ? 1ll : (1ll << (2 * retries))) : (4ll << (2 * retries));
+        cap = std::max<long long>(32, std::min<long long>(wave * mult, 1ll << 28));
+        shcap = std::max<long long>(32, std::min<long long>((tight ? wave : cap) * shadows_per_hit, 1ll << 28));
+    };
+
 retry:
     CK(cudaMemsetAsync(s->accum, 0, n_pix * sizeof(float4), st));
     CK(cudaMemsetAsync(s->counters, 0, DT_MAX_PIPES * DT_CNT_COUNT * sizeof(int), st));
+    if (total == 0) {                                   // this rank owns no strip of the image (more ranks than strips): an empty share, not an error
+        if (stats) *stats = S;
+        return DT_OK;
+    }
     // ---- sync-free wave loop: every ray of the frame fits one batch and the ray tree has a known depth bound, so all
     // waves are enqueued back to back (wave sizes live in device memory), shadow(k) runs on a second stream while
     // closest(k+1) / shade(k+1) proceed, and the frame is dealt to several such pipelines.  One host sync per frame.
     const bool bounded = !(pt && dc.russian_roulette) && s->dev.max_recursion_depth <= 16;
-    if (!primary_only && !defer_mode && bounded && total <= (long long)wave_max && !s->sync_waves && !(P.flags & DT_FLAG_SERIAL_WAVES)) {
+    if (!primary_only && !defer_mode && bounded && total <= (long long)wave_max && !host_loop) {
         const int n_waves = s->dev.max_recursion_depth + 1;
         int NP = s->n_pipes_env > 0 ? s->n_pipes_env : (int)1;
         NP = (int)std::min<long long>(std::min(NP, DT_MAX_PIPES), std::max<long long>(1, my_tiles));
@@ -344,9 +502,8 @@ retry:
             wps[p].per_sample = tiles_p * 32;
             const long long total_p = wps[p].per_sample * dc.spp;
             n0[p] = (int)total_p;
-            const long long cap = std::max<long long>(32, fan <= 1 ? total_p : std::min<long long>(total_p * 4, 1ll << 28));
-            const long long shcap = std::max<long long>(32, total_p * shadows_per_hit);
-            if (shcap > (1ll << 29)) { g_err = "shadow queue too large; lower max_wave_rays"; return DT_ERR_INVALID; }
+            long long cap, shcap;
+            queue_caps(total_p, cap, shcap);
             if ((rc = ensure_queues(s, pp, (int)cap, (int)shcap, false))) return rc;
         }
         // The whole frame -- generate, 7 x (closest, sort, shade, shadow, advance) on two streams, counter read-back -- is
@@ -360,7 +517,7 @@ retry:
                 DtPipe& pp = s->pipes[p];
                 if (p > 0) CK(cudaStreamWaitEvent(pp.A, s->ev_fork, 0));
                 CK(cudaStreamWaitEvent(pp.B, s->ev_fork, 0));
-                timed(tg, pp.A, [&] { k_generate<<<(n0[p] + 255) / 256, 256, 0, pp.A>>>(dc, wps[p], pp.q[0], 0, 0, n0[p], s->accum); });
+                timed(tg, pp.A, [&] { if (n0[p] > 0) k_generate<<<(n0[p] + 255) / 256, 256, 0, pp.A>>>(dc, wps[p], pp.q[0], 0, 0, n0[p], s->accum); });
                 s->h_counters[DT_MAX_PIPES * DT_CNT_COUNT + p] = n0[p];          // pinned scratch past the readback area
                 CK(cudaMemcpyAsync(pp.counters + DT_CNT_CUR, s->h_counters + DT_MAX_PIPES * DT_CNT_COUNT + p, sizeof(int), cudaMemcpyHostToDevice, pp.A));
                 n_launches++;
@@ -379,7 +536,7 @@ retry:
             auto launch_shadow = [&](DtPipe& pp, int k) {
                 const int q = k % 3, cur = k & 1;
                 int* c = pp.counters;
-                timed(ts, pp.B, [&] { launch_traverse<true>(s, pp.q[cur], pp.sq[q], c + dt_cnt_shadow(q), 0, c + dt_cnt_fetch_b(q), s->accum, pp.B, s->shadow_spare); });
+                timed(ts, pp.B, [&] { launch_traverse<true>(s, pp.q[cur], pp.sq[q], c + dt_cnt_shadow(q), 0, pp.shadow_capacity, c + dt_cnt_fetch_b(q), s->accum, pp.B, s->shadow_spare); });
                 cudaEventRecord(pp.ev_shadow[q], pp.B);
                 n_launches++;
             };
@@ -389,7 +546,7 @@ retry:
                     DtPipe& pp = s->pipes[p];
                     int* c = pp.counters;
                     DtShadowQueue& sq = pp.sq[q];
-                    timed(tc, pp.A, [&] { launch_traverse<false>(s, pp.q[cur], sq, c + DT_CNT_CUR, 0, c + DT_CNT_FETCH_A, s->accum, pp.A); });
+                    timed(tc, pp.A, [&] { launch_traverse<false>(s, pp.q[cur], sq, c + DT_CNT_CUR, 0, pp.capacity, c + DT_CNT_FETCH_A, s->accum, pp.A); });
                     if (s->shadow_order && k >= 1) { CK(cudaStreamWaitEvent(pp.B, pp.ev_shade[(k - 1) % 3], 0)); launch_shadow(pp, k - 1); }
                     if (k >= 3) CK(cudaStreamWaitEvent(pp.A, pp.ev_shadow[q], 0));           // shadow(k-3) must have drained this queue
                     if (do_sort) timed(tsort, pp.A, [&] { n_launches += launch_sort(s, pp, pp.q[cur], c + DT_CNT_CUR, 0, pp.A); });
@@ -399,7 +556,7 @@ retry:
                                                                 sq, pp.shadow_capacity, sc, s->accum); });
                     if (!s->shadow_order) { CK(cudaEventRecord(pp.ev_shade[q], pp.A)); CK(cudaStreamWaitEvent(pp.B, pp.ev_shade[q], 0)); launch_shadow(pp, k); }
                     if (k >= 2) CK(cudaStreamWaitEvent(pp.A, pp.ev_shadow[(k + 1) % 3], 0));  // shadow(k-2): its queue is recycled for wave k+1
-                    k_wave_advance<<<1, 1, 0, pp.A>>>(c, (k + 1) % 3);
+                    k_wave_advance<<<1, 1, 0, pp.A>>>(c, (k + 1) % 3, pp.capacity, pp.shadow_capacity);
                     if (s->shadow_order) CK(cudaEventRecord(pp.ev_shade[q], pp.A));
                     n_launches += 3; n_closest++;
                 }
@@ -414,7 +571,7 @@ retry:
     return DT_OK;
         };
         std::string key;
-        if (s->use_graph) {
+        if (frame_graph) {
             key.append((const char*)&dc, sizeof dc); key.append((const char*)wps, sizeof(DtWaveParams) * NP); key.append((const char*)n0, sizeof(int) * NP);
             const int misc[7] = {NP, n_waves, do_sort ? 1 : 0, s->trav_mode, s->refill_threshold, (int)s->dev.n_shapes, s->shadow_order * 16 + s->shadow_spare};
             key.append((const char*)misc, sizeof misc);
@@ -422,11 +579,11 @@ retry:
             key.append((const char*)ptrs, sizeof ptrs);
             for (int p = 0; p < NP; p++) { const void* qp[3] = {s->pipes[p].q[0].o_time, s->pipes[p].sq[0].o_time, s->pipes[p].sort_perm}; key.append((const char*)qp, sizeof qp); }
         }
-        if (s->use_graph && s->frame_graph && key == s->frame_key) {
+        if (frame_graph && s->frame_graph && key == s->frame_key) {
             tg = s->g_tg; tc = s->g_tc; th = s->g_th; ts = s->g_ts; tsort = s->g_tsort;
             n_launches = s->g_launches; n_closest = s->g_closest;
             CK(cudaGraphLaunch(s->frame_graph, st));
-        } else if (s->use_graph) {
+        } else if (frame_graph) {
             if (s->frame_graph) { cudaGraphExecDestroy(s->frame_graph); s->frame_graph = nullptr; s->frame_key.clear(); }
             while (s->ev_pool.size() < (size_t)(2 * NP * (1 + 4 * n_waves))) { cudaEvent_t e; CK(cudaEventCreate(&e)); s->ev_pool.push_back(e); }   // none created inside the capture
             s->capturing = true;
@@ -480,8 +637,24 @@ retry:
             wave_max = std::max(4096, (wave_max / 4 + 31) & ~31);      // smaller batches -> falls back to the synchronised loop
             goto retry;
         }
-        S.rays_closest = tot_c + (uint64_t)(count_valid_pixels(P, W, H) * dc.spp);
+        S.rays_closest = tot_c + (uint64_t)(count_valid_pixels(P, W, H, dc.row_limit) * dc.spp);
         S.rays_shadow = tot_s;
+        S.retries = retries;
+        if (stats) *stats = S;
+        return DT_OK;
+    }
+    // ---- device-resident wave loop: unbounded depth (Russian roulette), deferred NEE, frames of several batches
+    if (!primary_only && s->dev_loop && retries == 0 && !host_loop) {
+        long long cap, shcap;
+        queue_caps(wave_max, cap, shcap);
+        bool overflow = false;
+        if ((rc = render_devloop(s, dc, wp, total, wave_max, (int)cap, (int)shcap, shadows_per_hit, defer_mode, do_sort, S, &overflow))) return rc;
+        if (overflow) {                                   // retried in the host-synchronised loop with smaller waves
+            retries++;
+            wave_max = std::max(4096, (wave_max / 4 + 31) & ~31);
+            goto retry;
+        }
+        S.rays_closest += (uint64_t)(count_valid_pixels(P, W, H, dc.row_limit) * dc.spp);
         S.retries = retries;
         if (stats) *stats = S;
         return DT_OK;
@@ -489,10 +662,10 @@ retry:
     {
         DtPipe& pp = s->pipes[0];
         {
-            const int capacity = primary_only ? wave_max : (fan <= 1 ? wave_max : (int)std::min<long long>((long long)wave_max * 4, 1ll << 28));
-            const long long shcap = primary_only ? 32 : std::max<long long>(32, (long long)wave_max * shadows_per_hit);
-            if (shcap > (1ll << 29)) { g_err = "shadow queue too large; lower max_wave_rays"; return DT_ERR_INVALID; }
-            if ((rc = ensure_queues(s, pp, capacity, (int)shcap, defer_mode))) return rc;
+            long long cap, shcap;
+            queue_caps(wave_max, cap, shcap);
+            if (primary_only) { cap = wave_max; shcap = 32; }
+            if ((rc = ensure_queues(s, pp, (int)cap, (int)shcap, defer_mode))) return rc;
         }
         int* c = pp.counters;
         DtShadowQueue& sq = pp.sq[0];
@@ -515,7 +688,7 @@ retry:
             CK(cudaMemsetAsync(c + DT_CNT_NEXT, 0, sizeof(int), st));
             CK(cudaMemsetAsync(c + DT_CNT_FETCH_A, 0, 2 * sizeof(int), st));
             s->t_closest.start(st);
-            launch_traverse<false>(s, pp.q[cur], sq, nullptr, count, c + DT_CNT_FETCH_A, s->accum);
+            launch_traverse<false>(s, pp.q[cur], sq, nullptr, count, pp.capacity, c + DT_CNT_FETCH_A, s->accum);
             s->t_closest.stop(st);
             S.kernel_launches++; S.launches_traverse_closest++;
             if (primary_only) { CK(cudaStreamSynchronize(st)); S.ms_traverse_closest += s->t_closest.take(); S.ms_generate += s->t_gen.take(); S.waves++; break; }
@@ -523,7 +696,7 @@ retry:
             if (defer_mode && prev_shadow > 0) {
                 k_filter_deferred<<<(prev_shadow + 255) / 256, 256, 0, st>>>(s->dev, sq, prev_shadow, pp.q[cur]);
                 s->t_shadow.start(st);
-                launch_traverse<true>(s, pp.q[cur], sq, nullptr, prev_shadow, c + DT_CNT_FETCH_B, s->accum);
+                launch_traverse<true>(s, pp.q[cur], sq, nullptr, prev_shadow, pp.shadow_capacity, c + DT_CNT_FETCH_B, s->accum);
                 s->t_shadow.stop(st);
                 shadow_timed = true;
                 S.kernel_launches += 2;
@@ -540,7 +713,7 @@ retry:
             S.kernel_launches++;
             if (!defer_mode) {
                 s->t_shadow.start(st);
-                launch_traverse<true>(s, pp.q[cur], sq, c + DT_CNT_SHADOW, 0, c + DT_CNT_FETCH_B, s->accum);
+                launch_traverse<true>(s, pp.q[cur], sq, c + DT_CNT_SHADOW, 0, pp.shadow_capacity, c + DT_CNT_FETCH_B, s->accum);
                 s->t_shadow.stop(st);
                 shadow_timed = true;
                 S.kernel_launches++;
@@ -567,7 +740,7 @@ retry:
         }
         if (!overflow && defer_mode && prev_shadow > 0) {
             CK(cudaMemsetAsync(c + DT_CNT_FETCH_B, 0, sizeof(int), st));
-            launch_traverse<true>(s, pp.q[cur], sq, nullptr, prev_shadow, c + DT_CNT_FETCH_B, s->accum);
+            launch_traverse<true>(s, pp.q[cur], sq, nullptr, prev_shadow, pp.shadow_capacity, c + DT_CNT_FETCH_B, s->accum);
             S.kernel_launches++;
         }
         if (overflow) {
@@ -577,7 +750,7 @@ retry:
             CK(cudaStreamSynchronize(st));
             goto retry;
         }
-        S.rays_closest += (uint64_t)(count_valid_pixels(P, W, H) * (primary_only ? 1 : dc.spp));
+        S.rays_closest += (uint64_t)(count_valid_pixels(P, W, H, dc.row_limit) * (primary_only ? 1 : dc.spp));
     }
     S.retries = retries;
     if (stats) *stats = S;
@@ -623,14 +796,16 @@ int dt_gpu_init(int device) {
     return n;
 }
 
-int dt_scene_create(const dt_scene_desc* desc, dt_scene** out) {
+int dt_scene_create(const dt_scene_desc* desc, dt_scene** out) { return dt_scene_create_opts(desc, nullptr, out); }
+
+int dt_scene_create_opts(const dt_scene_desc* desc, const dt_scene_options* opts, dt_scene** out) {
     if (!desc || !out) { g_err = "null argument"; return DT_ERR_INVALID; }
     *out = nullptr;
     DtHostScene hs;
     std::string err;
     // meshes of at least this many faces get their BLAS from the GPU flattener (dt_flatten_gpu.cu); smaller ones are not worth its launches
     int gpu_min_faces = 32768;
-    if (const char* e = getenv("DT_GPU_FLATTEN_MIN_FACES")) gpu_min_faces = atoi(e) < 0 ? 0x7FFFFFFF : std::max(1, atoi(e));
+    if (opts && opts->gpu_flatten_min_faces != 0) gpu_min_faces = opts->gpu_flatten_min_faces < 0 ? 0x7FFFFFFF : opts->gpu_flatten_min_faces;
     if (!dt_flatten_scene(desc, hs, err, gpu_min_faces)) { g_err = "scene description rejected: " + err; return DT_ERR_INVALID; }
     int rc = ensure_device();
     if (rc) return rc;
@@ -696,7 +871,7 @@ int dt_scene_create(const dt_scene_desc* desc, dt_scene** out) {
         if (node_cap - n_nodes > (1u << 16)) {                     // give the unused tail of the node allocation back
             const uint4* exact = nullptr;
             if ((rc = upload<uint4>(s->allocs, (const uint4*)nullptr, 0, &exact, n_nodes * 5))) return fail(rc);
-            CK(cudaMemcpy((void*)exact, nodes, n_nodes * sizeof(DtNode8), cudaMemcpyDeviceToDevice));
+            if (cudaMemcpy((void*)exact, nodes, n_nodes * sizeof(DtNode8), cudaMemcpyDeviceToDevice) != cudaSuccess) { g_err = "device copy of the BVH8 nodes failed"; return fail(DT_ERR_CUDA); }
             for (auto it = s->allocs.begin(); it != s->allocs.end(); ++it) if (*it == (void*)nodes) { s->allocs.erase(it); break; }
             cudaFree((void*)nodes);
             nodes = exact;
@@ -754,6 +929,8 @@ int dt_scene_create(const dt_scene_desc* desc, dt_scene** out) {
     if (const char* e = getenv("DT_SHADOW_SPARE")) s->shadow_spare = std::max(0, atoi(e));
     if (const char* e = getenv("DT_GRAPH")) s->use_graph = atoi(e);
     if (const char* e = getenv("DT_DEBUG_TIMING")) s->debug_timing = atoi(e);
+    if (const char* e = getenv("DT_DEVLOOP")) s->dev_loop = atoi(e);
+    if (const char* e = getenv("DT_TAIL_THRESHOLD")) s->tail_threshold = std::max(-1, atoi(e));
     if (const char* e = getenv("DT_PIPES")) s->n_pipes_env = std::min(DT_MAX_PIPES, std::max(0, atoi(e)));
     if (const char* e = getenv("DT_REFILL_THRESHOLD")) s->refill_threshold = std::min(32, std::max(1, atoi(e)));
     {
@@ -779,6 +956,8 @@ void dt_scene_destroy(dt_scene* s) {
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     dt_frame_release(s);
+    s->free_loop();
+    s->free_tail();
     s->free_queues();
     for (void* p : s->allocs) cudaFree(p);
     if (s->counters) cudaFree(s->counters);
@@ -813,11 +992,12 @@ int dt_render_device(dt_scene* s, const dt_camera_desc* cam, const dt_render_par
     cudaStream_t st = s->stream;
     const int n_pix = cam->width * cam->height;
     const int spp = cam->samples_per_pixel < 1 ? 1 : cam->samples_per_pixel;
+    const bool peer_frame = params && (params->flags & DT_FLAG_PEER_FRAME);
+    if (peer_frame && s->peer_hdr && (s->peer_w != cam->width || s->peer_h != cam->height)) { g_err = "imported peer frame has a different resolution"; return DT_ERR_INVALID; }
     s->t_resolve.start(st);
-    if (params && (params->flags & DT_FLAG_PEER_FRAME)) {
+    if (peer_frame) {
         float* dst_hdr = s->hdr; uint8_t* dst_ldr = s->ldr;
         if (s->peer_hdr) {
-            if (s->peer_w != cam->width || s->peer_h != cam->height) { g_err = "imported peer frame has a different resolution"; return DT_ERR_INVALID; }
             dst_hdr = cam->has_tonemapper ? s->peer_hdr : nullptr;        // the destination tonemaps the whole frame from radiance ...
             dst_ldr = cam->has_tonemapper ? nullptr : s->peer_ldr;        // ... or only needs the clamped bytes (main.cpp:118-125)
         }
@@ -825,7 +1005,7 @@ int dt_render_device(dt_scene* s, const dt_camera_desc* cam, const dt_render_par
         const int world = params->tile_world < 1 ? 1 : params->tile_world;
         const long long my_tiles = dt_rank_tile_count(tiles_x, tiles_y, params->tile_rank, world);
         const long long threads = my_tiles / DT_TILE_GROUP * 32;     // one warp per strip
-        k_resolve_tiles<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(s->accum, cam->width, cam->height, tiles_x, tiles_y, my_tiles, params->tile_rank, world, spp, dst_hdr, dst_ldr, s->counters);
+        if (threads > 0) k_resolve_tiles<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(s->accum, cam->width, cam->height, tiles_x, tiles_y, my_tiles, params->tile_rank, world, spp, dst_hdr, dst_ldr, s->counters);
     } else {
         k_resolve<<<(n_pix + 255) / 256, 256, 0, st>>>(s->accum, n_pix, spp, s->hdr, s->ldr, s->counters);
     }
@@ -907,7 +1087,7 @@ int dt_frame_import(dt_scene* s, const dt_frame_handle* in) {
 }
 
 int dt_frame_finish(dt_scene* s, const dt_camera_desc* cam, uint8_t* ldr_rgb, dt_stats* stats) {
-    if (!s || !cam || !ldr_rgb) { g_err = "null argument"; return DT_ERR_INVALID; }
+    if (!s || !cam) { g_err = "null argument"; return DT_ERR_INVALID; }
     int rc = check_cam(cam);
     if (rc) return rc;
     CK(cudaSetDevice(s->device));
@@ -942,7 +1122,8 @@ int dt_render(dt_scene* s, const dt_camera_desc* cam, const dt_render_params* pa
 }
 
 int dt_primary_hits(dt_scene* s, const dt_camera_desc* cam, int32_t* shape, int32_t* face, float* t) {
-    if (!s || !shape || !face || !t) { g_err = "null argument"; return DT_ERR_INVALID; }
+    if (!s || !cam || !shape || !face || !t) { g_err = "null argument"; return DT_ERR_INVALID; }
+    { const int crc = check_cam(cam); if (crc) return crc; }
     dt_render_params P; memset(&P, 0, sizeof P); P.seed = 1234; P.tile_world = 1;
     const long long n_slots = dt_rank_tile_count((cam->width + 7) / 8, (cam->height + 3) / 4, 0, 1) * 32;      // ray slots of the frame (whole strips)
     if (n_slots > (1ll << 28)) { g_err = "image too large for dt_primary_hits"; return DT_ERR_INVALID; }
@@ -952,7 +1133,10 @@ int dt_primary_hits(dt_scene* s, const dt_camera_desc* cam, int32_t* shape, int3
     if (rc) return rc;
     const int n_pix = cam->width * cam->height;
     int32_t *d_shape = nullptr, *d_face = nullptr; float* d_t = nullptr;
-    CK(cudaMalloc(&d_shape, (size_t)n_pix * 4)); CK(cudaMalloc(&d_face, (size_t)n_pix * 4)); CK(cudaMalloc(&d_t, (size_t)n_pix * 4));
+    if (cudaMalloc(&d_shape, (size_t)n_pix * 4) != cudaSuccess || cudaMalloc(&d_face, (size_t)n_pix * 4) != cudaSuccess || cudaMalloc(&d_t, (size_t)n_pix * 4) != cudaSuccess) {
+        cudaFree(d_shape); cudaFree(d_face); cudaFree(d_t);
+        g_err = "dt_primary_hits: cudaMalloc failed"; return DT_ERR_CUDA;
+    }
     cudaStream_t st = s->stream;
     k_unpack_hits<<<((int)n_slots + 255) / 256, 256, 0, st>>>(s->pipes[0].q[0].hit0, s->pipes[0].q[0].hit_face, s->pipes[0].q[0].pixel, (int)n_slots, d_shape, d_face, d_t, 1);
     cudaMemcpyAsync(shape, d_shape, (size_t)n_pix * 4, cudaMemcpyDeviceToHost, st);
@@ -992,7 +1176,7 @@ static int trace_generic(dt_scene* s, const float* origins, const float* dirs, c
             DtRayQueue q; memset(&q, 0, sizeof q);
             q.o_time = o4; q.d_tmax = d4; q.hit0 = hit0; q.hit_face = hface; q.pixel = nullptr;
             DtShadowQueue sq; memset(&sq, 0, sizeof sq);
-            launch_traverse<false>(s, q, sq, nullptr, (int)n, fetch, nullptr);
+            launch_traverse<false>(s, q, sq, nullptr, (int)n, (int)n, fetch, nullptr);
             k_unpack_hits<<<((int)n + 255) / 256, 256, 0, st>>>(hit0, hface, nullptr, (int)n, d_shape, d_face, d_t, 0);
             cudaMemcpyAsync(shape, d_shape, (size_t)n * 4, cudaMemcpyDeviceToHost, st);
             cudaMemcpyAsync(face, d_face, (size_t)n * 4, cudaMemcpyDeviceToHost, st);

@@ -176,7 +176,7 @@ bool dt_flatten_scene(const dt_scene_desc* d, DtHostScene& out, std::string& err
                 if (b2[(size_t)n.right].first != b.first + b2[(size_t)n.left].count) { err = "BVH2 face ranges are not contiguous"; return false; }
             } else {
                 b.left = b.right = -1; b.first = n.first_face; b.count = n.face_count;
-                if (b.count == 0 || b.first + b.count > (uint32_t)m.n_faces) { err = "BVH2 leaf range out of bounds"; return false; }
+                if (b.count == 0 || (uint64_t)b.first + (uint64_t)b.count > (uint64_t)m.n_faces) { err = "BVH2 leaf range out of bounds"; return false; }
             }
         }
         if (b2[0].first != 0 || b2[0].count != (uint32_t)m.n_faces) { err = "BVH2 root does not cover all faces"; return false; }

@@ -40,13 +40,20 @@ __global__ void k_b2_init(const dt_bvh2_node* in, int n_nodes, int n_faces, DtB2
         b.left = n.left; b.right = n.right; b.first = n.first_face; b.count = 2u;
     } else {
         b.left = b.right = -1; b.first = n.first_face; b.count = n.face_count;
-        if (n.face_count == 0u || n.first_face + n.face_count > (uint32_t)n_faces || n.first_face + n.face_count < n.first_face) atomicOr(error, ERR_LEAF_RANGE);
+        if (n.face_count == 0u || (unsigned long long)n.first_face + n.face_count > (unsigned long long)n_faces) atomicOr(error, ERR_LEAF_RANGE);
         else {
             for (uint32_t f = n.first_face; f < n.first_face + n.face_count; f++) leaf_of[f] = i;
             atomicAdd(faces_in_leaves, n.face_count);
         }
     }
     b2[i] = b;
+}
+
+// every face must lie in some leaf; together with "the leaf sizes sum to n_faces" (faces_in_leaves) this is "exactly one leaf
+// per face", i.e. the leaf ranges tile [0, n_faces) without gaps or overlaps (the host flattener's contiguity / root-coverage checks)
+__global__ void k_check_cover(const int* leaf_of, int n_faces, int* error) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f < n_faces && leaf_of[f] < 0) atomicOr(error, ERR_LEAF_RANGE);
 }
 
 // split_big_leaves (dt_flatten.cu): a leaf of k > 1 faces (all centroids on one side of the reference's split plane,
@@ -172,15 +179,19 @@ bool dt_flatten_mesh_gpu(const dt_mesh& m, const DtFaceDev* d_faces, const float
     const unsigned int h_counters0[2] = {0u, (unsigned int)n_in};                   // faces covered by leaves, binary-tree node count
     GCK(cudaMemcpyAsync(counters, h_counters0, sizeof h_counters0, cudaMemcpyHostToDevice, st));
     k_b2_init<<<(n_in + TB - 1) / TB, TB, 0, st>>>(bvh, n_in, n_faces, b2, leaf_of, counters, error);
-    k_split_big_leaves<<<(n_in + TB - 1) / TB, TB, 0, st>>>(b2, n_in, b2_cap, counters + 1, d_faces, d_verts, error);
+    k_check_cover<<<(n_faces + TB - 1) / TB, TB, 0, st>>>(leaf_of, n_faces, error);
     int h_error = 0; unsigned int h_counters[2] = {0, 0};
+    // the structural checks are read back BEFORE any kernel dereferences a leaf range (k_split_big_leaves reads faces[first + k])
     GCK(cudaMemcpyAsync(&h_error, error, sizeof(int), cudaMemcpyDeviceToHost, st));
     GCK(cudaMemcpyAsync(h_counters, counters, sizeof h_counters, cudaMemcpyDeviceToHost, st));
     GCK(cudaStreamSynchronize(st));
     if (h_error & ERR_CHILD_ORDER) { err = "BVH2 child index order violated"; return false; }
-    if (h_error & ERR_LEAF_RANGE) { err = "BVH2 leaf range out of bounds"; return false; }
-    if (h_error & ERR_CAPACITY) { err = "BVH2 leaf ranges overlap (more than 2n-1 nodes after splitting)"; return false; }
+    if (h_error & ERR_LEAF_RANGE) { err = "BVH2 leaf range out of bounds or faces not covered by any leaf"; return false; }
     if (h_counters[0] != (unsigned int)n_faces) { err = "BVH2 leaves do not cover every face exactly once"; return false; }
+    k_split_big_leaves<<<(n_in + TB - 1) / TB, TB, 0, st>>>(b2, n_in, b2_cap, counters + 1, d_faces, d_verts, error);
+    GCK(cudaMemcpyAsync(&h_error, error, sizeof(int), cudaMemcpyDeviceToHost, st));
+    GCK(cudaStreamSynchronize(st));
+    if (h_error & ERR_CAPACITY) { err = "BVH2 leaf ranges overlap (more than 2n-1 nodes after splitting)"; return false; }
 
     // level-synchronous collapse; nodes of this mesh are written at d_nodes[node_off ...]
     const int root_item = 0;

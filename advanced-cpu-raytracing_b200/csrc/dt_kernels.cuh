@@ -16,6 +16,9 @@ struct DtCamDev {
     int width, height, spp;
     float focus_distance, aperture_size;
     int path_tracing, importance_sampling, nee, russian_roulette;
+    int jitter_aa;                 // DT_FLAG_JITTER_AA: keep the sub-pixel sample position (off = the reference's int truncation, main.cpp:83)
+    int row_limit;                 // rows y >= row_limit get no camera rays (DT_FLAG_REF_ROW_BANDS: the reference's 8 row bands leave the
+                                   // bottom H mod 8 rows unrendered, main.cpp:38-39); height otherwise
 };
 
 // Tile ownership across ranks.  Every row of 8x4-pixel tiles is
@@ -49,7 +52,16 @@ enum { DT_CNT_NEXT = 0, DT_CNT_SHADOW = 1, DT_CNT_FETCH_A = 2, DT_CNT_FETCH_B = 
        DT_CNT_SHADOW2 = 8, DT_CNT_FETCH_B2 = 9,   // second shadow queue (shadow(k) overlaps closest(k+1))
        DT_CNT_SHADOW3 = 14, DT_CNT_FETCH_B3 = 15, // third shadow queue (shadow(k) may run until advance(k+2))
        DT_CNT_TOT_CLOSEST = 10, DT_CNT_TOT_SHADOW = 12,   // 64-bit totals (two ints each)
-       DT_CNT_COUNT = 16 };
+       // device-resident wave loop (k_loop_begin / k_loop_end / k_tail)
+       DT_CNT_PREV_SHADOW = 16,   // deferred-NEE shadow rays of the previous wave, traced after this wave's closest-hit pass
+       DT_CNT_GEN_N = 17, DT_CNT_GEN_BASE = 18,           // top-up of this wave: new camera samples, first queue slot
+       DT_CNT_WAVES = 19,         // waves that held any work
+       DT_CNT_NEXT_PRIMARY = 20,  // 64-bit: camera samples generated so far
+       DT_CNT_GEN_K0 = 22,        // 64-bit: first camera-sample index of this wave's top-up
+       DT_CNT_ITERS = 24,         // executions of the WHILE body (two waves each)
+       DT_CNT_TAIL_WAVES = 25,    // longest block-local wave chain of k_tail
+       DT_CNT_TAIL_RAYS = 26,     // rays handed to k_tail
+       DT_CNT_COUNT = 32 };
 struct DtShadeCounters { int* next; int* shadow; int* overflow; };
 
 #define DT_DEAD_PIXEL 0xFFFFFFFFu
@@ -87,9 +99,10 @@ __device__ __forceinline__ void dt_accum(float4* accum, uint32_t pix, v3 c) {
 // ------------------------------------------------------------------ generate
 // Camera::GetImagePlanePosition (camera.cpp:74-80) + Raytracer::GenerateRay (raytracer.cpp:661-699) + the
 // stratified-sample / Gaussian-weight part of renderThreadMain (main.cpp:59-96).
-__device__ inline void dt_camera_ray(const DtCamDev& cam, int i, int j, DtRng& rng, v3& o, v3& d, float& mb_time) {
-    float su = (float)((i + 0.5) * (double)(cam.right_ - cam.left) / cam.width);
-    float sv = (float)((j + 0.5) * (double)(cam.top - cam.bottom) / cam.height);
+// (jx, jy) = position inside the pixel: 0.5 (the pixel centre, camera.cpp:76-77) unless DT_FLAG_JITTER_AA
+__device__ inline void dt_camera_ray(const DtCamDev& cam, int i, int j, float jx, float jy, DtRng& rng, v3& o, v3& d, float& mb_time) {
+    float su = (float)((i + (double)jx) * (double)(cam.right_ - cam.left) / cam.width);
+    float sv = (float)((j + (double)jy) * (double)(cam.top - cam.bottom) / cam.height);
     v3 ipp = vadd(vadd(F3(cam.q), vscale(F3(cam.right), su)), vscale(F3(cam.up), -sv));
     o = F3(cam.position);
     if (cam.aperture_size > 0.0001) {
@@ -109,10 +122,7 @@ __device__ inline void dt_camera_ray(const DtCamDev& cam, int i, int j, DtRng& r
     mb_time = rng01(rng);
 }
 
-__global__ void k_generate(DtCamDev cam, DtWaveParams wp, DtRayQueue q, int base, long long k0, int n, float4* accum) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n) return;
-    const long long k = k0 + idx;
+__device__ __forceinline__ void dt_generate_one(const DtCamDev& cam, const DtWaveParams& wp, const DtRayQueue& q, const int slot, const long long k, float4* accum) {
     const int s = (int)(k / wp.per_sample);
     const long long rem = k % wp.per_sample;
     int tx, ty;
@@ -120,8 +130,7 @@ __global__ void k_generate(DtCamDev cam, DtWaveParams wp, DtRayQueue q, int base
     const int lane = (int)(rem & 31);
     const int x = tx * 8 + (lane & 7);
     const int y = ty * 4 + (lane >> 3);
-    const int slot = base + idx;
-    if (!live || x >= cam.width || y >= cam.height) {
+    if (!live || x >= cam.width || y >= cam.row_limit) {
         q.pixel[slot] = DT_DEAD_PIXEL;
         return;
     }
@@ -129,6 +138,7 @@ __global__ void k_generate(DtCamDev cam, DtWaveParams wp, DtRayQueue q, int base
     DtRng rng; rng.key = dt_hash(dt_hash(pix, (uint32_t)s) ^ wp.seed_lo, wp.seed_hi); rng.ctr = 0;
     int px = x, py = y;
     float w = 1.0f;
+    float cam_jx = 0.5f, cam_jy = 0.5f;
     if (cam.spp > 1) {
         const int nRows = (int)sqrt((double)cam.spp), nCols = nRows;
         const int st = s % (nRows * nCols);
@@ -136,8 +146,15 @@ __global__ void k_generate(DtCamDev cam, DtWaveParams wp, DtRayQueue q, int base
         float psi1 = rng01(rng), psi2 = rng01(rng);
         float sx = (col + psi1) / nCols;
         float sy = (row + psi2) / nRows;
-        px = (int)(sx + x);          // RenderPixel(int,int,...) truncates the float sample position (main.cpp:83)
-        py = (int)(sy + y);
+        if (cam.jitter_aa) {
+            // opt-in (DT_FLAG_JITTER_AA): the sample position keeps its sub-pixel jitter.  The reference means to do
+            // this but RenderPixel(int,int,...) truncates it away (main.cpp:83), so parity mode leaves it off.
+            cam_jx = sx; cam_jy = sy;
+        }
+        if (!cam.jitter_aa) {
+            px = (int)(sx + x);      // RenderPixel(int,int,...) truncates the float sample position (main.cpp:83)
+            py = (int)(sy + y);
+        }
         const float sigma = 1.0f / 6.0f;                     // gaussian.h:3-21, main.cpp:52
         const float sigmaSqr = sigma * sigma;
         const float c1 = (float)(1.0f / (2.0f * DT_PI * sigmaSqr));
@@ -147,13 +164,26 @@ __global__ void k_generate(DtCamDev cam, DtWaveParams wp, DtRayQueue q, int base
         atomicAdd(reinterpret_cast<float*>(accum + pix) + 3, w);
     }
     v3 o, d; float mb;
-    dt_camera_ray(cam, px, py, rng, o, d, mb);
+    dt_camera_ray(cam, px, py, cam_jx, cam_jy, rng, o, d, mb);
     q.o_time[slot] = make_float4(o.x, o.y, o.z, mb);
     q.d_tmax[slot] = make_float4(d.x, d.y, d.z, CUDART_INF_F);
     q.pixel[slot] = pix;
     q.weight_n[slot] = make_float4(w, w, w, 1.0f);
     q.thr_beer[slot] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
     q.misc[slot] = make_int4(0x7FFFFFFF /* set by shade from the scene */, 0, (int)dt_hash(rng.key, 0x9E37u), DT_FLAG_PRIMARY);
+}
+
+__global__ void k_generate(DtCamDev cam, DtWaveParams wp, DtRayQueue q, int base, long long k0, int n, float4* accum) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    dt_generate_one(cam, wp, q, base + idx, k0 + idx, accum);
+}
+// device-resident wave loop: the top-up size / slot / first sample index of this wave were written by k_loop_begin
+__global__ void k_generate_dev(DtCamDev cam, DtWaveParams wp, DtRayQueue q, const int* c, float4* accum) {
+    const int n = c[DT_CNT_GEN_N], base = c[DT_CNT_GEN_BASE];
+    const long long k0 = *reinterpret_cast<const long long*>(c + DT_CNT_GEN_K0);
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x)
+        dt_generate_one(cam, wp, q, base + idx, k0 + idx, accum);
 }
 
 // ------------------------------------------------------------------ traversal (persistent warps)
@@ -176,8 +206,8 @@ __device__ __forceinline__ void dt_store_shadow(const DtShadowQueue& sq, int i, 
 #endif
 // Static variant: a warp fetches 32 consecutive rays and runs them to completion.
 template <bool ANY, bool WW>
-__global__ void __launch_bounds__(128, ANY ? DT_TRAV_MINBLOCKS_ANY : DT_TRAV_MINBLOCKS) k_traverse(DtSceneDev S, DtRayQueue q, DtShadowQueue sq, const int* n_ptr, int n_fixed, int* fetch_counter, float4* accum) {
-    const int n = n_ptr ? *n_ptr : n_fixed;
+__global__ void __launch_bounds__(128, ANY ? DT_TRAV_MINBLOCKS_ANY : DT_TRAV_MINBLOCKS) k_traverse(DtSceneDev S, DtRayQueue q, DtShadowQueue sq, const int* n_ptr, int n_fixed, int n_cap, int* fetch_counter, float4* accum) {
+    const int n = min(n_ptr ? *n_ptr : n_fixed, n_cap);        // a device-side counter may have run past the queue capacity (overflow): never index beyond it
     const int lane = threadIdx.x & 31;
     for (;;) {
         int base = 0;
@@ -211,9 +241,9 @@ __device__ __forceinline__ unsigned long long dt_now() { unsigned long long t; a
 #endif
 
 template <bool ANY, bool WW>
-__global__ void __launch_bounds__(128, ANY ? DT_TRAV_MINBLOCKS_ANY : DT_TRAV_MINBLOCKS) k_traverse_dyn(DtSceneDev S, DtRayQueue q, DtShadowQueue sq, const int* n_ptr, int n_fixed, int* fetch_counter,
+__global__ void __launch_bounds__(128, ANY ? DT_TRAV_MINBLOCKS_ANY : DT_TRAV_MINBLOCKS) k_traverse_dyn(DtSceneDev S, DtRayQueue q, DtShadowQueue sq, const int* n_ptr, int n_fixed, int n_cap, int* fetch_counter,
                                                       float4* accum, int refill_threshold) {
-    const int n = n_ptr ? *n_ptr : n_fixed;
+    const int n = min(n_ptr ? *n_ptr : n_fixed, n_cap);        // a device-side counter may have run past the queue capacity (overflow): never index beyond it
     const int lane = threadIdx.x & 31;
     const unsigned FULL = 0xFFFFFFFFu;
     const unsigned lanes_lt = (1u << lane) - 1u;
@@ -702,12 +732,17 @@ __host__ __device__ __forceinline__ int dt_cnt_fetch_b(int q) { return q == 0 ? 
 
 // Device-side bookkeeping between two waves of the sync-free loop (one thread), after shade(k): the next wave's size, and the
 // recycling of shadow queue `q_recycle` (= the queue wave k+1 will fill; last used by wave k-2, whose shadow pass is complete).
-__global__ void k_wave_advance(int* c, int q_recycle) {
+// A wave that overflowed a queue (DT_CNT_OVERFLOW set by dt_emit_child / dt_emit_shadow, or a counter past its capacity) ends the
+// frame on the device: the next wave's size becomes 0, so every later launch of the frame is a no-op and nothing indexes past an
+// allocation before the host sees the flag and retries with smaller waves.
+__global__ void k_wave_advance(int* c, int q_recycle, int capacity, int shadow_capacity) {
     unsigned long long* tot_c = reinterpret_cast<unsigned long long*>(c + DT_CNT_TOT_CLOSEST);
     unsigned long long* tot_s = reinterpret_cast<unsigned long long*>(c + DT_CNT_TOT_SHADOW);
-    *tot_c += (unsigned long long)c[DT_CNT_NEXT];
-    *tot_s += (unsigned long long)c[dt_cnt_shadow(q_recycle)];
-    c[DT_CNT_CUR] = c[DT_CNT_NEXT];
+    const bool overflow = c[DT_CNT_OVERFLOW] != 0 || c[DT_CNT_NEXT] > capacity;
+    if (overflow) c[DT_CNT_OVERFLOW] = 1;
+    *tot_c += (unsigned long long)min(c[DT_CNT_NEXT], capacity);
+    *tot_s += (unsigned long long)min(c[dt_cnt_shadow(q_recycle)], shadow_capacity);
+    c[DT_CNT_CUR] = overflow ? 0 : c[DT_CNT_NEXT];
     c[DT_CNT_NEXT] = 0;
     c[DT_CNT_FETCH_A] = 0;
     c[dt_cnt_shadow(q_recycle)] = 0;
@@ -726,6 +761,171 @@ __global__ void k_filter_deferred(DtSceneDev S, DtShadowQueue sq, int n, DtRayQu
     const DtShapeDev& sh = S.shapes[hs];
     if (S.materials[sh.material - 1].type == DT_MAT_EMISSIVE && sh.id == df.y)
         sq.contrib_pix[i] = make_float4(0.f, 0.f, 0.f, sq.contrib_pix[i].w);
+}
+
+// ------------------------------------------------------------------ device-resident wave loop
+// Path tracing with Russian roulette has no depth bound and frames of many samples need several batches, so the number of waves
+// is only known on the device.  Instead of one host round trip per wave the whole frame is ONE CUDA graph: a WHILE node whose
+// body is two waves (even: queue 0 -> 1, odd: 1 -> 0; kernel parameters are fixed inside a graph) followed by k_tail.  All wave
+// sizes live in the counter block; k_loop_begin tops the wave up with new camera samples, k_loop_end advances to the next wave
+// and (odd wave) decides through the graph's conditional handle whether the body runs again.
+__device__ __forceinline__ bool dt_deferred_skipped(const DtSceneDev& S, const int2 df, const float4* __restrict__ child_hit0) {
+    if (df.x < 0) return false;
+    const int hs = __float_as_int(child_hit0[df.x].w);
+    if (hs < 0) return false;
+    const DtShapeDev& sh = S.shapes[hs];
+    return S.materials[sh.material - 1].type == DT_MAT_EMISSIVE && sh.id == df.y;
+}
+__global__ void k_filter_deferred_dev(DtSceneDev S, DtShadowQueue sq, const int* n_ptr, int n_cap, DtRayQueue next) {
+    const int n = min(*n_ptr, n_cap);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        if (dt_deferred_skipped(S, sq.defer[i], next.hit0)) sq.contrib_pix[i] = make_float4(0.f, 0.f, 0.f, sq.contrib_pix[i].w);
+}
+
+__global__ void __launch_bounds__(2 * DT_SORT_BINS) k_loop_begin(int* c, int wave_max, long long total, int* sort_hist) {
+    if (sort_hist) sort_hist[threadIdx.x] = 0;                                   // bin counts + running cursors of this wave's sort stage
+    if (threadIdx.x != 0) return;
+    const int count = c[DT_CNT_CUR];
+    long long* np = reinterpret_cast<long long*>(c + DT_CNT_NEXT_PRIMARY);
+    int n_new = 0;
+    if (count < wave_max && *np < total && c[DT_CNT_OVERFLOW] == 0) n_new = (int)min((long long)(wave_max - count), total - *np);
+    c[DT_CNT_GEN_N] = n_new; c[DT_CNT_GEN_BASE] = count;
+    *reinterpret_cast<long long*>(c + DT_CNT_GEN_K0) = *np;
+    *np += n_new;
+    c[DT_CNT_CUR] = count + n_new;
+    c[DT_CNT_NEXT] = 0; c[DT_CNT_SHADOW] = 0; c[DT_CNT_FETCH_A] = 0; c[DT_CNT_FETCH_B] = 0;
+}
+
+// handle_valid: this is the odd wave of the WHILE body -> decide whether the body runs again.  The loop hands over to k_tail
+// once every camera sample has been generated and at most tail_threshold rays are alive (tail_threshold < 0: never).
+__global__ void k_loop_end(int* c, int capacity, int shadow_capacity, int defer, long long total, int tail_threshold, int handle_valid, cudaGraphConditionalHandle handle) {
+    unsigned long long* tot_c = reinterpret_cast<unsigned long long*>(c + DT_CNT_TOT_CLOSEST);
+    unsigned long long* tot_s = reinterpret_cast<unsigned long long*>(c + DT_CNT_TOT_SHADOW);
+    const bool overflow = c[DT_CNT_OVERFLOW] != 0 || c[DT_CNT_NEXT] > capacity || c[DT_CNT_SHADOW] > shadow_capacity;
+    if (overflow) c[DT_CNT_OVERFLOW] = 1;
+    const int n_shadow = min(c[DT_CNT_SHADOW], shadow_capacity);
+    if (c[DT_CNT_CUR] > 0 || c[DT_CNT_PREV_SHADOW] > 0) c[DT_CNT_WAVES]++;
+    *tot_c += (unsigned long long)min(c[DT_CNT_NEXT], capacity);
+    *tot_s += (unsigned long long)n_shadow;
+    c[DT_CNT_PREV_SHADOW] = (defer && !overflow) ? n_shadow : 0;
+    c[DT_CNT_CUR] = overflow ? 0 : c[DT_CNT_NEXT];
+    if (handle_valid) {
+        c[DT_CNT_ITERS]++;
+        const long long np = *reinterpret_cast<const long long*>(c + DT_CNT_NEXT_PRIMARY);
+        const bool more = !overflow && (c[DT_CNT_CUR] > 0 || np < total || c[DT_CNT_PREV_SHADOW] > 0);
+        const bool tail = np >= total && c[DT_CNT_CUR] <= tail_threshold && c[DT_CNT_PREV_SHADOW] <= tail_threshold;
+        cudaGraphSetConditional(handle, (more && !tail) ? 1u : 0u);
+    }
+}
+
+// The last few thousand rays of a Russian-roulette frame live for thousands of bounces (paths trapped between two surfaces: the
+// reference's RR never ends a pure GI chain, raytracer.cpp:137-147).  A wave of a handful of rays is all launch latency, so the
+// survivors are dealt out to the blocks of ONE kernel and every block runs the complete wave loop -- closest hit, deferred NEE,
+// shade, shadow -- on block-private queues with __syncthreads() where the frame loop has kernel boundaries.  The ray tree and
+// the per-path RNG streams are the frame loop's, so the image does not depend on where the hand-over happens.
+struct DtTailMem {
+    DtRayQueue q[2];              // G x capacity entries each (block b owns [b * capacity, (b + 1) * capacity))
+    float4* miss[2];
+    DtShadowQueue sq;             // G x shadow_capacity
+    int capacity, shadow_capacity;
+};
+__device__ __forceinline__ DtRayQueue dt_queue_at(const DtRayQueue& q, size_t off) {
+    DtRayQueue r;
+    r.o_time = q.o_time + off; r.d_tmax = q.d_tmax + off; r.hit0 = q.hit0 + off; r.hit_face = q.hit_face + off; r.pixel = q.pixel + off;
+    r.weight_n = q.weight_n + off; r.thr_beer = q.thr_beer + off; r.misc = q.misc + off; r.sort_key = q.sort_key ? q.sort_key + off : nullptr;
+    return r;
+}
+__global__ void __launch_bounds__(128, DT_SHADE_MINBLOCKS) k_tail(DtSceneDev S, DtCamDev cam, DtRayQueue gq, const float4* gmiss, DtShadowQueue gsq, int* c, DtTailMem M, int defer, float4* accum) {
+    __shared__ int sc[8];         // 0 rays of this wave, 1 next wave, 2 shadow rays emitted, 3 overflow, 4 deferred shadow rays of the previous wave
+    const int b = blockIdx.x, G = gridDim.x, tid = threadIdx.x;
+    const int n = c[DT_CNT_CUR], nps = defer ? c[DT_CNT_PREV_SHADOW] : 0;
+    if ((n == 0 && nps == 0) || c[DT_CNT_OVERFLOW] != 0) return;
+    DtRayQueue L[2] = {dt_queue_at(M.q[0], (size_t)b * M.capacity), dt_queue_at(M.q[1], (size_t)b * M.capacity)};
+    float4* Lmiss[2] = {M.miss[0] ? M.miss[0] + (size_t)b * M.capacity : nullptr, M.miss[1] ? M.miss[1] + (size_t)b * M.capacity : nullptr};
+    DtShadowQueue Ls;
+    Ls.o_time = M.sq.o_time + (size_t)b * M.shadow_capacity; Ls.d_tmax = M.sq.d_tmax + (size_t)b * M.shadow_capacity;
+    Ls.contrib_pix = M.sq.contrib_pix + (size_t)b * M.shadow_capacity; Ls.defer = M.sq.defer ? M.sq.defer + (size_t)b * M.shadow_capacity : nullptr;
+    const int chunk = (n + G - 1) / G;
+    const int lo = min(n, b * chunk), hi = min(n, lo + chunk);
+    if (tid < 8) sc[tid] = 0;
+    __syncthreads();
+    for (int j = tid; j < hi - lo; j += blockDim.x) {
+        const int g = lo + j;
+        L[0].o_time[j] = gq.o_time[g]; L[0].d_tmax[j] = gq.d_tmax[g]; L[0].pixel[j] = gq.pixel[g];
+        L[0].weight_n[j] = gq.weight_n[g]; L[0].thr_beer[j] = gq.thr_beer[g]; L[0].misc[j] = gq.misc[g];
+        if (Lmiss[0] && gmiss) Lmiss[0][j] = gmiss[g];
+    }
+    if (tid == 0) { sc[0] = hi - lo; if (b == 0) c[DT_CNT_TAIL_RAYS] = n; }
+    // deferred NEE entries follow the block that owns their GI child; entries without a child are dealt round-robin
+    for (int e = tid; e < nps; e += blockDim.x) {
+        const int2 df = gsq.defer[e];
+        const bool mine = df.x >= 0 ? (df.x >= lo && df.x < hi) : (e % G == b);
+        if (!mine) continue;
+        const int slot = atomicAdd(&sc[4], 1);
+        if (slot >= M.shadow_capacity) { sc[3] = 1; continue; }
+        Ls.o_time[slot] = gsq.o_time[e]; Ls.d_tmax[slot] = gsq.d_tmax[e]; Ls.contrib_pix[slot] = gsq.contrib_pix[e];
+        Ls.defer[slot] = make_int2(df.x >= 0 ? df.x - lo : -1, df.y);
+    }
+    __syncthreads();
+    int p = 0, waves = 0;
+    unsigned long long n_closest = 0, n_shadow = 0;          // thread 0 only
+    for (;;) {
+        const int cur = sc[0], prev = min(sc[4], M.shadow_capacity);
+        if ((cur == 0 && prev == 0) || sc[3] != 0) break;
+        const DtRayQueue& in = L[p];
+        for (int j = tid; j < cur; j += blockDim.x) {
+            if (in.pixel[j] == DT_DEAD_PIXEL) continue;
+            const float4 o = in.o_time[j], d = in.d_tmax[j];
+            DtTrav T; uint2 stack[DT_STACK_SIZE];
+            dt_trav_init<false>(T, S, V(o.x, o.y, o.z), V(d.x, d.y, d.z), o.w, CUDART_INF_F);
+            while (!dt_trav_step<false, true>(T, stack, S, in.o_time + j, in.d_tmax + j)) {}
+            dt_store_closest(in, j, T.best);
+        }
+        __syncthreads();
+        if (defer) {
+            for (int e = tid; e < prev; e += blockDim.x) {
+                if (dt_deferred_skipped(S, Ls.defer[e], in.hit0)) continue;
+                const float4 o = Ls.o_time[e], d = Ls.d_tmax[e];
+                DtTrav T; uint2 stack[DT_STACK_SIZE];
+                dt_trav_init<true>(T, S, V(o.x, o.y, o.z), V(d.x, d.y, d.z), o.w, d.w);
+                while (!dt_trav_step<true, true>(T, stack, S, Ls.o_time + e, Ls.d_tmax + e)) {}
+                dt_store_shadow(Ls, e, T.best, accum);
+            }
+            __syncthreads();
+        }
+        if (tid == 0) { sc[1] = 0; sc[2] = 0; }
+        __syncthreads();
+        const DtShadeCounters cnt = {&sc[1], &sc[2], &sc[3]};
+        for (int j = tid; j < cur; j += blockDim.x)
+            dt_shade_ray(j, S, cam, in, Lmiss[p], L[1 - p], Lmiss[1 - p], M.capacity, Ls, M.shadow_capacity, cnt, accum);
+        __syncthreads();
+        const int ns = min(sc[2], M.shadow_capacity);
+        if (!defer) {
+            for (int e = tid; e < ns; e += blockDim.x) {
+                const float4 o = Ls.o_time[e], d = Ls.d_tmax[e];
+                DtTrav T; uint2 stack[DT_STACK_SIZE];
+                dt_trav_init<true>(T, S, V(o.x, o.y, o.z), V(d.x, d.y, d.z), o.w, d.w);
+                while (!dt_trav_step<true, true>(T, stack, S, Ls.o_time + e, Ls.d_tmax + e)) {}
+                dt_store_shadow(Ls, e, T.best, accum);
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            waves++;
+            if (sc[1] > M.capacity || sc[2] > M.shadow_capacity) sc[3] = 1;
+            n_closest += (unsigned long long)min(sc[1], M.capacity); n_shadow += (unsigned long long)ns;
+            sc[0] = min(sc[1], M.capacity);
+            sc[4] = defer ? ns : 0;
+        }
+        p ^= 1;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        atomicAdd(reinterpret_cast<unsigned long long*>(c + DT_CNT_TOT_CLOSEST), n_closest);
+        atomicAdd(reinterpret_cast<unsigned long long*>(c + DT_CNT_TOT_SHADOW), n_shadow);
+        atomicMax(c + DT_CNT_TAIL_WAVES, waves);
+        if (sc[3] != 0) atomicAdd(c + DT_CNT_OVERFLOW, 1);
+    }
 }
 
 // ------------------------------------------------------------------ resolve
@@ -831,8 +1031,9 @@ __global__ void k_tm_logsum(const float* hdr, int n_pix, double* sum) {
     }
 }
 // histogram of byte `shift/8` of the keys whose higher bytes equal `prefix`
-__global__ void k_tm_hist(const float* vals, size_t n, uint32_t prefix, uint32_t prefix_mask, int shift, unsigned int* hist) {
+__global__ void k_tm_hist(const float* vals, size_t n, const uint32_t* prefix_ptr, uint32_t prefix_mask, int shift, unsigned int* hist) {
     __shared__ unsigned int sh[256];
+    const uint32_t prefix = *prefix_ptr;                  // refined by k_tm_pick of the previous pass: no host round trip between the passes
     for (int k = threadIdx.x; k < 256; k += blockDim.x) sh[k] = 0;
     __syncthreads();
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {

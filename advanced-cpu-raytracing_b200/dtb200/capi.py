@@ -24,6 +24,16 @@ DT_FLAG_SKIP_TONEMAP = 1
 DT_FLAG_NO_SORT = 2
 DT_FLAG_SERIAL_WAVES = 4
 DT_FLAG_PEER_FRAME = 8
+DT_FLAG_JITTER_AA = 16
+DT_FLAG_REF_ROW_BANDS = 32
+DT_FLAG_TEST_TIGHT_QUEUES = 64
+DT_FLAG_FORCE_SORT = 128
+DT_FLAG_HOST_WAVE_LOOP = 256
+DT_FLAG_FRAME_GRAPH = 512
+
+
+class dt_scene_options(C.Structure):
+    _fields_ = [("gpu_flatten_min_faces", C.c_int32), ("reserved", C.c_int32 * 7)]
 
 
 class dt_material(C.Structure):
@@ -149,7 +159,7 @@ class dt_frame_handle(C.Structure):
 
 
 DORKTRACER_SYMBOLS = [
-    "dt_gpu_init", "dt_device_count", "dt_scene_create", "dt_scene_destroy", "dt_render", "dt_render_device",
+    "dt_gpu_init", "dt_device_count", "dt_scene_create", "dt_scene_create_opts", "dt_scene_destroy", "dt_render", "dt_render_device",
     "dt_finish_device", "dt_primary_hits", "dt_trace_closest", "dt_trace_occluded", "dt_tonemap",
     "dt_scene_stream", "dt_last_error", "dt_version",
     "dt_frame_export", "dt_frame_import", "dt_frame_release", "dt_frame_finish", "dt_bvh2_build", "dt_scene_accel_checksum",
@@ -220,6 +230,8 @@ def load_dorktracer():
     lib.dt_device_count.restype = C.c_int
     lib.dt_scene_create.argtypes = [C.POINTER(dt_scene_desc), C.POINTER(vp)]
     lib.dt_scene_create.restype = C.c_int
+    lib.dt_scene_create_opts.argtypes = [C.POINTER(dt_scene_desc), C.POINTER(dt_scene_options), C.POINTER(vp)]
+    lib.dt_scene_create_opts.restype = C.c_int
     lib.dt_scene_destroy.argtypes = [vp]
     lib.dt_scene_destroy.restype = None
     lib.dt_render.argtypes = [vp, C.POINTER(dt_camera_desc), C.POINTER(dt_render_params), C.c_void_p, C.c_void_p, C.POINTER(dt_stats)]

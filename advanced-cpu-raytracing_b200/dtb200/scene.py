@@ -95,7 +95,8 @@ class HostScene:
 class GpuScene:
     """dt_scene handle on the CUDA hot path (include/dorktracer.h).  No fallback: raises without the library/GPU."""
 
-    def __init__(self, host_scene, device=None):
+    def __init__(self, host_scene, device=None, gpu_flatten_min_faces=0):
+        """gpu_flatten_min_faces: dt_scene_options (0 = library default, < 0 = host flattener only)."""
         self.lib = capi.load_dorktracer()
         if device is not None:
             rc = self.lib.dt_gpu_init(int(device))
@@ -103,7 +104,9 @@ class GpuScene:
                 raise RuntimeError("dt_gpu_init failed: %s" % self.lib.dt_last_error().decode())
         self.host = host_scene
         self.handle = C.c_void_p()
-        rc = self.lib.dt_scene_create(host_scene.desc_ptr, C.byref(self.handle))
+        opts = capi.dt_scene_options()
+        opts.gpu_flatten_min_faces = int(gpu_flatten_min_faces)
+        rc = self.lib.dt_scene_create_opts(host_scene.desc_ptr, C.byref(opts), C.byref(self.handle))
         if rc != 0:
             raise RuntimeError("dt_scene_create failed (%d): %s" % (rc, self.lib.dt_last_error().decode()))
 
@@ -159,11 +162,12 @@ class GpuScene:
     def frame_release(self):
         self.lib.dt_frame_release(self.handle)
 
-    def frame_finish(self, cam, ldr=None):
-        if ldr is None:
+    def frame_finish(self, cam, ldr=None, on_device=False):
+        """on_device: tonemap / clamp only, the finished LDR frame stays in device memory (no D2H)."""
+        if ldr is None and not on_device:
             ldr = np.zeros((cam.height, cam.width, 3), np.uint8)
         stats = capi.dt_stats()
-        rc = self.lib.dt_frame_finish(self.handle, C.byref(cam), ldr.ctypes.data_as(C.c_void_p), C.byref(stats))
+        rc = self.lib.dt_frame_finish(self.handle, C.byref(cam), None if on_device else ldr.ctypes.data_as(C.c_void_p), C.byref(stats))
         if rc != 0:
             self._err("dt_frame_finish", rc)
         return ldr, stats

@@ -204,7 +204,7 @@ def _env_map(w=256, h=128):
     return env.astype(np.float32)
 
 
-def gen_config4(out_dir, width=1920, height=1080, spp=256, depth=4, blob=(0, 0), name="config4", nee=True, rr=True, importance=True):
+def gen_config4(out_dir, width=1920, height=1080, spp=256, depth=4, blob=(0, 0), name="config4", nee=True, rr=True, importance=True, n_cameras=1):
     """Path-traced box + spheres: area light + light mesh + spherical HDR environment light, Torrance-Sparrow
     (kdfresnel) and modified Blinn-Phong BRDFs, photographic tonemapper.  blob=(nlon,nlat) adds a displaced
     sphere mesh of that tessellation (config 5 uses 3162 x 1581 ~ 10 M triangles)."""
@@ -214,7 +214,9 @@ def gen_config4(out_dir, width=1920, height=1080, spp=256, depth=4, blob=(0, 0),
     extra = ("        <Renderer>PathTracing</Renderer>\n        <RendererParams>%s</RendererParams>\n"
              "        <Tonemap>\n            <TMO>Photographic</TMO>\n            <TMOOptions>0.18 1</TMOOptions>\n            <Saturation>1.0</Saturation>\n            <Gamma>2.2</Gamma>\n        </Tonemap>\n" % params)
     xml = "<Scene>\n    <MaxRecursionDepth>%d</MaxRecursionDepth>\n    <BackgroundColor>0 0 0</BackgroundColor>\n    <ShadowRayEpsilon>1e-3</ShadowRayEpsilon>\n" % depth
-    xml += "    <Cameras>\n" + _xml_camera(1, (0, 0, 24), (0, -1, 0), (0, 1, 0), 40, 1, width, height, name + ".exr", spp, extra) + "    </Cameras>\n"
+    # n_cameras identical cameras: the reference renders every camera of a scene in one process (main.cpp:142), which gives
+    # the CPU arm of bench.py several steps per scene load
+    xml += "    <Cameras>\n" + "".join(_xml_camera(k + 1, (0, 0, 24), (0, -1, 0), (0, 1, 0), 40, 1, width, height, name + ".exr", spp, extra) for k in range(n_cameras)) + "    </Cameras>\n"
     xml += ("    <Lights>\n        <AreaLight id=\"1\">\n            <Position>0 9.9 0</Position>\n            <Normal>0 -1 0</Normal>\n            <Radiance>18 17 15</Radiance>\n            <Size>4</Size>\n        </AreaLight>\n"
             "        <SphericalDirectionalLight id=\"2\">\n            <ImageId>1</ImageId>\n        </SphericalDirectionalLight>\n    </Lights>\n")
     xml += ("    <BRDFs>\n        <TorranceSparrow id=\"1\" kdfresnel=\"true\">\n            <Exponent>40</Exponent>\n        </TorranceSparrow>\n"

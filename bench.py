@@ -2,26 +2,30 @@
 """bench.py — headline benchmark of the render hot path (contract: see the task's bench section).
 
 Metric (BASELINE.json): Mrays/s (primary + secondary + shadow) for the whole job, frame ms.
-A *step* is one frame of the workload through the hot path:
-  N = 1 : BASELINE.json configs[1] — ~1M-triangle mesh (procedural "blob": the named bunny/dragon assets are
-          stripped from the reference mount), mirror + dielectric recursion depth 6, 2 point lights, 1920x1080.
-  N > 1 : the same scene and view with sqrt(N) x the resolution per axis (per-GPU pixel count fixed -> weak
-          scaling); the image is tile-sharded (strips of eight 8x4-pixel tiles, round-robin) across the ranks, each rank renders
-          its tiles with the whole scene replicated, and the per-rank radiance frames are combined on rank 0
-          without a full-frame exchange: rank 0 exports its frame buffers (CUDA IPC) and every rank's resolve kernel
-          stores its tiles straight into them over NVLink (P2P stores), then one barrier.  Fallback when the IPC
-          mapping is unavailable: ONE NCCL reduce (every pixel is non-zero on exactly one rank, so SUM == gather).
+A *step* is one frame of the workload through the hot path.
 
-  value      device time only: scene + camera resident, CUDA events on the library's stream (+ the reduce)
-  e2e        the public C-ABI call dt_render() with a pinned HOST LDR buffer: D2H of the frame inside the
-             timed region, wall clock between device synchronisations
-  roofline   closest-hit traversal kernel: algorithmic bytes/ray (736 B for config 2) x rays
-             / its CUDA-event time (measured live in a separate DT_FLAG_SERIAL_WAVES pass, each kernel alone on
-             the GPU), against the measured HBM peak (MEASURED_PEAKS.json); `traffic` and the issue-slot / SIMT
-             figures come from the committed ncu capture (profiles/ncu_traverse_summary.json)
-  cpu_baseline  the compiled reference (oracle/_ref/raytracer) on this box's host cores, same frame
+  --config 5 (default, the configuration BASELINE.json quotes the metric on): the synthetic procedural 10 M-triangle scene
+        (9 991 932 triangles: config-4 box + displaced-sphere mesh), path tracing with next-event estimation + importance
+        sampling + Russian roulette, area light + mesh light + spherical HDR environment light, Torrance-Sparrow / modified
+        Blinn-Phong BRDFs, photographic tonemapper, 3840x2160 — at a STATED REDUCED sample count (--spp, default 16 instead of
+        1024: a 1024-spp frame is 85 s on one B200).  N > 1: THE SAME FRAME is sharded over the ranks (strips of eight
+        8x4-pixel tiles, round-robin; what the reference does with row bands over its threads, main.cpp:38-39) -> strong
+        scaling.  Every rank's resolve kernel stores its strips of radiance straight into rank 0's frame over NVLink (CUDA IPC
+        peer memory, no collective), one barrier, then rank 0 tonemaps the whole frame.
+  --config 2: ~1 M-triangle mesh, mirror + dielectric recursion depth 6, 2 point lights, 1920x1080, 1 spp (the round-1
+        headline; weak scaling: sqrt(N) x the resolution per axis).  Its N=1 numbers also ride along in `other_workloads`.
 
-`--impl reference` times the reference's own CPU renderer on the same workload (rank 0 only).
+  value      device time only: scene + camera resident, CUDA events on the library's stream (render + resolve + tonemap,
+             + the barrier for N > 1), L2 flushed between iterations
+  e2e        the public C-ABI call dt_render() with a pinned HOST LDR buffer: camera / parameters in, D2H of the finished
+             frame inside the timed region, wall clock between device synchronisations
+  roofline   the dominant kernel (the traversal kernel with the larger share of the frame).  Primary bound = SM issue slots
+             (the binding roof: warp instructions per ray from the committed ncu capture x rays / live CUDA-event time of the
+             kernel's launches, against 4 issue slots x #SM x SM clock); secondary = HBM (SURVEY.md 8d algorithmic bytes per
+             ray x rays / the same live time, against MEASURED_PEAKS.json).  Live times come from a separate
+             DT_FLAG_SERIAL_WAVES pass inside this run (each kernel alone on the GPU).
+  cpu_baseline / --impl reference   the compiled reference (oracle/_ref/raytracer) on this box's host cores, SAME scene, on a
+             bounded sample of the workload (reduced resolution and samples: the reference manages ~1-3 Mrays/s here).
 """
 import argparse
 import ctypes as C
@@ -40,8 +44,15 @@ sys.path.insert(0, os.path.join(REPO, "advanced-cpu-raytracing_b200"))
 
 METRIC = "Mrays/s (primary+secondary+shadow), whole job"
 UNIT = "Mrays/s"
-B_RAY_CLOSEST = 736.0          # 32 in + 32 out + 6 x 80 B nodes + 4 x 48 B triangles
-B_RAY_SHADOW = 708.0           # same minus the 32 B hit record plus a 4 B flag
+
+# SURVEY.md 8(d) algorithmic bytes per ray: 32 in + 32 out + 80 B x nodes on one root-to-leaf chain + 4 x 48 B triangles;
+# shadow rays the same minus the 32 B hit record plus a 4 B flag.
+WORKLOADS = {
+    5: {"b_closest": 896.0, "b_shadow": 868.0, "width": 3840, "height": 2160, "spp": 16, "scaling": "strong",
+        "ref_sample": (480, 272, 4)},      # reference arm: same scene, 480x272, 4 spp (about 12 M rays per step)
+    2: {"b_closest": 736.0, "b_shadow": 708.0, "width": 1920, "height": 1080, "spp": 1, "scaling": "weak",
+        "ref_sample": (1920, 1080, 1)},
+}
 
 
 def env_int(name, default):
@@ -51,16 +62,36 @@ def env_int(name, default):
         return default
 
 
-def make_workload(tmp, nlon=1000, nlat=499):
+def make_workload(cfg, tmp, width, height, spp, n_cameras=1):
+    """Generates the scene files (seeded, procedural) and returns the XML path."""
     from dtb200 import scenegen
-    return scenegen.gen_config2(os.path.join(tmp, "c2"), nlon=nlon, nlat=nlat, width=1920, height=1080, depth=6)
+    if cfg == 2:
+        return scenegen.gen_config2(os.path.join(tmp, "c2"), nlon=1000, nlat=499, width=width, height=height, depth=6)
+    return scenegen.gen_config5(os.path.join(tmp, "c5"), width=width, height=height, spp=spp, n_cameras=n_cameras)
 
 
-def scaled_resolution(n):
+def workload_config(cfg, spp, n_tris=None):
+    """The `config` object of the JSON line: static description of the workload, IDENTICAL in both arms."""
+    w = WORKLOADS[cfg]
+    if cfg == 5:
+        return {"workload": "config5: synthetic procedural 10M-triangle scene (9991932 triangles), path tracing (NEE + importance sampling + Russian roulette), "
+                            "area + mesh + spherical-environment lights, Torrance-Sparrow / modified Blinn-Phong BRDFs, photographic tonemap, 3840x2160, "
+                            "%d spp (BASELINE.json configs[4] names 1024 spp; reduced and stated so that a step is seconds, not minutes)" % spp,
+                "resolution": [w["width"], w["height"]], "spp": spp, "triangles": 9991932,
+                "sharding": "the same frame at every N: strips of 64x4 pixels dealt round-robin over the GPUs (strong scaling), scene replicated",
+                "l2": "flushed between timed iterations (256 MiB write); the 680 MB acceleration structure exceeds the 126 MB L2 anyway"}
+    return {"workload": "config2: 996002-triangle procedural mesh + ground + dielectric sphere, mirror/dielectric depth 6, 2 point lights, 1920x1080, 1 spp",
+            "resolution": [w["width"], w["height"]], "spp": 1, "triangles": 996002,
+            "sharding": "N > 1: sqrt(N) x the resolution per axis, strips of 64x4 pixels dealt round-robin (weak scaling), scene replicated",
+            "l2": "flushed between timed iterations (256 MiB write)"}
+
+
+def scaled_resolution(cfg, n):
+    w = WORKLOADS[cfg]
+    if w["scaling"] == "strong" or n == 1:
+        return w["width"], w["height"]
     s = math.sqrt(n)
-    w = int(round(1920 * s / 8.0)) * 8
-    h = int(round(1080 * s / 8.0)) * 8
-    return w, h
+    return int(round(w["width"] * s / 8.0)) * 8, int(round(w["height"] * s / 8.0)) * 8
 
 
 def best_threads(height, cores):
@@ -143,14 +174,18 @@ class ClockSampler(threading.Thread):
                 "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
-def run_reference_frame(xml_path, threads, probe=False):
-    """One frame of the compiled reference (oracle/_ref).  Returns (seconds, closest, shadow)."""
+# ------------------------------------------------------------------ CPU arms (the reference itself, or the oracle port)
+def run_reference(xml_path, threads, probe=False):
+    """One run of the compiled reference (oracle/_ref) over ALL cameras of the XML.  Returns (seconds, closest, shadow):
+    seconds = the binary's own 'Rendering took' (all cameras, excluding scene load), ray counts from the probe build."""
     ref_dir = os.path.join(REPO, "oracle", "_ref")
     exe = os.path.join(ref_dir, "raytracer_probe" if probe else "raytracer")
     env = dict(os.environ, DT_THREADS=str(threads))
     cwd = os.path.dirname(os.path.abspath(xml_path))
-    p = subprocess.run([exe, os.path.basename(xml_path)], cwd=cwd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=3600)
-    out = p.stdout.decode(errors="replace")
+    with tempfile.TemporaryFile() as out_f:
+        p = subprocess.run([exe, os.path.basename(xml_path)], cwd=cwd, env=env, stdout=out_f, stderr=subprocess.STDOUT, timeout=3600)
+        out_f.seek(max(0, out_f.tell() - 4000))
+        out = out_f.read().decode(errors="replace")
     if p.returncode != 0:
         raise RuntimeError("reference run failed: " + out[-500:])
     sec = float(re.search(r"Rendering took: ([0-9.eE+-]+)s", out).group(1))
@@ -175,32 +210,56 @@ def oracle_port_frame(xml_path, threads):
     return time.perf_counter() - t0, int(st.rays_closest), int(st.rays_shadow)
 
 
+_ray_count_cache = {}
+
+
+def cpu_sample(cfg, tmp, frames):
+    """Times `frames` steps of the CPU arm on the bounded sample of workload `cfg`.  Returns (seconds per step, rays per step,
+    threads, kind, description of the sample)."""
+    sw, sh, sspp = WORKLOADS[cfg]["ref_sample"]
+    cores = os.cpu_count() or 1
+    threads = best_threads(sh, cores)
+    what = ("full %dx%d frame" % (sw, sh)) if cfg == 2 else ("the same 9991932-triangle scene at %dx%d, %d spp (reduced from 3840x2160)" % (sw, sh, sspp))
+    if have_ref():
+        xml1 = make_workload(cfg, os.path.join(tmp, "probe"), sw, sh, sspp)
+        if cfg not in _ray_count_cache:
+            _ray_count_cache[cfg] = run_reference(xml1, threads, probe=True)[1:]   # ray counts: untimed probe build, one frame
+        nc, ns = _ray_count_cache[cfg]
+        if cfg == 2 or frames == 1:
+            secs = [run_reference(xml1, threads)[0] for _ in range(frames)]
+            sec = sum(secs) / len(secs)
+        else:
+            # the reference renders every <Camera> of a scene in one process (main.cpp:142): `frames` identical cameras give
+            # `frames` steps with ONE scene load (12 s for the 10 M-triangle PLY); its timer spans all of them
+            xmlk = make_workload(cfg, os.path.join(tmp, "timed"), sw, sh, sspp, n_cameras=frames)
+            sec = run_reference(xmlk, threads)[0] / frames
+        kind = "reference"
+    else:
+        xml1 = make_workload(cfg, os.path.join(tmp, "probe"), sw, sh, sspp)
+        secs = []
+        for _ in range(frames):
+            s_, nc, ns = oracle_port_frame(xml1, threads)
+            secs.append(s_)
+        sec = sum(secs) / len(secs)
+        kind = "port"
+    desc = "%s; %d render threads (largest divisor of the height <= %d host cores); %d rays per step; time = the binary's own 'Rendering took' (scene load excluded)" % (what, threads, cores, nc + ns)
+    return sec, nc + ns, threads, kind, desc
+
+
 def reference_arm(args, rank, world):
     if rank != 0:
         return 0
+    cfg = args.config
     tmp = tempfile.mkdtemp(prefix="dt_bench_ref_")
-    xml = make_workload(tmp)
-    cores = os.cpu_count() or 1
-    threads = best_threads(1080, cores)
-    kind = "reference" if have_ref() else "port"
-    if kind == "reference":
-        _, nc, ns = run_reference_frame(xml, threads, probe=True)         # ray counts (untimed probe build)
-        frame = lambda: run_reference_frame(xml, threads)[0]
-    else:
-        _, nc, ns = oracle_port_frame(xml, threads)
-        frame = lambda: oracle_port_frame(xml, threads)[0]
-    for _ in range(args.warmup):
-        frame()
-    secs = [frame() for _ in range(args.steps)]
-    ms = 1e3 * sum(secs) / len(secs)
-    value = (nc + ns) / (ms * 1e3)
+    if args.warmup > 0:
+        cpu_sample(cfg, os.path.join(tmp, "w"), args.warmup)
+    sec, rays, threads, kind, desc = cpu_sample(cfg, os.path.join(tmp, "t"), args.steps)
+    value = rays / (sec * 1e6)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "config2: 996002-triangle procedural mesh + ground + dielectric sphere, mirror/dielectric depth 6, 2 point lights, 1920x1080, 1 spp",
-                   "rays_per_step": nc + ns, "note": "CPU arm renders the N=1 frame (bounded sample) on the host cores"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
-                         "sample": "full 1920x1080 frame of the workload, %d render threads (largest divisor of 1080 <= %d host cores), time = the binary's own 'Rendering took'" % (threads, cores)},
+        "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": WORKLOADS[cfg]["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(cfg, args.spp),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": desc},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -208,15 +267,20 @@ def reference_arm(args, rank, world):
     return 0
 
 
+# ------------------------------------------------------------------ our arm
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=5, choices=[2, 5])
+    ap.add_argument("--spp", type=int, default=0, help="samples per pixel of config 5 (a perfect square; default 16)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--tris", default="1000x499", help="blob tessellation nlon x nlat (default = 996000 triangles)")
+    ap.add_argument("--no-other", action="store_true", help="skip the config-2 ride-along numbers")
     args = ap.parse_args()
+    if args.spp <= 0:
+        args.spp = WORKLOADS[args.config]["spp"]
     rank, local_rank, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)
 
     if args.impl == "reference":
@@ -234,19 +298,24 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    nlon, nlat = (int(x) for x in args.tris.split("x"))
+    cfg = args.config
+    wl = WORKLOADS[cfg]
+    W, H = scaled_resolution(cfg, world)
     tmp = tempfile.mkdtemp(prefix="dt_bench_r%d_" % rank)
-    xml = make_workload(tmp, nlon, nlat)
-    if capi.load_dorktracer().dt_gpu_init(local_rank) < 0:
-        raise RuntimeError(capi.load_dorktracer().dt_last_error().decode())
-    t0 = time.perf_counter()
-    hs = HostScene(xml, gpu_build=True)          # Mesh::ConstructBVH on the GPU (dt_bvh2_build), bit-identical to the host build
-    t_load = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    gs = GpuScene(hs, device=local_rank)
-    t_upload = time.perf_counter() - t0
+    xml = make_workload(cfg, tmp, W, H, args.spp)
+    lib = capi.load_dorktracer()
+    if lib.dt_gpu_init(local_rank) < 0:
+        raise RuntimeError(lib.dt_last_error().decode())
+
+    def load_scene(path):
+        t0 = time.perf_counter()
+        hs_ = HostScene(path, gpu_build=True)          # Mesh::ConstructBVH on the GPU (dt_bvh2_build), bit-identical to the host build
+        t1 = time.perf_counter()
+        gs_ = GpuScene(hs_, device=local_rank)
+        return hs_, gs_, t1 - t0, time.perf_counter() - t1
+
+    hs, gs, t_load, t_upload = load_scene(xml)
     cam = hs.camera(0)
-    W, H = scaled_resolution(world)
     cam.width, cam.height = W, H
     n_pix = W * H
 
@@ -261,9 +330,9 @@ def main():
         return torch.as_tensor(_Wrap(), device="cuda")
 
     # Multi-GPU gather: rank 0 exports its frame buffers (CUDA IPC), the others import them and their resolve kernel
-    # stores the owned tiles straight into rank 0's memory over NVLink (DT_FLAG_PEER_FRAME); one barrier orders
-    # "all tiles written" before "rank 0 reads".  If the IPC mapping is unavailable the ranks fall back, together, to
-    # the NCCL reduce of the per-rank radiance frames.
+    # stores the owned strips straight into rank 0's memory over NVLink (DT_FLAG_PEER_FRAME); one barrier orders
+    # "all strips written" before "rank 0 reads".  If the IPC mapping is unavailable the ranks fall back, together, to
+    # the NCCL reduce of the per-rank radiance frames (SUM == gather: every pixel is non-zero on exactly one rank).
     peer = False
     if world > 1 and not os.environ.get("DT_BENCH_NO_PEER"):
         ok = 1
@@ -288,17 +357,17 @@ def main():
 
     split_ms = [0.0, 0.0]                                                      # this rank's render / wait-at-the-barrier parts of the timed steps
 
-    def device_step(timed):
-        """value path: inputs resident, no host copies.  Returns (ms, stats)."""
+    def device_step(timed, scene=None, camera=None):
+        """value path: inputs resident, no host copies; the frame ends tonemapped / clamped in device memory."""
+        g, c = scene or gs, camera or cam
         flush_buf.fill_(rank + 1)                                              # L2 flush between iterations
         if world > 1:
             dist.barrier()                                                     # untimed: the ranks start the step together (the flush skews them)
         torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         e0.record(lib_stream)
-        ptr, st = gs.render_device(cam, tile_rank=rank, tile_world=world, flags=peer_flags)
+        ptr, st = g.render_device(c, tile_rank=rank, tile_world=world, flags=peer_flags)
         e1.record(lib_stream)
-        ms = None
         if world > 1:
             r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             r0.record()
@@ -309,11 +378,20 @@ def main():
             r1.record()
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) + r0.elapsed_time(r1)
+            if rank == 0 and c.has_tonemapper:                                 # global tonemap of the gathered frame (device only)
+                e1.record(lib_stream)
+                g.frame_finish(c, on_device=True)
+                e2.record(lib_stream)
+                torch.cuda.synchronize()
+                ms += e1.elapsed_time(e2)
             if timed:
                 split_ms[0] += e0.elapsed_time(e1); split_ms[1] += r0.elapsed_time(r1)
         else:
+            if c.has_tonemapper:
+                g.frame_finish(c, on_device=True)
+            e2.record(lib_stream)
             torch.cuda.synchronize()
-            ms = e0.elapsed_time(e1)
+            ms = e0.elapsed_time(e2)
         return ms, st
 
     def e2e_step():
@@ -341,7 +419,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(3, args.warmup)):
+    n_warm = max(3, args.warmup)
+    for _ in range(n_warm):
         device_step(False)
     barrier()
     sampler = ClockSampler(local_rank)
@@ -349,20 +428,20 @@ def main():
     t_wall0 = time.perf_counter()
     ms_sum, launches = 0.0, 0
     rays_c = rays_s = 0
-    ov_closest = ov_shadow = ov_shade = 0.0
+    waves = 0
     for _ in range(args.steps):
         ms, st = device_step(True)
         ms_sum += ms
         launches += int(st.kernel_launches)
         rays_c += int(st.rays_closest); rays_s += int(st.rays_shadow)
-        ov_closest += st.ms_traverse_closest; ov_shadow += st.ms_traverse_shadow; ov_shade += st.ms_shade
+        waves += int(st.waves)
     barrier()
-    if world > 1 and os.environ.get("DT_BENCH_VERBOSE"):
-        print("[bench] rank %d: render %.3f ms + barrier wait %.3f ms per step" % (rank, split_ms[0] / args.steps, split_ms[1] / args.steps), file=sys.stderr, flush=True)
     t_wall = time.perf_counter() - t_wall0
     clocks = sampler.stop()
+    if world > 1 and os.environ.get("DT_BENCH_VERBOSE"):
+        print("[bench] rank %d: render %.3f ms + barrier wait %.3f ms per step" % (rank, split_ms[0] / args.steps, split_ms[1] / args.steps), file=sys.stderr, flush=True)
 
-    # e2e (host buffers)
+    # e2e (host buffers), the same number of steps
     for _ in range(2):
         e2e_step()
     barrier()
@@ -373,28 +452,28 @@ def main():
     e2e_s = time.perf_counter() - t0
 
     # roofline pass (untimed for `value`): the same frame with DT_FLAG_SERIAL_WAVES, so that the CUDA-event time of each
-    # traversal launch is that of the kernel running alone (in the default mode shadow(k) overlaps closest(k+1))
-    n_roof = max(3, min(10, args.steps))
-    ms_closest = ms_shadow = ms_shade = ms_gen = 0.0
+    # traversal launch is that of the kernel running alone
+    n_roof = 2 if cfg == 5 else max(3, min(10, args.steps))
+    ms_closest = ms_shadow = ms_shade = ms_gen = ms_sort = 0.0
     rays_c_roof = rays_s_roof = 0
-    n_closest_launches = 0
+    n_closest_launches = n_waves_roof = 0
     for _ in range(n_roof):
         flush_buf.fill_(rank + 1)
         torch.cuda.synchronize()
         _, st = gs.render_device(cam, tile_rank=rank, tile_world=world, flags=capi.DT_FLAG_SERIAL_WAVES | peer_flags)
-        ms_closest += st.ms_traverse_closest; ms_shadow += st.ms_traverse_shadow; ms_shade += st.ms_shade; ms_gen += st.ms_generate
+        ms_closest += st.ms_traverse_closest; ms_shadow += st.ms_traverse_shadow; ms_shade += st.ms_shade; ms_gen += st.ms_generate; ms_sort += st.ms_sort
         rays_c_roof += int(st.rays_closest); rays_s_roof += int(st.rays_shadow)
-        n_closest_launches += int(st.launches_traverse_closest)
+        n_closest_launches += int(st.launches_traverse_closest); n_waves_roof += int(st.waves)
     barrier()
 
     # max over ranks of the times, sum over ranks of the rays
-    vals = torch.tensor([ms_sum, e2e_s, ms_closest, ms_shadow], dtype=torch.float64, device="cuda")
-    cnts = torch.tensor([rays_c, rays_s, launches, n_closest_launches], dtype=torch.float64, device="cuda")
+    vals = torch.tensor([ms_sum, e2e_s], dtype=torch.float64, device="cuda")
+    cnts = torch.tensor([rays_c, rays_s, launches], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
         dist.all_reduce(cnts, op=dist.ReduceOp.SUM)
-    ms_sum_max, e2e_s_max, ms_closest_max, ms_shadow_max = vals.tolist()
-    rays_c_all, rays_s_all, launches_all, closest_launches_all = cnts.tolist()
+    ms_sum_max, e2e_s_max = vals.tolist()
+    rays_c_all, rays_s_all, launches_all = cnts.tolist()
 
     if rank == 0:
         rays_per_step = (rays_c_all + rays_s_all) / args.steps
@@ -402,62 +481,97 @@ def main():
         value = rays_per_step / (ms_per_step * 1e3)
         e2e_value = rays_per_step / (e2e_s_max / args.steps * 1e6)
         peaks_path = os.path.join(REPO, "MEASURED_PEAKS.json")
-        peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+        peak, peak_src, sm_mhz_max = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)", 1965.0
         if os.path.exists(peaks_path):
             try:
-                peak = float(json.load(open(peaks_path))["hbm_gbs"]); peak_src = "measured (MEASURED_PEAKS.json hbm_gbs, copy)"
+                pk = json.load(open(peaks_path))
+                peak = float(pk["hbm_gbs"]); peak_src = "measured (MEASURED_PEAKS.json hbm_gbs, copy)"
+                sm_mhz_max = float(pk.get("sm_max_mhz", sm_mhz_max))
             except Exception:
                 pass
-        # roofline of the dominant kernel (closest-hit traversal): rank-0-local figures
-        gb_closest = B_RAY_CLOSEST * rays_c_roof / 1e9
-        achieved = gb_closest / (ms_closest / 1e3) if ms_closest > 0 else 0.0
-        gb_shadow = B_RAY_SHADOW * rays_s_roof / 1e9
-        achieved_shadow = gb_shadow / (ms_shadow / 1e3) if ms_shadow > 0 else 0.0
         ncu = {}
         try:
-            ncu = json.load(open(os.path.join(REPO, "profiles", "ncu_traverse_summary.json")))
+            ncu = json.load(open(os.path.join(REPO, "profiles", "ncu_config%d_summary.json" % cfg)))
         except Exception:
             pass
+        # dominant kernel = the traversal kernel with the larger share of the frame (kernels alone: SERIAL_WAVES pass, rank 0)
+        kinds = {"closest": ("k_traverse_dyn<false> (closest-hit, persistent warps)", ms_closest, rays_c_roof, wl["b_closest"]),
+                 "shadow": ("k_traverse_dyn<true> (any-hit / shadow rays, persistent warps)", ms_shadow, rays_s_roof, wl["b_shadow"])}
+        dom = "shadow" if ms_shadow > ms_closest else "closest"
+        other = "closest" if dom == "shadow" else "shadow"
+
+        def roof(which):
+            name, ms_k, rays_k, b_ray = kinds[which]
+            launches_k = max(1, n_waves_roof if which == "shadow" else n_closest_launches)
+            gbs = b_ray * rays_k / 1e9 / (ms_k / 1e3) if ms_k > 0 else 0.0
+            nk = (ncu.get("kernels") or {}).get(which) or {}
+            inst_per_ray = nk.get("warp_inst_per_ray")
+            n_sm = int(torch.cuda.get_device_properties(local_rank).multi_processor_count)
+            issue_peak = 4.0 * n_sm * sm_mhz_max * 1e6 / 1e9                                   # G warp-instructions / s
+            issue = None
+            if inst_per_ray and ms_k > 0:
+                ach = inst_per_ray * rays_k / (ms_k / 1e3) / 1e9
+                issue = {"achieved": ach, "peak": issue_peak, "unit": "Gwarp-inst/s", "frac": ach / issue_peak, "warp_inst_per_ray": inst_per_ray,
+                         "ncu_issue_active_pct": nk.get("issue_active_pct"), "ncu_threads_per_inst": nk.get("threads_per_inst"), "ncu_branch_uniform_pct": nk.get("branch_uniform_pct")}
+            hbm = {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "algorithmic_bytes_per_ray": b_ray,
+                   "algorithmic_bytes_per_launch": b_ray * rays_k / launches_k, "peak_source": peak_src}
+            return name, ms_k, rays_k, launches_k, issue, hbm, nk
+
+        name, ms_k, rays_k, launches_k, issue, hbm, nk = roof(dom)
+        _, _, _, _, issue2, hbm2, _ = roof(other)
+        how = ("CUDA events around each launch of %d frames rendered with DT_FLAG_SERIAL_WAVES (kernel alone on the GPU), L2 flushed before each frame; "
+               "warp instructions per ray from the committed ncu capture of the same workload" % n_roof)
+        if issue:
+            roofline = {"bound": "issue", "kernel": name, "achieved": issue["achieved"], "peak": issue["peak"], "unit": issue["unit"], "frac": issue["frac"],
+                        "traffic": nk.get("traffic_bytes_per_launch"), "issue": issue, "hbm": hbm}
+        else:   # no ncu summary for this workload committed yet: the HBM figure alone
+            roofline = dict(hbm, kernel=name, traffic=None, issue=None, hbm=hbm)
+        roofline.update({"rays_per_launch": rays_k / launches_k, "avg_launch_ms": ms_k / launches_k, "how": how, "ncu_source": ncu.get("source"),
+                         "other_kernel": {"kernel": kinds[other][0], "issue": issue2, "hbm": hbm2}})
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {
-                "workload": "config2: %d-triangle procedural mesh + ground + dielectric sphere, mirror/dielectric depth 6, 2 point lights, %dx%d, 1 spp%s"
-                            % (hs.n_triangles(), W, H, "" if world == 1 else " (1920x1080 x %d pixels, tile-sharded over %d GPUs, %s)" % (world, world, "tiles stored into rank 0's frame over NVLink by the resolve kernel (CUDA IPC peer memory) + one barrier" if peer else "NCCL reduce to rank 0")),
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": n_warm,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(cfg, args.spp),
+            "details": {
+                "resolution_rendered": [W, H], "triangles": hs.n_triangles(),
                 "rays_per_step": rays_per_step, "closest_rays_per_step": rays_c_all / args.steps, "shadow_rays_per_step": rays_s_all / args.steps,
-                "l2": "flushed between timed iterations (256 MiB write)", "timing": "CUDA events on the library stream (+ barrier / reduce), max over ranks", "gather": ("peer-memory stores" if peer else "nccl-reduce") if world > 1 else "none",
+                "waves_per_step_rank0": waves / args.steps,
+                "timing": "CUDA events on the library stream (render + resolve + tonemap; + barrier / reduce for N > 1), max over ranks",
+                "gather": ("peer-memory stores (CUDA IPC, fused into the resolve kernel) + one barrier" if peer else "nccl-reduce") if world > 1 else "none",
                 "scene_load_s": t_load, "scene_upload_s": t_upload,
-                "stage_ms_per_step_rank0_kernels_alone": {"generate": ms_gen / n_roof, "traverse_closest": ms_closest / n_roof, "shade": ms_shade / n_roof, "traverse_shadow": ms_shadow / n_roof,
-                                                          "note": "DT_FLAG_SERIAL_WAVES pass of %d frames after the timed region" % n_roof},
-                "stage_ms_per_step_rank0_overlapped": {"traverse_closest": ov_closest / args.steps, "shade": ov_shade / args.steps, "traverse_shadow": ov_shadow / args.steps,
-                                                       "note": "timed region; shadow(k) runs concurrently with closest(k+1)/shade(k+1), so these sum to more than ms_per_step"},
+                "stage_ms_per_step_rank0_kernels_alone": {"generate": ms_gen / n_roof, "traverse_closest": ms_closest / n_roof, "sort": ms_sort / n_roof, "shade": ms_shade / n_roof,
+                                                          "traverse_shadow": ms_shadow / n_roof, "note": "DT_FLAG_SERIAL_WAVES pass of %d frames after the timed region" % n_roof},
                 "wall_s_timed_region": t_wall,
             },
-            "roofline": {"bound": "hbm", "kernel": "k_traverse<false> (closest-hit, persistent warps)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": ncu.get("traffic_bytes_per_launch"), "peak_source": peak_src,
-                         "algorithmic_bytes_per_ray": B_RAY_CLOSEST, "rays_per_launch": rays_c_roof / max(1, n_closest_launches),
-                         "algorithmic_bytes_per_launch": B_RAY_CLOSEST * rays_c_roof / max(1, n_closest_launches),
-                         "avg_launch_ms": ms_closest / max(1, n_closest_launches),
-                         "how": "CUDA events around each of the %d closest-hit launches of %d frames rendered with DT_FLAG_SERIAL_WAVES (kernel alone on the GPU), L2 flushed before each frame" % (n_closest_launches, n_roof),
-                         "ncu": ncu.get("ncu"), "ncu_source": ncu.get("source"),
-                         "shadow_kernel": {"achieved": achieved_shadow, "frac": achieved_shadow / peak, "algorithmic_bytes_per_ray": B_RAY_SHADOW}},
+            "roofline": roofline,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": C.sizeof(capi.dt_camera_desc) + C.sizeof(capi.dt_render_params),
                     "d2h_bytes_per_step": n_pix * 3, "ms_per_step": 1e3 * e2e_s_max / args.steps},
             "gpu_launches": int(launches_all),
             "clocks": clocks,
         }
+        if world == 1 and cfg == 5 and not args.no_other:
+            # the round-1 headline workload rides along (N = 1 only): config 2, 20 frames, device-timed like `value`
+            try:
+                gs.close()
+                xml2 = make_workload(2, tmp, 1920, 1080, 1)
+                hs2, gs2, _, _ = load_scene(xml2)
+                cam2 = hs2.camera(0)
+                lib_stream = torch.cuda.ExternalStream(gs2.stream_ptr, device=torch.device("cuda", local_rank))
+                for _ in range(5):
+                    device_step(False, gs2, cam2)
+                tot, rr = 0.0, 0
+                for _ in range(20):
+                    ms, st = device_step(False, gs2, cam2)
+                    tot += ms; rr = int(st.rays_closest) + int(st.rays_shadow)
+                line["other_workloads"] = {"config2": {"workload": workload_config(2, 1)["workload"], "value": rr / (tot / 20 * 1e3), "unit": UNIT, "ms_per_step": tot / 20,
+                                                       "rays_per_step": rr, "steps": 20, "warmup": 5, "timing": "device, as `value`"}}
+                gs2.close()
+            except Exception as e:
+                line["other_workloads"] = {"config2": {"error": str(e)[:200]}}
         if world == 1 and not args.no_cpu_baseline:
             try:
-                cores = os.cpu_count() or 1
-                threads = best_threads(1080, cores)
-                if have_ref():
-                    sec, _, _ = run_reference_frame(xml, threads)
-                    kind = "reference"
-                else:
-                    sec, _, _ = oracle_port_frame(xml, threads)
-                    kind = "port"
-                line["cpu_baseline"] = {"value": rays_per_step / (sec * 1e6), "unit": UNIT, "cores": threads, "kind": kind, "seconds": sec,
-                                        "sample": "one full 1920x1080 frame of the same workload (%d rays), %d render threads on %d host cores" % (int(rays_per_step), threads, cores)}
+                sec, rays, threads, kind, desc = cpu_sample(cfg, os.path.join(tmp, "cpu"), 1)
+                line["cpu_baseline"] = {"value": rays / (sec * 1e6), "unit": UNIT, "cores": threads, "kind": kind, "seconds": sec, "sample": desc}
             except Exception as e:  # the baseline is reported, never required
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": str(e)[:200]}
         print(json.dumps(line), flush=True)

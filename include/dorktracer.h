@@ -225,16 +225,30 @@ typedef struct dt_render_params {
     int32_t flags;                      /* DT_FLAG_*                                                               */
 } dt_render_params;
 
-enum { DT_FLAG_SKIP_TONEMAP = 1,        /* leave hdr untouched, do not write ldr from the tonemapper               */
-       DT_FLAG_NO_SORT = 2,             /* disable the sort-by-material stage (A/B measurement)                    */
-       DT_FLAG_SERIAL_WAVES = 4,
-       DT_FLAG_PEER_FRAME = 8 };        /* multi-GPU: resolve ONLY the owned tiles, straight into the frame buffers of
-                                           the rank that called dt_frame_export (this rank's own buffers if it did
-                                           not dt_frame_import): the gather is fused into the resolve kernel as P2P
-                                           stores over NVLink, no collective and no full-frame exchange             */      /* measurement mode: one kernel at a time, host sync per wave, so that the
-                                           per-stage CUDA-event times in dt_stats are those of each kernel running
-                                           ALONE (default: waves enqueued back to back, shadow(k) overlapping
-                                           closest(k+1), stage times overlap)                                       */
+/* dt_render_params.flags.  Everything that changes what a render call does travels here (or in dt_scene_options), not in
+ * environment variables; the DT_* environment variables the library still reads are measurement knobs for A/B runs on the GPU
+ * box (grid sizes, stream priorities, debug timing; listed in profiles/README.md) and never change results. */
+enum {
+    DT_FLAG_SKIP_TONEMAP = 1,       /* leave hdr untouched, do not write ldr from the tonemapper                                  */
+    DT_FLAG_NO_SORT = 2,            /* disable the sort-by-material stage between closest-hit and shade (A/B measurement)          */
+    DT_FLAG_SERIAL_WAVES = 4,       /* measurement mode: one kernel at a time, host sync per wave, so that the per-stage CUDA-event
+                                       times in dt_stats are those of each kernel running ALONE (default: waves enqueued back to
+                                       back, shadow(k) overlapping closest(k+1), stage times overlap)                              */
+    DT_FLAG_PEER_FRAME = 8,         /* multi-GPU: resolve ONLY the owned tiles, straight into the frame buffers of the rank that
+                                       called dt_frame_export (this rank's own buffers if it did not dt_frame_import): the gather
+                                       is fused into the resolve kernel as P2P stores over NVLink, no collective and no full-frame
+                                       exchange                                                                                    */
+    DT_FLAG_JITTER_AA = 16,         /* multi-sample cameras keep the sub-pixel sample position.  The reference intends
+                                       this but RenderPixel(int,int,..) truncates it away (main.cpp:83), so the default (parity)
+                                       sends every sample through the pixel centre                                                 */
+    DT_FLAG_REF_ROW_BANDS = 32,     /* parity with the reference's 8 row bands (main.cpp:15,38-39): the bottom H mod 8 rows get no
+                                       camera rays and stay black.  Default: every row is rendered                                 */
+    DT_FLAG_TEST_TIGHT_QUEUES = 64, /* test hook: size the wavefront queues of the first attempt for a ray-tree fan-out of 1, so
+                                       that fanning scenes overflow them and take the retry path (dt_stats.retries > 0)            */
+    DT_FLAG_FORCE_SORT = 128,       /* sort by material even in scenes with fewer than three materials                             */
+    DT_FLAG_HOST_WAVE_LOOP = 256,   /* one host round trip per wave instead of the device-resident wave loop (A/B, debugging)       */
+    DT_FLAG_FRAME_GRAPH = 512       /* bounded-depth frames: replay the enqueued frame as a CUDA graph instead of ~50 launches      */
+};
 
 typedef struct dt_stats {
     uint64_t rays_closest;              /* closest-hit queries  (== Raytracer::IntersectObjects calls)  */
@@ -255,6 +269,13 @@ int dt_gpu_init(int device);
 int dt_device_count(void);
 
 int dt_scene_create(const dt_scene_desc* desc, dt_scene** out);
+/* Same with options.  gpu_flatten_min_faces: meshes of at least this many faces get their BVH8 from the GPU flattener
+ * (0 = default 32768, < 0 = never: host flattener only; both produce identical bytes, see dt_scene_accel_checksum). */
+typedef struct dt_scene_options {
+    int32_t gpu_flatten_min_faces;
+    int32_t reserved[7];                /* must be zero */
+} dt_scene_options;
+int dt_scene_create_opts(const dt_scene_desc* desc, const dt_scene_options* opts, dt_scene** out);
 void dt_scene_destroy(dt_scene* scene);
 
 /* Render one camera.  ldr_rgb: W*H*3 bytes, row-major RGB, top row first (main.cpp:109,146); hdr_rgb: W*H*3
@@ -278,7 +299,8 @@ int dt_finish_device(dt_scene* scene, const dt_camera_desc* cam, const float* hd
  * frame buffers as CUDA IPC handles (plain bytes: ship them with any host-side transport), the other ranks import them;
  * renders issued with DT_FLAG_PEER_FRAME then store their tiles directly into the destination's memory.  The caller
  * orders "all ranks finished rendering" before "destination reads the frame" (one barrier); dt_frame_finish then
- * tonemaps (if the camera has a tonemapper) and copies the complete LDR frame to the host. */
+ * tonemaps (if the camera has a tonemapper) and copies the complete LDR frame to the host (ldr_rgb == NULL: the finished
+ * frame stays in device memory; used to time the device work of a frame without the D2H copy). */
 typedef struct dt_frame_handle {
     unsigned char hdr[64];              /* cudaIpcMemHandle_t of the float W*H*3 radiance frame */
     unsigned char ldr[64];              /* cudaIpcMemHandle_t of the uint8 W*H*3 LDR frame      */
@@ -326,6 +348,17 @@ void* dt_scene_stream(dt_scene* scene);
 
 const char* dt_last_error(void);
 const char* dt_version(void);
+
+/* Instrumented debug builds only (make variant DEFS=-DDT_TRAV_STATS / -DDT_TIMELINE; the shipped library does not export
+ * these): traversal event counters, per-warp timeline records, per-ray step histogram.  Used by tests/_trav_stats.py and
+ * tests/_timeline.py on the GPU box. */
+#ifdef DT_TRAV_STATS
+void dt_debug_stats(unsigned long long* out /* [8] */, int reset);
+#endif
+#ifdef DT_TIMELINE
+int dt_debug_timeline(unsigned long long* out /* 4 words per record */, int max_records);
+void dt_debug_steps_hist(unsigned int* out /* [128] */, int reset);
+#endif
 
 #ifdef __cplusplus
 }

@@ -257,14 +257,10 @@ def test_sort_stage_is_a_pure_reordering():
     hs, _ = golden_scene("cornellbox_recursive_conductors")
     cam = hs.camera(0)
     base = None
-    for mode in ("0", "2"):
-        os.environ["DT_SORT"] = mode
-        try:
-            gs = GpuScene(hs)
-            ldr, hdr, st = gs.render(cam)
-            gs.close()
-        finally:
-            os.environ.pop("DT_SORT", None)
+    for flags in (capi.DT_FLAG_NO_SORT, capi.DT_FLAG_FORCE_SORT):
+        gs = GpuScene(hs)
+        ldr, hdr, st = gs.render(cam, flags=flags)
+        gs.close()
         if base is None:
             base = (ldr, int(st.rays_closest), int(st.rays_shadow))
         else:
@@ -569,15 +565,7 @@ def test_gpu_build_of_the_config2_mesh_matches_the_host_build(tmp_path):
 
 def _scene_with_flattener(hs, min_faces):
     """GpuScene whose BLAS came from the host flattener (min_faces < 0) or the GPU flattener (meshes >= min_faces)."""
-    old = os.environ.get("DT_GPU_FLATTEN_MIN_FACES")
-    os.environ["DT_GPU_FLATTEN_MIN_FACES"] = str(min_faces)
-    try:
-        return GpuScene(hs)
-    finally:
-        if old is None:
-            del os.environ["DT_GPU_FLATTEN_MIN_FACES"]
-        else:
-            os.environ["DT_GPU_FLATTEN_MIN_FACES"] = old
+    return GpuScene(hs, gpu_flatten_min_faces=min_faces)      # dt_scene_options
 
 
 @pytest.mark.parametrize("name", ["scienceTree", "cornellbox_recursive_conductors", "simple"])
@@ -636,3 +624,109 @@ def test_gpu_flattener_splits_multi_face_leaves_like_the_host(tmp_path):
         _assert_hits_equal(b.primary_hits(cam), oracle_primary_hits(hs, cam))
     finally:
         a.close(); b.close()
+
+
+# ------------------------------------------------------------------ wave-loop robustness (round 2)
+def test_queue_overflow_is_contained_and_the_retry_matches():
+    """DT_FLAG_TEST_TIGHT_QUEUES sizes the first attempt's queues for a fan-out of 1; the dielectric scene fans out 2x per
+    bounce, so the first attempt overflows on the device.  Nothing may be indexed past an allocation (the remaining waves
+    become no-ops: k_wave_advance), the host retries with smaller waves, and the retried frame is the normal frame."""
+    hs, _ = golden_scene("cornellbox_recursive_alt2")
+    cam = hs.camera(0)
+    ref = GpuScene(hs)
+    ldr0, hdr0, st0 = ref.render(cam)
+    ref.close()
+    assert st0.retries == 0
+    gs = GpuScene(hs)                                              # fresh scene: no larger queues left over from earlier renders
+    ldr, hdr, st = gs.render(cam, flags=capi.DT_FLAG_TEST_TIGHT_QUEUES)
+    assert st.retries >= 1, "the tight queues did not overflow: the retry path was not exercised"
+    assert (int(st.rays_closest), int(st.rays_shadow)) == (int(st0.rays_closest), int(st0.rays_shadow))
+    frac, mx = ldr_mismatch_fraction(ldr, ldr0, 0)
+    assert frac <= 1e-5 and mx <= 1, (frac, mx)
+    ldr2, _, st2 = gs.render(cam)                                  # and the scene is still healthy afterwards
+    assert st2.retries == 0 and ldr_mismatch_fraction(ldr2, ldr0, 0)[1] <= 1
+    gs.close()
+
+
+def test_rank_without_strips_renders_an_empty_share():
+    """More ranks than 64x4-pixel strips: the extra ranks own nothing and must return an empty frame, not an error."""
+    hs, _ = golden_scene("simple")
+    cam = hs.camera(0)
+    cam.width, cam.height = 48, 4                                   # one strip
+    gs = GpuScene(hs)
+    full, _, st_full = gs.render(cam)
+    ldr, hdr, st = gs.render(cam, tile_rank=1, tile_world=2)
+    assert int(st.rays_closest) == 0 and not ldr.any() and not hdr.any()
+    ldr0, _, st0 = gs.render(cam, tile_rank=0, tile_world=2)
+    assert (ldr0 == full).all() and int(st0.rays_closest) == int(st_full.rays_closest)
+    _, st_dev = gs.render_device(cam, tile_rank=1, tile_world=2, flags=capi.DT_FLAG_PEER_FRAME)
+    assert int(st_dev.rays_closest) == 0
+    gs.close()
+
+
+def _assert_same_estimate(a, b, what):
+    """Same ray tree, same per-path random numbers; only the order of the float atomicAdds into the accumulator differs."""
+    (ldr_a, hdr_a, st_a), (ldr_b, hdr_b, st_b) = a, b
+    assert (int(st_a.rays_closest), int(st_a.rays_shadow)) == (int(st_b.rays_closest), int(st_b.rays_shadow)), what
+    assert np.allclose(hdr_a, hdr_b, rtol=2e-3, atol=1e-3), (what, float(np.abs(hdr_a - hdr_b).max()))
+    frac, mx = ldr_mismatch_fraction(ldr_a, ldr_b, 1)
+    assert frac <= 1e-3, (what, frac, mx)
+
+
+@pytest.mark.parametrize("nee", [True, False])
+def test_device_resident_wave_loop_equals_the_host_loop(tmp_path, nee):
+    """Russian-roulette path tracing (unbounded depth) through the device-resident loop (graph WHILE node + k_tail) against the
+    host-synchronised loop (DT_FLAG_HOST_WAVE_LOOP): same seed -> identical ray counts and the same image.  nee=True runs
+    the deferred mesh-light NEE (shadow rays traced one wave later); small waves force many top-ups."""
+    p = scenegen.gen_config4(str(tmp_path / "c4"), width=192, height=112, spp=16, depth=3, nee=nee)
+    hs = HostScene(p)
+    cam = hs.camera(0)
+    gs = GpuScene(hs)
+    host = gs.render(cam, seed=7, flags=capi.DT_FLAG_HOST_WAVE_LOOP, max_wave_rays=1 << 16)
+    for wave in (1 << 16, 1 << 23):                                  # 2nd: the whole frame is one batch and goes to k_tail early
+        dev = gs.render(cam, seed=7, max_wave_rays=wave)
+        _assert_same_estimate(dev, host, "wave %d" % wave)
+        assert dev[2].waves >= host[2].waves // 2 and dev[2].kernel_launches > 0
+    gs.close()
+
+
+def test_device_resident_wave_loop_on_a_tiny_frame_is_all_tail(tmp_path):
+    """A frame smaller than the hand-over threshold is rendered by k_tail's block-local wave loops alone."""
+    p = scenegen.gen_config4(str(tmp_path / "c4t"), width=64, height=40, spp=4, depth=2)
+    hs = HostScene(p)
+    cam = hs.camera(0)
+    gs = GpuScene(hs)
+    _assert_same_estimate(gs.render(cam, seed=3), gs.render(cam, seed=3, flags=capi.DT_FLAG_HOST_WAVE_LOOP), "tiny frame")
+    gs.close()
+
+
+def test_multi_batch_whitted_frame_through_the_device_loop(tmp_path):
+    """Bounded-depth frame of several batches (multi-sample camera, small waves): device loop == host loop == one batch."""
+    hs, _ = golden_scene("spheres_mirror")
+    cam = hs.camera(0)
+    cam.width, cam.height, cam.samples_per_pixel = 240, 240, 4
+    gs = GpuScene(hs)
+    one = gs.render(cam, seed=5)
+    dev = gs.render(cam, seed=5, max_wave_rays=1 << 15)
+    host = gs.render(cam, seed=5, max_wave_rays=1 << 15, flags=capi.DT_FLAG_HOST_WAVE_LOOP)
+    _assert_same_estimate(dev, host, "device vs host loop")
+    _assert_same_estimate(dev, one, "batched vs single wave")
+    gs.close()
+
+
+def test_ref_row_bands_and_jitter_flags():
+    """DT_FLAG_REF_ROW_BANDS: the reference's 8 row bands leave rows >= 8 * (H / 8) unrendered (main.cpp:38-39).
+    DT_FLAG_JITTER_AA: samples keep their sub-pixel position -> silhouettes are anti-aliased, the mean stays."""
+    hs, _ = golden_scene("two_spheres")
+    cam = hs.camera(0)
+    cam.width, cam.height = 160, 117
+    gs = GpuScene(hs)
+    full, _, _ = gs.render(cam)
+    banded, _, st = gs.render(cam, flags=capi.DT_FLAG_REF_ROW_BANDS)
+    assert (banded[:112] == full[:112]).all() and not banded[112:].any() and full[112:].any()
+    cam.samples_per_pixel = 16
+    plain, hp, _ = gs.render(cam, seed=2)
+    jit, hj, _ = gs.render(cam, seed=2, flags=capi.DT_FLAG_JITTER_AA)
+    assert len(np.unique(plain.reshape(-1, 3), axis=0)) < len(np.unique(jit.reshape(-1, 3), axis=0))      # edge pixels take intermediate values
+    assert abs(float(hj.mean()) - float(hp.mean())) / float(hp.mean()) < 0.02
+    gs.close()
