@@ -2,6 +2,7 @@
 #include "dt_flatten.h"
 #include "dt_flatten_gpu.h"
 #include "dt_kernels.cuh"
+#include "../../include/dorktracer_debug.h"
 
 #include <algorithm>
 #include <chrono>
@@ -722,11 +723,17 @@ retry:
             CK(cudaStreamSynchronize(st));
             CK(cudaGetLastError());
             S.ms_generate += s->t_gen.take();
-            S.ms_traverse_closest += s->t_closest.take();
+            const float ms_c = s->t_closest.take(), ms_s = shadow_timed ? s->t_shadow.take() : 0.f;
+            S.ms_traverse_closest += ms_c;
             S.ms_shade += s->t_shade.take();
             S.ms_sort += s->t_sort.take();
-            if (shadow_timed) S.ms_traverse_shadow += s->t_shadow.take();
+            S.ms_traverse_shadow += ms_s;
             S.waves++;
+            if (count >= wave_max / 2) {                                   // a "bulk" wave (dt_stats)
+                S.bulk_waves++;
+                S.ms_bulk_closest += ms_c; S.rays_bulk_closest += (uint64_t)count;
+                S.ms_bulk_shadow += ms_s; S.rays_bulk_shadow += (uint64_t)(defer_mode ? prev_shadow : std::min(s->h_counters[DT_CNT_SHADOW], pp.shadow_capacity));
+            }
             if (s->debug_timing >= 2) fprintf(stderr, "[dt-tl] wave %u: %d closest rays, %d shadow rays | closest %.3f sort %.3f shade %.3f shadow %.3f ms (cumulative)\n", S.waves - 1, count,
                                               s->h_counters[DT_CNT_SHADOW], S.ms_traverse_closest, S.ms_sort, S.ms_shade, S.ms_traverse_shadow);
             if (s->h_counters[DT_CNT_OVERFLOW] != 0) { overflow = true; break; }

@@ -869,10 +869,17 @@ __global__ void __launch_bounds__(128, DT_SHADE_MINBLOCKS) k_tail(DtSceneDev S, 
     __syncthreads();
     int p = 0, waves = 0;
     unsigned long long n_closest = 0, n_shadow = 0;          // thread 0 only
+#ifdef DT_TAIL_PROFILE
+    long long tp[5] = {0, 0, 0, 0, 0}, tp_last = clock64(); long long tp_rays = 0;
+#define DT_TP(i) { const long long now_ = clock64(); tp[i] += now_ - tp_last; tp_last = now_; }
+#else
+#define DT_TP(i)
+#endif
     for (;;) {
         const int cur = sc[0], prev = min(sc[4], M.shadow_capacity);
         if ((cur == 0 && prev == 0) || sc[3] != 0) break;
         const DtRayQueue& in = L[p];
+        DT_TP(4)
         for (int j = tid; j < cur; j += blockDim.x) {
             if (in.pixel[j] == DT_DEAD_PIXEL) continue;
             const float4 o = in.o_time[j], d = in.d_tmax[j];
@@ -882,6 +889,7 @@ __global__ void __launch_bounds__(128, DT_SHADE_MINBLOCKS) k_tail(DtSceneDev S, 
             dt_store_closest(in, j, T.best);
         }
         __syncthreads();
+        DT_TP(0)
         if (defer) {
             for (int e = tid; e < prev; e += blockDim.x) {
                 if (dt_deferred_skipped(S, Ls.defer[e], in.hit0)) continue;
@@ -893,12 +901,14 @@ __global__ void __launch_bounds__(128, DT_SHADE_MINBLOCKS) k_tail(DtSceneDev S, 
             }
             __syncthreads();
         }
+        DT_TP(1)
         if (tid == 0) { sc[1] = 0; sc[2] = 0; }
         __syncthreads();
         const DtShadeCounters cnt = {&sc[1], &sc[2], &sc[3]};
         for (int j = tid; j < cur; j += blockDim.x)
             dt_shade_ray(j, S, cam, in, Lmiss[p], L[1 - p], Lmiss[1 - p], M.capacity, Ls, M.shadow_capacity, cnt, accum);
         __syncthreads();
+        DT_TP(2)
         const int ns = min(sc[2], M.shadow_capacity);
         if (!defer) {
             for (int e = tid; e < ns; e += blockDim.x) {
@@ -910,6 +920,10 @@ __global__ void __launch_bounds__(128, DT_SHADE_MINBLOCKS) k_tail(DtSceneDev S, 
             }
         }
         __syncthreads();
+        DT_TP(3)
+#ifdef DT_TAIL_PROFILE
+        tp_rays += cur;
+#endif
         if (tid == 0) {
             waves++;
             if (sc[1] > M.capacity || sc[2] > M.shadow_capacity) sc[3] = 1;
@@ -925,7 +939,12 @@ __global__ void __launch_bounds__(128, DT_SHADE_MINBLOCKS) k_tail(DtSceneDev S, 
         atomicAdd(reinterpret_cast<unsigned long long*>(c + DT_CNT_TOT_SHADOW), n_shadow);
         atomicMax(c + DT_CNT_TAIL_WAVES, waves);
         if (sc[3] != 0) atomicAdd(c + DT_CNT_OVERFLOW, 1);
+#ifdef DT_TAIL_PROFILE
+        if (waves > 1000) printf("[dt-tail] block %d: %d waves, %lld ray-waves | cycles per wave: closest %lld, deferred shadow %lld, shade %lld, shadow %lld, bookkeeping %lld\n",
+                                 b, waves, tp_rays, tp[0] / waves, tp[1] / waves, tp[2] / waves, tp[3] / waves, tp[4] / waves);
+#endif
     }
+#undef DT_TP
 }
 
 // ------------------------------------------------------------------ resolve

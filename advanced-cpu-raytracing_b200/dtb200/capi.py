@@ -150,7 +150,9 @@ class dt_stats(C.Structure):
                 ("waves", C.c_uint32), ("kernel_launches", C.c_uint32), ("ms_total", C.c_float),
                 ("ms_generate", C.c_float), ("ms_traverse_closest", C.c_float), ("ms_traverse_shadow", C.c_float),
                 ("ms_shade", C.c_float), ("ms_sort", C.c_float), ("ms_resolve", C.c_float), ("ms_tonemap", C.c_float),
-                ("launches_traverse_closest", C.c_uint32), ("retries", C.c_uint32)]
+                ("launches_traverse_closest", C.c_uint32), ("retries", C.c_uint32),
+                ("bulk_waves", C.c_uint32), ("ms_bulk_closest", C.c_float), ("ms_bulk_shadow", C.c_float), ("pad_", C.c_uint32),
+                ("rays_bulk_closest", C.c_uint64), ("rays_bulk_shadow", C.c_uint64)]
 
 
 # Every symbol include/dorktracer.h declares (tests check that the library exports all of them).

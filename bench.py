@@ -457,6 +457,7 @@ def main():
     ms_closest = ms_shadow = ms_shade = ms_gen = ms_sort = 0.0
     rays_c_roof = rays_s_roof = 0
     n_closest_launches = n_waves_roof = 0
+    bulk = {"waves": 0, "ms_closest": 0.0, "ms_shadow": 0.0, "rays_closest": 0, "rays_shadow": 0}
     for _ in range(n_roof):
         flush_buf.fill_(rank + 1)
         torch.cuda.synchronize()
@@ -464,6 +465,8 @@ def main():
         ms_closest += st.ms_traverse_closest; ms_shadow += st.ms_traverse_shadow; ms_shade += st.ms_shade; ms_gen += st.ms_generate; ms_sort += st.ms_sort
         rays_c_roof += int(st.rays_closest); rays_s_roof += int(st.rays_shadow)
         n_closest_launches += int(st.launches_traverse_closest); n_waves_roof += int(st.waves)
+        bulk["waves"] += int(st.bulk_waves); bulk["ms_closest"] += st.ms_bulk_closest; bulk["ms_shadow"] += st.ms_bulk_shadow
+        bulk["rays_closest"] += int(st.rays_bulk_closest); bulk["rays_shadow"] += int(st.rays_bulk_shadow)
     barrier()
 
     # max over ranks of the times, sum over ranks of the rays
@@ -495,14 +498,21 @@ def main():
         except Exception:
             pass
         # dominant kernel = the traversal kernel with the larger share of the frame (kernels alone: SERIAL_WAVES pass, rank 0)
-        kinds = {"closest": ("k_traverse_dyn<false> (closest-hit, persistent warps)", ms_closest, rays_c_roof, wl["b_closest"]),
-                 "shadow": ("k_traverse_dyn<true> (any-hit / shadow rays, persistent warps)", ms_shadow, rays_s_roof, wl["b_shadow"])}
-        dom = "shadow" if ms_shadow > ms_closest else "closest"
+        # Path-traced frames: only the "bulk" waves (at least half of max_wave_rays alive) count -- the thousands of tail waves
+        # of a Russian-roulette frame hold a handful of rays each and are all launch latency (dt_stats.bulk_*).
+        use_bulk = cfg == 5 and bulk["waves"] > 0
+        if use_bulk:
+            kinds = {"closest": ("k_traverse_dyn<false> (closest-hit, persistent warps)", bulk["ms_closest"], bulk["rays_closest"], wl["b_closest"], bulk["waves"]),
+                     "shadow": ("k_traverse_dyn<true> (any-hit / shadow rays, persistent warps)", bulk["ms_shadow"], bulk["rays_shadow"], wl["b_shadow"], bulk["waves"])}
+        else:
+            kinds = {"closest": ("k_traverse_dyn<false> (closest-hit, persistent warps)", ms_closest, rays_c_roof, wl["b_closest"], n_closest_launches),
+                     "shadow": ("k_traverse_dyn<true> (any-hit / shadow rays, persistent warps)", ms_shadow, rays_s_roof, wl["b_shadow"], n_waves_roof)}
+        dom = "shadow" if kinds["shadow"][1] > kinds["closest"][1] else "closest"
         other = "closest" if dom == "shadow" else "shadow"
 
         def roof(which):
-            name, ms_k, rays_k, b_ray = kinds[which]
-            launches_k = max(1, n_waves_roof if which == "shadow" else n_closest_launches)
+            name, ms_k, rays_k, b_ray, launches_k = kinds[which]
+            launches_k = max(1, launches_k)
             gbs = b_ray * rays_k / 1e9 / (ms_k / 1e3) if ms_k > 0 else 0.0
             nk = (ncu.get("kernels") or {}).get(which) or {}
             inst_per_ray = nk.get("warp_inst_per_ray")
@@ -519,8 +529,8 @@ def main():
 
         name, ms_k, rays_k, launches_k, issue, hbm, nk = roof(dom)
         _, _, _, _, issue2, hbm2, _ = roof(other)
-        how = ("CUDA events around each launch of %d frames rendered with DT_FLAG_SERIAL_WAVES (kernel alone on the GPU), L2 flushed before each frame; "
-               "warp instructions per ray from the committed ncu capture of the same workload" % n_roof)
+        how = ("CUDA events around each launch of %d frames rendered with DT_FLAG_SERIAL_WAVES (kernel alone on the GPU), L2 flushed before each frame%s; "
+               "warp instructions per ray from the committed ncu capture of the same workload" % (n_roof, "; launches of the %d bulk waves (>= half of max_wave_rays alive) only" % bulk["waves"] if use_bulk else ""))
         if issue:
             roofline = {"bound": "issue", "kernel": name, "achieved": issue["achieved"], "peak": issue["peak"], "unit": issue["unit"], "frac": issue["frac"],
                         "traffic": nk.get("traffic_bytes_per_launch"), "issue": issue, "hbm": hbm}

@@ -260,6 +260,13 @@ typedef struct dt_stats {
     float ms_generate, ms_traverse_closest, ms_traverse_shadow, ms_shade, ms_sort, ms_resolve, ms_tonemap;
     uint32_t launches_traverse_closest; /* number of closest-hit traversal launches                      */
     uint32_t retries;                   /* queue-overflow retries with a smaller wave                    */
+    /* "Bulk" waves = waves whose closest-hit pass held at least half of max_wave_rays; filled by the host-synchronised loop
+       (DT_FLAG_SERIAL_WAVES / DT_FLAG_HOST_WAVE_LOOP) only.  The launches a roofline figure is taken from: the thousands of
+       tail waves of a Russian-roulette frame hold a handful of rays each and are all launch latency. */
+    uint32_t bulk_waves;
+    float ms_bulk_closest, ms_bulk_shadow;
+    uint32_t pad_;
+    uint64_t rays_bulk_closest, rays_bulk_shadow;
 } dt_stats;
 
 typedef struct dt_scene dt_scene;       /* opaque; owns all device memory of one GPU */
@@ -349,16 +356,6 @@ void* dt_scene_stream(dt_scene* scene);
 const char* dt_last_error(void);
 const char* dt_version(void);
 
-/* Instrumented debug builds only (make variant DEFS=-DDT_TRAV_STATS / -DDT_TIMELINE; the shipped library does not export
- * these): traversal event counters, per-warp timeline records, per-ray step histogram.  Used by tests/_trav_stats.py and
- * tests/_timeline.py on the GPU box. */
-#ifdef DT_TRAV_STATS
-void dt_debug_stats(unsigned long long* out /* [8] */, int reset);
-#endif
-#ifdef DT_TIMELINE
-int dt_debug_timeline(unsigned long long* out /* 4 words per record */, int max_records);
-void dt_debug_steps_hist(unsigned int* out /* [128] */, int reset);
-#endif
 
 #ifdef __cplusplus
 }

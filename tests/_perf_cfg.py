@@ -7,13 +7,19 @@ import sys, os, time, hashlib
 R = %r
 sys.path.insert(0, R + '/tests'); sys.path.insert(0, R + '/advanced-cpu-raytracing_b200')
 import numpy as np
+import ctypes as C
+from dtb200 import capi
+name = os.environ.get('DT_AB_LIB', '')
+if name:
+    real = os.path.join(capi.PKG_DIR, 'libdorktracer.so')
+    capi._libs[real] = C.CDLL(os.path.join(capi.PKG_DIR, 'libdorktracer_%%s.so' %% name), mode=C.RTLD_GLOBAL)
 from dtb200.scene import GpuScene, HostScene
 from dtb200 import scenegen
 cfg = sys.argv[1]
 t0 = time.time()
 if cfg == 'c3': p = scenegen.gen_config3('/tmp/gen/c3')
 elif cfg == 'c4': p = scenegen.gen_config4('/tmp/gen/c4', spp=int(os.environ.get('DT_AB_SPP', '16')))
-elif cfg == 'c5': p = scenegen.gen_config5('/tmp/gen/c5', spp=int(os.environ.get('DT_AB_SPP', '4')))
+elif cfg == 'c5': p = scenegen.gen_config5('/tmp/gen/c5', spp=int(os.environ.get('DT_AB_SPP', '4')), sphere_lift=float(os.environ.get('DT_AB_LIFT', '0.25')))
 else: raise SystemExit('unknown config')
 hs = HostScene(p); cam = hs.camera(0); t1 = time.time()
 gs = GpuScene(hs); t2 = time.time()
@@ -36,4 +42,6 @@ for spec in sys.argv[2:] or ['']:
         env[k] = v
     out = subprocess.run([sys.executable, '-c', CHILD, cfg], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=3000).stdout.decode()
     lines = out.strip().splitlines()
+    for l in lines[:-1]:
+        if l.startswith('[dt'): print('    ' + l)
     print('[%s] %s' % (spec, lines[-1] if lines else 'NO OUTPUT'), flush=True)

@@ -96,3 +96,27 @@ def blur_dof_scene(path, width=240, height=160, spp=100):
     with open(path, "w") as f:
         f.write(xml)
     return path
+
+
+def glass_closeup_scene(path, width=160, height=160, depth=4):
+    """A dielectric sphere filling the whole frame: every camera ray spawns a reflected and a refracted child
+    (raytracer.cpp:316-411), so wave k+1 holds up to twice the rays of wave k -- the fan-out the wavefront queues are sized for."""
+    xml = """<Scene><MaxRecursionDepth>%d</MaxRecursionDepth><BackgroundColor>30 40 70</BackgroundColor><ShadowRayEpsilon>1e-3</ShadowRayEpsilon>
+<Cameras><Camera id="1"><Position>0 0 3</Position><Gaze>0 0 -1</Gaze><Up>0 1 0</Up><NearPlane>-0.3 0.3 -0.3 0.3</NearPlane>
+<NearDistance>1</NearDistance><ImageResolution>%d %d</ImageResolution><ImageName>glass.png</ImageName></Camera></Cameras>
+<Lights><AmbientLight>20 20 20</AmbientLight><PointLight id="1"><Position>4 6 6</Position><Intensity>9000 9000 9000</Intensity></PointLight>
+<PointLight id="2"><Position>-5 3 4</Position><Intensity>4000 5000 6000</Intensity></PointLight></Lights>
+<Materials><Material id="1" type="dielectric"><AmbientReflectance>0 0 0</AmbientReflectance><DiffuseReflectance>0 0 0</DiffuseReflectance><SpecularReflectance>0 0 0</SpecularReflectance>
+<AbsorptionCoefficient>0.05 0.01 0.01</AbsorptionCoefficient><RefractionIndex>1.5</RefractionIndex></Material>
+<Material id="2"><AmbientReflectance>1 1 1</AmbientReflectance><DiffuseReflectance>0.6 0.5 0.3</DiffuseReflectance><SpecularReflectance>0.2 0.2 0.2</SpecularReflectance><PhongExponent>10</PhongExponent></Material></Materials>
+<VertexData>0 0 0
+-8 -2 -8
+8 -2 -8
+8 -2 8
+-8 -2 8</VertexData>
+<Objects><Mesh id="1"><Material>2</Material><Faces>2 4 3
+2 5 4</Faces></Mesh>
+<Sphere id="1"><Material>1</Material><Center>1</Center><Radius>1.2</Radius></Sphere></Objects></Scene>""" % (depth, width, height)
+    with open(path, "w") as f:
+        f.write(xml)
+    return path

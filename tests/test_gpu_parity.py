@@ -14,7 +14,7 @@ from dtb200 import capi, scenegen
 from dtb200.scene import GpuScene, HostScene, gpu_tonemap
 from oracle_util import (ldr_mismatch_fraction, oracle_primary_hits, oracle_render, oracle_tonemap, oracle_trace_closest,
                          oracle_trace_occluded, psnr)
-from scenes_util import DIELECTRIC, PINS, blur_dof_scene, brdf_scene, golden_scene
+from scenes_util import DIELECTRIC, PINS, blur_dof_scene, brdf_scene, glass_closeup_scene, golden_scene
 
 pytestmark = pytest.mark.gpu
 
@@ -627,11 +627,12 @@ def test_gpu_flattener_splits_multi_face_leaves_like_the_host(tmp_path):
 
 
 # ------------------------------------------------------------------ wave-loop robustness (round 2)
-def test_queue_overflow_is_contained_and_the_retry_matches():
-    """DT_FLAG_TEST_TIGHT_QUEUES sizes the first attempt's queues for a fan-out of 1; the dielectric scene fans out 2x per
-    bounce, so the first attempt overflows on the device.  Nothing may be indexed past an allocation (the remaining waves
-    become no-ops: k_wave_advance), the host retries with smaller waves, and the retried frame is the normal frame."""
-    hs, _ = golden_scene("cornellbox_recursive_alt2")
+def test_queue_overflow_is_contained_and_the_retry_matches(tmp_path):
+    """DT_FLAG_TEST_TIGHT_QUEUES sizes the first attempt's queues for a fan-out of 1; a glass sphere filling the frame fans out
+    2x per bounce, so the first attempt overflows on the device.  Nothing may be indexed past an allocation (the remaining
+    waves become no-ops: k_wave_advance), the host retries with smaller waves, and the retried frame is the normal frame and
+    the oracle's."""
+    hs = HostScene(glass_closeup_scene(str(tmp_path / "glass.xml")))
     cam = hs.camera(0)
     ref = GpuScene(hs)
     ldr0, hdr0, st0 = ref.render(cam)
@@ -646,6 +647,9 @@ def test_queue_overflow_is_contained_and_the_retry_matches():
     ldr2, _, st2 = gs.render(cam)                                  # and the scene is still healthy afterwards
     assert st2.retries == 0 and ldr_mismatch_fraction(ldr2, ldr0, 0)[1] <= 1
     gs.close()
+    oldr, _, ost = oracle_render(hs, cam)
+    assert (int(st0.rays_closest), int(st0.rays_shadow)) == (int(ost.rays_closest), int(ost.rays_shadow))
+    assert ldr_mismatch_fraction(ldr0, oldr, 1)[0] <= 1e-3
 
 
 def test_rank_without_strips_renders_an_empty_share():
