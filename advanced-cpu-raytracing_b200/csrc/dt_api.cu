@@ -306,7 +306,7 @@ int talloc(std::vector<void*>& allocs, T** p, size_t n) {
     return DT_OK;
 }
 
-// Block-private queues of k_tail: `grid` blocks x `cap` rays (+ cap x shadows_per_hit shadow rays).
+// Block-private queues of k_tail: `grid` blocks x `cap` rays (+ 3 x cap x shadows_per_hit shadow rays).
 int ensure_tail(dt_scene* s, int shadows_per_hit, bool need_defer) {
     if (s->tail_grid > 0 && s->tail_has_miss == s->has_env && (s->tail_has_defer || !need_defer) && s->tail.shadow_capacity >= s->tail.capacity * shadows_per_hit) return DT_OK;
     s->free_tail();
@@ -317,7 +317,7 @@ int ensure_tail(dt_scene* s, int shadows_per_hit, bool need_defer) {
     DtTailMem& M = s->tail;
     memset(&M, 0, sizeof M);
     M.capacity = 1024; M.shadow_capacity = M.capacity * shadows_per_hit;
-    const size_t nq = (size_t)grid * M.capacity, ns = (size_t)grid * M.shadow_capacity;
+    const size_t nq = (size_t)grid * M.capacity, ns = (size_t)grid * 3 * M.shadow_capacity;      // three rotating shadow buffers per block
     int rc;
 #define A(pp_, n_) talloc(s->tail_allocs, pp_, n_)
     for (int k = 0; k < 2; k++) {

@@ -818,15 +818,19 @@ __global__ void k_loop_end(int* c, int capacity, int shadow_capacity, int defer,
     }
 }
 
-// The last few thousand rays of a Russian-roulette frame live for thousands of bounces (paths trapped between two surfaces: the
-// reference's RR never ends a pure GI chain, raytracer.cpp:137-147).  A wave of a handful of rays is all launch latency, so the
-// survivors are dealt out to the blocks of ONE kernel and every block runs the complete wave loop -- closest hit, deferred NEE,
-// shade, shadow -- on block-private queues with __syncthreads() where the frame loop has kernel boundaries.  The ray tree and
-// the per-path RNG streams are the frame loop's, so the image does not depend on where the hand-over happens.
+// The last few thousand rays of a Russian-roulette frame live for thousands of bounces (the reference's RR never ends a pure GI
+// chain, raytracer.cpp:137-147; on the 10 M-triangle mesh a few rays slip between two triangles into the closed mesh and bounce
+// inside it).  A wave of a handful of rays is all latency, so the survivors are dealt out to the blocks of ONE kernel and every
+// block runs the complete wave loop -- closest hit, deferred NEE, shade, shadow -- on block-private queues with barriers where
+// the frame loop has kernel boundaries.  The bounce chain closest(i) -> shade(i) -> closest(i + 1) is the critical path (one
+// dependent DRAM / L2 access after the other); the shadow rays are not on it, so the block is split into two PATH warps, which run
+// that chain, and two SHADOW warps, which trace the shadow rays emitted two waves earlier (three rotating shadow buffers; the
+// deferred mesh-light entries of wave i - 2 need the closest hits of wave i - 1, which stay intact while wave i is processed).
+// The ray tree and the per-path RNG streams are the frame loop's, so the image does not depend on where the hand-over happens.
 struct DtTailMem {
     DtRayQueue q[2];              // G x capacity entries each (block b owns [b * capacity, (b + 1) * capacity))
     float4* miss[2];
-    DtShadowQueue sq;             // G x shadow_capacity
+    DtShadowQueue sq;             // G x 3 x shadow_capacity (three rotating buffers per block)
     int capacity, shadow_capacity;
 };
 __device__ __forceinline__ DtRayQueue dt_queue_at(const DtRayQueue& q, size_t off) {
@@ -835,19 +839,31 @@ __device__ __forceinline__ DtRayQueue dt_queue_at(const DtRayQueue& q, size_t of
     r.weight_n = q.weight_n + off; r.thr_beer = q.thr_beer + off; r.misc = q.misc + off; r.sort_key = q.sort_key ? q.sort_key + off : nullptr;
     return r;
 }
+__device__ __forceinline__ DtShadowQueue dt_shadow_queue_at(const DtShadowQueue& q, size_t off) {
+    DtShadowQueue r;
+    r.o_time = q.o_time + off; r.d_tmax = q.d_tmax + off; r.contrib_pix = q.contrib_pix + off; r.defer = q.defer ? q.defer + off : nullptr;
+    return r;
+}
+#define DT_TAIL_PATH_THREADS 64
 __global__ void __launch_bounds__(128, DT_SHADE_MINBLOCKS) k_tail(DtSceneDev S, DtCamDev cam, DtRayQueue gq, const float4* gmiss, DtShadowQueue gsq, int* c, DtTailMem M, int defer, float4* accum) {
-    __shared__ int sc[8];         // 0 rays of this wave, 1 next wave, 2 shadow rays emitted, 3 overflow, 4 deferred shadow rays of the previous wave
+    // 0 rays of this wave, 1 rays emitted for the next wave, 2 overflow, 3..5 entries of the three shadow buffers
+    __shared__ int sc[8];
+#ifdef DT_TAIL_PROFILE
+    __shared__ long long tp_shadow;
+#endif
     const int b = blockIdx.x, G = gridDim.x, tid = threadIdx.x;
     const int n = c[DT_CNT_CUR], nps = defer ? c[DT_CNT_PREV_SHADOW] : 0;
     if ((n == 0 && nps == 0) || c[DT_CNT_OVERFLOW] != 0) return;
-    DtRayQueue L[2] = {dt_queue_at(M.q[0], (size_t)b * M.capacity), dt_queue_at(M.q[1], (size_t)b * M.capacity)};
-    float4* Lmiss[2] = {M.miss[0] ? M.miss[0] + (size_t)b * M.capacity : nullptr, M.miss[1] ? M.miss[1] + (size_t)b * M.capacity : nullptr};
-    DtShadowQueue Ls;
-    Ls.o_time = M.sq.o_time + (size_t)b * M.shadow_capacity; Ls.d_tmax = M.sq.d_tmax + (size_t)b * M.shadow_capacity;
-    Ls.contrib_pix = M.sq.contrib_pix + (size_t)b * M.shadow_capacity; Ls.defer = M.sq.defer ? M.sq.defer + (size_t)b * M.shadow_capacity : nullptr;
+    const DtRayQueue L[2] = {dt_queue_at(M.q[0], (size_t)b * M.capacity), dt_queue_at(M.q[1], (size_t)b * M.capacity)};
+    float4* const Lmiss[2] = {M.miss[0] ? M.miss[0] + (size_t)b * M.capacity : nullptr, M.miss[1] ? M.miss[1] + (size_t)b * M.capacity : nullptr};
+    const DtShadowQueue B[3] = {dt_shadow_queue_at(M.sq, ((size_t)b * 3 + 0) * M.shadow_capacity), dt_shadow_queue_at(M.sq, ((size_t)b * 3 + 1) * M.shadow_capacity),
+                                dt_shadow_queue_at(M.sq, ((size_t)b * 3 + 2) * M.shadow_capacity)};
     const int chunk = (n + G - 1) / G;
     const int lo = min(n, b * chunk), hi = min(n, lo + chunk);
     if (tid < 8) sc[tid] = 0;
+#ifdef DT_TAIL_PROFILE
+    if (tid == 0) tp_shadow = 0;
+#endif
     __syncthreads();
     for (int j = tid; j < hi - lo; j += blockDim.x) {
         const int g = lo + j;
@@ -856,92 +872,91 @@ __global__ void __launch_bounds__(128, DT_SHADE_MINBLOCKS) k_tail(DtSceneDev S, 
         if (Lmiss[0] && gmiss) Lmiss[0][j] = gmiss[g];
     }
     if (tid == 0) { sc[0] = hi - lo; if (b == 0) c[DT_CNT_TAIL_RAYS] = n; }
-    // deferred NEE entries follow the block that owns their GI child; entries without a child are dealt round-robin
+    // The deferred NEE entries of the frame loop's last wave follow the block that owns their GI child; entries without a child
+    // are dealt round-robin.  They enter as "emitted one wave ago" (buffer 2), i.e. they are traced during the second tail wave.
     for (int e = tid; e < nps; e += blockDim.x) {
         const int2 df = gsq.defer[e];
         const bool mine = df.x >= 0 ? (df.x >= lo && df.x < hi) : (e % G == b);
         if (!mine) continue;
-        const int slot = atomicAdd(&sc[4], 1);
-        if (slot >= M.shadow_capacity) { sc[3] = 1; continue; }
-        Ls.o_time[slot] = gsq.o_time[e]; Ls.d_tmax[slot] = gsq.d_tmax[e]; Ls.contrib_pix[slot] = gsq.contrib_pix[e];
-        Ls.defer[slot] = make_int2(df.x >= 0 ? df.x - lo : -1, df.y);
+        const int slot = atomicAdd(&sc[5], 1);
+        if (slot >= M.shadow_capacity) { sc[2] = 1; continue; }
+        B[2].o_time[slot] = gsq.o_time[e]; B[2].d_tmax[slot] = gsq.d_tmax[e]; B[2].contrib_pix[slot] = gsq.contrib_pix[e];
+        B[2].defer[slot] = make_int2(df.x >= 0 ? df.x - lo : -1, df.y);
     }
     __syncthreads();
-    int p = 0, waves = 0;
+    int waves = 0;
     unsigned long long n_closest = 0, n_shadow = 0;          // thread 0 only
 #ifdef DT_TAIL_PROFILE
-    long long tp[5] = {0, 0, 0, 0, 0}, tp_last = clock64(); long long tp_rays = 0;
+    long long tp[3] = {0, 0, 0}, tp_last = clock64(), tp_rays = 0;
 #define DT_TP(i) { const long long now_ = clock64(); tp[i] += now_ - tp_last; tp_last = now_; }
 #else
 #define DT_TP(i)
 #endif
-    for (;;) {
-        const int cur = sc[0], prev = min(sc[4], M.shadow_capacity);
-        if ((cur == 0 && prev == 0) || sc[3] != 0) break;
-        const DtRayQueue& in = L[p];
-        DT_TP(4)
-        for (int j = tid; j < cur; j += blockDim.x) {
-            if (in.pixel[j] == DT_DEAD_PIXEL) continue;
-            const float4 o = in.o_time[j], d = in.d_tmax[j];
-            DtTrav T; uint2 stack[DT_STACK_SIZE];
-            dt_trav_init<false>(T, S, V(o.x, o.y, o.z), V(d.x, d.y, d.z), o.w, CUDART_INF_F);
-            while (!dt_trav_step<false, true>(T, stack, S, in.o_time + j, in.d_tmax + j)) {}
-            dt_store_closest(in, j, T.best);
-        }
-        __syncthreads();
-        DT_TP(0)
-        if (defer) {
-            for (int e = tid; e < prev; e += blockDim.x) {
-                if (dt_deferred_skipped(S, Ls.defer[e], in.hit0)) continue;
-                const float4 o = Ls.o_time[e], d = Ls.d_tmax[e];
+    for (int i = 0;; i++) {
+        const int cur = sc[0];
+        const int jb = (i + 1) % 3;                               // shadow buffer filled during wave i - 2
+        const int pend = min(sc[3 + jb], M.shadow_capacity);
+        if ((cur == 0 && sc[3] == 0 && sc[4] == 0 && sc[5] == 0) || sc[2] != 0) break;
+        const DtRayQueue& in = L[i & 1];
+        if (tid < DT_TAIL_PATH_THREADS) {
+            // ---- path warps: closest(i) -> shade(i)
+            for (int j = tid; j < cur; j += DT_TAIL_PATH_THREADS) {
+                if (in.pixel[j] == DT_DEAD_PIXEL) continue;
+                const float4 o = in.o_time[j], d = in.d_tmax[j];
+                DtTrav T; uint2 stack[DT_STACK_SIZE];
+                dt_trav_init<false>(T, S, V(o.x, o.y, o.z), V(d.x, d.y, d.z), o.w, CUDART_INF_F);
+                while (!dt_trav_step<false, true>(T, stack, S, in.o_time + j, in.d_tmax + j)) {}
+                dt_store_closest(in, j, T.best);
+            }
+            asm volatile("bar.sync 1, %0;" :: "n"(DT_TAIL_PATH_THREADS) : "memory");          // all closest hits of the wave are stored (GI children read none, but shade reads hit0 by index)
+            DT_TP(0)
+            const DtShadeCounters cnt = {&sc[1], &sc[3 + i % 3], &sc[2]};
+            for (int j = tid; j < cur; j += DT_TAIL_PATH_THREADS)
+                dt_shade_ray(j, S, cam, in, Lmiss[i & 1], L[(i + 1) & 1], Lmiss[(i + 1) & 1], M.capacity, B[i % 3], M.shadow_capacity, cnt, accum);
+            DT_TP(1)
+        } else if (pend > 0) {
+            // ---- shadow warps: the shadow rays emitted by shade(i - 2); deferred mesh-light entries look at the closest hit of
+            // their GI child, a ray of wave i - 1 (queue (i - 1) & 1: its hit records are not rewritten before closest(i + 1))
+#ifdef DT_TAIL_PROFILE
+            const long long t0 = clock64();
+#endif
+            const DtShadowQueue& Q = B[jb];
+            const float4* child_hit0 = L[(i + 1) & 1].hit0;
+            for (int e = tid - DT_TAIL_PATH_THREADS; e < pend; e += blockDim.x - DT_TAIL_PATH_THREADS) {
+                if (defer && dt_deferred_skipped(S, Q.defer[e], child_hit0)) continue;
+                const float4 o = Q.o_time[e], d = Q.d_tmax[e];
                 DtTrav T; uint2 stack[DT_STACK_SIZE];
                 dt_trav_init<true>(T, S, V(o.x, o.y, o.z), V(d.x, d.y, d.z), o.w, d.w);
-                while (!dt_trav_step<true, true>(T, stack, S, Ls.o_time + e, Ls.d_tmax + e)) {}
-                dt_store_shadow(Ls, e, T.best, accum);
+                while (!dt_trav_step<true, true>(T, stack, S, Q.o_time + e, Q.d_tmax + e)) {}
+                dt_store_shadow(Q, e, T.best, accum);
             }
-            __syncthreads();
+#ifdef DT_TAIL_PROFILE
+            if (tid == DT_TAIL_PATH_THREADS) tp_shadow += clock64() - t0;
+#endif
         }
-        DT_TP(1)
-        if (tid == 0) { sc[1] = 0; sc[2] = 0; }
         __syncthreads();
-        const DtShadeCounters cnt = {&sc[1], &sc[2], &sc[3]};
-        for (int j = tid; j < cur; j += blockDim.x)
-            dt_shade_ray(j, S, cam, in, Lmiss[p], L[1 - p], Lmiss[1 - p], M.capacity, Ls, M.shadow_capacity, cnt, accum);
+        if (tid == 0) {
+            if (cur > 0) waves++;
+            if (sc[1] > M.capacity || sc[3 + i % 3] > M.shadow_capacity) sc[2] = 1;
+            n_closest += (unsigned long long)min(sc[1], M.capacity); n_shadow += (unsigned long long)min(sc[3 + i % 3], M.shadow_capacity);
+            sc[0] = min(sc[1], M.capacity);
+            sc[1] = 0;
+            sc[3 + jb] = 0;                                       // traced; shade(i + 1) fills this buffer next
+#ifdef DT_TAIL_PROFILE
+            tp_rays += cur;
+#endif
+        }
         __syncthreads();
         DT_TP(2)
-        const int ns = min(sc[2], M.shadow_capacity);
-        if (!defer) {
-            for (int e = tid; e < ns; e += blockDim.x) {
-                const float4 o = Ls.o_time[e], d = Ls.d_tmax[e];
-                DtTrav T; uint2 stack[DT_STACK_SIZE];
-                dt_trav_init<true>(T, S, V(o.x, o.y, o.z), V(d.x, d.y, d.z), o.w, d.w);
-                while (!dt_trav_step<true, true>(T, stack, S, Ls.o_time + e, Ls.d_tmax + e)) {}
-                dt_store_shadow(Ls, e, T.best, accum);
-            }
-        }
-        __syncthreads();
-        DT_TP(3)
-#ifdef DT_TAIL_PROFILE
-        tp_rays += cur;
-#endif
-        if (tid == 0) {
-            waves++;
-            if (sc[1] > M.capacity || sc[2] > M.shadow_capacity) sc[3] = 1;
-            n_closest += (unsigned long long)min(sc[1], M.capacity); n_shadow += (unsigned long long)ns;
-            sc[0] = min(sc[1], M.capacity);
-            sc[4] = defer ? ns : 0;
-        }
-        p ^= 1;
-        __syncthreads();
     }
     if (tid == 0) {
         atomicAdd(reinterpret_cast<unsigned long long*>(c + DT_CNT_TOT_CLOSEST), n_closest);
         atomicAdd(reinterpret_cast<unsigned long long*>(c + DT_CNT_TOT_SHADOW), n_shadow);
         atomicMax(c + DT_CNT_TAIL_WAVES, waves);
-        if (sc[3] != 0) atomicAdd(c + DT_CNT_OVERFLOW, 1);
+        if (sc[2] != 0) atomicAdd(c + DT_CNT_OVERFLOW, 1);
 #ifdef DT_TAIL_PROFILE
-        if (waves > 1000) printf("[dt-tail] block %d: %d waves, %lld ray-waves | cycles per wave: closest %lld, deferred shadow %lld, shade %lld, shadow %lld, bookkeeping %lld\n",
-                                 b, waves, tp_rays, tp[0] / waves, tp[1] / waves, tp[2] / waves, tp[3] / waves, tp[4] / waves);
+        if (waves > 1000) printf("[dt-tail] block %d: %d waves, %lld ray-waves | cycles per wave: closest %lld, shade %lld, barrier + bookkeeping %lld | shadow warps %lld\n",
+                                 b, waves, tp_rays, tp[0] / waves, tp[1] / waves, tp[2] / waves, tp_shadow / waves);
 #endif
     }
 #undef DT_TP

@@ -252,7 +252,14 @@ __device__ __forceinline__ void dt_trav_init(DtTrav& T, const DtSceneDev& S, v3 
 }
 
 // Visit the nearest pending child node of the current group: load 80 B, test 8 boxes, refill ng / tg.
-template <bool ANY>
+// ORDERED: visit the hit children front to back along the ray's direction octant.  Closest-hit queries always do; occlusion
+// queries take plain slot order (any hit will do, and the permutation is not free).  Measured on config 5 (profiles/
+// r2_ab_anyhit_ordered_config5.log): front-to-back any-hit is 5 % slower in the wave kernels and changes nothing for the lone
+// shadow rays of k_tail.
+#ifndef DT_ANYHIT_ORDERED
+#define DT_ANYHIT_ORDERED 0       // A/B knob: 1 = front-to-back occlusion queries in the wave kernels too
+#endif
+template <bool ANY, bool ORDERED = (DT_ANYHIT_ORDERED != 0) || !ANY>
 __device__ __forceinline__ void dt_trav_node(DtTrav& T, uint2* __restrict__ stack, const DtSceneDev& S) {
     const uint32_t one = S.one_bits;
     DT_STAT(0);
@@ -262,7 +269,7 @@ __device__ __forceinline__ void dt_trav_node(DtTrav& T, uint2* __restrict__ stac
     T.ng.y &= ~(1u << child_bit);
     if (T.ng.y > 0x00FFFFFFu) { if (T.sp < DT_STACK_SIZE) stack[T.sp++] = T.ng; }
     // occlusion queries visit the children in plain slot order (any hit will do): no octant permutation
-    const uint32_t slot = ANY ? (uint32_t)(child_bit - 24) : ((uint32_t)(child_bit - 24) ^ (T.r.oct_inv4 & 0xFFu));
+    const uint32_t slot = !ORDERED ? (uint32_t)(child_bit - 24) : ((uint32_t)(child_bit - 24) ^ (T.r.oct_inv4 & 0xFFu));
     const uint32_t rel = __popc(imask & ~(0xFFFFFFFFu << slot));
     const uint32_t ni = T.ng.x + rel;
     const uint4* np = (T.cur_shape >= 0 ? S.blas_nodes : S.tlas_nodes) + (size_t)ni * 5;
@@ -273,7 +280,7 @@ __device__ __forceinline__ void dt_trav_node(DtTrav& T, uint2* __restrict__ stac
     // node group: inner hits in visiting priority at bits 24..31 + the node's inner mask (a group without hits reads as empty);
     // primitive group: hit leaf slots at bits 0..7 + the node's leaf mask at bits 8..15 (slot -> primitive index by popcount)
     T.ng.x = n1.x;
-    T.ng.y = hi ? (((ANY ? hi : dt_perm8(hi, T.r.oct_inv4 & 7u)) << 24) | im) : 0u;
+    T.ng.y = hi ? (((!ORDERED ? hi : dt_perm8(hi, T.r.oct_inv4 & 7u)) << 24) | im) : 0u;
     T.tg.x = n1.y;
     T.tg.y = hl ? (hl | (lm << 8)) : 0u;
 }
@@ -418,14 +425,14 @@ __device__ __forceinline__ bool dt_trav_prim(DtTrav& T, uint2* __restrict__ stac
 // WW = true: descend nodes until some primitive group is pending, then drain it ("while-while").
 // Returns true when the ray is finished (ANY: best.shape >= 0 <=> occluded).
 // ray_o / ray_d: where the world-space ray of this traversal can be re-read (queue entry or caller's copy).
-template <bool ANY, bool WW>
+template <bool ANY, bool WW, bool ORDERED = (DT_ANYHIT_ORDERED != 0) || !ANY>
 __device__ __forceinline__ bool dt_trav_step(DtTrav& T, uint2* __restrict__ stack, const DtSceneDev& S, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d) {
     DT_STAT(5);
     if (WW) {
-        while (T.ng.y > 0x00FFFFFFu && T.tg.y == 0u) dt_trav_node<ANY>(T, stack, S);
+        while (T.ng.y > 0x00FFFFFFu && T.tg.y == 0u) dt_trav_node<ANY, ORDERED>(T, stack, S);
         if (T.tg.y == 0u && T.ng.y != 0u && T.ng.y <= 0x00FFFFFFu) { T.tg = T.ng; T.ng = make_uint2(0u, 0u); }
     } else {
-        if (T.ng.y > 0x00FFFFFFu) dt_trav_node<ANY>(T, stack, S);
+        if (T.ng.y > 0x00FFFFFFu) dt_trav_node<ANY, ORDERED>(T, stack, S);
         else { T.tg = T.ng; T.ng = make_uint2(0u, 0u); }
     }
     while (T.tg.y != 0u) {

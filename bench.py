@@ -7,8 +7,8 @@ A *step* is one frame of the workload through the hot path.
   --config 5 (default, the configuration BASELINE.json quotes the metric on): the synthetic procedural 10 M-triangle scene
         (9 991 932 triangles: config-4 box + displaced-sphere mesh), path tracing with next-event estimation + importance
         sampling + Russian roulette, area light + mesh light + spherical HDR environment light, Torrance-Sparrow / modified
-        Blinn-Phong BRDFs, photographic tonemapper, 3840x2160 — at a STATED REDUCED sample count (--spp, default 16 instead of
-        1024: a 1024-spp frame is 85 s on one B200).  N > 1: THE SAME FRAME is sharded over the ranks (strips of eight
+        Blinn-Phong BRDFs, photographic tonemapper, 3840x2160 — at a STATED REDUCED sample count (--spp, default 64 instead of
+        1024: a 1024-spp frame is 85 s on one B200, a 64-spp frame 5.4 s).  N > 1: THE SAME FRAME is sharded over the ranks (strips of eight
         8x4-pixel tiles, round-robin; what the reference does with row bands over its threads, main.cpp:38-39) -> strong
         scaling.  Every rank's resolve kernel stores its strips of radiance straight into rank 0's frame over NVLink (CUDA IPC
         peer memory, no collective), one barrier, then rank 0 tonemaps the whole frame.
@@ -48,7 +48,7 @@ UNIT = "Mrays/s"
 # SURVEY.md 8(d) algorithmic bytes per ray: 32 in + 32 out + 80 B x nodes on one root-to-leaf chain + 4 x 48 B triangles;
 # shadow rays the same minus the 32 B hit record plus a 4 B flag.
 WORKLOADS = {
-    5: {"b_closest": 896.0, "b_shadow": 868.0, "width": 3840, "height": 2160, "spp": 16, "scaling": "strong",
+    5: {"b_closest": 896.0, "b_shadow": 868.0, "width": 3840, "height": 2160, "spp": 64, "scaling": "strong",
         "ref_sample": (480, 272, 4)},      # reference arm: same scene, 480x272, 4 spp (about 12 M rays per step)
     2: {"b_closest": 736.0, "b_shadow": 708.0, "width": 1920, "height": 1080, "spp": 1, "scaling": "weak",
         "ref_sample": (1920, 1080, 1)},
@@ -275,7 +275,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=int, default=5, choices=[2, 5])
-    ap.add_argument("--spp", type=int, default=0, help="samples per pixel of config 5 (a perfect square; default 16)")
+    ap.add_argument("--spp", type=int, default=0, help="samples per pixel of config 5 (a perfect square; default 64)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other", action="store_true", help="skip the config-2 ride-along numbers")
     args = ap.parse_args()

@@ -721,7 +721,7 @@ def test_multi_batch_whitted_frame_through_the_device_loop(tmp_path):
 def test_ref_row_bands_and_jitter_flags():
     """DT_FLAG_REF_ROW_BANDS: the reference's 8 row bands leave rows >= 8 * (H / 8) unrendered (main.cpp:38-39).
     DT_FLAG_JITTER_AA: samples keep their sub-pixel position -> silhouettes are anti-aliased, the mean stays."""
-    hs, _ = golden_scene("two_spheres")
+    hs, _ = golden_scene("cornellbox_recursive_conductors")      # the box fills the frame: no black rows of its own
     cam = hs.camera(0)
     cam.width, cam.height = 160, 117
     gs = GpuScene(hs)
