@@ -10,12 +10,14 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace {
 
 thread_local std::string g_err;
 int g_device = -1;
+thread_local int tl_device = -1;          // dt_multi_create: the device a worker thread creates its scene on (overrides g_device)
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { g_err = std::string(#call) + ": " + cudaGetErrorString(e_); return DT_ERR_CUDA; } } while (0)
 
@@ -27,8 +29,9 @@ int ensure_device() {
         return DT_ERR_NO_DEVICE;
     }
     if (g_device < 0) g_device = 0;
-    if (g_device >= n) { g_err = "CUDA device index out of range"; return DT_ERR_NO_DEVICE; }
-    e = cudaSetDevice(g_device);
+    const int dev = tl_device >= 0 ? tl_device : g_device;
+    if (dev >= n) { g_err = "CUDA device index out of range"; return DT_ERR_NO_DEVICE; }
+    e = cudaSetDevice(dev);
     if (e != cudaSuccess) { g_err = std::string("cudaSetDevice: ") + cudaGetErrorString(e); return DT_ERR_CUDA; }
     return DT_OK;
 }
@@ -114,8 +117,9 @@ struct dt_scene {
     int* h_counters = nullptr;    // pinned mirror (+ scratch)
     float4* accum = nullptr; size_t accum_pix = 0;
     float* hdr = nullptr; uint8_t* ldr = nullptr; size_t out_pix = 0;
-    float* peer_hdr = nullptr; uint8_t* peer_ldr = nullptr;     // another rank's frame buffers (dt_frame_import)
+    float* peer_hdr = nullptr; uint8_t* peer_ldr = nullptr;     // another rank's frame buffers (dt_frame_import) / device 0's (dt_multi)
     int peer_w = 0, peer_h = 0;
+    bool peer_is_ipc = false;     // the peer pointers are CUDA IPC mappings (closed by dt_frame_release)
     bool frame_exported = false;  // other processes hold IPC mappings of hdr / ldr: they must not be reallocated
     double* tm_logsum = nullptr; unsigned int* tm_hist = nullptr; unsigned long long* tm_rank = nullptr; uint32_t* tm_prefix = nullptr;
     Timer t_total, t_gen, t_closest, t_shadow, t_shade, t_sort, t_resolve, t_tm;
@@ -817,7 +821,7 @@ int dt_scene_create_opts(const dt_scene_desc* desc, const dt_scene_options* opts
     int rc = ensure_device();
     if (rc) return rc;
     dt_scene* s = new dt_scene();
-    s->device = g_device;
+    s->device = tl_device >= 0 ? tl_device : g_device;
     memset(&s->dev, 0, sizeof s->dev);
     auto fail = [&](int code) { dt_scene_destroy(s); return code; };
     cudaDeviceProp prop;
@@ -1005,7 +1009,8 @@ int dt_render_device(dt_scene* s, const dt_camera_desc* cam, const dt_render_par
     if (peer_frame) {
         float* dst_hdr = s->hdr; uint8_t* dst_ldr = s->ldr;
         if (s->peer_hdr) {
-            dst_hdr = cam->has_tonemapper ? s->peer_hdr : nullptr;        // the destination tonemaps the whole frame from radiance ...
+            const bool want_hdr = cam->has_tonemapper || (params->flags & DT_FLAG_PEER_HDR);
+            dst_hdr = want_hdr ? s->peer_hdr : nullptr;                   // the destination tonemaps the whole frame from radiance ...
             dst_ldr = cam->has_tonemapper ? nullptr : s->peer_ldr;        // ... or only needs the clamped bytes (main.cpp:118-125)
         }
         const int tiles_x = (cam->width + 7) / 8, tiles_y = (cam->height + 3) / 4;
@@ -1074,9 +1079,11 @@ int dt_frame_export(dt_scene* s, int32_t width, int32_t height, dt_frame_handle*
 int dt_frame_release(dt_scene* s) {
     if (!s) return DT_OK;
     cudaSetDevice(s->device);
-    if (s->peer_hdr) cudaIpcCloseMemHandle(s->peer_hdr);
-    if (s->peer_ldr) cudaIpcCloseMemHandle(s->peer_ldr);
-    s->peer_hdr = nullptr; s->peer_ldr = nullptr; s->peer_w = s->peer_h = 0;
+    if (s->peer_is_ipc) {
+        if (s->peer_hdr) cudaIpcCloseMemHandle(s->peer_hdr);
+        if (s->peer_ldr) cudaIpcCloseMemHandle(s->peer_ldr);
+    }
+    s->peer_hdr = nullptr; s->peer_ldr = nullptr; s->peer_w = s->peer_h = 0; s->peer_is_ipc = false;
     return DT_OK;
 }
 
@@ -1089,7 +1096,7 @@ int dt_frame_import(dt_scene* s, const dt_frame_handle* in) {
     CK(cudaIpcOpenMemHandle((void**)&s->peer_hdr, h, cudaIpcMemLazyEnablePeerAccess));
     memcpy(&h, in->ldr, 64);
     CK(cudaIpcOpenMemHandle((void**)&s->peer_ldr, h, cudaIpcMemLazyEnablePeerAccess));
-    s->peer_w = in->width; s->peer_h = in->height;
+    s->peer_w = in->width; s->peer_h = in->height; s->peer_is_ipc = true;
     return DT_OK;
 }
 
@@ -1124,6 +1131,101 @@ int dt_render(dt_scene* s, const dt_camera_desc* cam, const dt_render_params* pa
     rc = finish_core(s, cam, hdr_dev, flags, ldr_rgb, &S);
     if (rc) return rc;
     S.ms_total += S.ms_tonemap;
+    if (stats) *stats = S;
+    return DT_OK;
+}
+
+
+// ------------------------------------------------------------------ one process, several GPUs
+// The reference's main() is one process that splits rows over its threads (main.cpp:38-39,164-185).  dt_multi does the same
+// over the GPUs of the box: the scene is replicated, one host thread per GPU renders that GPU's strips (tile_rank = device,
+// tile_world = n), every resolve kernel stores its strips straight into device 0's frame through peer access over NVLink
+// (the DT_FLAG_PEER_FRAME path, with plain peer pointers instead of CUDA IPC mappings), the thread join is the barrier, and
+// device 0 tonemaps / copies the complete frame out.
+struct dt_multi {
+    std::vector<dt_scene*> scenes;
+};
+
+int dt_multi_create(const dt_scene_desc* desc, int n_devices, dt_multi** out) {
+    if (!desc || !out) { g_err = "null argument"; return DT_ERR_INVALID; }
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) { g_err = "no CUDA device available; this library has no CPU fallback"; return DT_ERR_NO_DEVICE; }
+    const int n = n_devices <= 0 ? count : n_devices;
+    if (n > count) { g_err = "dt_multi_create: " + std::to_string(n) + " devices requested, " + std::to_string(count) + " visible"; return DT_ERR_INVALID; }
+    dt_multi* m = new dt_multi();
+    m->scenes.assign((size_t)n, nullptr);
+    std::vector<int> rcs((size_t)n, DT_OK);
+    std::vector<std::string> errs((size_t)n);
+    std::vector<std::thread> th;
+    for (int d = 0; d < n; d++) th.emplace_back([&, d] {
+        tl_device = d;
+        rcs[(size_t)d] = dt_scene_create_opts(desc, nullptr, &m->scenes[(size_t)d]);
+        if (rcs[(size_t)d] == DT_OK && d > 0) {
+            int can = 0;
+            cudaSetDevice(d);
+            if (cudaDeviceCanAccessPeer(&can, d, 0) != cudaSuccess || !can) { rcs[(size_t)d] = DT_ERR_UNSUPPORTED; g_err = "device " + std::to_string(d) + " has no peer access to device 0"; }
+            else { const cudaError_t e = cudaDeviceEnablePeerAccess(0, 0); if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { rcs[(size_t)d] = DT_ERR_CUDA; g_err = std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e); } cudaGetLastError(); }
+        }
+        errs[(size_t)d] = g_err;
+        tl_device = -1;
+    });
+    for (auto& t : th) t.join();
+    for (int d = 0; d < n; d++) if (rcs[(size_t)d] != DT_OK) {
+        g_err = "dt_multi_create, device " + std::to_string(d) + ": " + errs[(size_t)d];
+        const int rc = rcs[(size_t)d];
+        dt_multi_destroy(m);
+        return rc;
+    }
+    *out = m;
+    return DT_OK;
+}
+
+void dt_multi_destroy(dt_multi* m) {
+    if (!m) return;
+    for (dt_scene* s : m->scenes) if (s) { s->peer_hdr = nullptr; s->peer_ldr = nullptr; dt_scene_destroy(s); }
+    delete m;
+}
+
+int dt_multi_device_count(const dt_multi* m) { return m ? (int)m->scenes.size() : 0; }
+
+int dt_multi_render(dt_multi* m, const dt_camera_desc* cam, const dt_render_params* params, uint8_t* ldr_rgb, float* hdr_rgb, dt_stats* stats) {
+    if (!m || !ldr_rgb) { g_err = "null argument"; return DT_ERR_INVALID; }
+    int rc = check_cam(cam);
+    if (rc) return rc;
+    const int n = (int)m->scenes.size();
+    dt_scene* s0 = m->scenes[0];
+    CK(cudaSetDevice(s0->device));
+    const size_t n_pix = (size_t)cam->width * cam->height;
+    if ((rc = ensure_outputs(s0, n_pix))) return rc;
+    for (int d = 1; d < n; d++) { dt_scene* s = m->scenes[(size_t)d]; s->peer_hdr = s0->hdr; s->peer_ldr = s0->ldr; s->peer_w = cam->width; s->peer_h = cam->height; s->peer_is_ipc = false; }
+    dt_render_params P; memset(&P, 0, sizeof P); P.seed = 1234;
+    if (params) P = *params;
+    P.tile_world = n;
+    P.flags |= DT_FLAG_PEER_FRAME | (hdr_rgb ? DT_FLAG_PEER_HDR : 0);
+    std::vector<int> rcs((size_t)n, DT_OK);
+    std::vector<std::string> errs((size_t)n);
+    std::vector<dt_stats> st((size_t)n);
+    std::vector<std::thread> th;
+    for (int d = 0; d < n; d++) th.emplace_back([&, d] {
+        dt_render_params Pd = P; Pd.tile_rank = d;
+        float* hdr_dev = nullptr;
+        rcs[(size_t)d] = dt_render_device(m->scenes[(size_t)d], cam, &Pd, &hdr_dev, &st[(size_t)d]);
+        errs[(size_t)d] = g_err;
+    });
+    for (auto& t : th) t.join();                                                   // = "all strips are in device 0's frame"
+    for (int d = 0; d < n; d++) if (rcs[(size_t)d] != DT_OK) { g_err = "dt_multi_render, device " + std::to_string(d) + ": " + errs[(size_t)d]; return rcs[(size_t)d]; }
+    dt_stats S = st[0];
+    for (int d = 1; d < n; d++) {
+        const dt_stats& t = st[(size_t)d];
+        S.rays_closest += t.rays_closest; S.rays_shadow += t.rays_shadow; S.nan_pixels += t.nan_pixels; S.kernel_launches += t.kernel_launches;
+        S.waves = std::max(S.waves, t.waves); S.ms_total = std::max(S.ms_total, t.ms_total); S.retries = std::max(S.retries, t.retries);
+    }
+    CK(cudaSetDevice(s0->device));
+    if (hdr_rgb) CK(cudaMemcpyAsync(hdr_rgb, s0->hdr, n_pix * 3 * sizeof(float), cudaMemcpyDeviceToHost, s0->stream));
+    dt_stats F; memset(&F, 0, sizeof F);
+    if ((rc = finish_core(s0, cam, s0->hdr, P.flags, ldr_rgb, &F))) return rc;
+    S.kernel_launches += F.kernel_launches; S.ms_tonemap = F.ms_tonemap; S.ms_total += F.ms_tonemap;
     if (stats) *stats = S;
     return DT_OK;
 }

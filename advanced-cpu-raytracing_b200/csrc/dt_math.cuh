@@ -63,7 +63,7 @@ __device__ __forceinline__ v3 apply_transform(const double* t, v3 v, float w) {
 __device__ __forceinline__ double angle_between_unit(v3 a, v3 b) {
     float d = vdot(a, b);
     float c = fminf(1.0f, fmaxf(-1.0f, d));
-    return acos((double)c) * (180.0f / DT_PI);
+    return (double)acosf(c) * (180.0f / DT_PI);       // std::acos(float) is the FLOAT overload in the reference; only the scaling is double
 }
 __device__ __forceinline__ double cos_deg(double a) { return cos(a * (DT_PI / 180.0f)); }
 

@@ -264,10 +264,11 @@ __device__ inline void sphere_surface(const DtSceneDev& S, const DtShapeDev& sh,
 }
 
 // ---------------------------------------------------------------- BRDFs (brdf*.cpp)
-// The reference evaluates its lobes in double through degrees: cos(rad(deg(acos(c)))) and pow(., exponent).  Two algebraic
-// shortcuts keep the double results to ~1e-15 relative (the LDR tolerance is 4e-3) and remove the bulk of the shading
-// kernel's double-precision transcendental work on path-traced frames (three BRDF evaluations per hit):
-//  * cos_deg(angle_between_unit(a, b)) is the clamped dot product itself (the degree <-> radian factors are exact inverses in double);
+// The reference evaluates its lobes through degrees: cos(rad(deg(acosf(c)))) in double around a FLOAT acos (std::acos(float),
+// helperMath.cpp:156) and pow(., exponent).  Two algebraic shortcuts stay within that float acos' own rounding (<= 1e-7 absolute
+// in the cosine; the LDR tolerance is 4e-3, and the LDR images are byte-identical on every scene rendered both ways) and remove
+// the bulk of the shading kernel's double-precision transcendental work on path-traced frames (three BRDF evaluations per hit):
+//  * cos_deg(angle_between_unit(a, b)) is the clamped dot product itself (the degree <-> radian factors are inverses);
 //  * pow(x, e) with an integer exponent (every shipped scene; <Exponent> is parsed as a number) is repeated squaring in double.
 // The `theta_i >= 90` cut-off is taken on the cosine: (float)(acos(c) * 180/pi) >= 90.0f  <=>  c <= 6.657903e-08f (computed
 // by bisection over all floats).  The two "Original" variants still divide by the cosine of the float-rounded angle: kept as is.

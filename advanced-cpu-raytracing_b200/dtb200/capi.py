@@ -30,6 +30,7 @@ DT_FLAG_TEST_TIGHT_QUEUES = 64
 DT_FLAG_FORCE_SORT = 128
 DT_FLAG_HOST_WAVE_LOOP = 256
 DT_FLAG_FRAME_GRAPH = 512
+DT_FLAG_PEER_HDR = 1024
 
 
 class dt_scene_options(C.Structure):
@@ -164,6 +165,7 @@ DORKTRACER_SYMBOLS = [
     "dt_gpu_init", "dt_device_count", "dt_scene_create", "dt_scene_create_opts", "dt_scene_destroy", "dt_render", "dt_render_device",
     "dt_finish_device", "dt_primary_hits", "dt_trace_closest", "dt_trace_occluded", "dt_tonemap",
     "dt_scene_stream", "dt_last_error", "dt_version",
+    "dt_multi_create", "dt_multi_render", "dt_multi_device_count", "dt_multi_destroy",
     "dt_frame_export", "dt_frame_import", "dt_frame_release", "dt_frame_finish", "dt_bvh2_build", "dt_scene_accel_checksum",
 ]
 DTHOST_SYMBOLS = [
@@ -250,6 +252,14 @@ def load_dorktracer():
     lib.dt_trace_occluded.restype = C.c_int
     lib.dt_tonemap.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]
     lib.dt_tonemap.restype = C.c_int
+    lib.dt_multi_create.argtypes = [C.POINTER(dt_scene_desc), C.c_int, C.POINTER(vp)]
+    lib.dt_multi_create.restype = C.c_int
+    lib.dt_multi_render.argtypes = [vp, C.POINTER(dt_camera_desc), C.POINTER(dt_render_params), C.c_void_p, C.c_void_p, C.POINTER(dt_stats)]
+    lib.dt_multi_render.restype = C.c_int
+    lib.dt_multi_device_count.argtypes = [vp]
+    lib.dt_multi_device_count.restype = C.c_int
+    lib.dt_multi_destroy.argtypes = [vp]
+    lib.dt_multi_destroy.restype = None
     lib.dt_frame_export.argtypes = [vp, C.c_int32, C.c_int32, C.POINTER(dt_frame_handle)]
     lib.dt_frame_export.restype = C.c_int
     lib.dt_frame_import.argtypes = [vp, C.POINTER(dt_frame_handle)]

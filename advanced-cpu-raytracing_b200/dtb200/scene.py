@@ -226,6 +226,45 @@ class GpuScene:
             pass
 
 
+class GpuMulti:
+    """dt_multi handle: one process, the first n GPUs of the box (include/dorktracer.h)."""
+
+    def __init__(self, host_scene, n_devices=0):
+        self.lib = capi.load_dorktracer()
+        self.host = host_scene
+        self.handle = C.c_void_p()
+        rc = self.lib.dt_multi_create(host_scene.desc_ptr, int(n_devices), C.byref(self.handle))
+        if rc != 0:
+            raise RuntimeError("dt_multi_create failed (%d): %s" % (rc, self.lib.dt_last_error().decode()))
+
+    @property
+    def n_devices(self):
+        return self.lib.dt_multi_device_count(self.handle)
+
+    def render(self, cam, seed=1234, flags=0, max_wave_rays=0, want_hdr=True):
+        W, H = cam.width, cam.height
+        ldr = np.zeros((H, W, 3), np.uint8)
+        hdr = np.zeros((H, W, 3), np.float32) if want_hdr else None
+        params = capi.dt_render_params(seed, 0, 1, max_wave_rays, flags)
+        stats = capi.dt_stats()
+        rc = self.lib.dt_multi_render(self.handle, C.byref(cam), C.byref(params), ldr.ctypes.data_as(C.c_void_p),
+                                      hdr.ctypes.data_as(C.c_void_p) if hdr is not None else None, C.byref(stats))
+        if rc != 0:
+            raise RuntimeError("dt_multi_render failed (%d): %s" % (rc, self.lib.dt_last_error().decode()))
+        return ldr, hdr, stats
+
+    def close(self):
+        if self.handle:
+            self.lib.dt_multi_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def gpu_tonemap(hdr, key, burn, saturation, gamma):
     lib = capi.load_dorktracer()
     hdr = np.ascontiguousarray(hdr, np.float32)

@@ -247,7 +247,8 @@ enum {
                                        that fanning scenes overflow them and take the retry path (dt_stats.retries > 0)            */
     DT_FLAG_FORCE_SORT = 128,       /* sort by material even in scenes with fewer than three materials                             */
     DT_FLAG_HOST_WAVE_LOOP = 256,   /* one host round trip per wave instead of the device-resident wave loop (A/B, debugging)       */
-    DT_FLAG_FRAME_GRAPH = 512       /* bounded-depth frames: replay the enqueued frame as a CUDA graph instead of ~50 launches      */
+    DT_FLAG_FRAME_GRAPH = 512,      /* bounded-depth frames: replay the enqueued frame as a CUDA graph instead of ~50 launches      */
+    DT_FLAG_PEER_HDR = 1024         /* with DT_FLAG_PEER_FRAME: gather the radiance frame too when the camera has no tonemapper      */
 };
 
 typedef struct dt_stats {
@@ -317,6 +318,18 @@ int dt_frame_export(dt_scene* scene, int32_t width, int32_t height, dt_frame_han
 int dt_frame_import(dt_scene* scene, const dt_frame_handle* in);
 int dt_frame_release(dt_scene* scene);
 int dt_frame_finish(dt_scene* scene, const dt_camera_desc* cam, uint8_t* ldr_rgb, dt_stats* stats);
+
+/* One process, several GPUs ("the library drives all GPUs internally").  The reference's main() is one process
+ * that splits the rows of a frame over its threads (main.cpp:38-39,164-185); dt_multi splits its strips over the first
+ * n_devices GPUs of the box (<= 0: all visible): scene replicated, one host thread per GPU, every GPU's resolve kernel stores
+ * its strips into device 0's frame through peer access over NVLink, device 0 tonemaps / copies the frame out.  Same outputs
+ * and semantics as dt_render (tile_rank / tile_world of params are ignored). */
+typedef struct dt_multi dt_multi;
+int dt_multi_create(const dt_scene_desc* desc, int n_devices, dt_multi** out);
+int dt_multi_render(dt_multi* m, const dt_camera_desc* cam, const dt_render_params* params,
+                    uint8_t* ldr_rgb, float* hdr_rgb, dt_stats* stats);
+int dt_multi_device_count(const dt_multi* m);
+void dt_multi_destroy(dt_multi* m);
 
 /* Parity/debug: primary-ray closest hits.  shape = index into desc.shapes (-1 miss), face = canonical
  * (post-build) face index of the (base) mesh or -1 for spheres, t = hit distance (INFINITY on miss). */

@@ -7,14 +7,25 @@ this repository).  Outputs go ONLY to oracle/_ref/ (git-ignored, travels to the 
 
   oracle/_ref/raytracer        reference + P1 + P2 + P3            (timed CPU baseline, `--impl reference`)
   oracle/_ref/raytracer_probe  the same + ray counters + hit dump  (parity oracle; never timed)
+  oracle/_ref/raytracer_dropin the reference's parser / Scene / Camera / main() with its render loop (main.cpp:164-192)
+                               replaced by ONE call into libdorktracer.so: the reference sources + the flattener
+                               advanced-cpu-raytracing_b200/dropin/dt_flatten_scene.cpp, patches P1-P4, Q1 and D1-D3 below.
+                               The proof that the C ABI is a drop-in for the reference's own host code (needs a GPU to RUN).
 
 Recorded patches (each is applied by exact-anchor replacement and asserted to match exactly once):
   P1  InstancedMesh::SetMaterial also sets Shape::material_id  (instancedMesh.cpp:11-13; without it any
       instanced scene with a light segfaults at raytracer.cpp:590)
   P2  MeshLight face pick uses uniform_int_distribution(0, faceCount-1)  (meshLight.h:22; out-of-bounds)
   P3  THREAD_COUNT (main.cpp:15) becomes a run-time value read from $DT_THREADS (default 8, as shipped)
+  P4  Mesh::surfaceArea (mesh.hpp:19) is initialised to 0 in the constructor: parser.cpp:608 accumulates face areas into
+      it without ever setting it, so MeshLight::getSample's selection weight (meshLight.h:31) depends on heap garbage
+      (observed: radiance of a mesh-lit scene changes in the 6th digit once a PLY mesh is parsed before the LightMesh)
   Q1  (quiet) the one-line-per-PLY-face print in Scene::createFace (parser.cpp:813) is removed; it is
       pure stdout noise (10M lines on config 5) and does not touch the hot path.
+Drop-in edits of main.cpp (raytracer_dropin):
+  D1  after scene.loadFromXml(argv[1]) (main.cpp:136): dt_dropin_create(scene)  -- flatten the Scene, create the GPU scene
+  D2  main.cpp:164-185 (thread spawn over renderThreadMain ... join) -> dt_dropin_render(gpu, cam, image, hdrImage)
+  D3  main.cpp:190 cam.GetTonemappedImage(...) removed (dt_render tonemaps); stbi_write_hdr / stbi_write_png stay
 Probe-only instrumentation (raytracer_probe):
   I1  thread-local closest/shadow ray counters (one per Raytracer::IntersectObjects / CastShadowRay call),
       summed and printed as "DT_RAYS closest=<n> shadow=<n>"
@@ -67,6 +78,9 @@ def apply_common(d):
         t, "#define THREAD_COUNT 8",
         "#include <cstdlib>\nstatic int dt_thread_count(){ const char* e = getenv(\"DT_THREADS\"); "
         "int n = e ? atoi(e) : 8; return n > 0 ? n : 8; }\n#define THREAD_COUNT (dt_thread_count())", "P3"))
+    # P4
+    edit(os.path.join(d, "mesh.cpp"), lambda t: patch(
+        t, "this->vertexOffset = 0;\n    this->textureOffset = 0;", "this->vertexOffset = 0;\n    this->textureOffset = 0;\n    this->surfaceArea = 0;", "P4"))
     # Q1
     edit(os.path.join(d, "parser.cpp"), lambda t: patch(
         t, 'std::cout << " total area of mesh: " << mesh->surfaceArea << std::endl;\n\n    return face;',
@@ -151,7 +165,26 @@ def apply_probe(d):
     edit(os.path.join(d, "main.cpp"), main)
 
 
-def compile_variant(srcdir, out_bin):
+REPO = os.path.dirname(HERE)
+PKG = os.path.join(REPO, "advanced-cpu-raytracing_b200")
+DROPIN_SRC = os.path.join(PKG, "dropin", "dt_flatten_scene.cpp")
+
+
+def apply_dropin(d):
+    def main(t):
+        t = patch(t, "int main(int argc, char* argv[])\n{",
+                  "void* dt_dropin_create(DorkTracer::Scene& scene);\nint dt_dropin_render(void* gpu, DorkTracer::Camera& cam, unsigned char* image, float* hdrImage);\n"
+                  "void dt_dropin_destroy(void* gpu);\n\nint main(int argc, char* argv[])\n{", "D0")
+        t = patch(t, "    scene.loadFromXml(argv[1]);\n", "    scene.loadFromXml(argv[1]);\n    void* dt_gpu = dt_dropin_create(scene);\n    if(!dt_gpu) return 1;\n", "D1")
+        a = t.index("        std::vector<std::thread> renderThreads;")
+        b = t.index("        if(cam.hasTonemapper)\n        {\n            // Post process")
+        t = t[:a] + "        if(dt_dropin_render(dt_gpu, cam, image, hdrImage) != 0) return 1;      // replaces main.cpp:164-185\n\n" + t[b:]      # D2
+        t = patch(t, "            cam.GetTonemappedImage(width,height, hdrImage, image);\n", "", "D3")
+        return t
+    edit(os.path.join(d, "main.cpp"), main)
+
+
+def compile_variant(srcdir, out_bin, dropin=False):
     cpps = sorted(f for f in os.listdir(srcdir) if f.endswith(".cpp"))
     objdir = os.path.join(srcdir, "_obj")
     os.makedirs(objdir, exist_ok=True)
@@ -162,7 +195,13 @@ def compile_variant(srcdir, out_bin):
         return o
     with ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as ex:
         objs = list(ex.map(cc, cpps))
-    subprocess.run(["g++"] + objs + ["-o", out_bin, "-lpthread"], check=True)
+    if dropin:
+        # the flattener reads private members of the reference's classes: -fno-access-control for THIS translation unit only
+        o = os.path.join(objdir, "dt_flatten_scene.o")
+        subprocess.run(["g++"] + CXXFLAGS + ["-fno-access-control", "-I" + os.path.join(REPO, "include"), "-I" + srcdir, "-c", DROPIN_SRC, "-o", o], cwd=srcdir, check=True)
+        subprocess.run(["g++"] + objs + [o, "-o", out_bin, "-L" + PKG, "-ldorktracer", "-Wl,-rpath,$ORIGIN/../../advanced-cpu-raytracing_b200", "-lpthread"], check=True)
+    else:
+        subprocess.run(["g++"] + objs + ["-o", out_bin, "-lpthread"], check=True)
 
 
 def copy_sources(dst):
@@ -173,8 +212,10 @@ def copy_sources(dst):
 
 
 def build(force=False):
-    want = [os.path.join(OUT, "raytracer"), os.path.join(OUT, "raytracer_probe")]
-    if not force and all(os.path.exists(w) for w in want):
+    want = [os.path.join(OUT, "raytracer"), os.path.join(OUT, "raytracer_probe"), os.path.join(OUT, "raytracer_dropin")]
+    lib = os.path.join(PKG, "libdorktracer.so")
+    stale = os.path.exists(want[2]) and os.path.exists(DROPIN_SRC) and os.path.getmtime(DROPIN_SRC) > os.path.getmtime(want[2])
+    if not force and not stale and all(os.path.exists(w) for w in want):
         return True
     if not os.path.isdir(REF_SRC):
         # GPU box: only the prebuilt files exist.
@@ -188,6 +229,10 @@ def build(force=False):
         b = os.path.join(tmp, "probe"); os.makedirs(b)
         copy_sources(b); apply_common(b); apply_probe(b)
         compile_variant(b, want[1])
+        if os.path.exists(lib):                    # links against the CUDA library (built by `make cuda` first)
+            c = os.path.join(tmp, "dropin"); os.makedirs(c)
+            copy_sources(c); apply_common(c); apply_dropin(c)
+            compile_variant(c, want[2], dropin=True)
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
     return True

@@ -13,8 +13,15 @@
  * PNGs (archive/hw1_outputs, six "pins" scenes, committed as fixtures under tests/golden/) and — in the build
  * container — against the compiled reference oracle/_ref/raytracer_probe (hit ids, radiance, LDR bytes).
  *
- * Random numbers: the reference draws from unseeded, thread-racy std::mt19937s, so Monte-Carlo scenes are
- * only statistically comparable; here every pixel owns a SplitMix64 stream keyed by (seed, pixel).
+ * Random numbers: the reference draws from std::mt19937s that are default-seeded or seeded from an UNSEEDED rand()
+ * (raytracer.cpp:10,14, main.cpp:49, areaLight.h:28, meshLight.h:17, sphericalEnvironmentLight.h:19), so with ONE render
+ * thread it is deterministic.  Two modes:
+ *   dto_render                every pixel owns a SplitMix64 stream keyed by (seed, pixel): thread-count independent, used for
+ *                             statistical comparisons with the GPU path (whose RNG is counter-based too);
+ *   dto_render_reference_rng  replays the reference's generators -- glibc rand() from its default seed, mt19937, libstdc++'s
+ *                             generate_canonical / uniform_real_distribution / uniform_int_distribution -- in the reference's
+ *                             call order on one thread, so that a Monte-Carlo render is BIT-IDENTICAL (radiance bits and ray
+ *                             counts) to `DT_THREADS=1 oracle/_ref/raytracer_probe` (tests/test_cpu_oracle_host.py).
  */
 #include "dorktracer.h"
 
@@ -64,7 +71,7 @@ static void orthonormal_basis(v3 r, v3* u, v3* v) {            /* helperMath.cpp
 static double angle_between_unit(v3 a, v3 b) {                 /* helperMath.cpp:154-157 */
     float d = vdot(a, b);
     float c = fminf(1.0f, fmaxf(-1.0f, d));
-    return acos((double)c) * RAD2DEG;
+    return acosf(c) * RAD2DEG;             /* std::acos(float) is the FLOAT overload; the product with RAD2DEG (a double) is double */
 }
 static double cos_deg(double a) { return cos(a * DEG2RAD); }   /* helperMath.cpp:158-161 */
 
@@ -102,11 +109,75 @@ typedef struct {
     v3 throughput;
 } Ray;
 
+/* ---- the reference's generators (reference-RNG mode) ----
+ * std::mt19937 = mersenne_twister_engine<uint_fast32_t, 32, 624, 397, 31, 0x9908b0df, 11, 0xffffffff, 7, 0x9d2c5680, 15,
+ * 0xefc60000, 18, 1812433253>, default seed 5489. */
+typedef struct { uint32_t mt[624]; int idx; } Mt19937;
+static void mt_seed(Mt19937* m, uint32_t seed) {
+    m->mt[0] = seed;
+    for (int i = 1; i < 624; i++) m->mt[i] = 1812433253u * (m->mt[i - 1] ^ (m->mt[i - 1] >> 30)) + (uint32_t)i;
+    m->idx = 624;
+}
+static uint32_t mt_next(Mt19937* m) {
+    if (m->idx >= 624) {
+        for (int i = 0; i < 624; i++) {
+            uint32_t y = (m->mt[i] & 0x80000000u) | (m->mt[(i + 1) % 624] & 0x7FFFFFFFu);
+            m->mt[i] = m->mt[(i + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+        }
+        m->idx = 0;
+    }
+    uint32_t y = m->mt[m->idx++];
+    y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= y >> 18;
+    return y;
+}
+/* libstdc++ std::generate_canonical<double, 53>(mt19937&) (bits/random.tcc): two 32-bit draws, low word first */
+static double mt_canonical(Mt19937* m) {
+    double sum = (double)mt_next(m);
+    sum += (double)mt_next(m) * 4294967296.0;
+    double ret = sum / 18446744073709551616.0;
+    if (ret >= 1.0) ret = nextafter(1.0, 0.0);
+    return ret;
+}
+/* libstdc++ std::uniform_int_distribution<int>(0, n - 1)(mt19937&) (bits/uniform_int_dist.h, GCC >= 11): the generator's
+ * range is exactly 32 bits, so Lemire's nearly-divisionless method with a 64-bit product (_S_nd<uint64_t>) */
+static uint32_t mt_uniform_int(Mt19937* m, uint32_t n) {
+    uint64_t product = (uint64_t)mt_next(m) * (uint64_t)n;
+    uint32_t low = (uint32_t)product;
+    if (low < n) {
+        uint32_t threshold = (0u - n) % n;
+        while (low < threshold) { product = (uint64_t)mt_next(m) * (uint64_t)n; low = (uint32_t)product; }
+    }
+    return (uint32_t)(product >> 32);
+}
+/* glibc rand() = random() TYPE_3 (additive feedback, x^31 + x^3 + 1) from the default seed 1: the reference never calls srand */
+typedef struct { uint32_t r[34 + 310 + 64]; int next; } GlibcRand;
+static void glibc_rand_init(GlibcRand* g, uint32_t seed) {
+    int32_t* r = (int32_t*)g->r;
+    r[0] = (int32_t)seed;
+    for (int i = 1; i < 31; i++) { r[i] = (int32_t)((16807LL * r[i - 1]) % 2147483647); if (r[i] < 0) r[i] += 2147483647; }
+    for (int i = 31; i < 34; i++) g->r[i] = g->r[i - 31];
+    for (int i = 34; i < 34 + 310 + 64; i++) g->r[i] = g->r[i - 31] + g->r[i - 3];
+    g->next = 344;
+}
+static uint32_t glibc_rand(GlibcRand* g) { return g->r[g->next++] >> 1; }      /* 64 values are plenty (one per generator) */
+
+#define DTO_MAX_LIGHT_STREAMS 16
+typedef struct {
+    Mt19937 main_gen;                          /* main.cpp:49    std::mt19937 randomGen(rand()) of the (single) render thread        */
+    Mt19937 rand_gen;                          /* raytracer.cpp:10  Raytracer::randGen = mt19937(rand())                             */
+    Mt19937 dof_gen;                           /* raytracer.cpp:14  dofLensSampleGenerator = mt19937(rand())                         */
+    Mt19937 area[DTO_MAX_LIGHT_STREAMS];       /* areaLight.h:28    sampleGen = mt19937()                                            */
+    Mt19937 mesh[DTO_MAX_LIGHT_STREAMS];       /* meshLight.h:17    sampleGen = mt19937()                                            */
+    Mt19937 env[DTO_MAX_LIGHT_STREAMS];        /* sphericalEnvironmentLight.h:19  gen = mt19937(rand()), seeded while parsing        */
+} RefRng;
+enum { RS_MAIN, RS_RAND, RS_DOF, RS_AREA, RS_MESH, RS_ENV };
+
 typedef struct {
     const dt_scene_desc* sc;
     const dt_camera_desc* cam;
     uint64_t rng;
     uint64_t n_closest, n_shadow;
+    RefRng* ref;     /* non-NULL: reference-RNG mode */
 } Ctx;
 
 /* SplitMix64 -> double in [0,1) (uniform_real_distribution<double> over mt19937 has 53 random bits too) */
@@ -117,7 +188,22 @@ static inline double rnd01(Ctx* c) {
     z = z ^ (z >> 31);
     return (double)(z >> 11) * (1.0 / 9007199254740992.0);
 }
-static inline float rnd_normalized(Ctx* c) { return (float)(0.0f + (1.0f - 0.0f) * rnd01(c)); }   /* raytracer.cpp:24-28 */
+/* One canonical double in [0,1) from the generator the reference uses at this call site (reference-RNG mode) or from the
+ * pixel's SplitMix64 stream.  std::uniform_real_distribution<double>(a, b)(g) = generate_canonical(g) * (b - a) + a. */
+static inline double rnd_s(Ctx* c, int stream, int idx) {
+    if (!c->ref) return rnd01(c);
+    RefRng* r = c->ref;
+    if (idx >= DTO_MAX_LIGHT_STREAMS) idx = DTO_MAX_LIGHT_STREAMS - 1;
+    switch (stream) {
+        case RS_MAIN: return mt_canonical(&r->main_gen);
+        case RS_RAND: return mt_canonical(&r->rand_gen);
+        case RS_DOF: return mt_canonical(&r->dof_gen);
+        case RS_AREA: return mt_canonical(&r->area[idx]);
+        case RS_MESH: return mt_canonical(&r->mesh[idx]);
+        default: return mt_canonical(&r->env[idx]);
+    }
+}
+static inline float rnd_normalized(Ctx* c) { return (float)(0.0f + (1.0f - 0.0f) * rnd_s(c, RS_RAND, 0)); }   /* raytracer.cpp:24-28 */
 
 /* ---- shape.hpp:78-100 ---- */
 static int box_intersect(const float* mn, const float* mx, const Ray* ray) {
@@ -667,13 +753,13 @@ static v3 env_sample_idx(const dt_scene_desc* sc, int li, v3 dir) {
     v3 s = image_sample(im, i, j);
     return vscale(vscale(s, 2), (float)M_PI);   /* Vec3f * 2 * M_PI: both factors narrow to float (helperMath.cpp:22) */
 }
-static v3 env_direction(Ctx* c, v3 normal) {
+static v3 env_direction(Ctx* c, int li, v3 normal) {
     v3 n = vunit(normal);
     v3 cand;
     for (int guard = 0;; guard++) {
-        cand.x = (float)(-1.0f + 2.0 * rnd01(c));
-        cand.y = (float)(-1.0f + 2.0 * rnd01(c));
-        cand.z = (float)(-1.0f + 2.0 * rnd01(c));
+        cand.x = (float)(-1.0f + 2.0 * rnd_s(c, RS_ENV, li));
+        cand.y = (float)(-1.0f + 2.0 * rnd_s(c, RS_ENV, li));
+        cand.z = (float)(-1.0f + 2.0 * rnd_s(c, RS_ENV, li));
         float length = vlen(cand);
         if (length <= 1.0f && vdot(n, cand) > 0.0f) break;    /* `candidate / length;` is a no-op in the reference */
         if (guard > 100000) break;
@@ -713,8 +799,8 @@ static v3 sample_direct_lighting(Ctx* c, Ray* ray, const dt_material* mat, v3 w_
     }
     for (int i = 0; i < sc->n_area_lights; i++) {
         const dt_area_light* l = &sc->area_lights[i];
-        float offU = (float)(-0.5f + rnd01(c));                 /* areaLight.h:34-40 */
-        float offV = (float)(-0.5f + rnd01(c));
+        float offU = (float)(-0.5f + rnd_s(c, RS_AREA, i));     /* areaLight.h:34-40 */
+        float offV = (float)(-0.5f + rnd_s(c, RS_AREA, i));
         v3 sp = vadd(vadd(F3(l->position), vscale(F3(l->u), (l->extent * offU))), vscale(F3(l->v), (l->extent * offV)));
         if (is_in_shadow(c, ray, sp)) continue;
         v3 w_i = vsub(sp, ray->hit.hitPoint);
@@ -728,7 +814,7 @@ static v3 sample_direct_lighting(Ctx* c, Ray* ray, const dt_material* mat, v3 w_
         color = vadd(color, shade(sc, ray, mat, w_i, w_o, E));
     }
     for (int i = 0; i < sc->n_env_lights; i++) {
-        v3 dir = env_direction(c, ray->hit.normal);
+        v3 dir = env_direction(c, i, ray->hit.normal);
         v3 E = env_sample_idx(sc, i, dir);
         v3 w_i = ray->hit.normal;
         color = vadd(color, shade(sc, ray, mat, w_i, w_o, E));
@@ -752,11 +838,13 @@ static v3 sample_direct_lighting(Ctx* c, Ray* ray, const dt_material* mat, v3 w_
         const dt_shape* lsh = &sc->shapes[l->shape];
         const dt_mesh* lm = &sc->meshes[lsh->mesh];
         /* meshLight.h:27-47 with patch P2 (uniform face pick over [0, faceCount-1]) */
-        int fi = (int)(rnd01(c) * lm->n_faces);
+        int fi;
+        if (c->ref) fi = (int)mt_uniform_int(&c->ref->mesh[i < DTO_MAX_LIGHT_STREAMS ? i : DTO_MAX_LIGHT_STREAMS - 1], (uint32_t)lm->n_faces);
+        else fi = (int)(rnd01(c) * lm->n_faces);
         if (fi >= lm->n_faces) fi = lm->n_faces - 1;
         const dt_face* face = &lm->faces[fi];
         double weight = face->area / lm->surface_area;
-        double rand1 = rnd01(c), rand2 = rnd01(c);
+        double rand1 = rnd_s(c, RS_MESH, i), rand2 = rnd_s(c, RS_MESH, i);
         v3 a = mesh_vertex(lm, face->v0_id), b = mesh_vertex(lm, face->v1_id), cc = mesh_vertex(lm, face->v2_id);
         v3 q = vadd(vscale(b, (float)(1 - rand2)), vscale(cc, (float)rand2));
         v3 pos = vadd(vscale(a, (float)(1 - sqrt(rand1))), vscale(q, (float)sqrt(rand1)));
@@ -985,9 +1073,9 @@ static Ray generate_ray(Ctx* c, int i, int j) {
     ray.throughput = V(1.0f, 1.0f, 1.0f);
     if (cam->aperture_size > 0.0001) {
         v3 ap = ray.origin;
-        float first01 = (float)(-1.0f + 2.0 * rnd01(c));
+        float first01 = (float)(-1.0f + 2.0 * rnd_s(c, RS_DOF, 0));
         ap = vadd(ap, vscale(F3(cam->up), (first01 * cam->aperture_size * 0.5f)));
-        float second01 = (float)(-1.0f + 2.0 * rnd01(c));
+        float second01 = (float)(-1.0f + 2.0 * rnd_s(c, RS_DOF, 0));
         ap = vadd(ap, vscale(F3(cam->right), (second01 * cam->aperture_size * 0.5f)));
         v3 dir = vunit(vsub(ray.origin, ipp));
         float tFd = cam->focus_distance / vdot(dir, F3(cam->gaze));
@@ -1029,6 +1117,7 @@ static int clamp_channel(float f) {
 typedef struct {
     const dt_scene_desc* sc; const dt_camera_desc* cam; uint64_t seed;
     int y0, y1; uint8_t* ldr; float* hdr; uint64_t n_closest, n_shadow;
+    RefRng* ref;
 } Job;
 
 static uint64_t mix64(uint64_t z) {
@@ -1040,7 +1129,7 @@ static uint64_t mix64(uint64_t z) {
 static void* render_rows(void* arg) {
     Job* job = (Job*)arg;
     const dt_camera_desc* cam = job->cam;
-    Ctx c; c.sc = job->sc; c.cam = cam; c.n_closest = c.n_shadow = 0; c.rng = 0;
+    Ctx c; c.sc = job->sc; c.cam = cam; c.n_closest = c.n_shadow = 0; c.rng = 0; c.ref = job->ref;
     int width = cam->width;
     int spp = cam->samples_per_pixel;
     int nRows = (int)sqrt((double)spp), nCols = nRows;
@@ -1051,12 +1140,13 @@ static void* render_rows(void* arg) {
     float* sy = (float*)malloc(sizeof(float) * (size_t)(spp > 0 ? spp : 1));
     for (int y = job->y0; y < job->y1; y++) {
         for (int x = 0; x < width; x++) {
-            c.rng = mix64(job->seed ^ mix64((uint64_t)(x + (uint64_t)y * (uint64_t)width) + 0x51ED270B7F4A7C15ull));
+            if (!c.ref) c.rng = mix64(job->seed ^ mix64((uint64_t)(x + (uint64_t)y * (uint64_t)width) + 0x51ED270B7F4A7C15ull));
             v3 color = V(0, 0, 0);
             if (spp > 1) {
                 int i = 0;
                 for (int row = 0; row < nRows; row++) for (int col = 0; col < nCols; col++) {
-                    float psi1 = (float)rnd01(&c), psi2 = (float)rnd01(&c);
+                    float psi1 = (float)rnd_s(&c, RS_MAIN, 0);
+                    float psi2 = (float)rnd_s(&c, RS_MAIN, 0);
                     sx[i] = (col + psi1) / nCols;
                     sy[i] = (row + psi2) / nRows;
                     i++;
@@ -1168,9 +1258,57 @@ int dto_render(const dt_scene_desc* sc, const dt_camera_desc* cam, uint64_t seed
     return DT_OK;
 }
 
+/* Reference-RNG mode: the FIRST camera of a scene rendered by the reference with one render thread (DT_THREADS=1; patch P3 of
+ * oracle/build_ref.py).  Order of the reference's rand() calls from program start: one per SphericalDirectionalLight while
+ * parsing (sphericalEnvironmentLight.h:19), Raytracer::randGen, Raytracer::dofLensSampleGenerator (raytracer.cpp:10,14), then
+ * the render thread's sample generator (main.cpp:49).  Pixels in row-major order, all generators shared by all pixels. */
+int dto_render_reference_rng(const dt_scene_desc* sc, const dt_camera_desc* cam, uint8_t* ldr, float* hdr, dt_stats* stats) {
+    if (!sc || !cam || !ldr) return DT_ERR_INVALID;
+    if (sc->n_area_lights > DTO_MAX_LIGHT_STREAMS || sc->n_mesh_lights > DTO_MAX_LIGHT_STREAMS || sc->n_env_lights > DTO_MAX_LIGHT_STREAMS) return DT_ERR_UNSUPPORTED;
+    RefRng* ref = (RefRng*)malloc(sizeof(RefRng));
+    GlibcRand g;
+    glibc_rand_init(&g, 1u);
+    for (int i = 0; i < DTO_MAX_LIGHT_STREAMS; i++) { mt_seed(&ref->area[i], 5489u); mt_seed(&ref->mesh[i], 5489u); mt_seed(&ref->env[i], 5489u); }
+    for (int i = 0; i < sc->n_env_lights; i++) mt_seed(&ref->env[i], glibc_rand(&g));
+    mt_seed(&ref->rand_gen, glibc_rand(&g));
+    mt_seed(&ref->dof_gen, glibc_rand(&g));
+    mt_seed(&ref->main_gen, glibc_rand(&g));
+    int H = cam->height, W = cam->width;
+    float* own_hdr = NULL;
+    if (!hdr && cam->has_tonemapper) { own_hdr = (float*)malloc(sizeof(float) * (size_t)W * H * 3); hdr = own_hdr; }
+    Job job; memset(&job, 0, sizeof job);
+    job.sc = sc; job.cam = cam; job.seed = 0; job.ldr = ldr; job.hdr = hdr; job.y0 = 0; job.y1 = H; job.ref = ref;
+    render_rows(&job);
+    if (cam->has_tonemapper) dto_tonemap(hdr, W, H, cam->tm_key, cam->tm_burn, cam->tm_saturation, cam->tm_gamma, ldr);
+    if (stats) { memset(stats, 0, sizeof *stats); stats->rays_closest = job.n_closest; stats->rays_shadow = job.n_shadow; }
+    free(own_hdr); free(ref);
+    return DT_OK;
+}
+
+/* Test hook: the raw streams behind the reference-RNG mode, compared in tests/test_cpu_oracle_host.py with what g++'s own
+ * libstdc++ / glibc produce.  what = 0: rand() after srand(seed); 1: mt19937(seed)(); 2: uniform_real_distribution<>(0,1)
+ * (= generate_canonical) over mt19937(seed); 3: uniform_int_distribution<>(0, param - 1) over mt19937(seed). */
+int dto_debug_reference_rng(int what, uint32_t seed, uint32_t param, int n, double* out) {
+    if (!out || n < 0) return DT_ERR_INVALID;
+    if (what == 0) {
+        if (n > 64) return DT_ERR_INVALID;
+        GlibcRand g; glibc_rand_init(&g, seed);
+        for (int i = 0; i < n; i++) out[i] = (double)glibc_rand(&g);
+        return DT_OK;
+    }
+    Mt19937 m; mt_seed(&m, seed);
+    for (int i = 0; i < n; i++) {
+        if (what == 1) out[i] = (double)mt_next(&m);
+        else if (what == 2) out[i] = mt_canonical(&m);
+        else if (what == 3 && param > 0) out[i] = (double)mt_uniform_int(&m, param);
+        else return DT_ERR_INVALID;
+    }
+    return DT_OK;
+}
+
 int dto_primary_hits(const dt_scene_desc* sc, const dt_camera_desc* cam, int32_t* shape, int32_t* face, float* t) {
     if (!sc || !cam) return DT_ERR_INVALID;
-    Ctx c; c.sc = sc; c.cam = cam; c.rng = 1; c.n_closest = c.n_shadow = 0;
+    Ctx c; c.sc = sc; c.cam = cam; c.rng = 1; c.n_closest = c.n_shadow = 0; c.ref = NULL;
     for (int y = 0; y < cam->height; y++) for (int x = 0; x < cam->width; x++) {
         Ray ray = generate_ray(&c, x, y);
         intersect_objects(&c, &ray);
@@ -1184,7 +1322,7 @@ int dto_primary_hits(const dt_scene_desc* sc, const dt_camera_desc* cam, int32_t
 
 int dto_trace_closest(const dt_scene_desc* sc, const float* origins, const float* dirs, int64_t n, int32_t* shape, int32_t* face, float* t) {
     if (!sc) return DT_ERR_INVALID;
-    Ctx c; c.sc = sc; c.cam = NULL; c.rng = 1; c.n_closest = c.n_shadow = 0;
+    Ctx c; c.sc = sc; c.cam = NULL; c.rng = 1; c.n_closest = c.n_shadow = 0; c.ref = NULL;
     for (int64_t i = 0; i < n; i++) {
         Ray ray; memset(&ray, 0, sizeof ray);
         ray.origin = F3(&origins[3 * i]); ray.dir = F3(&dirs[3 * i]);
@@ -1199,7 +1337,7 @@ int dto_trace_closest(const dt_scene_desc* sc, const float* origins, const float
 
 int dto_trace_occluded(const dt_scene_desc* sc, const float* origins, const float* dirs, const float* tmax, int64_t n, uint8_t* occluded) {
     if (!sc) return DT_ERR_INVALID;
-    Ctx c; c.sc = sc; c.cam = NULL; c.rng = 1; c.n_closest = c.n_shadow = 0;
+    Ctx c; c.sc = sc; c.cam = NULL; c.rng = 1; c.n_closest = c.n_shadow = 0; c.ref = NULL;
     for (int64_t i = 0; i < n; i++) {
         Ray sr; memset(&sr, 0, sizeof sr);
         sr.origin = F3(&origins[3 * i]); sr.dir = F3(&dirs[3 * i]);

@@ -16,7 +16,7 @@ sys.path.insert(0, os.path.join(REPO, "advanced-cpu-raytracing_b200"))
 
 from dtb200 import capi  # noqa: E402
 
-DTORACLE_SYMBOLS = ["dto_render", "dto_primary_hits", "dto_tonemap", "dto_trace_closest", "dto_trace_occluded"]
+DTORACLE_SYMBOLS = ["dto_render", "dto_render_reference_rng", "dto_debug_reference_rng", "dto_primary_hits", "dto_tonemap", "dto_trace_closest", "dto_trace_occluded"]
 
 
 def load_dtoracle():
@@ -24,6 +24,10 @@ def load_dtoracle():
     lib = capi._load(os.path.join(REPO, "oracle", "libdtoracle.so"), "oracle library")
     lib.dto_render.argtypes = [C.POINTER(capi.dt_scene_desc), C.POINTER(capi.dt_camera_desc), C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(capi.dt_stats)]
     lib.dto_render.restype = C.c_int
+    lib.dto_render_reference_rng.argtypes = [C.POINTER(capi.dt_scene_desc), C.POINTER(capi.dt_camera_desc), C.c_void_p, C.c_void_p, C.POINTER(capi.dt_stats)]
+    lib.dto_render_reference_rng.restype = C.c_int
+    lib.dto_debug_reference_rng.argtypes = [C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p]
+    lib.dto_debug_reference_rng.restype = C.c_int
     lib.dto_primary_hits.argtypes = [C.POINTER(capi.dt_scene_desc), C.POINTER(capi.dt_camera_desc), C.c_void_p, C.c_void_p, C.c_void_p]
     lib.dto_primary_hits.restype = C.c_int
     lib.dto_tonemap.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]
@@ -38,6 +42,7 @@ def load_dtoracle():
 REF_DIR = os.path.join(REPO, "oracle", "_ref")
 REF_BIN = os.path.join(REF_DIR, "raytracer")
 REF_PROBE = os.path.join(REF_DIR, "raytracer_probe")
+REF_DROPIN = os.path.join(REF_DIR, "raytracer_dropin")      # the reference's host code with its render loop replaced by libdorktracer.so
 
 
 def have_ref():
@@ -54,6 +59,19 @@ def oracle_render(host_scene, cam, seed=1234, threads=None, want_hdr=True):
                         ldr.ctypes.data_as(C.c_void_p), hdr.ctypes.data_as(C.c_void_p) if hdr is not None else None, C.byref(stats))
     if rc != 0:
         raise RuntimeError("dto_render failed %d" % rc)
+    return ldr, hdr, stats
+
+
+def oracle_render_reference_rng(host_scene, cam):
+    """The oracle replaying the reference's own generators on one thread (bit-comparable with DT_THREADS=1 raytracer_probe)."""
+    lib = load_dtoracle()
+    W, H = cam.width, cam.height
+    ldr = np.zeros((H, W, 3), np.uint8)
+    hdr = np.zeros((H, W, 3), np.float32)
+    stats = capi.dt_stats()
+    rc = lib.dto_render_reference_rng(host_scene.desc_ptr, C.byref(cam), ldr.ctypes.data_as(C.c_void_p), hdr.ctypes.data_as(C.c_void_p), C.byref(stats))
+    if rc != 0:
+        raise RuntimeError("dto_render_reference_rng failed %d" % rc)
     return ldr, hdr, stats
 
 
@@ -101,7 +119,11 @@ def oracle_tonemap(hdr, key, burn, saturation, gamma):
     return ldr
 
 
-def run_reference(xml_path, probe=True, threads=None, cwd=None, timeout=3600, width_height=None):
+def have_dropin():
+    return os.path.exists(REF_DROPIN)
+
+
+def run_reference(xml_path, probe=True, threads=None, cwd=None, timeout=3600, width_height=None, exe=None, extra_env=None):
     """Run the compiled reference on an XML scene.  Returns dict(png, hits, hdr, seconds, closest, shadow).
 
     The reference resolves plyFile / inputs/<image> against the cwd and writes <ImageName> into it, so it is
@@ -120,7 +142,10 @@ def run_reference(xml_path, probe=True, threads=None, cwd=None, timeout=3600, wi
     if probe:
         env["DT_DUMP_HITS"] = hits_p
         env["DT_DUMP_HDR"] = hdr_p
-    exe = REF_PROBE if probe else REF_BIN
+    if exe is None:
+        exe = REF_PROBE if probe else REF_BIN
+    if extra_env:
+        env.update(extra_env)
     before = set(os.listdir(tmp))
     p = subprocess.run([exe, os.path.basename(xml_path)], cwd=tmp, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=timeout)
     out = p.stdout.decode(errors="replace")
@@ -157,3 +182,20 @@ def psnr(a, b):
     if mse == 0:
         return 99.0
     return float(10 * np.log10(255.0 ** 2 / mse))
+
+
+def mc_compare(hdr, ref_hdr, cam, clip=20.0):
+    """Two Monte-Carlo radiance frames as estimates of the same image.  The reference itself produces the occasional NaN / inf
+    pixel (0/0 in a BRDF lobe at grazing angles; it only prints "nan color!!", raytracer.cpp:128-131) and fireflies of 1e3-1e4
+    (unweighted GI, 1/d^2 lights), so: pixels non-finite on either side are excluded and counted, the mean is compared plainly and
+    clipped at `clip`, and both frames go through the SAME tonemapper (oracle restatement of tonemapper.h, the camera's parameters)
+    with non-finite values zeroed before the LDR PSNR / RMSE is taken."""
+    ok = np.isfinite(hdr).all(axis=2) & np.isfinite(ref_hdr).all(axis=2)
+    a, b = hdr[ok].astype(np.float64), ref_hdr[ok].astype(np.float64)
+    sa, sb = np.where(np.isfinite(hdr), hdr, 0).astype(np.float32), np.where(np.isfinite(ref_hdr), ref_hdr, 0).astype(np.float32)
+    la = oracle_tonemap(sa, cam.tm_key, cam.tm_burn, cam.tm_saturation, cam.tm_gamma)
+    lb = oracle_tonemap(sb, cam.tm_key, cam.tm_burn, cam.tm_saturation, cam.tm_gamma)
+    mse = float(np.mean((la.astype(np.float64) - lb.astype(np.float64)) ** 2))
+    return {"finite": float(ok.mean()), "mean_rel": abs(a.mean() - b.mean()) / b.mean(),
+            "clip_rel": abs(np.minimum(a, clip).mean() - np.minimum(b, clip).mean()) / np.minimum(b, clip).mean(),
+            "psnr": psnr(la, lb), "rmse": mse ** 0.5}
