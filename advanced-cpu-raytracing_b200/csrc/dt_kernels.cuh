@@ -209,6 +209,7 @@ template <bool ANY, bool WW>
 __global__ void __launch_bounds__(128, ANY ? DT_TRAV_MINBLOCKS_ANY : DT_TRAV_MINBLOCKS) k_traverse(DtSceneDev S, DtRayQueue q, DtShadowQueue sq, const int* n_ptr, int n_fixed, int n_cap, int* fetch_counter, float4* accum) {
     const int n = min(n_ptr ? *n_ptr : n_fixed, n_cap);        // a device-side counter may have run past the queue capacity (overflow): never index beyond it
     const int lane = threadIdx.x & 31;
+    DT_DECLARE_STACK(stack);
     for (;;) {
         int base = 0;
         if (lane == 0) base = atomicAdd(fetch_counter, 32);
@@ -220,7 +221,6 @@ __global__ void __launch_bounds__(128, ANY ? DT_TRAV_MINBLOCKS_ANY : DT_TRAV_MIN
             const float4 o = ANY ? sq.o_time[i] : q.o_time[i];
             const float4 d = ANY ? sq.d_tmax[i] : q.d_tmax[i];
             DtTrav T;
-            uint2 stack[DT_STACK_SIZE];
             dt_trav_init<ANY>(T, S, V(o.x, o.y, o.z), V(d.x, d.y, d.z), o.w, ANY ? d.w : CUDART_INF_F);
             while (!dt_trav_step<ANY, WW>(T, stack, S, (ANY ? sq.o_time : q.o_time) + i, (ANY ? sq.d_tmax : q.d_tmax) + i)) {}
             if (ANY) dt_store_shadow(sq, i, T.best, accum); else dt_store_closest(q, i, T.best);
@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(128, ANY ? DT_TRAV_MINBLOCKS_ANY : DT_TRAV_MIN
     const unsigned FULL = 0xFFFFFFFFu;
     const unsigned lanes_lt = (1u << lane) - 1u;
     DtTrav T;
-    uint2 stack[DT_STACK_SIZE];
+    DT_DECLARE_STACK(stack);
     int ray = -1;
     bool drained = false;
 #ifdef DT_TIMELINE
@@ -886,6 +886,7 @@ __global__ void __launch_bounds__(128, DT_SHADE_MINBLOCKS) k_tail(DtSceneDev S, 
     __syncthreads();
     int waves = 0;
     unsigned long long n_closest = 0, n_shadow = 0;          // thread 0 only
+    DT_DECLARE_STACK(stack);
 #ifdef DT_TAIL_PROFILE
     long long tp[3] = {0, 0, 0}, tp_last = clock64(), tp_rays = 0;
 #define DT_TP(i) { const long long now_ = clock64(); tp[i] += now_ - tp_last; tp_last = now_; }
@@ -903,7 +904,7 @@ __global__ void __launch_bounds__(128, DT_SHADE_MINBLOCKS) k_tail(DtSceneDev S, 
             for (int j = tid; j < cur; j += DT_TAIL_PATH_THREADS) {
                 if (in.pixel[j] == DT_DEAD_PIXEL) continue;
                 const float4 o = in.o_time[j], d = in.d_tmax[j];
-                DtTrav T; uint2 stack[DT_STACK_SIZE];
+                DtTrav T;
                 dt_trav_init<false>(T, S, V(o.x, o.y, o.z), V(d.x, d.y, d.z), o.w, CUDART_INF_F);
                 while (!dt_trav_step<false, true>(T, stack, S, in.o_time + j, in.d_tmax + j)) {}
                 dt_store_closest(in, j, T.best);
@@ -925,7 +926,7 @@ __global__ void __launch_bounds__(128, DT_SHADE_MINBLOCKS) k_tail(DtSceneDev S, 
             for (int e = tid - DT_TAIL_PATH_THREADS; e < pend; e += blockDim.x - DT_TAIL_PATH_THREADS) {
                 if (defer && dt_deferred_skipped(S, Q.defer[e], child_hit0)) continue;
                 const float4 o = Q.o_time[e], d = Q.d_tmax[e];
-                DtTrav T; uint2 stack[DT_STACK_SIZE];
+                DtTrav T;
                 dt_trav_init<true>(T, S, V(o.x, o.y, o.z), V(d.x, d.y, d.z), o.w, d.w);
                 while (!dt_trav_step<true, true>(T, stack, S, Q.o_time + e, Q.d_tmax + e)) {}
                 dt_store_shadow(Q, e, T.best, accum);

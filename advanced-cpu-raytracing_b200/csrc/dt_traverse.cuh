@@ -237,6 +237,42 @@ struct DtTrav {
 };
 // The traversal stack is a SEPARATE local array (uint2 stack[DT_STACK_SIZE] in the kernel): with the dynamically indexed
 // array inside DtTrav the whole struct lives in local memory; on its own, the scalar state above stays in registers.
+//
+// north_star names a "shared-memory short stack": -DDT_SMEM_STACK=n keeps the n entries nearest the stack BOTTOM of every lane
+// in shared memory (s[entry][lane]: conflict-free, 8 B x 128 threads x n per block) and only deeper entries in the local
+// array.  Measured A/B (profiles/r2_ab_smem_stack.log) decides the default.
+#ifndef DT_SMEM_STACK
+#define DT_SMEM_STACK 0
+#endif
+struct DtStack {
+    uint2* loc;                 // per-thread local array
+#if DT_SMEM_STACK
+    uint2* sh;                  // &smem[0][threadIdx.x]; entry k at sh[k * 128]
+#endif
+};
+#if DT_SMEM_STACK
+#define DT_DECLARE_STACK(name) uint2 name##_loc[DT_STACK_SIZE - DT_SMEM_STACK]; __shared__ uint2 name##_sh[DT_SMEM_STACK][128]; \
+    DtStack name; name.loc = name##_loc; name.sh = &name##_sh[0][threadIdx.x & 127]
+#else
+#define DT_DECLARE_STACK(name) uint2 name##_loc[DT_STACK_SIZE]; DtStack name; name.loc = name##_loc
+#endif
+__device__ __forceinline__ void dt_push(const DtStack& s, int& sp, uint2 v) {
+    if (sp >= DT_STACK_SIZE) return;
+#if DT_SMEM_STACK
+    if (sp < DT_SMEM_STACK) s.sh[sp * 128] = v; else s.loc[sp - DT_SMEM_STACK] = v;
+#else
+    s.loc[sp] = v;
+#endif
+    sp++;
+}
+__device__ __forceinline__ uint2 dt_pop(const DtStack& s, int& sp) {
+    --sp;
+#if DT_SMEM_STACK
+    return sp < DT_SMEM_STACK ? s.sh[sp * 128] : s.loc[sp - DT_SMEM_STACK];
+#else
+    return s.loc[sp];
+#endif
+}
 
 template <bool ANY>
 __device__ __forceinline__ void dt_trav_init(DtTrav& T, const DtSceneDev& S, v3 wo, v3 wd, float mb_time, float tmax_in) {
@@ -260,14 +296,14 @@ __device__ __forceinline__ void dt_trav_init(DtTrav& T, const DtSceneDev& S, v3 
 #define DT_ANYHIT_ORDERED 0       // A/B knob: 1 = front-to-back occlusion queries in the wave kernels too
 #endif
 template <bool ANY, bool ORDERED = (DT_ANYHIT_ORDERED != 0) || !ANY>
-__device__ __forceinline__ void dt_trav_node(DtTrav& T, uint2* __restrict__ stack, const DtSceneDev& S) {
+__device__ __forceinline__ void dt_trav_node(DtTrav& T, const DtStack& stack, const DtSceneDev& S) {
     const uint32_t one = S.one_bits;
     DT_STAT(0);
     const uint32_t hits = T.ng.y;
     const uint32_t imask = T.ng.y & 0xFFu;
     const int child_bit = 31 - __clz(hits);
     T.ng.y &= ~(1u << child_bit);
-    if (T.ng.y > 0x00FFFFFFu) { if (T.sp < DT_STACK_SIZE) stack[T.sp++] = T.ng; }
+    if (T.ng.y > 0x00FFFFFFu) dt_push(stack, T.sp, T.ng);
     // occlusion queries visit the children in plain slot order (any hit will do): no octant permutation
     const uint32_t slot = !ORDERED ? (uint32_t)(child_bit - 24) : ((uint32_t)(child_bit - 24) ^ (T.r.oct_inv4 & 0xFFu));
     const uint32_t rel = __popc(imask & ~(0xFFFFFFFFu << slot));
@@ -304,7 +340,12 @@ __device__ __forceinline__ void dt_to_local(const DtShapeDev* sh, v3 wo, v3 wd, 
 // order arrives later with t_c a few ulps ABOVE t_b (two surfaces meeting at an edge or corner), the reference would have held
 // minT = t_c when it reached b, and b's own box tests (shape box, mesh box, BVH2 leaf box: `tmin < minT`) may have rejected b
 // -- flat boxes put tmin within an ulp of t_b.  This re-runs b's box tests exactly with minT = t_c.  Rare path (~1e-6 of rays).
-__device__ __noinline__ bool dt_best_survives(const DtSceneDev& S, const DtHit& b, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d, float minT) {
+// Out of line (it runs for ~1e-6 of the rays) and handed the four pointers it needs BY VALUE: a `const DtSceneDev&` would force
+// a 264-byte local-memory copy of the kernel parameter struct in every thread of the traversal kernels (STACK 688 -> 424).
+__device__ __noinline__ bool dt_best_survives_impl(const DtShapeDev* shapes, const DtMeshDev* meshes, const uint32_t* face_prim, const float4* leaf_boxes,
+                                                   float best_t, int best_shape, int best_face, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d, float minT) {
+    struct { const DtShapeDev* shapes; const DtMeshDev* meshes; const uint32_t* face_prim; const float4* leaf_boxes; } S = {shapes, meshes, face_prim, leaf_boxes};
+    struct { float t; int shape, face; } b = {best_t, best_shape, best_face};
     const DtShapeDev* sh = S.shapes + b.shape;
     if (sh->kind == DT_SHAPE_SPHERE) return true;                          // Sphere::Intersect has no box test
     const float4 o4 = *ray_o, d4 = *ray_d;
@@ -323,6 +364,9 @@ __device__ __noinline__ bool dt_best_survives(const DtSceneDev& S, const DtHit& 
     const float lmn[3] = {lb0.x, lb0.y, lb0.z}, lmx[3] = {lb1.x, lb1.y, lb1.z};
     return box_intersect_exact(lmn, lmx, lo, ld, minT);
 }
+__device__ __forceinline__ bool dt_best_survives(const DtSceneDev& S, const DtHit& b, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d, float minT) {
+    return dt_best_survives_impl(S.shapes, S.meshes, S.face_prim, S.leaf_boxes, b.t, b.shape, b.face, ray_o, ray_d, minT);
+}
 // c = (shape, face) precedes the best hit in the reference's scan order and lies within a few ulps behind it
 __device__ __forceinline__ bool dt_close_behind(float t, int shape, int face, const DtHit& best) {
     return best.shape >= 0 && t > best.t && t <= __fmul_rn(best.t, 1.000001f) && (shape < best.shape || (shape == best.shape && face < best.face));
@@ -330,7 +374,7 @@ __device__ __forceinline__ bool dt_close_behind(float t, int shape, int face, co
 
 // One primitive of the current primitive group.  Returns true when an ANY query is decided (occluded).
 template <bool ANY>
-__device__ __forceinline__ bool dt_trav_prim(DtTrav& T, uint2* __restrict__ stack, const DtSceneDev& S, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d, bool& entered_blas) {
+__device__ __forceinline__ bool dt_trav_prim(DtTrav& T, const DtStack& stack, const DtSceneDev& S, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d, bool& entered_blas) {
     DtHit& best = T.best;
     const int bit = __ffs(T.tg.y & 0xFFu) - 1;                                   // next hit leaf slot of the group
     const uint32_t prim = T.tg.x + (uint32_t)__popc((T.tg.y >> 8) & ((1u << bit) - 1u));
@@ -409,8 +453,8 @@ __device__ __forceinline__ bool dt_trav_prim(DtTrav& T, uint2* __restrict__ stac
     DtRayPrep lr;
     dt_prep(lr, lo, ld);
     if (!dt_box_test(m->bbox_min, m->bbox_max, lo, ld, lr, shape_min_t)) return false;
-    if (T.ng.y > 0x00FFFFFFu) { if (T.sp < DT_STACK_SIZE) stack[T.sp++] = T.ng; }
-    if (T.tg.y != 0u) { if (T.sp < DT_STACK_SIZE) stack[T.sp++] = T.tg; }
+    if (T.ng.y > 0x00FFFFFFu) dt_push(stack, T.sp, T.ng);
+    if (T.tg.y != 0u) dt_push(stack, T.sp, T.tg);
     DT_STAT(3);
     T.blas_sp = T.sp;
     T.cur_shape = si;
@@ -426,7 +470,7 @@ __device__ __forceinline__ bool dt_trav_prim(DtTrav& T, uint2* __restrict__ stac
 // Returns true when the ray is finished (ANY: best.shape >= 0 <=> occluded).
 // ray_o / ray_d: where the world-space ray of this traversal can be re-read (queue entry or caller's copy).
 template <bool ANY, bool WW, bool ORDERED = (DT_ANYHIT_ORDERED != 0) || !ANY>
-__device__ __forceinline__ bool dt_trav_step(DtTrav& T, uint2* __restrict__ stack, const DtSceneDev& S, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d) {
+__device__ __forceinline__ bool dt_trav_step(DtTrav& T, const DtStack& stack, const DtSceneDev& S, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d) {
     DT_STAT(5);
     if (WW) {
         while (T.ng.y > 0x00FFFFFFu && T.tg.y == 0u) dt_trav_node<ANY, ORDERED>(T, stack, S);
@@ -447,7 +491,7 @@ __device__ __forceinline__ bool dt_trav_step(DtTrav& T, uint2* __restrict__ stac
             dt_prep(T.r, V(wo.x, wo.y, wo.z), V(wd.x, wd.y, wd.z));
         }
         if (T.sp == 0) { if (ANY) T.best.shape = -1; return true; }
-        T.ng = stack[--T.sp];
+        T.ng = dt_pop(stack, T.sp);
     }
     return false;
 }
@@ -457,7 +501,7 @@ __device__ __forceinline__ bool dt_trav_step(DtTrav& T, uint2* __restrict__ stac
 template <bool ANY>
 __device__ __forceinline__ void dt_trace(const DtSceneDev& S, v3 wo, v3 wd, float mb_time, float tmax_in, DtHit& best) {
     DtTrav T;
-    uint2 stack[DT_STACK_SIZE];
+    DT_DECLARE_STACK(stack);
     dt_trav_init<ANY>(T, S, wo, wd, mb_time, tmax_in);
     const float4 ro = make_float4(wo.x, wo.y, wo.z, mb_time), rd = make_float4(wd.x, wd.y, wd.z, tmax_in);
     while (!dt_trav_step<ANY, true>(T, stack, S, &ro, &rd)) {}

@@ -14,6 +14,6 @@ for name in ["mc_all", "mc_area", "mc_mesh", "mc_env", "mc_c5shape"]:
         for seed in (11, 12, 13):
             ldr, hdr, st = gs.render(cam, seed=seed)
             m = mc_compare(hdr, g['hi_hdr'], cam)
-            print('%-10s spp %6d seed %d | finite %.4f | mean rel %.4f | clip20 rel %.4f | psnr %.2f dB (rmse %.2f) | nan_pixels %d | %.0f ms' % (
-                name, spp, seed, m['finite'], m['mean_rel'], m['clip_rel'], m['psnr'], m['rmse'], st.nan_pixels, st.ms_total), flush=True)
+            print('%-10s spp %6d seed %d | finite %.4f | mean rel %.4f | clip20 rel %.4f | psnr %.2f dB (rmse %.2f), %.2f dB trimmed | nan_pixels %d | %.0f ms' % (
+                name, spp, seed, m['finite'], m['mean_rel'], m['clip_rel'], m['psnr'], m['rmse'], m['psnr_trim2'], st.nan_pixels, st.ms_total), flush=True)
         gs.close()

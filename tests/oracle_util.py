@@ -196,6 +196,9 @@ def mc_compare(hdr, ref_hdr, cam, clip=20.0):
     la = oracle_tonemap(sa, cam.tm_key, cam.tm_burn, cam.tm_saturation, cam.tm_gamma)
     lb = oracle_tonemap(sb, cam.tm_key, cam.tm_burn, cam.tm_saturation, cam.tm_gamma)
     mse = float(np.mean((la.astype(np.float64) - lb.astype(np.float64)) ** 2))
-    return {"finite": float(ok.mean()), "mean_rel": abs(a.mean() - b.mean()) / b.mean(),
+    # the same without the 2 % of the pixels that differ most: fireflies saturate a few random pixels of EITHER frame
+    per_pix = np.sort(((la.astype(np.float64) - lb.astype(np.float64)) ** 2).mean(axis=2).ravel())
+    mse_trim = float(per_pix[:max(1, int(per_pix.size * 0.98))].mean())
+    return {"finite": float(ok.mean()), "psnr_trim2": 99.0 if mse_trim == 0 else float(10 * np.log10(255.0 ** 2 / mse_trim)), "mean_rel": abs(a.mean() - b.mean()) / b.mean(),
             "clip_rel": abs(np.minimum(a, clip).mean() - np.minimum(b, clip).mean()) / np.minimum(b, clip).mean(),
             "psnr": psnr(la, lb), "rmse": mse ** 0.5}
