@@ -845,3 +845,50 @@ def test_monte_carlo_against_the_high_spp_reference_render(name, spp, psnr_min, 
     assert m["clip_rel"] < 0.01, (name, m)
     if mean_tol is not None:
         assert m["mean_rel"] < mean_tol, (name, m)
+
+
+# ------------------------------------------------------------------ reference behaviours no other scene renders
+@pytest.mark.parametrize("tonemap", [False, True])
+def test_reference_quirks_scene_parity(tmp_path, tonemap):
+    """`replace_background` texture, `replace_ks` through the diffuse slot, `blend_kd`, `degamma`, radiance beyond 2^31 through the
+    LDR clamp (INT_MIN -> 0), and the photographic tonemapper on a deterministic frame: primary hits bit-exact, LDR within one
+    level on >= 99.9 % of the pixels against the oracle AND, where it is present, against the compiled reference itself."""
+    from scenes_util import quirks_scene
+    p = quirks_scene(str(tmp_path / "q"), tonemap=tonemap)
+    hs = HostScene(p)
+    cam = hs.camera(0)
+    gs = GpuScene(hs)
+    _assert_hits_equal(gs.primary_hits(cam), oracle_primary_hits(hs, cam))
+    ldr, hdr, st = gs.render(cam)
+    gs.close()
+    oldr, ohdr, ost = oracle_render(hs, cam)
+    frac, mx = ldr_mismatch_fraction(ldr, oldr, 1)
+    assert frac <= 1e-3, (frac, mx)
+    assert (int(st.rays_closest), int(st.rays_shadow)) == (int(ost.rays_closest), int(ost.rays_shadow))
+    if not tonemap:
+        overflow = (ohdr >= 2147483648.0)
+        assert overflow.any() and (ldr[overflow] == 0).all() and (ldr == 255).any()
+    if have_ref():
+        ref = run_reference(p, probe=False)
+        frac, mx = ldr_mismatch_fraction(ldr, ref["png"], 1)
+        assert frac <= 1e-3, ("vs compiled reference", frac, mx)
+
+
+@pytest.mark.parametrize("blur_instance", [False, True])
+def test_env_map_on_miss_under_whitted_statistics(tmp_path, blur_instance):
+    """Whitted + spherical environment light (env lookups on the misses of mirror / dielectric children and camera rays), a
+    transformed MeshInstance -- static or motion-blurred -- and a motion-blurred mesh, 256 spp against the oracle at 256 spp with
+    independent random numbers: mean radiance within 0.5 %, PSNR >= 40 dB (two oracle seeds: 0.01 %, 48-49 dB)."""
+    from scenes_util import env_whitted_scene
+    p = env_whitted_scene(str(tmp_path / "e"), spp=256, blur_instance=blur_instance)
+    hs = HostScene(p)
+    cam = hs.camera(0)
+    gs = GpuScene(hs)
+    ldr, hdr, st = gs.render(cam, seed=8)
+    gs.close()
+    oldr, ohdr, ost = oracle_render(hs, cam, seed=2)
+    m_g, m_o = float(hdr.mean()), float(ohdr.mean())
+    assert abs(m_g - m_o) / m_o < 0.005, (m_g, m_o)
+    assert psnr(ldr, oldr) >= 40.0, psnr(ldr, oldr)
+    assert abs(int(st.rays_closest) - int(ost.rays_closest)) / int(ost.rays_closest) < 0.01
+    assert st.nan_pixels == 0
