@@ -27,7 +27,7 @@ cuda: $(PKG)/libdorktracer.so
 cli: $(PKG)/raytracer_gpu
 
 $(PKG)/libdthost.so: $(filter-out $(PKG)/host/dth_main.cpp,$(HOST_SRCS)) $(HOST_HDRS)
-	$(CXX) $(HOSTFLAGS) -shared -o $@ $(filter-out $(PKG)/host/dth_main.cpp,$(HOST_SRCS)) -lz
+	$(CXX) $(HOSTFLAGS) -shared -o $@ $(filter-out $(PKG)/host/dth_main.cpp,$(HOST_SRCS)) -lz -lpthread
 
 oracle/libdtoracle.so: oracle/dt_oracle.c include/dorktracer.h
 	$(CC) $(ORACLEFLAGS) -shared -o $@ oracle/dt_oracle.c -lm -lpthread
@@ -36,7 +36,7 @@ $(PKG)/libdorktracer.so: $(CUDA_SRCS) $(CUDA_HDRS)
 	$(NVCC) $(NVCCFLAGS) -shared -o $@ $(CUDA_SRCS) -lcudart
 
 $(PKG)/raytracer_gpu: $(PKG)/host/dth_main.cpp $(PKG)/libdthost.so $(PKG)/libdorktracer.so
-	$(CXX) $(HOSTFLAGS) -o $@ $(PKG)/host/dth_main.cpp -L$(PKG) -ldthost -ldorktracer -Wl,-rpath,'$$ORIGIN'
+	$(CXX) $(HOSTFLAGS) -o $@ $(PKG)/host/dth_main.cpp -L$(PKG) -ldthost -ldorktracer -lpthread -Wl,-rpath,'$$ORIGIN'
 
 clean:
 	rm -f $(PKG)/*.so oracle/*.so $(PKG)/raytracer_gpu

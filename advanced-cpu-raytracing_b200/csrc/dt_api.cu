@@ -80,6 +80,7 @@ struct DtPipe {
     int* counters = nullptr;      // this pipe's block of dt_scene::counters
     int* sort_perm = nullptr;     // material-sorted order of the current wave (sort stage)
     int* sort_hist = nullptr;     // DT_SORT_BINS bin counts + DT_SORT_BINS running cursors
+    DtSpatialSort ss = {};        // counter tables of the hit-cell sort (k_ssort_*)
     DtPipe() { memset(q, 0, sizeof q); memset(sq, 0, sizeof sq); }
     void free_queues() { for (void* p : allocs) cudaFree(p); allocs.clear(); capacity = shadow_capacity = 0; }
 };
@@ -129,6 +130,9 @@ struct dt_scene {
                                   // the critical path find SM slots while it runs (r1e_ab_shadow_order.log: 3.90 ms against 4.03 ms with 0)
     int shadow_order = 1;         // 1: shadow(k) released together with closest(k+1) (see the wave loop); 0: right after shade(k)
     int sort_mode = 1;            // sort-by-material stage: 0 off, 1 auto (scenes with >= 3 materials), 2 always (DT_SORT)
+    int sort_spatial = 0;         // hit-cell sort (k_ssort_*) instead of the material sort: 0 off (default: measured slower, profiles/r2_ab_spatial_sort.log),
+                                  // -1 path-traced frames only, 1..6 every frame, with at most this many cell bits per axis (DT_SORT_SPATIAL)
+    int sort_refine = 1;          // second level of the hit-cell sort (DT_SORT_REFINE)
 
     // device-resident wave loop (path tracing with Russian roulette, multi-batch frames): one CUDA graph per frame shape
     int dev_loop = 1;             // DT_DEVLOOP=0: host-synchronised loop instead (A/B)
@@ -200,6 +204,11 @@ int ensure_queues(dt_scene* s, DtPipe& pp, int capacity, int shadow_capacity, bo
     }
     if ((rc = qalloc(pp, &pp.sort_perm, capacity))) return rc;
     if ((rc = qalloc(pp, &pp.sort_hist, 2 * DT_SORT_BINS))) return rc;
+    pp.ss = DtSpatialSort();
+    if (s->sort_spatial != 0) {                      // counter tables of the opt-in hit-cell sort
+        if ((rc = qalloc(pp, &pp.ss.hist, DT_SSORT_MAX_BINS)) || (rc = qalloc(pp, &pp.ss.cursor, DT_SSORT_MAX_BINS)) || (rc = qalloc(pp, &pp.ss.blocksum, DT_SSORT_MAX_BINS / DT_SSORT_SCAN_BLOCK))) return rc;
+        CK(cudaMemset(pp.ss.hist, 0, DT_SSORT_MAX_BINS * sizeof(int)));
+    }
     pp.capacity = capacity; pp.shadow_capacity = shadow_capacity; pp.has_miss = s->has_env; pp.has_defer = need_defer;
     return DT_OK;
 }
@@ -276,7 +285,18 @@ int tonemap_device(dt_scene* s, const float* hdr, int W, int H, float key, float
 struct RenderOut { float* hdr_dev; };
 
 // Sort stage (k_sort_*): fills pp.sort_perm with the material-sorted order of wave queue `q`; returns launches.
-int launch_sort(dt_scene* s, DtPipe& pp, const DtRayQueue& q, const int* n_ptr, int n_fixed, cudaStream_t st, bool zero_hist = true) {
+int launch_sort(dt_scene* s, DtPipe& pp, const DtRayQueue& q, const int* n_ptr, int n_fixed, cudaStream_t st, bool zero_hist = true, int spatial_bits = 0) {
+    if (spatial_bits > 0) {                          // by hit cell, then material (see k_ssort_hist)
+        DtSpatialSort ss = pp.ss;
+        ss.max_axis_bits = std::min(spatial_bits, DT_SSORT_MAX_AXIS_BITS); ss.refine = s->sort_refine;
+        const int grid = s->num_sms * 8, scan_grid = DT_SSORT_MAX_BINS / DT_SSORT_SCAN_BLOCK;
+        k_ssort_hist<<<grid, 256, 0, st>>>(s->dev, q, n_ptr, n_fixed, ss);
+        k_ssort_scan_a<<<scan_grid, 256, 0, st>>>(n_ptr, n_fixed, ss);
+        k_ssort_scan_b<<<scan_grid, 256, 0, st>>>(n_ptr, n_fixed, ss);
+        k_ssort_scatter<<<grid, 256, 0, st>>>(q, n_ptr, n_fixed, ss, pp.sort_perm);
+        if (ss.refine) k_ssort_refine<<<grid, 256, 0, st>>>(q, n_ptr, n_fixed, pp.sort_perm);
+        return ss.refine ? 5 : 4;
+    }
     if (zero_hist) cudaMemsetAsync(pp.sort_hist, 0, 2 * DT_SORT_BINS * sizeof(int), st);           // bin counts + running cursors (the device loop zeroes them in k_loop_begin)
     const int grid = s->num_sms * 4;
     k_sort_hist<<<grid, 256, 0, st>>>(s->dev, q, n_ptr, n_fixed, pp.sort_hist);
@@ -341,7 +361,7 @@ int ensure_tail(dt_scene* s, int shadows_per_hit, bool need_defer) {
 // Device-resident wave loop (see k_loop_begin in dt_kernels.cuh): the whole frame is one graph launch and one host sync.
 // *overflow: a queue overflowed on the device (the frame is incomplete; the caller retries with smaller waves).
 int render_devloop(dt_scene* s, const DtCamDev& dc, const DtWaveParams& wp, long long total, int wave_max, int capacity, int shadow_capacity,
-                   int shadows_per_hit, bool defer_mode, bool do_sort, dt_stats& S, bool* overflow) {
+                   int shadows_per_hit, bool defer_mode, bool do_sort, int sort_spatial, dt_stats& S, bool* overflow) {
     DtPipe& pp = s->pipes[0];
     int rc;
     if ((rc = ensure_queues(s, pp, capacity, shadow_capacity, defer_mode))) return rc;
@@ -354,7 +374,7 @@ int render_devloop(dt_scene* s, const DtCamDev& dc, const DtWaveParams& wp, long
 
     std::string key;
     key.append((const char*)&dc, sizeof dc); key.append((const char*)&wp, sizeof wp);
-    const long long misc[12] = {total, wave_max, pp.capacity, pp.shadow_capacity, defer_mode, do_sort, tail_threshold, s->trav_mode, s->refill_threshold, s->dev.n_shapes, s->tail_grid, s->grid_shade};
+    const long long misc[12] = {total, wave_max, pp.capacity, pp.shadow_capacity, defer_mode, do_sort + 2 * sort_spatial + 64 * s->sort_refine, tail_threshold, s->trav_mode, s->refill_threshold, s->dev.n_shapes, s->tail_grid, s->grid_shade};
     key.append((const char*)misc, sizeof misc);
     const void* ptrs[6] = {s->accum, c, pp.q[0].o_time, sq.o_time, pp.sort_perm, s->tail.q[0].o_time};
     key.append((const char*)ptrs, sizeof ptrs);
@@ -384,7 +404,7 @@ int render_devloop(dt_scene* s, const DtCamDev& dc, const DtWaveParams& wp, long
                 launch_traverse<true>(s, pp.q[cur], sq, c + DT_CNT_PREV_SHADOW, 0, pp.shadow_capacity, c + DT_CNT_FETCH_B, s->accum, st);
                 launches += 2;
             }
-            if (do_sort) launches += launch_sort(s, pp, pp.q[cur], c + DT_CNT_CUR, 0, st, false);
+            if (do_sort) launches += launch_sort(s, pp, pp.q[cur], c + DT_CNT_CUR, 0, st, false, sort_spatial);
             {
                 DtShadeCounters sc = {c + DT_CNT_NEXT, c + DT_CNT_SHADOW, c + DT_CNT_OVERFLOW};
                 k_shade<<<s->grid_shade, 128, 0, st>>>(s->dev, dc, pp.q[cur], pp.miss[cur], c + DT_CNT_CUR, 0, do_sort ? pp.sort_perm : nullptr, pp.q[1 - cur], pp.miss[1 - cur], pp.capacity,
@@ -453,7 +473,10 @@ int render_core(dt_scene* s, const dt_camera_desc* cam, const dt_render_params* 
     wave_max = (wave_max + 31) & ~31;
     const int fan = s->fanout_hint + (pt ? 1 : 0);
     const int shadows_per_hit = std::max(1, s->lights_shadowed);
-    const bool do_sort = !primary_only && !(P.flags & DT_FLAG_NO_SORT) && s->sort_mode != 0 && (s->sort_mode == 2 || (P.flags & DT_FLAG_FORCE_SORT) || s->dev.n_materials >= 3);
+    const bool sort_allowed = !primary_only && !(P.flags & DT_FLAG_NO_SORT) && s->sort_mode != 0;
+    // hit-cell sort (k_ssort_*): path-traced frames by default (their waves are incoherent), any frame with DT_SORT_SPATIAL=1..6
+    const int sort_spatial = (!sort_allowed || (P.flags & DT_FLAG_SORT_MATERIAL_ONLY)) ? 0 : (s->sort_spatial < 0 ? (pt ? DT_SSORT_MAX_AXIS_BITS : 0) : std::min(s->sort_spatial, DT_SSORT_MAX_AXIS_BITS));
+    const bool do_sort = sort_allowed && (sort_spatial > 0 || s->sort_mode == 2 || (P.flags & DT_FLAG_FORCE_SORT) || s->dev.n_materials >= 3);
     const bool host_loop = s->sync_waves || (P.flags & (DT_FLAG_HOST_WAVE_LOOP | DT_FLAG_SERIAL_WAVES));
     const bool frame_graph = s->use_graph || (P.flags & DT_FLAG_FRAME_GRAPH);
     uint32_t retries = 0;
@@ -554,7 +577,7 @@ retry:
                     timed(tc, pp.A, [&] { launch_traverse<false>(s, pp.q[cur], sq, c + DT_CNT_CUR, 0, pp.capacity, c + DT_CNT_FETCH_A, s->accum, pp.A); });
                     if (s->shadow_order && k >= 1) { CK(cudaStreamWaitEvent(pp.B, pp.ev_shade[(k - 1) % 3], 0)); launch_shadow(pp, k - 1); }
                     if (k >= 3) CK(cudaStreamWaitEvent(pp.A, pp.ev_shadow[q], 0));           // shadow(k-3) must have drained this queue
-                    if (do_sort) timed(tsort, pp.A, [&] { n_launches += launch_sort(s, pp, pp.q[cur], c + DT_CNT_CUR, 0, pp.A); });
+                    if (do_sort) timed(tsort, pp.A, [&] { n_launches += launch_sort(s, pp, pp.q[cur], c + DT_CNT_CUR, 0, pp.A, true, sort_spatial); });
                     timed(th, pp.A, [&] {
                         DtShadeCounters sc = {c + DT_CNT_NEXT, c + dt_cnt_shadow(q), c + DT_CNT_OVERFLOW};
                         k_shade<<<s->grid_shade, 128, 0, pp.A>>>(s->dev, dc, pp.q[cur], pp.miss[cur], c + DT_CNT_CUR, 0, do_sort ? pp.sort_perm : nullptr, pp.q[1 - cur], pp.miss[1 - cur], pp.capacity,
@@ -578,7 +601,7 @@ retry:
         std::string key;
         if (frame_graph) {
             key.append((const char*)&dc, sizeof dc); key.append((const char*)wps, sizeof(DtWaveParams) * NP); key.append((const char*)n0, sizeof(int) * NP);
-            const int misc[7] = {NP, n_waves, do_sort ? 1 : 0, s->trav_mode, s->refill_threshold, (int)s->dev.n_shapes, s->shadow_order * 16 + s->shadow_spare};
+            const int misc[7] = {NP, n_waves, (do_sort ? 1 : 0) + 2 * sort_spatial + 64 * s->sort_refine, s->trav_mode, s->refill_threshold, (int)s->dev.n_shapes, s->shadow_order * 16 + s->shadow_spare};
             key.append((const char*)misc, sizeof misc);
             const void* ptrs[2] = {s->accum, s->counters};
             key.append((const char*)ptrs, sizeof ptrs);
@@ -653,7 +676,7 @@ retry:
         long long cap, shcap;
         queue_caps(wave_max, cap, shcap);
         bool overflow = false;
-        if ((rc = render_devloop(s, dc, wp, total, wave_max, (int)cap, (int)shcap, shadows_per_hit, defer_mode, do_sort, S, &overflow))) return rc;
+        if ((rc = render_devloop(s, dc, wp, total, wave_max, (int)cap, (int)shcap, shadows_per_hit, defer_mode, do_sort, sort_spatial, S, &overflow))) return rc;
         if (overflow) {                                   // retried in the host-synchronised loop with smaller waves
             retries++;
             wave_max = std::max(4096, (wave_max / 4 + 31) & ~31);
@@ -707,7 +730,7 @@ retry:
                 S.kernel_launches += 2;
             }
             CK(cudaMemsetAsync(c + DT_CNT_SHADOW, 0, sizeof(int), st));
-            if (do_sort) { s->t_sort.start(st); S.kernel_launches += launch_sort(s, pp, pp.q[cur], nullptr, count, st); s->t_sort.stop(st); }
+            if (do_sort) { s->t_sort.start(st); S.kernel_launches += launch_sort(s, pp, pp.q[cur], nullptr, count, st, true, sort_spatial); s->t_sort.stop(st); }
             s->t_shade.start(st);
             {
                 DtShadeCounters sc = {c + DT_CNT_NEXT, c + DT_CNT_SHADOW, c + DT_CNT_OVERFLOW};
@@ -915,6 +938,11 @@ int dt_scene_create_opts(const dt_scene_desc* desc, const dt_scene_options* opts
     memcpy(D.background_color, desc->background_color, 12);
     D.shadow_ray_epsilon = desc->shadow_ray_epsilon;
     memcpy(D.ambient_light, desc->ambient_light, 12);
+    for (int a = 0; a < 3; a++) {
+        const float ext = hs.world_max[a] - hs.world_min[a];
+        D.sort_min[a] = hs.world_min[a];
+        D.sort_scale[a] = (ext > 0.f && ext < 1e30f) ? 1.0f / ext : 0.f;
+    }
     s->n_triangles = hs.n_triangles;
     s->lights_shadowed = desc->n_point_lights + desc->n_area_lights + desc->n_directional_lights + desc->n_spot_lights + desc->n_mesh_lights;
     s->has_env = desc->n_env_lights > 0;
@@ -936,6 +964,8 @@ int dt_scene_create_opts(const dt_scene_desc* desc, const dt_scene_options* opts
     if (const char* e = getenv("DT_TRAVERSE_MODE")) s->trav_mode = std::min(3, std::max(0, atoi(e)));
     if (const char* e = getenv("DT_SYNC_WAVES")) s->sync_waves = atoi(e);
     if (const char* e = getenv("DT_SORT")) s->sort_mode = std::min(2, std::max(0, atoi(e)));
+    if (const char* e = getenv("DT_SORT_SPATIAL")) s->sort_spatial = std::min(DT_SSORT_MAX_AXIS_BITS, std::max(-1, atoi(e)));
+    if (const char* e = getenv("DT_SORT_REFINE")) s->sort_refine = atoi(e) != 0;
     if (const char* e = getenv("DT_SHADOW_ORDER")) s->shadow_order = atoi(e);
     if (const char* e = getenv("DT_SHADOW_SPARE")) s->shadow_spare = std::max(0, atoi(e));
     if (const char* e = getenv("DT_GRAPH")) s->use_graph = atoi(e);

@@ -104,6 +104,7 @@ struct DtSceneDev {
     int32_t background_color[3];
     float shadow_ray_epsilon;
     float ambient_light[3];
+    float sort_min[3], sort_scale[3];   // world bounds of the scene for the hit-cell sort: cell coordinate = (p - sort_min) * sort_scale in [0, 1)
 };
 
 // ---- wavefront queues (SoA in HBM) ----

@@ -298,6 +298,7 @@ bool dt_flatten_scene(const dt_scene_desc* d, DtHostScene& out, std::string& err
             }
             b2[(size_t)t.node] = nd;
         }
+        for (int a = 0; a < 3; a++) { out.world_min[a] = b2[0].mn[a]; out.world_max[a] = b2[0].mx[a]; }
         DtWideBvh wide;
         if (!dt_collapse_bvh8(b2, wide, err)) return false;
         out.tlas_nodes = wide.nodes;

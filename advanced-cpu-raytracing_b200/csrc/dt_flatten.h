@@ -40,6 +40,7 @@ struct DtHostScene {
     int max_stack_need = 0;
     int tlas_depth = 0, blas_depth = 0;   // BVH8 depths (blas_depth: host-flattened meshes only)
     uint64_t n_triangles = 0;
+    float world_min[3] = {0.f, 0.f, 0.f}, world_max[3] = {0.f, 0.f, 0.f};    // union of the shapes' world boxes (TLAS root)
     std::vector<int> gpu_meshes;          // meshes left to the GPU flattener (dt_flatten_gpu.cu): faces / verts / DtMeshDev are filled, the BLAS is not
 };
 

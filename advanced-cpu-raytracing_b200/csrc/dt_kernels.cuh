@@ -240,6 +240,9 @@ __device__ unsigned int g_dt_steps_hist[2][64];      // [ANY][min(63, steps / 8)
 __device__ __forceinline__ unsigned long long dt_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #endif
 
+#ifndef DT_TRI_BATCH
+#define DT_TRI_BATCH 0            // A/B knob: > 0 = lanes with pending primitives park until this many lanes hold some (dt_trav_step_nodes / _prims)
+#endif
 template <bool ANY, bool WW>
 __global__ void __launch_bounds__(128, ANY ? DT_TRAV_MINBLOCKS_ANY : DT_TRAV_MINBLOCKS) k_traverse_dyn(DtSceneDev S, DtRayQueue q, DtShadowQueue sq, const int* n_ptr, int n_fixed, int n_cap, int* fetch_counter,
                                                       float4* accum, int refill_threshold) {
@@ -282,6 +285,24 @@ __global__ void __launch_bounds__(128, ANY ? DT_TRAV_MINBLOCKS_ANY : DT_TRAV_MIN
         unsigned act = __ballot_sync(FULL, ray >= 0);
         if (act == 0u) { if (drained) break; else continue; }
         for (;;) {
+#if DT_TRI_BATCH > 0
+            {
+                const float4* ro = (ANY ? sq.o_time : q.o_time) + ray;
+                const float4* rd = (ANY ? sq.d_tmax : q.d_tmax) + ray;
+                bool fin = false;
+                if (ray >= 0 && T.tg.y == 0u) fin = dt_trav_step_nodes<ANY>(T, stack, S, ro, rd);
+                const bool has_prims = ray >= 0 && !fin && T.tg.y != 0u;
+                const unsigned pend = __ballot_sync(FULL, has_prims);
+                const unsigned adv = __ballot_sync(FULL, ray >= 0 && !fin && T.tg.y == 0u);
+                if (pend != 0u && (__popc(pend) >= DT_TRI_BATCH || adv == 0u)) {
+                    if (has_prims) fin = dt_trav_step_prims<ANY>(T, stack, S, ro, rd);
+                }
+                if (fin) {
+                    if (ANY) dt_store_shadow(sq, ray, T.best, accum); else dt_store_closest(q, ray, T.best);
+                    ray = -1;
+                }
+            }
+#else
             if (ray >= 0) {
 #ifdef DT_TIMELINE
                 tl_steps++;
@@ -294,6 +315,7 @@ __global__ void __launch_bounds__(128, ANY ? DT_TRAV_MINBLOCKS_ANY : DT_TRAV_MIN
                     ray = -1;
                 }
             }
+#endif
             act = __ballot_sync(FULL, ray >= 0);
             if (act == 0u) break;
             if (!drained && __popc(act) < refill_threshold) break;
@@ -437,16 +459,34 @@ __device__ __forceinline__ void dt_shade_ray(const int i, const DtSceneDev& S, c
     int shadow_stride = 0;
     int shadow_slot = n_shadow > 0 ? dt_agg_reserve(counters.shadow, n_shadow, shadow_stride) : 0;
 
-    // ---- ComputeGlobalIllumination (raytracer.cpp:135-191) ----
-    if (cam.path_tracing) {
-        bool go = true;
-        if (cam.russian_roulette) {
-            float probTest = rng01(rng);
-            float maxT = fmaxf(thr.x, fmaxf(thr.x, thr.z));
-            if (probTest > maxT && depth <= 0) go = false;
-            else thr = vdiv(thr, maxT);
-        } else if (depth <= 0) go = false;
-        if (go) {
+    // kd / ks of this hit (Get{Diffuse,Specular}ReflectanceCoeff, raytracer.cpp:478-539): light-independent, evaluated once
+    const v3 kd = reflectance_coeff(S, sh, mat, hitPoint, sf.u, sf.v, false);
+    const v3 ks = reflectance_coeff(S, sh, mat, hitPoint, sf.u, sf.v, true);
+
+    // ---- ComputeGlobalIllumination (raytracer.cpp:135-191), then ambient + SampleDirectLighting (:98-108, 701-806) ----
+    // ONE loop over "incoming directions": item -1 is the GI sample, items 0.. are the lights in the reference's order (point, area,
+    // environment, directional, spot, mesh), so the RNG draws and the throughput updates happen in the reference's sequence while
+    // Shade() -- the BRDF switch, by far the largest piece of code in this kernel -- exists once instead of seven times
+    // (the kernel was 38 000 SASS instructions and a fifth of its stall samples were instruction-cache misses).
+    const int e_point = S.n_point_lights, e_area = e_point + S.n_area_lights, e_env = e_area + S.n_env_lights,
+              e_dir = e_env + S.n_directional_lights, e_spot = e_dir + S.n_spot_lights, e_mesh = e_spot + S.n_mesh_lights;
+    v3 local = vmul(F3(S.ambient_light), F3(mat.ambient));
+    const v3 so = vadd(hitPoint, vscale(normal, S.shadow_ray_epsilon));
+    for (int item = cam.path_tracing ? -1 : 0; item < (direct ? e_mesh : 0); item++) {
+        v3 w_i, E;
+        float lightT = CUDART_INF_F;
+        int kind;                       // 0 GI child, 1 shadow ray, 2 added unshadowed (environment light)
+        int defer_light = -1;
+        v3 child_d = V(0.f, 0.f, 0.f);
+        if (item < 0) {
+            bool go = true;
+            if (cam.russian_roulette) {
+                float probTest = rng01(rng);
+                float maxT = fmaxf(thr.x, fmaxf(thr.x, thr.z));
+                if (probTest > maxT && depth <= 0) go = false;
+                else thr = vdiv(thr, maxT);
+            } else if (depth <= 0) go = false;
+            if (!go) continue;
             gi_slot = dt_agg_inc(counters.next);
             float rand1 = rng01(rng), rand2 = rng01(rng);
             float phi = (float)(2 * DT_PI * rand1);
@@ -455,86 +495,52 @@ __device__ __forceinline__ void dt_shade_ray(const int i, const DtSceneDev& S, c
             orthonormal_basis(normal, u, v);
             v3 nd = vadd(vadd(vscale(vscale(u, sinf(theta)), cosf(phi)), vscale(normal, cosf(theta))), vscale(vscale(v, sinf(theta)), sinf(phi)));
             nd = vunit(nd);
-            DtChild c;
-            c.o = vadd(hitPoint, vscale(normal, (float)0.0001)); c.d = nd; c.mb = mb;
-            v3 res = V(1.f, 1.f, 1.f);
-            v3 f = shade_term(S, sh, mat, hitPoint, normal, sf.u, sf.v, nd, w_o, V(1.f, 1.f, 1.f), &res);
-            c.W = vmul(W, vscale(vscale(f, 2.0f), DT_PI_F));
-            c.n_medium = n_medium; c.thr = thr; c.beer_thr = 0.f;
-            c.depth = depth - 1; c.beer_mat = 0; c.rng_key = dt_hash(rng.key, 0xA511E9B3u); c.flags = 0; c.miss = V(0, 0, 0);
-            gi_slot = dt_emit_child(out, out_miss, counters, out_capacity, pix, c, gi_slot);
-            if (mat.brdf >= 0) thr = vmul(thr, res);                              // Shade(): ray.throughput *= res
-        }
-    }
-
-    // ---- ambient + SampleDirectLighting (raytracer.cpp:98-108, 701-806) ----
-    if (direct) {
-        v3 local = vmul(F3(S.ambient_light), F3(mat.ambient));
-        const v3 so = vadd(hitPoint, vscale(normal, S.shadow_ray_epsilon));
-        for (int l = 0; l < S.n_point_lights; l++) {
-            const dt_point_light& L = S.point_lights[l];
+            child_d = nd; w_i = nd; E = V(1.f, 1.f, 1.f); kind = 0;
+        } else if (item < e_point) {
+            const dt_point_light& L = S.point_lights[item];
             v3 lp = F3(L.position);
             v3 dir = vsub(lp, hitPoint);
-            float lightT = vlen(dir);
-            v3 sdir = vdiv(dir, lightT);
-            v3 w_i = sdir;                                                        // makeUnit(lp - hitPoint) == the same three divisions
-            v3 E = vdiv(F3(L.intensity), (lightT * lightT));
-            v3 res = V(1.f, 1.f, 1.f);
-            v3 c = shade_term(S, sh, mat, hitPoint, normal, sf.u, sf.v, w_i, w_o, E, &res);
-            if (mat.brdf >= 0) thr = vmul(thr, res);
-            dt_emit_shadow(sq, counters, shadow_capacity, so, sdir, mb, lightT, vmul(W, c), pix, -1, -1, shadow_slot); shadow_slot += shadow_stride;
-        }
-        for (int l = 0; l < S.n_area_lights; l++) {
-            const dt_area_light& L = S.area_lights[l];
+            lightT = vlen(dir);
+            w_i = vdiv(dir, lightT);                                              // makeUnit(lp - hitPoint) == the same three divisions
+            E = vdiv(F3(L.intensity), (lightT * lightT));
+            kind = 1;
+        } else if (item < e_area) {
+            const dt_area_light& L = S.area_lights[item - e_point];
             float offU = -0.5f + rng01(rng), offV = -0.5f + rng01(rng);          // areaLight.h:34-40
             v3 sp = vadd(vadd(F3(L.position), vscale(F3(L.u), (L.extent * offU))), vscale(F3(L.v), (L.extent * offV)));
             v3 dir = vsub(sp, hitPoint);
-            float lightT = vlen(dir);
-            v3 w_i = vdiv(dir, lightT);
+            lightT = vlen(dir);
+            w_i = vdiv(dir, lightT);
             float dSqr = lightT * lightT;
             float lCos = vdot(F3(L.normal), vneg(w_i));
             if (lCos < 0) lCos = vdot(F3(L.normal), w_i);
             float area = L.extent * L.extent;
-            v3 E = vscale(F3(L.radiance), (area * lCos / dSqr));
-            v3 res = V(1.f, 1.f, 1.f);
-            v3 c = shade_term(S, sh, mat, hitPoint, normal, sf.u, sf.v, w_i, w_o, E, &res);
-            if (mat.brdf >= 0) thr = vmul(thr, res);
-            dt_emit_shadow(sq, counters, shadow_capacity, so, w_i, mb, lightT, vmul(W, c), pix, -1, -1, shadow_slot); shadow_slot += shadow_stride;
-        }
-        for (int l = 0; l < S.n_env_lights; l++) {                                // no shadow ray (raytracer.cpp:741-755)
+            E = vscale(F3(L.radiance), (area * lCos / dSqr));
+            kind = 1;
+        } else if (item < e_env) {                                                // no shadow ray (raytracer.cpp:741-755)
             v3 nn = vunit(normal);
             v3 cand = V(0, 0, 0);
             for (int guard = 0; guard < 4096; guard++) {                          // rejection sampling, un-normalised result
                 cand.x = -1.0f + 2.0f * rng01(rng); cand.y = -1.0f + 2.0f * rng01(rng); cand.z = -1.0f + 2.0f * rng01(rng);
                 if (vlen(cand) <= 1.0f && vdot(nn, cand) > 0.0f) break;
             }
-            v3 E = env_sample(S, l, cand);
-            v3 res = V(1.f, 1.f, 1.f);
-            v3 c = shade_term(S, sh, mat, hitPoint, normal, sf.u, sf.v, normal, w_o, E, &res);
-            if (mat.brdf >= 0) thr = vmul(thr, res);
-            local = vadd(local, c);
-        }
-        for (int l = 0; l < S.n_directional_lights; l++) {
-            const dt_directional_light& L = S.directional_lights[l];
-            v3 w_i = vneg(F3(L.dir));
-            v3 res = V(1.f, 1.f, 1.f);
-            v3 c = shade_term(S, sh, mat, hitPoint, normal, sf.u, sf.v, w_i, w_o, F3(L.radiance), &res);
-            if (mat.brdf >= 0) thr = vmul(thr, res);
-            dt_emit_shadow(sq, counters, shadow_capacity, so, w_i, mb, CUDART_INF_F, vmul(W, c), pix, -1, -1, shadow_slot); shadow_slot += shadow_stride;
-        }
-        for (int l = 0; l < S.n_spot_lights; l++) {
-            const dt_spot_light& L = S.spot_lights[l];
+            E = env_sample(S, item - e_area, cand);
+            w_i = normal;
+            kind = 2;
+        } else if (item < e_dir) {
+            const dt_directional_light& L = S.directional_lights[item - e_env];
+            w_i = vneg(F3(L.dir));
+            E = F3(L.radiance);
+            kind = 1;
+        } else if (item < e_spot) {
+            const dt_spot_light& L = S.spot_lights[item - e_dir];
             v3 dir = vsub(F3(L.pos), hitPoint);
-            float lightT = vlen(dir);
-            v3 w_i = vdiv(dir, lightT);
-            v3 E = spot_irradiance(L, hitPoint);
-            v3 res = V(1.f, 1.f, 1.f);
-            v3 c = shade_term(S, sh, mat, hitPoint, normal, sf.u, sf.v, w_i, w_o, E, &res);
-            if (mat.brdf >= 0) thr = vmul(thr, res);
-            dt_emit_shadow(sq, counters, shadow_capacity, so, w_i, mb, lightT, vmul(W, c), pix, -1, -1, shadow_slot); shadow_slot += shadow_stride;
-        }
-        for (int l = 0; l < S.n_mesh_lights; l++) {
-            const dt_mesh_light& L = S.mesh_lights[l];
+            lightT = vlen(dir);
+            w_i = vdiv(dir, lightT);
+            E = spot_irradiance(L, hitPoint);
+            kind = 1;
+        } else {
+            const dt_mesh_light& L = S.mesh_lights[item - e_spot];
             const DtShapeDev& lsh = S.shapes[L.shape];
             const DtMeshDev& lm = S.meshes[lsh.mesh];
             int fi = (int)(rng01(rng) * lm.n_faces);                              // meshLight.h:27-47 (+P2)
@@ -548,18 +554,31 @@ __device__ __forceinline__ void dt_shade_ray(const int i, const DtSceneDev& S, c
             v3 pos = vadd(vscale(a, (1 - sr)), vscale(qq, sr));
             pos = apply_transform(lsh.fwd, pos, 1.0f);
             v3 dir = vsub(pos, hitPoint);
-            float lightT = vlen(dir);
-            v3 w_i = vdiv(dir, lightT);
-            v3 rad = vscale(vscale(vscale(F3(L.radiance), fc.light_weight), 2.f), DT_PI_F);
-            v3 res = V(1.f, 1.f, 1.f);
-            v3 c = shade_term(S, sh, mat, hitPoint, normal, sf.u, sf.v, w_i, w_o, rad, &res);
-            if (mat.brdf >= 0) thr = vmul(thr, res);
+            lightT = vlen(dir);
+            w_i = vdiv(dir, lightT);
+            E = vscale(vscale(vscale(F3(L.radiance), fc.light_weight), 2.f), DT_PI_F);
             // hitMeshLightId (raytracer.cpp:91-95,107,781): this light is skipped when the GI child of this very
             // hit lands on the emissive shape with the same id -> decided one wave later (deferred entry).
-            dt_emit_shadow(sq, counters, shadow_capacity, so, w_i, mb, lightT, vmul(W, c), pix, gi_slot, L.id, shadow_slot); shadow_slot += shadow_stride;
+            defer_light = L.id;
+            kind = 1;
         }
-        dt_accum(accum, pix, vmul(W, local));
+        v3 res = V(1.f, 1.f, 1.f);
+        const v3 c = shade_term(mat, S, kd, ks, normal, w_i, w_o, E, &res);
+        if (kind == 0) {
+            DtChild ch;
+            ch.o = vadd(hitPoint, vscale(normal, (float)0.0001)); ch.d = child_d; ch.mb = mb;
+            ch.W = vmul(W, vscale(vscale(c, 2.0f), DT_PI_F));
+            ch.n_medium = n_medium; ch.thr = thr; ch.beer_thr = 0.f;
+            ch.depth = depth - 1; ch.beer_mat = 0; ch.rng_key = dt_hash(rng.key, 0xA511E9B3u); ch.flags = 0; ch.miss = V(0, 0, 0);
+            gi_slot = dt_emit_child(out, out_miss, counters, out_capacity, pix, ch, gi_slot);
+        }
+        if (mat.brdf >= 0) thr = vmul(thr, res);                                  // Shade(): ray.throughput *= res
+        if (kind == 1) {
+            dt_emit_shadow(sq, counters, shadow_capacity, so, w_i, mb, lightT, vmul(W, c), pix, defer_light >= 0 ? gi_slot : -1, defer_light, shadow_slot);
+            shadow_slot += shadow_stride;
+        } else if (kind == 2) local = vadd(local, c);
     }
+    if (direct) dt_accum(accum, pix, vmul(W, local));
 
     if (depth <= 0) return;        // all three recursive helpers start with `if(recDepth <= 0) return 0`
 
@@ -681,7 +700,9 @@ __global__ void __launch_bounds__(256) k_sort_hist(DtSceneDev S, DtRayQueue q, c
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int k = dt_sort_key(S, q, i);
         q.sort_key[i] = (uint32_t)k;
-        atomicAdd(&h[k], 1);
+        // a wave holds a handful of distinct keys: the lanes that share one send ONE shared-memory atomic, not up to 32 serialised ones
+        const unsigned peers = __match_any_sync(__activemask(), k);
+        if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&h[k], __popc(peers));
     }
     __syncthreads();
     if (h[threadIdx.x]) atomicAdd(&hist[threadIdx.x], h[threadIdx.x]);
@@ -715,13 +736,170 @@ __global__ void __launch_bounds__(256) k_sort_scatter(DtRayQueue q, const int* n
         for (int k = 0; k < 8; k++) {
             const int i = c0 + k * 256 + threadIdx.x;
             key[k] = i < n ? (int)q.sort_key[i] : -1;
-            rank[k] = key[k] >= 0 ? atomicAdd(&cnt[key[k]], 1) : 0;
+            // one atomic per distinct key of the warp (see k_sort_hist); the lanes that share a key rank themselves by lane index
+            const unsigned peers = __match_any_sync(0xFFFFFFFFu, key[k]);
+            const int leader = __ffs(peers) - 1;
+            int base_rank = 0;
+            if ((int)(threadIdx.x & 31) == leader && key[k] >= 0) base_rank = atomicAdd(&cnt[key[k]], __popc(peers));
+            base_rank = __shfl_sync(0xFFFFFFFFu, base_rank, leader);
+            rank[k] = base_rank + __popc(peers & ((1u << (threadIdx.x & 31)) - 1u));
         }
         __syncthreads();
         if (cnt[threadIdx.x]) base[threadIdx.x] = offs[threadIdx.x] + atomicAdd(&cursors[threadIdx.x], cnt[threadIdx.x]);
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < 8; k++) if (key[k] >= 0) perm[base[key[k]] + rank[k]] = c0 + k * 256 + threadIdx.x;
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------ sort by hit cell (+ material)
+// Path-traced waves are incoherent: after one diffuse bounce the queue order is unrelated to where the rays are, the lanes of a
+// traversal warp walk unrelated subtrees (11-14 live threads per issued instruction on config 5) and every node is a fresh L2 /
+// HBM sector.  The children and the shadow rays of a hit START at the hit point, and k_shade emits them in the order it
+// processes the hits, so ordering the HITS in space before shading hands the next closest-hit pass and this wave's shadow pass
+// warps of rays with neighbouring origins (shadow rays: neighbouring origins AND the same light), and groups the shading warps'
+// surface / material reads as a side effect.  Key, most significant first:
+//     Morton code of the hit cell (b bits per axis, b grows with the wave: 1..DT_SSORT_MAX_AXIS_BITS) | material class (4 bits)
+//     | 9 more Morton bits (3 per axis)
+// The upper part (<= 22 bits) is counting-sorted through global atomics (histogram, scan, scatter: the order inside a bin is
+// arbitrary); k_ssort_refine then sorts chunks of 2048 consecutive entries by the full key in shared memory, which orders the
+// ~100-300 hits of a coarse cell by the finer cell.  Misses and dead slots (class 0) are spread over the bins of their class
+// so that they do not serialise on one counter.
+#define DT_SSORT_CLASS_BITS 4
+#define DT_SSORT_MAX_AXIS_BITS 6                  // 16 classes << 18 = 4 Mi bins: a 16 MiB counter table, L2-resident
+#define DT_SSORT_LO_BITS 9
+#define DT_SSORT_SCAN_BLOCK 4096                  // bins per block of the scan kernels
+#define DT_SSORT_MAX_BINS (1 << (DT_SSORT_CLASS_BITS + 3 * DT_SSORT_MAX_AXIS_BITS))
+#define DT_SSORT_CHUNK 2048
+struct DtSpatialSort {
+    int* hist;                    // DT_SSORT_MAX_BINS counters, all zero between waves (k_ssort_scan_b re-zeroes what a wave touched)
+    int* cursor;                  // DT_SSORT_MAX_BINS running offsets
+    int* blocksum;                // DT_SSORT_MAX_BINS / DT_SSORT_SCAN_BLOCK partial sums
+    int max_axis_bits;            // <= DT_SSORT_MAX_AXIS_BITS (A/B knob)
+    int refine;                   // run k_ssort_refine
+};
+// bits per axis of the coarse cell for a wave of n rays: ~1000 rays per 4^b, so that occupied cells (surfaces are 2-D) hold tens of rays
+__device__ __forceinline__ int dt_ssort_axis_bits(int n, int max_bits) {
+    int b = 1;
+    while (b < max_bits && (1024 << (2 * (b + 1))) <= n) b++;
+    return b;
+}
+__device__ __forceinline__ uint32_t dt_part1by2(uint32_t x) {      // spread the low 10 bits: bit k -> bit 3k
+    x &= 0x3FFu;
+    x = (x | (x << 16)) & 0x030000FFu;
+    x = (x | (x << 8)) & 0x0300F00Fu;
+    x = (x | (x << 4)) & 0x030C30C3u;
+    x = (x | (x << 2)) & 0x09249249u;
+    return x;
+}
+__device__ __forceinline__ uint32_t dt_ssort_key(const DtSceneDev& S, const DtRayQueue& q, int i, int b) {
+    int shape = -1;
+    float4 h0 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q.pixel[i] != DT_DEAD_PIXEL) { h0 = q.hit0[i]; shape = __float_as_int(h0.w); }
+    if (shape < 0) return (((uint32_t)i * 2654435761u) >> (32 - 3 * b)) << (DT_SSORT_CLASS_BITS + DT_SSORT_LO_BITS);          // class 0, any cell
+    const int m = S.shapes[shape].material;
+    const uint32_t cls = 1u + (uint32_t)(m < 1 ? 0 : (m - 1) % ((1 << DT_SSORT_CLASS_BITS) - 1));
+    const float4 o = q.o_time[i], d = q.d_tmax[i];
+    const int top = (1 << (b + 3)) - 1;
+    const float fs = (float)(top + 1);
+    const int qx = min(top, max(0, (int)((o.x + d.x * h0.x - S.sort_min[0]) * S.sort_scale[0] * fs)));
+    const int qy = min(top, max(0, (int)((o.y + d.y * h0.x - S.sort_min[1]) * S.sort_scale[1] * fs)));
+    const int qz = min(top, max(0, (int)((o.z + d.z * h0.x - S.sort_min[2]) * S.sort_scale[2] * fs)));
+    const uint32_t hi = dt_part1by2((uint32_t)qx >> 3) | (dt_part1by2((uint32_t)qy >> 3) << 1) | (dt_part1by2((uint32_t)qz >> 3) << 2);
+    const uint32_t lo = dt_part1by2((uint32_t)qx & 7u) | (dt_part1by2((uint32_t)qy & 7u) << 1) | (dt_part1by2((uint32_t)qz & 7u) << 2);
+    return (((hi << DT_SSORT_CLASS_BITS) | cls) << DT_SSORT_LO_BITS) | lo;
+}
+__global__ void __launch_bounds__(256) k_ssort_hist(DtSceneDev S, DtRayQueue q, const int* n_ptr, int n_fixed, DtSpatialSort ss) {
+    const int n = n_ptr ? *n_ptr : n_fixed;
+    const int b = dt_ssort_axis_bits(n, ss.max_axis_bits);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t k = dt_ssort_key(S, q, i, b);
+        q.sort_key[i] = k;
+        atomicAdd(&ss.hist[k >> DT_SSORT_LO_BITS], 1);
+    }
+}
+// exclusive scan of the bin counts, two launches: per-block sums, then every block adds up the sums of the blocks before it
+__global__ void __launch_bounds__(256) k_ssort_scan_a(const int* n_ptr, int n_fixed, DtSpatialSort ss) {
+    const int n = n_ptr ? *n_ptr : n_fixed;
+    const int bins = 1 << (DT_SSORT_CLASS_BITS + 3 * dt_ssort_axis_bits(n, ss.max_axis_bits));
+    const int base = blockIdx.x * DT_SSORT_SCAN_BLOCK;
+    if (base >= bins) return;
+    __shared__ int wsum[8];
+    int v = 0;
+    const int4* h4 = reinterpret_cast<const int4*>(ss.hist + base);
+    if (base + DT_SSORT_SCAN_BLOCK <= bins) {
+        for (int k = threadIdx.x; k < DT_SSORT_SCAN_BLOCK / 4; k += 256) { const int4 x = h4[k]; v += x.x + x.y + x.z + x.w; }
+    } else {
+        for (int k = threadIdx.x; base + k < bins; k += 256) v += ss.hist[base + k];
+    }
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < 8; w++) t += wsum[w]; ss.blocksum[blockIdx.x] = t; }
+}
+__global__ void __launch_bounds__(256) k_ssort_scan_b(const int* n_ptr, int n_fixed, DtSpatialSort ss) {
+    const int n = n_ptr ? *n_ptr : n_fixed;
+    const int bins = 1 << (DT_SSORT_CLASS_BITS + 3 * dt_ssort_axis_bits(n, ss.max_axis_bits));
+    const int base = blockIdx.x * DT_SSORT_SCAN_BLOCK;
+    if (base >= bins) return;
+    __shared__ int wsum[8];
+    __shared__ int s_prefix;
+    int v = 0;
+    for (int k = threadIdx.x; k < (int)blockIdx.x; k += 256) v += ss.blocksum[k];
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < 8; w++) t += wsum[w]; s_prefix = t; }
+    __syncthreads();
+    // thread t owns 16 consecutive bins
+    const int per = DT_SSORT_SCAN_BLOCK / 256;
+    int x[per], sum = 0;
+    const int first = base + threadIdx.x * per;
+#pragma unroll
+    for (int k = 0; k < per; k++) { x[k] = first + k < bins ? ss.hist[first + k] : 0; sum += x[k]; }
+    int incl = sum;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += y; }
+    __syncthreads();
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    int woff = 0;
+    for (int w = 0; w < warp; w++) woff += wsum[w];
+    int run = s_prefix + woff + incl - sum;
+#pragma unroll
+    for (int k = 0; k < per; k++) if (first + k < bins) { ss.cursor[first + k] = run; run += x[k]; ss.hist[first + k] = 0; }
+}
+__global__ void __launch_bounds__(256) k_ssort_scatter(DtRayQueue q, const int* n_ptr, int n_fixed, DtSpatialSort ss, int* perm) {
+    const int n = n_ptr ? *n_ptr : n_fixed;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        perm[atomicAdd(&ss.cursor[q.sort_key[i] >> DT_SSORT_LO_BITS], 1)] = i;
+}
+// chunks of DT_SSORT_CHUNK consecutive entries of the coarse order, bitonic-sorted by the full key in shared memory
+__global__ void __launch_bounds__(256) k_ssort_refine(DtRayQueue q, const int* n_ptr, int n_fixed, int* perm) {
+    const int n = n_ptr ? *n_ptr : n_fixed;
+    __shared__ unsigned long long e[DT_SSORT_CHUNK];
+    for (int c0 = blockIdx.x * DT_SSORT_CHUNK; c0 < n; c0 += gridDim.x * DT_SSORT_CHUNK) {
+        for (int k = threadIdx.x; k < DT_SSORT_CHUNK; k += 256) {
+            const int j = c0 + k;
+            unsigned long long v = ~0ull;
+            if (j < n) { const int i = perm[j]; v = ((unsigned long long)q.sort_key[i] << 32) | (unsigned int)i; }
+            e[k] = v;
+        }
+        __syncthreads();
+        for (int size = 2; size <= DT_SSORT_CHUNK; size <<= 1) {
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                for (int t = threadIdx.x; t < DT_SSORT_CHUNK / 2; t += 256) {
+                    const int lo = 2 * t - (t & (stride - 1));
+                    const int hi = lo + stride;
+                    const bool up = (lo & size) == 0;
+                    const unsigned long long a = e[lo], b = e[hi];
+                    if ((a > b) == up) { e[lo] = b; e[hi] = a; }
+                }
+                __syncthreads();
+            }
+        }
+        for (int k = threadIdx.x; k < DT_SSORT_CHUNK; k += 256) { const int j = c0 + k; if (j < n) perm[j] = (int)(unsigned int)e[k]; }
         __syncthreads();
     }
 }

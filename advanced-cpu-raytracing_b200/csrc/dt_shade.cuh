@@ -374,11 +374,8 @@ __device__ inline v3 reflectance_coeff(const DtSceneDev& S, const DtShapeDev& sh
 //   BRDF material:  res * Li * cos_i          -> returns res (cos applied by caller as in the reference order)
 //   otherwise:      kd*Li*cos + ks*Li*pow(..)
 // Li is passed in so the float evaluation order is the reference's.
-struct DtShadeCtx { v3 kd, ks; bool kd_ks_ready; };
-__device__ inline v3 shade_term(const DtSceneDev& S, const DtShapeDev& sh, const dt_material& mat, v3 hitPoint, v3 normal, float u, float v,
-                                v3 w_i, v3 w_o, v3 Li, v3* brdf_res) {
-    v3 kd = reflectance_coeff(S, sh, mat, hitPoint, u, v, false);
-    v3 ks = reflectance_coeff(S, sh, mat, hitPoint, u, v, true);
+// kd / ks depend on the hit only (material + diffuse texture): evaluated once per hit, not once per light.
+__device__ __forceinline__ v3 shade_term(const dt_material& mat, const DtSceneDev& S, v3 kd, v3 ks, v3 normal, v3 w_i, v3 w_o, v3 Li, v3* brdf_res) {
     if (mat.brdf >= 0) {
         float costheta_i = fmaxf(0.0f, vdot(w_i, normal));
         v3 res = brdf_apply(S, mat, kd, ks, w_i, w_o, normal);

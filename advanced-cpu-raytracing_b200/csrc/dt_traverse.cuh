@@ -496,6 +496,40 @@ __device__ __forceinline__ bool dt_trav_step(DtTrav& T, const DtStack& stack, co
     return false;
 }
 
+// The same step in two halves for the batched-triangle variant of k_traverse_dyn (-DDT_TRI_BATCH=n, A/B): lanes whose node visit
+// produced primitives PARK (dt_trav_step_nodes leaves them alone) until at least n lanes of the warp hold primitives or no lane can
+// advance without testing one; dt_trav_step_prims then drains the parked groups with that many lanes live instead of the 2-4 the
+// per-lane order yields.  Each lane still performs exactly the node visits and primitive tests of dt_trav_step, in the same order.
+template <bool ANY>
+__device__ __forceinline__ bool dt_trav_step_tail(DtTrav& T, const DtStack& stack, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d) {
+    if (T.ng.y <= 0x00FFFFFFu && T.tg.y == 0u) {
+        if (T.cur_shape >= 0 && T.sp == T.blas_sp) {
+            T.cur_shape = -1;
+            const float4 wo = *ray_o, wd = *ray_d;
+            dt_prep(T.r, V(wo.x, wo.y, wo.z), V(wd.x, wd.y, wd.z));
+        }
+        if (T.sp == 0) { if (ANY) T.best.shape = -1; return true; }
+        T.ng = dt_pop(stack, T.sp);
+    }
+    return false;
+}
+template <bool ANY, bool ORDERED = (DT_ANYHIT_ORDERED != 0) || !ANY>
+__device__ __forceinline__ bool dt_trav_step_nodes(DtTrav& T, const DtStack& stack, const DtSceneDev& S, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d) {
+    DT_STAT(5);
+    if (T.ng.y > 0x00FFFFFFu) dt_trav_node<ANY, ORDERED>(T, stack, S);
+    else { T.tg = T.ng; T.ng = make_uint2(0u, 0u); }
+    return dt_trav_step_tail<ANY>(T, stack, ray_o, ray_d);
+}
+template <bool ANY>
+__device__ __forceinline__ bool dt_trav_step_prims(DtTrav& T, const DtStack& stack, const DtSceneDev& S, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d) {
+    while (T.tg.y != 0u) {
+        bool entered = false;
+        if (dt_trav_prim<ANY>(T, stack, S, ray_o, ray_d, entered)) return true;
+        if (entered) break;
+    }
+    return dt_trav_step_tail<ANY>(T, stack, ray_o, ray_d);
+}
+
 // ANY = true: occlusion query (CastShadowRay): finishes as soon as any hit with 0 < t < tmax_in exists,
 // skipping Emissive mesh shapes; best.shape >= 0 marks "occluded".
 template <bool ANY>

@@ -31,6 +31,7 @@ DT_FLAG_FORCE_SORT = 128
 DT_FLAG_HOST_WAVE_LOOP = 256
 DT_FLAG_FRAME_GRAPH = 512
 DT_FLAG_PEER_HDR = 1024
+DT_FLAG_SORT_MATERIAL_ONLY = 2048
 
 
 class dt_scene_options(C.Structure):
@@ -173,6 +174,8 @@ DTHOST_SYMBOLS = [
     "dth_scene_camera_image_name", "dth_scene_set_image", "dth_scene_image_path", "dth_scene_image_loaded",
     "dth_camera_look_at", "dth_camera_default", "dth_write_png", "dth_last_error",
     "dth_set_bvh_builder", "dth_last_bvh_build_seconds",
+    "dth_write_png_parallel", "dth_write_hdr",
+    "dth_writer_create", "dth_writer_submit_png", "dth_writer_submit_hdr", "dth_writer_wait", "dth_writer_destroy",
 ]
 
 _libs = {}
@@ -221,6 +224,20 @@ def load_dthost():
     lib.dth_set_bvh_builder.restype = None
     lib.dth_last_bvh_build_seconds.argtypes = []
     lib.dth_last_bvh_build_seconds.restype = C.c_double
+    lib.dth_write_png_parallel.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
+    lib.dth_write_png_parallel.restype = C.c_int
+    lib.dth_write_hdr.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_void_p]
+    lib.dth_write_hdr.restype = C.c_int
+    lib.dth_writer_create.argtypes = [C.c_int, C.c_int]
+    lib.dth_writer_create.restype = vp
+    lib.dth_writer_submit_png.argtypes = [vp, C.c_char_p, C.c_int, C.c_int, C.c_void_p]
+    lib.dth_writer_submit_png.restype = C.c_int
+    lib.dth_writer_submit_hdr.argtypes = [vp, C.c_char_p, C.c_int, C.c_int, C.c_void_p]
+    lib.dth_writer_submit_hdr.restype = C.c_int
+    lib.dth_writer_wait.argtypes = [vp, C.POINTER(C.c_double)]
+    lib.dth_writer_wait.restype = C.c_int
+    lib.dth_writer_destroy.argtypes = [vp]
+    lib.dth_writer_destroy.restype = None
     return lib
 
 

@@ -24,5 +24,10 @@ struct ImageData {
 bool png_load(const std::string& path, ImageData& out, std::string& err);
 bool exr_load(const std::string& path, ImageData& out, std::string& err);   // scanline, NONE/ZIP/ZIPS, half/float
 bool png_write(const std::string& path, int w, int h, const uint8_t* rgb, std::string& err);
+// dth_output.cpp: band-parallel PNG encoder (same pixels as png_write) and the flat-RGBE .hdr writer
+bool png_write_parallel(const std::string& path, int w, int h, const uint8_t* rgb, int n_threads, std::string& err);
+bool hdr_write(const std::string& path, int w, int h, const float* rgb, std::string& err);
 
 }  // namespace dth
+
+extern "C" void dth_internal_set_error(const char* msg);   // sets dth_last_error() of the calling thread

@@ -11,25 +11,6 @@
 
 #include "../../include/dorktracer_host.h"
 
-static void write_rgbe(const char* path, int w, int h, const float* rgb) {     // main.cpp:191 (stbi_write_hdr): flat RGBE
-    FILE* f = fopen(path, "wb");
-    if (!f) return;
-    fprintf(f, "#?RADIANCE\nFORMAT=32-bit_rle_rgbe\n\n-Y %d +X %d\n", h, w);
-    std::vector<unsigned char> row((size_t)w * 4);
-    for (int y = 0; y < h; y++) {
-        for (int x = 0; x < w; x++) {
-            const float* p = rgb + ((size_t)y * w + x) * 3;
-            float m = p[0] > p[1] ? p[0] : p[1]; if (p[2] > m) m = p[2];
-            unsigned char* o = &row[(size_t)x * 4];
-            if (!(m > 1e-32f)) { o[0] = o[1] = o[2] = o[3] = 0; continue; }
-            int e; float n = frexpf(m, &e) * 256.0f / m;
-            o[0] = (unsigned char)(p[0] * n); o[1] = (unsigned char)(p[1] * n); o[2] = (unsigned char)(p[2] * n); o[3] = (unsigned char)(e + 128);
-        }
-        fwrite(row.data(), 1, row.size(), f);
-    }
-    fclose(f);
-}
-
 int main(int argc, char* argv[]) {
     if (argc < 2) { fprintf(stderr, "usage: %s scene.xml [--device N] [--seed S]\n", argv[0]); return 2; }
     int device = 0; unsigned long long seed = 1234;
@@ -45,6 +26,9 @@ int main(int argc, char* argv[]) {
         if (!dth_scene_image_loaded(hs, i)) { fprintf(stderr, "image '%s' could not be decoded (PNG/EXR only in the stand-alone driver)\n", dth_scene_image_path(hs, i)); return 1; }
     dt_scene* gs = nullptr;
     if (dt_scene_create(dth_scene_desc(hs), &gs) != DT_OK) { fprintf(stderr, "%s\n", dt_last_error()); return 1; }
+    // main.cpp:186-195 encodes HDR + PNG on the main thread after every camera; here the files are encoded by a writer queue
+    // (host/dth_output.cpp) while the next camera renders, and joined once at the end (still inside "Rendering took").
+    dth_writer* writer = dth_writer_create(2, 0);
     auto start = std::chrono::steady_clock::now();
     for (int c = 0; c < dth_scene_num_cameras(hs); c++) {
         const dt_camera_desc* cam = dth_scene_camera(hs, c);
@@ -56,16 +40,20 @@ int main(int argc, char* argv[]) {
         printf("Resolution: %dx%d, Running on: GPU %d\n", cam->width, cam->height, device);
         if (dt_render(gs, cam, &p, ldr.data(), hdr.empty() ? nullptr : hdr.data(), &st) != DT_OK) { fprintf(stderr, "%s\n", dt_last_error()); return 1; }
         std::string name = dth_scene_camera_image_name(hs, c);
-        if (cam->has_tonemapper) write_rgbe(name.c_str(), cam->width, cam->height, hdr.data());
+        if (cam->has_tonemapper) dth_writer_submit_hdr(writer, name.c_str(), cam->width, cam->height, hdr.data());
         size_t dot = name.find_last_of('.');
         std::string png = name.substr(0, dot) + ".png";
-        if (dth_write_png(png.c_str(), cam->width, cam->height, ldr.data()) != DT_OK) { fprintf(stderr, "%s\n", dth_last_error()); return 1; }
+        if (dth_writer_submit_png(writer, png.c_str(), cam->width, cam->height, ldr.data()) != DT_OK) { fprintf(stderr, "cannot queue %s\n", png.c_str()); return 1; }
         printf("%s: %llu closest + %llu shadow rays, %.3f ms on device (%.1f Mrays/s), %u waves\n", png.c_str(),
                (unsigned long long)st.rays_closest, (unsigned long long)st.rays_shadow, st.ms_total,
                (st.rays_closest + st.rays_shadow) / (st.ms_total * 1e3), st.waves);
     }
+    double encode_s = 0.0;
+    if (dth_writer_wait(writer, &encode_s) != DT_OK) { fprintf(stderr, "%s\n", dth_last_error()); return 1; }
     auto end = std::chrono::steady_clock::now();
+    printf("Image encoding: %gs on the writer threads (overlapped with rendering)\n", encode_s);
     printf("Rendering took: %gs\n", std::chrono::duration<double>(end - start).count());
+    dth_writer_destroy(writer);
     dt_scene_destroy(gs);
     dth_scene_free(hs);
     return 0;

@@ -909,5 +909,6 @@ int dth_write_png(const char* path, int w, int h, const uint8_t* rgb) {
 }
 
 const char* dth_last_error(void) { return g_err.c_str(); }
+void dth_internal_set_error(const char* msg) { g_err = msg ? msg : ""; }
 
 }  // extern "C"

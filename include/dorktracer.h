@@ -248,7 +248,8 @@ enum {
     DT_FLAG_FORCE_SORT = 128,       /* sort by material even in scenes with fewer than three materials                             */
     DT_FLAG_HOST_WAVE_LOOP = 256,   /* one host round trip per wave instead of the device-resident wave loop (A/B, debugging)       */
     DT_FLAG_FRAME_GRAPH = 512,      /* bounded-depth frames: replay the enqueued frame as a CUDA graph instead of ~50 launches      */
-    DT_FLAG_PEER_HDR = 1024         /* with DT_FLAG_PEER_FRAME: gather the radiance frame too when the camera has no tonemapper      */
+    DT_FLAG_PEER_HDR = 1024,        /* with DT_FLAG_PEER_FRAME: gather the radiance frame too when the camera has no tonemapper      */
+    DT_FLAG_SORT_MATERIAL_ONLY = 2048 /* ignore DT_SORT_SPATIAL (the opt-in hit-cell sort, an A/B knob): sort the hits by material only */
 };
 
 typedef struct dt_stats {

@@ -56,6 +56,23 @@ int dth_camera_default(const float pos[3], const float gaze_dir[3], const float 
 /* Minimal image writers for the stand-alone driver (main.cpp:191-195 uses stb_image_write). */
 int dth_write_png(const char* path, int width, int height, const uint8_t* rgb);
 
+/* Band-parallel PNG encoder (rows deflated on n_threads threads into one zlib stream; 0 = all cores, at most 16) and the flat
+ * RGBE .hdr writer (what stbi_write_hdr emits for main.cpp:191). */
+int dth_write_png_parallel(const char* path, int width, int height, const uint8_t* rgb, int n_threads);
+int dth_write_hdr(const char* path, int width, int height, const float* rgb);
+
+/* Asynchronous output: the reference encodes PNG / HDR on the main thread after every camera, inside its timed
+ * region (main.cpp:186-195).  A dth_writer owns `n_files_in_parallel` worker threads (1..8); submit copies the pixels and returns
+ * at once, so the caller renders the next camera while the previous image is encoded (each PNG on `encode_threads` threads,
+ * 0 = all cores, at most 16).  dth_writer_wait blocks until every submitted file is on disk, returns the first error (text in
+ * dth_last_error) and optionally the seconds the workers spent encoding.  dth_writer_destroy waits, then joins the workers. */
+typedef struct dth_writer dth_writer;
+dth_writer* dth_writer_create(int n_files_in_parallel, int encode_threads);
+int dth_writer_submit_png(dth_writer* writer, const char* path, int width, int height, const uint8_t* rgb);
+int dth_writer_submit_hdr(dth_writer* writer, const char* path, int width, int height, const float* rgb);
+int dth_writer_wait(dth_writer* writer, double* busy_seconds);
+void dth_writer_destroy(dth_writer* writer);
+
 const char* dth_last_error(void);
 
 #ifdef __cplusplus

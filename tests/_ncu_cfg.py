@@ -2,6 +2,10 @@
 import sys, os
 R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, R + '/tests'); sys.path.insert(0, R + '/advanced-cpu-raytracing_b200')
+import ctypes as C
+from dtb200 import capi
+if os.environ.get('DT_AB_LIB'):
+    capi._libs[os.path.join(capi.PKG_DIR, 'libdorktracer.so')] = C.CDLL(os.path.join(capi.PKG_DIR, 'libdorktracer_%s.so' % os.environ['DT_AB_LIB']), mode=C.RTLD_GLOBAL)
 from dtb200.scene import GpuScene, HostScene
 from dtb200 import scenegen
 cfg = sys.argv[1]
