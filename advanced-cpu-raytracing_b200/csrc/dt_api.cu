@@ -832,7 +832,13 @@ int dt_gpu_init(int device) {
 
 int dt_scene_create(const dt_scene_desc* desc, dt_scene** out) { return dt_scene_create_opts(desc, nullptr, out); }
 
+static int scene_create_impl(const dt_scene_desc* desc, const dt_scene_options* opts, dt_scene** out);
 int dt_scene_create_opts(const dt_scene_desc* desc, const dt_scene_options* opts, dt_scene** out) {
+    const int rc = scene_create_impl(desc, opts, out);
+    dt_resident_trees_clear();           // device copies of dt_bvh2_build trees this scene did not consume (dt_build.cu)
+    return rc;
+}
+static int scene_create_impl(const dt_scene_desc* desc, const dt_scene_options* opts, dt_scene** out) {
     if (!desc || !out) { g_err = "null argument"; return DT_ERR_INVALID; }
     *out = nullptr;
     DtHostScene hs;

@@ -29,6 +29,7 @@
 
 void dt_internal_set_error(const std::string& msg);      // dt_api.cu
 int dt_internal_ensure_device();
+void dt_resident_tree_put(const dt_bvh2_node* host, uint32_t n, dt_bvh2_node* dev);
 
 namespace {
 
@@ -195,6 +196,16 @@ __global__ void k_iota(uint32_t* id, int32_t* seg, const float* xyz, float* cx, 
     if (p < n) { id[p] = p; seg[p] = 0; cx[p] = xyz[3 * (size_t)p]; cy[p] = xyz[3 * (size_t)p + 1]; cz[p] = xyz[3 * (size_t)p + 2]; }
 }
 
+// inputs must be finite (a NaN centre would fall on neither side of a split): checked on the device, after the upload
+__global__ void k_check_finite(const float* boxes, size_t n_boxes, const float* centers, size_t n_centers, int* bad) {
+    bool ok = true;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n_boxes + n_centers; i += (size_t)gridDim.x * blockDim.x) {
+        const float v = i < n_boxes ? boxes[i] : centers[i - n_boxes];
+        ok &= fabsf(v) <= 3.0e38f;
+    }
+    if (!ok) atomicOr(bad, 1);
+}
+
 struct DevBuf {
     std::vector<void*> ptrs;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -204,14 +215,57 @@ struct DevBuf {
 
 }  // namespace
 
+// ---- resident trees: the most recent dt_bvh2_build results stay on the device until dt_scene_create consumes them ----
+// Keyed by the HOST array the caller received (pointer + node count) and guarded by a fingerprint of three nodes, so a caller that
+// edits or frees-and-reuses the array simply gets the ordinary upload.  At most DT_RESIDENT_MAX trees; the oldest is dropped.
+#include <mutex>
+namespace {
+struct ResidentTree { const dt_bvh2_node* host; uint32_t n; dt_bvh2_node* dev; int device; dt_bvh2_node probe[3]; };
+std::mutex g_res_mu;
+std::vector<ResidentTree> g_res;
+const size_t DT_RESIDENT_MAX = 4;
+void res_probe(const dt_bvh2_node* h, uint32_t n, dt_bvh2_node out[3]) { out[0] = h[0]; out[1] = h[n / 2]; out[2] = h[n - 1]; }
+}
+void dt_resident_tree_put(const dt_bvh2_node* host, uint32_t n, dt_bvh2_node* dev) {
+    ResidentTree t; t.host = host; t.n = n; t.dev = dev; t.device = 0;
+    cudaGetDevice(&t.device);
+    res_probe(host, n, t.probe);
+    std::lock_guard<std::mutex> lk(g_res_mu);
+    for (size_t k = 0; k < g_res.size(); k++) if (g_res[k].host == host) { cudaFree(g_res[k].dev); g_res.erase(g_res.begin() + (long)k); break; }
+    if (g_res.size() >= DT_RESIDENT_MAX) { cudaFree(g_res.front().dev); g_res.erase(g_res.begin()); }
+    g_res.push_back(t);
+}
+// the device copy of `host[0..n)` if dt_bvh2_build produced it on this device and the host array still holds it; the caller owns (cudaFree) the result
+dt_bvh2_node* dt_resident_tree_take(const dt_bvh2_node* host, uint32_t n) {
+    int device = 0;
+    cudaGetDevice(&device);
+    std::lock_guard<std::mutex> lk(g_res_mu);
+    for (size_t k = 0; k < g_res.size(); k++) {
+        ResidentTree& t = g_res[k];
+        if (t.host != host || t.n != n || t.device != device) continue;
+        dt_bvh2_node now[3];
+        res_probe(host, n, now);
+        dt_bvh2_node* dev = t.dev;
+        const bool same = memcmp(now, t.probe, sizeof now) == 0;
+        g_res.erase(g_res.begin() + (long)k);
+        if (same) return dev;
+        cudaFree(dev);
+        return nullptr;
+    }
+    return nullptr;
+}
+void dt_resident_trees_clear() {
+    std::lock_guard<std::mutex> lk(g_res_mu);
+    for (auto& t : g_res) cudaFree(t.dev);
+    g_res.clear();
+}
+
 extern "C" int dt_bvh2_build(int32_t n_faces, const float* centers, const float* face_boxes, const float* root_min, const float* root_max,
                              uint32_t* face_order, dt_bvh2_node* nodes_out, uint32_t node_capacity, uint32_t* n_nodes_out, float* ms_device) {
     if (n_faces <= 0 || !centers || !face_boxes || !root_min || !root_max || !face_order || !nodes_out || !n_nodes_out) BFAIL(DT_ERR_INVALID, "dt_bvh2_build: null or empty argument");
     const uint32_t n = (uint32_t)n_faces;
     const uint32_t capacity = 2u * n - 1u;
     if (node_capacity < capacity) BFAIL(DT_ERR_INVALID, "dt_bvh2_build: node array must hold 2 * n_faces - 1 nodes (mesh.cpp:29)");
-    for (size_t i = 0; i < (size_t)n * 6; i++) if (!(fabsf(face_boxes[i]) <= 3.0e38f)) BFAIL(DT_ERR_INVALID, "dt_bvh2_build: non-finite face box");
-    for (size_t i = 0; i < (size_t)n * 3; i++) if (!(fabsf(centers[i]) <= 3.0e38f)) BFAIL(DT_ERR_INVALID, "dt_bvh2_build: non-finite face centre");
     int rc = dt_internal_ensure_device();
     if (rc) return rc;
     DevBuf B;
@@ -229,6 +283,14 @@ extern "C" int dt_bvh2_build(int32_t n_faces, const float* centers, const float*
     BCK(cudaMemcpy(aos, centers, (size_t)n * 12, cudaMemcpyHostToDevice));
     BCK(cudaEventRecord(e0, st));
     const int TB = 256;
+    {
+        int h_bad = 0;
+        BCK(cudaMemsetAsync(overflow, 0, 4, st));
+        k_check_finite<<<1184, TB, 0, st>>>(fboxes, (size_t)n * 6, aos, (size_t)n * 3, overflow);
+        BCK(cudaMemcpyAsync(&h_bad, overflow, 4, cudaMemcpyDeviceToHost, st));
+        BCK(cudaStreamSynchronize(st));
+        if (h_bad) BFAIL(DT_ERR_INVALID, "dt_bvh2_build: non-finite face box or face centre");
+    }
     const uint32_t gp = (n + TB) / TB;                                                          // covers n + 1 positions
     k_iota<<<gp, TB, 0, st>>>(id[0], seg[0], aos, c[0][0], c[0][1], c[0][2], n);
     BNode root; memset(&root, 0, sizeof root);
@@ -270,5 +332,9 @@ extern "C" int dt_bvh2_build(int32_t n_faces, const float* centers, const float*
     BCK(cudaGetLastError());
     if (ms_device) { float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1); *ms_device = ms; }
     *n_nodes_out = h_n_nodes;
+    // hand the device copy of the tree to the flattener (dt_resident_tree_take): dt_scene_create would otherwise upload the same
+    // ~800 MB (config 5) that were just downloaded
+    for (size_t k = 0; k < B.ptrs.size(); k++) if (B.ptrs[k] == (void*)d_out) { B.ptrs.erase(B.ptrs.begin() + (long)k); break; }
+    dt_resident_tree_put(nodes_out, h_n_nodes, d_out);
     return DT_OK;
 }

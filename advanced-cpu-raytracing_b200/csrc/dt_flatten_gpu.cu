@@ -163,8 +163,12 @@ bool dt_flatten_mesh_gpu(const dt_mesh& m, const DtFaceDev* d_faces, const float
     if (n_faces <= 0 || n_in <= 0 || n_in > 2 * n_faces - 1) { err = "GPU flattener: mesh has no faces or too many BVH2 nodes"; return false; }
     const uint32_t b2_cap = 2u * (uint32_t)n_faces - 1u;
     Scratch S;
+    // a tree built by dt_bvh2_build on this device is still resident: no upload
+    dt_bvh2_node* resident = dt_resident_tree_take(m.bvh, (uint32_t)n_in);
+    struct ResidentGuard { dt_bvh2_node* p; ~ResidentGuard() { if (p) cudaFree(p); } } resident_guard = {resident};
     dt_bvh2_node* bvh; DtB2Node* b2; int *leaf_of, *error, *items[2], *child_ids; unsigned int *counters; uint32_t *n_int, *n_leaf, *s_int, *s_leaf, *prim_order;
-    GCK(S.get(&bvh, (size_t)n_in)); GCK(S.get(&b2, (size_t)b2_cap)); GCK(S.get(&leaf_of, (size_t)n_faces)); GCK(S.get(&error, 1)); GCK(S.get(&counters, 2));
+    if (resident) bvh = resident; else GCK(S.get(&bvh, (size_t)n_in));
+    GCK(S.get(&b2, (size_t)b2_cap)); GCK(S.get(&leaf_of, (size_t)n_faces)); GCK(S.get(&error, 1)); GCK(S.get(&counters, 2));
     GCK(S.get(&items[0], (size_t)n_faces)); GCK(S.get(&items[1], (size_t)n_faces)); GCK(S.get(&child_ids, (size_t)n_faces * 8));
     GCK(S.get(&n_int, (size_t)n_faces + 1)); GCK(S.get(&n_leaf, (size_t)n_faces + 1)); GCK(S.get(&s_int, (size_t)n_faces + 1)); GCK(S.get(&s_leaf, (size_t)n_faces + 1));
     GCK(S.get(&prim_order, (size_t)n_faces));
@@ -173,7 +177,7 @@ bool dt_flatten_mesh_gpu(const dt_mesh& m, const DtFaceDev* d_faces, const float
     uint8_t* scan_tmp; GCK(S.get(&scan_tmp, scan_bytes));
     cudaStream_t st = nullptr;
     const int TB = 128;
-    GCK(cudaMemcpyAsync(bvh, m.bvh, (size_t)n_in * sizeof(dt_bvh2_node), cudaMemcpyHostToDevice, st));
+    if (!resident) GCK(cudaMemcpyAsync(bvh, m.bvh, (size_t)n_in * sizeof(dt_bvh2_node), cudaMemcpyHostToDevice, st));
     GCK(cudaMemsetAsync(leaf_of, 0xFF, (size_t)n_faces * sizeof(int), st));
     GCK(cudaMemsetAsync(error, 0, sizeof(int), st));
     const unsigned int h_counters0[2] = {0u, (unsigned int)n_in};                   // faces covered by leaves, binary-tree node count

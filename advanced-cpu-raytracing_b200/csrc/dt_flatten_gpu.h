@@ -12,3 +12,7 @@ bool dt_flatten_mesh_gpu(const dt_mesh& m, const DtFaceDev* d_faces, const float
 
 // (sum of 32-bit words, position-weighted sum) of a device buffer
 bool dt_device_checksum(const void* p, size_t bytes, uint64_t out[2], std::string& err);
+
+// dt_build.cu: device copies of the trees dt_bvh2_build returned most recently (see there); `take` transfers ownership (cudaFree)
+dt_bvh2_node* dt_resident_tree_take(const dt_bvh2_node* host, uint32_t n);
+void dt_resident_trees_clear();

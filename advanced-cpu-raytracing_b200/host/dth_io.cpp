@@ -1,5 +1,9 @@
 #include "dth_io.h"
 #include <zlib.h>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -7,6 +11,8 @@
 #include <fstream>
 #include <sstream>
 #include <algorithm>
+#include <atomic>
+#include <thread>
 
 namespace dth {
 
@@ -22,8 +28,43 @@ static bool read_file(const std::string& path, std::vector<uint8_t>& buf) {
     return r == (size_t)n;
 }
 
+void parallel_for(size_t n, size_t grain, const std::function<void(size_t, size_t)>& fn) {
+    if (n == 0) return;
+    const size_t hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    const size_t nt = std::max<size_t>(1, std::min(hw, n / std::max<size_t>(1, grain)));
+    if (nt == 1) { fn(0, n); return; }
+    std::vector<std::thread> pool;
+    const size_t chunk = (n + nt - 1) / nt;
+    for (size_t t = 1; t < nt; t++) pool.emplace_back([&, t] { const size_t b = t * chunk, e = std::min(n, b + chunk); if (b < e) fn(b, e); });
+    fn(0, std::min(n, chunk));
+    for (auto& th : pool) th.join();
+}
+
 // ------------------------------------------------------------------ PLY
 namespace {
+// read-only view of a whole file: mmap when possible, a heap copy otherwise
+struct FileView {
+    const uint8_t* p = nullptr; size_t n = 0; bool mapped = false; std::vector<uint8_t> copy;
+    bool open(const std::string& path) {
+        const int fd = ::open(path.c_str(), O_RDONLY);
+        if (fd >= 0) {
+            struct stat st;
+            if (fstat(fd, &st) == 0 && st.st_size > 0) {
+                void* m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE | MAP_POPULATE, fd, 0);
+                if (m != MAP_FAILED) { p = (const uint8_t*)m; n = (size_t)st.st_size; mapped = true; }
+            }
+            ::close(fd);
+        }
+        if (mapped) return true;
+        if (!read_file(path, copy)) return false;
+        p = copy.data(); n = copy.size();
+        return true;
+    }
+    ~FileView() { if (mapped) munmap((void*)p, n); }
+    const uint8_t* data() const { return p; }
+    size_t size() const { return n; }
+    const uint8_t& operator[](size_t i) const { return p[i]; }
+};
 enum PlyType { T_I8, T_U8, T_I16, T_U16, T_I32, T_U32, T_F32, T_F64, T_BAD };
 PlyType ply_type(const std::string& s) {
     if (s == "char" || s == "int8") return T_I8;
@@ -62,8 +103,8 @@ inline double rd_bin(const uint8_t* p, PlyType t, bool swap) {
 }  // namespace
 
 bool ply_load(const std::string& path, PlyMesh& out, std::string& err) {
-    std::vector<uint8_t> buf;
-    if (!read_file(path, buf)) { err = "cannot read PLY file " + path; return false; }
+    FileView buf;                                   // mapped, not copied: a 10 M-triangle PLY is ~190 MB
+    if (!buf.open(path)) { err = "cannot read PLY file " + path; return false; }
     // header
     size_t pos = 0;
     auto getline_ = [&](std::string& line) -> bool {
@@ -99,6 +140,57 @@ bool ply_load(const std::string& path, PlyMesh& out, std::string& err) {
     }
     if (fmt < 0) { err = "PLY: unknown format"; return false; }
     out.positions.clear(); out.face_counts.clear(); out.face_indices.clear();
+    out.streamed = false; out.positions_f32.clear(); out.triangles.clear();
+
+    // ---- streamed path: binary little-endian, elements {vertex (scalars only), face (ONE list of 32-bit indices)}, all triangles ----
+    if (fmt == 1 && elems.size() == 2 && elems[0].name == "vertex" && elems[1].name == "face" && elems[1].props.size() == 1 && elems[1].props[0].is_list &&
+        ply_size(elems[1].props[0].count_type) == 1 && (elems[1].props[0].type == T_I32 || elems[1].props[0].type == T_U32) &&
+        (elems[1].props[0].name == "vertex_indices" || elems[1].props[0].name == "vertex_index")) {
+        size_t stride = 0, off[3] = {0, 0, 0}; PlyType ty[3] = {T_BAD, T_BAD, T_BAD};
+        bool scalars = true;
+        for (auto& p : elems[0].props) {
+            if (p.is_list) { scalars = false; break; }
+            const int a = p.name == "x" ? 0 : p.name == "y" ? 1 : p.name == "z" ? 2 : -1;
+            if (a >= 0) { off[a] = stride; ty[a] = p.type; }
+            stride += (size_t)ply_size(p.type);
+        }
+        const size_t nv = elems[0].count, nf = elems[1].count;
+        const bool xyz_ok = (ty[0] == T_F32 || ty[0] == T_F64) && ty[1] == ty[0] && ty[2] == ty[0];
+        if (scalars && xyz_ok && buf.size() - pos == nv * stride + nf * 13) {            // 13 = count byte + three 32-bit indices
+            const uint8_t* vp = buf.data() + pos;
+            const uint8_t* fp = vp + nv * stride;
+            std::atomic<bool> all_tris(true), in_range(true);
+            out.triangles.resize(nf * 3);
+            parallel_for(nf, 1 << 16, [&](size_t b, size_t e) {
+                bool tris = true, ok = true;
+                for (size_t i = b; i < e; i++) {
+                    const uint8_t* r = fp + i * 13;
+                    tris &= r[0] == 3;
+                    int32_t ix[3]; memcpy(ix, r + 1, 12);
+                    ok &= (uint32_t)ix[0] < nv && (uint32_t)ix[1] < nv && (uint32_t)ix[2] < nv;
+                    out.triangles[i * 3] = ix[0]; out.triangles[i * 3 + 1] = ix[1]; out.triangles[i * 3 + 2] = ix[2];
+                }
+                if (!tris) all_tris = false;
+                if (!ok) in_range = false;
+            });
+            if (all_tris && !in_range) { err = "PLY: face index out of range in " + path; return false; }
+            if (all_tris) {
+                out.positions_f32.resize(nv * 3);
+                const bool f32 = ty[0] == T_F32;
+                parallel_for(nv, 1 << 16, [&](size_t b, size_t e) {
+                    for (size_t i = b; i < e; i++)
+                        for (int a = 0; a < 3; a++) {
+                            const uint8_t* s = vp + i * stride + off[a];
+                            if (f32) memcpy(&out.positions_f32[i * 3 + a], s, 4);
+                            else { double d; memcpy(&d, s, 8); out.positions_f32[i * 3 + a] = (float)d; }
+                        }
+                });
+                out.streamed = true;
+                return true;
+            }
+            out.triangles.clear();                     // quads or polygons (sizes happened to add up): the generic reader below
+        }
+    }
 
     const bool swap = (fmt == 2);
     // ascii tokenizer state

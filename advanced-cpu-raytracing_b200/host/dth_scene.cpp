@@ -19,6 +19,7 @@
 #include <fstream>
 #include <limits>
 #include <memory>
+#include <mutex>
 #include <sstream>
 #include <string>
 #include <vector>
@@ -82,14 +83,25 @@ V3 m4_apply(const M4& t, V3 v, float w) {
 struct Box { V3 mn, mx; };
 
 // ---- owned storage ----
+// Per-face arrays of a 10 M-triangle mesh are ~1 GB: resize() must not zero them on one thread before the parallel workers fill
+// them, so these vectors default-initialise their PODs.
+template <class T> struct NoInitAlloc : std::allocator<T> {
+    template <class U> struct rebind { typedef NoInitAlloc<U> other; };
+    NoInitAlloc() = default;
+    template <class U> NoInitAlloc(const NoInitAlloc<U>&) {}
+    template <class U> void construct(U* p) { ::new ((void*)p) U; }
+    template <class U, class A0, class... A> void construct(U* p, A0&& a0, A&&... a) { ::new ((void*)p) U(std::forward<A0>(a0), std::forward<A>(a)...); }
+};
+template <class T> using BigVec = std::vector<T, NoInitAlloc<T>>;
+
 struct MeshStore {
     std::shared_ptr<std::vector<float>> vertices;   // shared for inline meshes (the reference copies vertex_data per mesh)
     std::shared_ptr<std::vector<float>> uvs;
     int vertex_offset = 0, texture_offset = 0;
-    std::vector<dt_face> faces;
-    std::vector<V3> centers;                        // build-time only (Face::center)
-    std::vector<Box> fboxes;                        // build-time only (Face::bbox)
-    std::vector<dt_bvh2_node> bvh;
+    BigVec<dt_face> faces;
+    BigVec<V3> centers;                             // build-time only (Face::center)
+    BigVec<Box> fboxes;                             // build-time only (Face::bbox)
+    BigVec<dt_bvh2_node> bvh;
     Box bbox;
     double surface_area = 0.0;                      // the reference leaves Mesh::surfaceArea uninitialised (mesh.hpp:19); we start at 0
     V3 vertex(int id) const { const float* p = &(*vertices)[(size_t)(id - 1 + vertex_offset) * 3]; return v3(p[0], p[1], p[2]); }
@@ -180,7 +192,7 @@ std::string resolve_path(const dth_scene& sc, const std::string& rel) {
 }
 
 // ---- Scene::computeFaceProperties (parser.cpp:579-611, 725-748) ----
-void face_properties(MeshStore& m, dt_face& f, V3& center, Box& fb) {
+void face_properties(const MeshStore& m, dt_face& f, V3& center, Box& fb) {
     V3 a = m.vertex(f.v0_id), b = m.vertex(f.v1_id), c = m.vertex(f.v2_id);
     center = (a + b + c) / 3.0f;                                           // computeFaceCenter
     V3 n = make_unit(cross(b - a, c - a));                                 // computeFaceNormal
@@ -190,13 +202,13 @@ void face_properties(MeshStore& m, dt_face& f, V3& center, Box& fb) {
     double e1 = len(a - b), e2 = len(a - c), e3 = len(b - c);              // computeFaceArea (Heron)
     double s = (e1 + e2 + e3) / 2.0f;
     double area = std::sqrt(s * (s - e1) * (s - e2) * (s - e3));
-    f.area = area;
-    m.surface_area += area;
+    f.area = area;                                                         // the caller adds it to Mesh::surfaceArea, in face order
 }
 void add_face(MeshStore& m, int v0, int v1, int v2, Box* mesh_box) {
     dt_face f; f.v0_id = v0; f.v1_id = v1; f.v2_id = v2;
     V3 c; Box fb;
     face_properties(m, f, c, fb);
+    m.surface_area += f.area;
     if (mesh_box) {                                                         // parser.cpp:1453-1460 / updateBBox :816-826
         mesh_box->mn = v3(std::min(fb.mn.x, mesh_box->mn.x), std::min(fb.mn.y, mesh_box->mn.y), std::min(fb.mn.z, mesh_box->mn.z));
         mesh_box->mx = v3(std::max(fb.mx.x, mesh_box->mx.x), std::max(fb.mx.y, mesh_box->mx.y), std::max(fb.mx.z, mesh_box->mx.z));
@@ -228,17 +240,24 @@ bool bvh_build(MeshStore& m) {
     if (!g_bvh_builder || n < g_bvh_builder_min_faces || n < 2) ok = bvh_build_host(m);
     else {
         static_assert(sizeof(V3) == 12 && sizeof(Box) == 24, "V3 / Box must be plain float triples");
-        std::vector<uint32_t> order((size_t)n);
-        m.bvh.assign((size_t)n * 2 - 1, dt_bvh2_node());
+        BigVec<uint32_t> order((size_t)n);
+        m.bvh.resize((size_t)n * 2 - 1);                                    // filled by the builder (not zeroed first: ~800 MB on config 5)
         uint32_t n_nodes = 0;
         float mn[3], mx[3]; put3(mn, m.bbox.mn); put3(mx, m.bbox.mx);
-        const int rc = g_bvh_builder(n, &m.centers[0].x, &m.fboxes[0].mn.x, mn, mx, order.data(), m.bvh.data(), (uint32_t)m.bvh.size(), &n_nodes, nullptr);
+        float ms_device = 0.f;
+        const int rc = g_bvh_builder(n, &m.centers[0].x, &m.fboxes[0].mn.x, mn, mx, order.data(), m.bvh.data(), (uint32_t)m.bvh.size(), &n_nodes, &ms_device);
+        const auto t1 = std::chrono::steady_clock::now();
         if (rc != 0) { g_err = "BVH builder failed with status " + std::to_string(rc); ok = false; }
         else {
             m.bvh.resize(n_nodes);
-            std::vector<dt_face> f((size_t)n); std::vector<V3> c((size_t)n); std::vector<Box> b((size_t)n);
-            for (int i = 0; i < n; i++) { f[i] = m.faces[order[i]]; c[i] = m.centers[order[i]]; b[i] = m.fboxes[order[i]]; }
+            BigVec<dt_face> f((size_t)n); BigVec<V3> c((size_t)n); BigVec<Box> b((size_t)n);
+            dth::parallel_for((size_t)n, 1 << 15, [&](size_t lo, size_t hi) {
+                for (size_t i = lo; i < hi; i++) { f[i] = m.faces[order[i]]; c[i] = m.centers[order[i]]; b[i] = m.fboxes[order[i]]; }
+            });
             m.faces.swap(f); m.centers.swap(c); m.fboxes.swap(b);
+            if (getenv("DTH_DEBUG_TIMING"))
+                fprintf(stderr, "[dth] BVH builder: call %.3f s (device work %.3f s, the rest is allocation + copies), face permutation %.3f s\n",
+                        std::chrono::duration<double>(t1 - t0).count(), ms_device * 1e-3, std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count());
         }
     }
     g_bvh_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -247,7 +266,7 @@ bool bvh_build(MeshStore& m) {
 bool bvh_build_host(MeshStore& m) {
     int n = (int)m.faces.size();
     if (n <= 0) { m.bvh.clear(); return true; }
-    m.bvh.assign((size_t)n * 2 - 1, dt_bvh2_node());
+    m.bvh.resize((size_t)n * 2 - 1);
     for (auto& nd : m.bvh) { nd.left = nd.right = -1; nd.first_face = nd.face_count = 0; memset(nd.bmin, 0, 12); memset(nd.bmax, 0, 12); }
     dt_bvh2_node& root = m.bvh[0];
     put3(root.bmin, m.bbox.mn); put3(root.bmax, m.bbox.mx);
@@ -687,8 +706,37 @@ bool parse_scene(dth_scene& sc, const dth::XmlNode* root) {
             bbox.mn = v3(FLT_MAX, FLT_MAX, FLT_MAX);
             if (ply) {
                 dth::PlyMesh pm; std::string err;
+                const auto t_ply0 = std::chrono::steady_clock::now();
                 if (!dth::ply_load(resolve_path(sc, ply), pm, err)) { g_err = err; return false; }
-                ms.vertices->resize(pm.positions.size());
+                const auto t_ply1 = std::chrono::steady_clock::now();
+                if (pm.streamed) {
+                    // the decoded arrays ARE the mesh arrays (no per-mesh copy of the vertex data, mesh.cpp:7-13), and the
+                    // per-face properties (parser.cpp:579-611) are filled in place by parallel workers; only Mesh::surfaceArea, a sum
+                    // whose order the light weights depend on, is accumulated sequentially.
+                    ms.vertices->swap(pm.positions_f32);
+                    const size_t nf = pm.triangles.size() / 3;
+                    ms.faces.resize(nf); ms.centers.resize(nf); ms.fboxes.resize(nf);
+                    std::mutex box_mu;
+                    dth::parallel_for(nf, 1 << 15, [&](size_t b, size_t e) {
+                        Box local = bbox;
+                        for (size_t i = b; i < e; i++) {
+                            dt_face f; f.v0_id = pm.triangles[i * 3] + 1; f.v1_id = pm.triangles[i * 3 + 1] + 1; f.v2_id = pm.triangles[i * 3 + 2] + 1;
+                            face_properties(ms, f, ms.centers[i], ms.fboxes[i]);
+                            ms.faces[i] = f;
+                            const Box& fb = ms.fboxes[i];
+                            local.mn = v3(std::min(fb.mn.x, local.mn.x), std::min(fb.mn.y, local.mn.y), std::min(fb.mn.z, local.mn.z));
+                            local.mx = v3(std::max(fb.mx.x, local.mx.x), std::max(fb.mx.y, local.mx.y), std::max(fb.mx.z, local.mx.z));
+                        }
+                        std::lock_guard<std::mutex> lk(box_mu);
+                        bbox.mn = v3(std::min(local.mn.x, bbox.mn.x), std::min(local.mn.y, bbox.mn.y), std::min(local.mn.z, bbox.mn.z));
+                        bbox.mx = v3(std::max(local.mx.x, bbox.mx.x), std::max(local.mx.y, bbox.mx.y), std::max(local.mx.z, bbox.mx.z));
+                    });
+                    for (size_t i = 0; i < nf; i++) ms.surface_area += ms.faces[i].area;
+                    if (getenv("DTH_DEBUG_TIMING"))
+                        fprintf(stderr, "[dth] %s: read + decode %.3f s, face properties %.3f s (%zu faces, streamed)\n", ply, std::chrono::duration<double>(t_ply1 - t_ply0).count(),
+                                std::chrono::duration<double>(std::chrono::steady_clock::now() - t_ply1).count(), nf);
+                }
+                if (!pm.streamed) ms.vertices->resize(pm.positions.size());
                 for (size_t i = 0; i < pm.positions.size(); i++) (*ms.vertices)[i] = (float)pm.positions[i];
                 size_t nf = pm.face_counts.size();
                 ms.faces.reserve(nf); ms.centers.reserve(nf); ms.fboxes.reserve(nf);
@@ -862,7 +910,7 @@ int dth_scene_load_xml(const char* xml_path, dth_scene** out) {
     sc->xml_dir = sl == std::string::npos ? "." : p.substr(0, sl);
     // free build-time face data after the BVH is built? kept: small relative to faces.
     if (!parse_scene(*sc, root.get())) return DT_ERR_INVALID;
-    for (auto& ms : sc->mesh_store) { std::vector<V3>().swap(ms.centers); std::vector<Box>().swap(ms.fboxes); }
+    for (auto& ms : sc->mesh_store) { BigVec<V3>().swap(ms.centers); BigVec<Box>().swap(ms.fboxes); }
     sc->finalize();
     *out = sc.release();
     return DT_OK;
