@@ -468,11 +468,24 @@ int render_core(dt_scene* s, const dt_camera_desc* cam, const dt_render_params* 
 
     const bool pt = dc.path_tracing != 0 && !primary_only;
     const bool defer_mode = pt && dc.nee && s->dev.n_mesh_lights > 0;
-    int wave_max = P.max_wave_rays > 0 ? P.max_wave_rays : (1 << 23);
-    wave_max = (int)std::min<long long>(wave_max, std::max<long long>(total, 32));
-    wave_max = (wave_max + 31) & ~31;
     const int fan = s->fanout_hint + (pt ? 1 : 0);
     const int shadows_per_hit = std::max(1, s->lights_shadowed);
+    int wave_max = P.max_wave_rays;
+    if (wave_max <= 0) {
+        // Default wave size: as large as HBM allows, up to 32 Mi rays.  Every wave ends in the drain of five persistent / grid-stride
+        // launches, so frames of many waves (path tracing) run ~3 % faster with 32 Mi-ray waves than with 8 Mi (config 5:
+        // profiles/r2_ab_wave_size.log); at ~2.2 KB of queue space per wave ray (4x fan-out, two shadow rays per hit) that is
+        // 75 GB of the B200's 180 GB.  The wave shrinks by halves until the queues fit into 45 % of the free device memory.
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) free_b = 0;
+        for (const DtPipe& pp : s->pipes) free_b += (size_t)pp.capacity * 256 + (size_t)pp.shadow_capacity * 152;      // what the current queues would give back (roughly)
+        const double per_ray = (fan <= 1 ? 1.0 : 4.0) * (2 * 108 + (s->has_env ? 32 : 0) + 4 + shadows_per_hit * (3 * 48 + 8.0));
+        wave_max = 1 << 25;
+        const long long mult = fan <= 1 ? 1 : 4;
+        while (wave_max > (1 << 20) && ((double)wave_max * per_ray > 0.45 * (double)free_b || mult * wave_max * shadows_per_hit > (1ll << 28))) wave_max >>= 1;   // 2^28: queue_caps' limit
+    }
+    wave_max = (int)std::min<long long>(wave_max, std::max<long long>(total, 32));
+    wave_max = (wave_max + 31) & ~31;
     const bool sort_allowed = !primary_only && !(P.flags & DT_FLAG_NO_SORT) && s->sort_mode != 0;
     // hit-cell sort (k_ssort_*): path-traced frames by default (their waves are incoherent), any frame with DT_SORT_SPATIAL=1..6
     const int sort_spatial = (!sort_allowed || (P.flags & DT_FLAG_SORT_MATERIAL_ONLY)) ? 0 : (s->sort_spatial < 0 ? (pt ? DT_SSORT_MAX_AXIS_BITS : 0) : std::min(s->sort_spatial, DT_SSORT_MAX_AXIS_BITS));

@@ -170,7 +170,10 @@ __device__ __forceinline__ void dt_generate_one(const DtCamDev& cam, const DtWav
     q.pixel[slot] = pix;
     q.weight_n[slot] = make_float4(w, w, w, 1.0f);
     q.thr_beer[slot] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
-    q.misc[slot] = make_int4(0x7FFFFFFF /* set by shade from the scene */, 0, (int)dt_hash(rng.key, 0x9E37u), DT_FLAG_PRIMARY);
+    // misc.y of a camera ray (no parent material): the sample's truncated pixel coordinate relative to the accumulation pixel.
+    // (int)(sx + x) is x except when the float sum rounds up to x + 1; the reference's background-texture lookup uses that
+    // coordinate (raytracer.cpp:49-55 with main.cpp:83), so it travels with the ray.
+    q.misc[slot] = make_int4(0x7FFFFFFF /* set by shade from the scene */, (px - x) | ((py - y) << 1), (int)dt_hash(rng.key, 0x9E37u), DT_FLAG_PRIMARY);
 }
 
 __global__ void k_generate(DtCamDev cam, DtWaveParams wp, DtRayQueue q, int base, long long k0, int n, float4* accum) {
@@ -399,7 +402,7 @@ __device__ __forceinline__ void dt_shade_ray(const int i, const DtSceneDev& S, c
         if (primary) {
             v3 c;
             if (S.bg_texture >= 0) {
-                const int x = (int)(pix % (uint32_t)cam.width), y = (int)(pix / (uint32_t)cam.width);
+                const int x = (int)(pix % (uint32_t)cam.width) + (misc.y & 1), y = (int)(pix / (uint32_t)cam.width) + ((misc.y >> 1) & 1);   // coordX / coordY of RenderPixel
                 c = tex_rgb_sample(S, S.textures[S.bg_texture], x / (float)cam.width, y / (float)cam.height);
             } else if (S.n_env_lights > 0) c = env_sample(S, 0, d);
             else c = V((float)S.background_color[0], (float)S.background_color[1], (float)S.background_color[2]);

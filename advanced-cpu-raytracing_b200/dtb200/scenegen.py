@@ -205,7 +205,7 @@ def _env_map(w=256, h=128):
 
 
 def gen_config4(out_dir, width=1920, height=1080, spp=256, depth=4, blob=(0, 0), name="config4", nee=True, rr=True, importance=True, n_cameras=1, sphere_lift=0.0,
-                lights=("area", "mesh", "env"), area_light_y=9.9):
+                lights=("area", "mesh", "env"), area_light_y=9.9, mirror_brdf=False):
     """Path-traced box + spheres: area light + light mesh + spherical HDR environment light, Torrance-Sparrow
     (kdfresnel) and modified Blinn-Phong BRDFs, photographic tonemapper.  blob=(nlon,nlat) adds a displaced
     sphere mesh of that tessellation (config 5 uses 3162 x 1581 ~ 10 M triangles).
@@ -246,7 +246,10 @@ def gen_config4(out_dir, width=1920, height=1080, spp=256, depth=4, blob=(0, 0),
     xml += mat(4, (0.4, 0.35, 0.2), (0.5, 0.5, 0.5), ' BRDF="1"', "            <RefractionIndex>1.8</RefractionIndex>\n")    # Torrance-Sparrow
     xml += mat(5, (0.2, 0.3, 0.6), (0.4, 0.4, 0.4), ' BRDF="2"')         # modified Blinn-Phong
     xml += mat(6, (0, 0, 0))                                               # emissive (set by LightMesh)
-    xml += mat(7, (0, 0, 0), (0, 0, 0), ' type="mirror"', "            <MirrorReflectance>0.9 0.9 0.9</MirrorReflectance>\n")
+    # mirror_brdf: the mirror also carries a BRDF, the one case where the GPU path's Russian-roulette throughput differs from the
+    # reference's (DESIGN.md "Documented deviations": Shade() scales ray.throughput for UNSHADOWED lights only, raytracer.cpp:192-206)
+    if mirror_brdf: xml += mat(7, (0.3, 0.3, 0.3), (0.3, 0.3, 0.3), ' type="mirror" BRDF="2"', "            <MirrorReflectance>0.9 0.9 0.9</MirrorReflectance>\n")
+    else: xml += mat(7, (0, 0, 0), (0, 0, 0), ' type="mirror"', "            <MirrorReflectance>0.9 0.9 0.9</MirrorReflectance>\n")
     xml += "    </Materials>\n"
     xml += "    <Textures>\n        <Images>\n            <Image id=\"1\">env.exr</Image>\n        </Images>\n    </Textures>\n"
     v = [(-10, -10, 10), (10, -10, 10), (10, 10, 10), (-10, 10, 10), (-10, -10, -10), (10, -10, -10), (10, 10, -10), (-10, 10, -10),

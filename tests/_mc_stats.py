@@ -7,7 +7,7 @@ import numpy as np
 from dtb200.scene import GpuScene, HostScene
 from oracle_util import mc_compare
 from test_cpu_monte_carlo_pin import mc_scene
-for name in ["mc_all", "mc_area", "mc_mesh", "mc_env", "mc_c5shape"]:
+for name in (sys.argv[1:] or ["mc_all", "mc_area", "mc_mesh", "mc_env", "mc_c5shape", "mc_rrbrdf"]):
     for spp in (256, 4096, 16384, 65536):
         p, g = mc_scene(name, '/tmp/mcs_%s_%d' % (name, spp), spp)
         hs = HostScene(p); cam = hs.camera(0); gs = GpuScene(hs)

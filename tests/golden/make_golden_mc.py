@@ -36,6 +36,7 @@ SCENES = {
     "mc_mesh": ("config4", dict(lights=["mesh"], depth=2)),
     "mc_env": ("config4", dict(lights=["env"], depth=2)),
     "mc_c5shape": ("config5", dict(nlon=96, nlat=48, depth=2)),          # config-4 scene + a 9 024-triangle displaced sphere, lifted spheres
+    "mc_rrbrdf": ("config4", dict(lights=["area", "mesh"], depth=2, area_light_y=7.5, mirror_brdf=True)),   # mirror WITH a BRDF: bounds the RR-throughput deviation
     "mc_blur": ("blur", dict()),                                         # thin lens, motion blur, rough mirror (no path tracing)
 }
 

@@ -21,7 +21,7 @@ from dtb200.scene import HostScene
 from oracle_util import have_ref, load_dtoracle, mc_compare, oracle_render, oracle_render_reference_rng, run_reference
 from scenes_util import GOLDEN_DIR, blur_dof_scene
 
-MC_FIXTURES = ["mc_all", "mc_area", "mc_mesh", "mc_env", "mc_c5shape", "mc_blur"]
+MC_FIXTURES = ["mc_all", "mc_area", "mc_mesh", "mc_env", "mc_c5shape", "mc_rrbrdf", "mc_blur"]
 needs_ref = pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built (GPU box or fresh clone)")
 
 
