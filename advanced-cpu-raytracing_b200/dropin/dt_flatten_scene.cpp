@@ -4,7 +4,7 @@
 // emits the flat dt_scene_desc of include/dorktracer.h, then forwards each camera to dt_render().  Nothing here parses,
 // builds or shades: the parser, Mesh::ConstructBVH, the light / material / texture classes stay the reference's.
 // main.cpp changes in three places (oracle/build_ref.py applies exactly these to a scratch copy of the reference):
-//     after  scene.loadFromXml(argv[1]);              ->  void* gpu = dt_dropin_create(scene, argc, argv);
+//     after  scene.loadFromXml(argv[1]);              ->  void* gpu = dt_dropin_create(scene);
 //     main.cpp:164-185 (thread spawn ... join)         ->  dt_dropin_render(gpu, cam, image, hdrImage);
 //     main.cpp:190 cam.GetTonemappedImage(...)         ->  removed (dt_render tonemaps when the camera has a tonemapper)
 // stbi_write_hdr / stbi_write_png (main.cpp:191,195) stay.
