@@ -18,7 +18,14 @@ __device__ __forceinline__ v3 vadd(v3 a, v3 b) { return V(__fadd_rn(a.x, b.x), _
 __device__ __forceinline__ v3 vsub(v3 a, v3 b) { return V(__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y), __fsub_rn(a.z, b.z)); }
 __device__ __forceinline__ v3 vmul(v3 a, v3 b) { return V(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y), __fmul_rn(a.z, b.z)); }
 __device__ __forceinline__ v3 vscale(v3 a, float s) { return V(__fmul_rn(a.x, s), __fmul_rn(a.y, s), __fmul_rn(a.z, s)); }
-__device__ __forceinline__ v3 vdiv(v3 a, float s) { return V(__fdiv_rn(a.x, s), __fdiv_rn(a.y, s), __fdiv_rn(a.z, s)); }
+// IEEE-exact x / y.  A ZERO numerator (components of axis-aligned normals, black colour channels: nine divisions of an average
+// config-5 hit) would send the whole warp through the out-of-line special-case path of the division (7 % of k_shade's issued
+// instructions, profiles/r2p_ncu_config5_shade_raw.csv); 0 / y is the product's signed zero whenever y is finite and non-zero.
+__device__ __forceinline__ float dt_fdiv(float x, float y) {
+    if (x == 0.0f && fabsf(y) > 0.0f && fabsf(y) < CUDART_INF_F) return __fmul_rn(x, y);
+    return __fdiv_rn(x, y);
+}
+__device__ __forceinline__ v3 vdiv(v3 a, float s) { return V(dt_fdiv(a.x, s), dt_fdiv(a.y, s), dt_fdiv(a.z, s)); }
 __device__ __forceinline__ v3 vneg(v3 a) { return V(__fmul_rn(a.x, -1.0f), __fmul_rn(a.y, -1.0f), __fmul_rn(a.z, -1.0f)); }   // helperMath.h:41-47
 // helperMath.cpp:54-58: a.x*b.x + a.y*b.y + a.z*b.z, left to right
 __device__ __forceinline__ float vdot(v3 a, v3 b) {
@@ -34,7 +41,7 @@ __device__ __forceinline__ v3 vcross(v3 a, v3 b) {
 __device__ __forceinline__ float vlen(v3 a) {
     return __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(a.x, a.x), __fmul_rn(a.y, a.y)), __fmul_rn(a.z, a.z)));
 }
-__device__ __forceinline__ v3 vunit(v3 a) { float l = vlen(a); return V(__fdiv_rn(a.x, l), __fdiv_rn(a.y, l), __fdiv_rn(a.z, l)); }
+__device__ __forceinline__ v3 vunit(v3 a) { float l = vlen(a); return V(dt_fdiv(a.x, l), dt_fdiv(a.y, l), dt_fdiv(a.z, l)); }
 
 // helperMath.cpp:59-85
 __device__ __forceinline__ void orthonormal_basis(v3 r, v3& u, v3& v) {

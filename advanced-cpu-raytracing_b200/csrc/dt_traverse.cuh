@@ -176,15 +176,31 @@ __device__ __forceinline__ uint32_t dt_perm8(uint32_t x, uint32_t oct) {
 // IEEE quotients); the three conditions tmax > 0, tmax >= tmin, tmin < minT must hold with a 2^-19 relative margin.  Rays
 // with a clamped reciprocal (|d| < 1e-30 on some axis), flat boxes and grazing hits fail the certificate and take the
 // exact path (box_intersect_exact), so the decision is always the reference's.
+// Upper / lower bound of the reference's IEEE quotient given its reciprocal-based approximation v (relative error < 2^-19).
+#define DT_CERT_EPS 1.9073486e-6f
+__device__ __forceinline__ float dt_cert_up(float v) { return __fadd_rn(v, __fadd_rn(__fmul_rn(fabsf(v), DT_CERT_EPS), 1e-30f)); }
+__device__ __forceinline__ float dt_cert_lo(float v) { return __fsub_rn(v, __fadd_rn(__fmul_rn(fabsf(v), DT_CERT_EPS), 1e-30f)); }
+// Second-level pass certificate for boxes the one-margin test cannot decide because the binding near and far plane belong to the
+// SAME axis -- flat boxes (axis-aligned quads as meshes, leaf boxes of axis-aligned triangles: every wall of a Cornell box) and
+// rays that start on a box face.  tmax >= tmin means near_a <= far_b for every pair of axes; for a == b that holds by construction
+// (near and far are min / max of the same two quotients, in the reference too), so only the six cross pairs need a margin.
+// n* / f* are the per-axis near / far approximations, tmin / tmax their max / min.
+__device__ __forceinline__ bool dt_cert_cross_axes(float nx, float fx, float ny, float fy, float nz, float fz, float tmin, float tmax, float minT) {
+    return dt_cert_lo(tmax) > 0.0f && dt_cert_up(tmin) < minT &&
+           dt_cert_up(nx) < dt_cert_lo(fminf(fy, fz)) && dt_cert_up(ny) < dt_cert_lo(fminf(fx, fz)) && dt_cert_up(nz) < dt_cert_lo(fminf(fx, fy));
+}
 __device__ __forceinline__ bool dt_leaf_box_certain(const float4 mn, const float4 mx, const DtRayPrep& r, float minT) {
     if (fabsf(r.idx) >= 1e30f || fabsf(r.idy) >= 1e30f || fabsf(r.idz) >= 1e30f) return false;
     const float x1 = __fmul_rn(__fsub_rn(mn.x, r.o.x), r.idx), x2 = __fmul_rn(__fsub_rn(mx.x, r.o.x), r.idx);
     const float y1 = __fmul_rn(__fsub_rn(mn.y, r.o.y), r.idy), y2 = __fmul_rn(__fsub_rn(mx.y, r.o.y), r.idy);
     const float z1 = __fmul_rn(__fsub_rn(mn.z, r.o.z), r.idz), z2 = __fmul_rn(__fsub_rn(mx.z, r.o.z), r.idz);
-    const float tmin = fmaxf(fmaxf(fminf(x1, x2), fminf(y1, y2)), fminf(z1, z2));
-    const float tmax = fminf(fminf(fmaxf(x1, x2), fmaxf(y1, y2)), fmaxf(z1, z2));
-    const float m = __fmul_rn(fmaxf(fabsf(tmin), fabsf(tmax)), 1.9073486e-6f);
-    return tmax > 1e-30f && tmax > m && __fsub_rn(tmax, tmin) > __fadd_rn(m, m) && __fadd_rn(tmin, m) < minT;
+    const float nx = fminf(x1, x2), fx = fmaxf(x1, x2), ny = fminf(y1, y2), fy = fmaxf(y1, y2), nz = fminf(z1, z2), fz = fmaxf(z1, z2);
+    const float tmin = fmaxf(fmaxf(nx, ny), nz);
+    const float tmax = fminf(fminf(fx, fy), fz);
+    const float m = __fmul_rn(fmaxf(fabsf(tmin), fabsf(tmax)), DT_CERT_EPS);
+    if (!(m < 1e30f)) return false;
+    if (tmax > 1e-30f && tmax > m && __fsub_rn(tmax, tmin) > __fadd_rn(m, m) && __fadd_rn(tmin, m) < minT) return true;
+    return dt_cert_cross_axes(nx, fx, ny, fy, nz, fz, tmin, tmax, minT);
 }
 
 // Three-way certificate for the per-shape slab tests (Mesh::bbox, InstancedMesh::bbox): +1 the reference's test certainly
@@ -194,13 +210,14 @@ __device__ __forceinline__ int dt_box_certificate(const float* mn, const float* 
     const float x1 = __fmul_rn(__fsub_rn(mn[0], o.x), r.idx), x2 = __fmul_rn(__fsub_rn(mx[0], o.x), r.idx);
     const float y1 = __fmul_rn(__fsub_rn(mn[1], o.y), r.idy), y2 = __fmul_rn(__fsub_rn(mx[1], o.y), r.idy);
     const float z1 = __fmul_rn(__fsub_rn(mn[2], o.z), r.idz), z2 = __fmul_rn(__fsub_rn(mx[2], o.z), r.idz);
-    const float tmin = fmaxf(fmaxf(fminf(x1, x2), fminf(y1, y2)), fminf(z1, z2));
-    const float tmax = fminf(fminf(fmaxf(x1, x2), fmaxf(y1, y2)), fmaxf(z1, z2));
-    const float m = __fadd_rn(__fmul_rn(fmaxf(fabsf(tmin), fabsf(tmax)), 1.9073486e-6f), 1e-30f);
+    const float nx = fminf(x1, x2), fx = fmaxf(x1, x2), ny = fminf(y1, y2), fy = fmaxf(y1, y2), nz = fminf(z1, z2), fz = fmaxf(z1, z2);
+    const float tmin = fmaxf(fmaxf(nx, ny), nz);
+    const float tmax = fminf(fminf(fx, fy), fz);
+    const float m = __fadd_rn(__fmul_rn(fmaxf(fabsf(tmin), fabsf(tmax)), DT_CERT_EPS), 1e-30f);
     if (!(m < 1e30f)) return 0;                                                        // NaN / overflow: undecided
     if (tmax > m && __fsub_rn(tmax, tmin) > __fadd_rn(m, m) && __fadd_rn(tmin, m) < minT) return 1;
     if (tmax < -m || __fsub_rn(tmin, tmax) > __fadd_rn(m, m) || __fsub_rn(tmin, m) > minT) return -1;
-    return 0;
+    return dt_cert_cross_axes(nx, fx, ny, fy, nz, fz, tmin, tmax, minT) ? 1 : 0;       // flat boxes, rays starting on a face
 }
 __device__ __forceinline__ bool dt_box_test(const float* mn, const float* mx, v3 o, v3 d, const DtRayPrep& r, float minT) {
     const int c = dt_box_certificate(mn, mx, o, r, minT);
