@@ -932,10 +932,6 @@ static int scene_create_impl(const dt_scene_desc* desc, const dt_scene_options* 
         D.blas_nodes = nodes;
         s->n_blas_nodes = n_nodes; s->n_prims = n_prims; s->n_faces = hs.faces.size();
     }
-    for (DtShapeDev& sd : hs.shapes) {          // the packed TLAS-visit words (dt_device.h); node roots are final only now (GPU-flattened meshes)
-        sd.trav_flags = (uint32_t)sd.kind | (sd.skip_shadow ? DT_SHF_SKIP_SHADOW : 0u) | (sd.has_motion_blur ? DT_SHF_MOTION_BLUR : 0u) | (sd.inv_is_identity ? DT_SHF_IDENTITY : 0u);
-        sd.node_root = sd.mesh >= 0 ? hs.meshes[(size_t)sd.mesh].node_root : 0u;
-    }
     if ((rc = upload<DtShapeDev>(s->allocs, hs.shapes.data(), hs.shapes.size(), &D.shapes))) return fail(rc);
     if ((rc = upload<DtMeshDev>(s->allocs, hs.meshes.data(), hs.meshes.size(), &D.meshes))) return fail(rc);
     if ((rc = upload<float>(s->allocs, hs.uvs.data(), hs.uvs.size(), &D.uvs))) return fail(rc);

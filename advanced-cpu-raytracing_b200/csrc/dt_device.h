@@ -11,7 +11,6 @@
 // Triangles are stored pre-gathered in BVH8 leaf order: 48 bytes = v0, v0-v1, v0-v2 (the exact float
 // differences Mesh::IntersectFace forms, mesh.cpp:208-210) + canonical face index.
 #pragma once
-#include <stddef.h>
 #include <stdint.h>
 #include <cuda_runtime.h>
 #include "../../include/dorktracer.h"
@@ -44,22 +43,12 @@ struct DtShapeDev {
     float radius;
     float center[3];
     int32_t inv_is_identity;      // inverseTransform == I exactly: the double transform is a no-op up to -0 -> +0
-    float bbox_min[3], bbox_max[3];   // MESH: Mesh::bbox (local); INSTANCE: InstancedMesh::bbox (world)     [byte offset 80]
-    // Everything a TLAS leaf visit needs sits in the two 16-byte words at offsets 80 and 96 (the box above + these two), so that
-    // the traversal kernels issue two 128-bit loads per candidate shape instead of five dependent scalar loads across this record
-    // and DtMeshDev:
-    uint32_t trav_flags;          // DT_SHF_*: kind | skip_shadow | has_motion_blur | inv_is_identity
-    uint32_t node_root;           // BVH8 root of the shape's mesh in blas_nodes (DtMeshDev::node_root; 0 for spheres)
+    float bbox_min[3], bbox_max[3];   // MESH: Mesh::bbox (local); INSTANCE: InstancedMesh::bbox (world)
+    float pad1[2];
     double inv[12];               // rows 0..2 of inverseTransform
     double invT[12];              // rows 0..2 of inverseTransposeTransform
     double fwd[12];               // rows 0..2 of transform
 };
-
-#define DT_SHF_KIND_MASK 0xFFu
-#define DT_SHF_SKIP_SHADOW 0x100u
-#define DT_SHF_MOTION_BLUR 0x200u
-#define DT_SHF_IDENTITY 0x400u
-static_assert(offsetof(DtShapeDev, bbox_min) == 80 && offsetof(DtShapeDev, trav_flags) == 104 && sizeof(DtShapeDev) % 16 == 0, "DtShapeDev: the TLAS-visit words must be 16-byte aligned");
 
 struct DtMeshDev {
     uint32_t node_root;           // index of this mesh's BVH8 root in blas_nodes

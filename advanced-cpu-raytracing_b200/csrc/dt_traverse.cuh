@@ -438,12 +438,8 @@ __device__ __forceinline__ bool dt_trav_prim(DtTrav& T, const DtStack& stack, co
     DT_STAT(2);
     const int si = __ldg(S.tlas_prims + prim);
     const DtShapeDev* sh = S.shapes + si;
-    // two 128-bit loads: the shape's box, its flags and the root of its BLAS (dt_device.h)
-    const float4 sb0 = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const char*>(sh) + 80));
-    const float4 sb1 = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const char*>(sh) + 96));
-    const uint32_t fl = __float_as_uint(sb1.z);
-    if (ANY && (fl & DT_SHF_SKIP_SHADOW)) return false;
-    const int kind = (int)(fl & DT_SHF_KIND_MASK);
+    if (ANY && sh->skip_shadow) return false;
+    const int kind = sh->kind;
     if (kind == DT_SHAPE_SPHERE) {
         v3 lo, ld;
         dt_to_local(sh, T.r.o, T.r.d, ray_o, lo, ld);       // TLAS level: T.r is the world ray
@@ -462,40 +458,25 @@ __device__ __forceinline__ bool dt_trav_prim(DtTrav& T, const DtStack& stack, co
     // Mesh / InstancedMesh: the reference's exact per-shape pre-tests, then descend into the BLAS.
     // ray.hitInfo.minT at the time the reference scans shape si: only hits of lower-index shapes exist.
     const float shape_min_t = ANY ? __fadd_rn(best.t, 0.01f) : ((best.shape >= 0 && si > best.shape) ? best.t : CUDART_INF_F);
-    const float smn[3] = {sb0.x, sb0.y, sb0.z}, smx[3] = {sb0.w, sb1.x, sb1.y};
     if (kind == DT_SHAPE_INSTANCE) {
         v3 so = T.r.o;
-        if (fl & DT_SHF_MOTION_BLUR) so = vadd(so, vscale(F3(sh->motion_blur), ray_o->w));
-        if (!dt_box_test(smn, smx, so, T.r.d, T.r, shape_min_t)) return false;       // instancedMesh.cpp:29 (T.r: world ray)
+        if (sh->has_motion_blur) so = vadd(so, vscale(F3(sh->motion_blur), ray_o->w));
+        if (!dt_box_test(sh->bbox_min, sh->bbox_max, so, T.r.d, T.r, shape_min_t)) return false;       // instancedMesh.cpp:29 (T.r: world ray)
     }
     v3 lo, ld;
+    dt_to_local(sh, T.r.o, T.r.d, ray_o, lo, ld);
+    const DtMeshDev* m = S.meshes + sh->mesh;
+    // mesh.cpp:172 (Mesh::bbox) and the root node of BVH::IntersectBVH (same box) in local space
     DtRayPrep lr;
-    if ((fl & (DT_SHF_IDENTITY | DT_SHF_MOTION_BLUR)) == DT_SHF_IDENTITY) {
-        // untransformed shape: the local ray is the world ray up to -0 -> +0 (dt_to_local), so the reciprocals and the octant of
-        // T.r carry over -- unless a direction component is a zero, whose SIGN decides the sign of the clamped reciprocal
-        lo = V(__fadd_rn(T.r.o.x, 0.0f), __fadd_rn(T.r.o.y, 0.0f), __fadd_rn(T.r.o.z, 0.0f));
-        ld = V(__fadd_rn(T.r.d.x, 0.0f), __fadd_rn(T.r.d.y, 0.0f), __fadd_rn(T.r.d.z, 0.0f));
-        if (ld.x == 0.0f || ld.y == 0.0f || ld.z == 0.0f) dt_prep(lr, lo, ld);
-        else { lr = T.r; lr.o = lo; lr.d = ld; }
-    } else {
-        dt_to_local(sh, T.r.o, T.r.d, ray_o, lo, ld);
-        dt_prep(lr, lo, ld);
-    }
-    // mesh.cpp:172 (Mesh::bbox) and the root node of BVH::IntersectBVH (same box) in local space.  A MESH shape carries its own
-    // mesh's box; an instance's record holds its world box, the base mesh's local box lives in DtMeshDev.
-    if (kind == DT_SHAPE_MESH) {
-        if (!dt_box_test(smn, smx, lo, ld, lr, shape_min_t)) return false;
-    } else {
-        const DtMeshDev* m = S.meshes + sh->mesh;
-        if (!dt_box_test(m->bbox_min, m->bbox_max, lo, ld, lr, shape_min_t)) return false;
-    }
+    dt_prep(lr, lo, ld);
+    if (!dt_box_test(m->bbox_min, m->bbox_max, lo, ld, lr, shape_min_t)) return false;
     if (T.ng.y > 0x00FFFFFFu) dt_push(stack, T.sp, T.ng);
     if (T.tg.y != 0u) dt_push(stack, T.sp, T.tg);
     DT_STAT(3);
     T.blas_sp = T.sp;
     T.cur_shape = si;
     T.r = lr;
-    T.ng = make_uint2(__float_as_uint(sb1.w), 0x80000000u);
+    T.ng = make_uint2(m->node_root, 0x80000000u);
     T.tg = make_uint2(0u, 0u);
     entered_blas = true;
     return false;

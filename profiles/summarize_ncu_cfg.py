@@ -18,11 +18,13 @@ UNIT = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us": 1
 def main():
     rows = list(csv.reader(open(sys.argv[1])))
     hdr, units = rows[0], rows[1]
-    rays = {"closest": float(sys.argv[2]), "shadow": float(sys.argv[3])}
+    rays = {"closest": float(sys.argv[2]), "shadow": float(sys.argv[3]), "shade": float(sys.argv[2])}      # k_shade (if captured) shades the closest-hit wave
     out = {"source": sys.argv[4], "kernels": {}}
     for r in rows[2:]:
         name = r[hdr.index("Kernel Name")]
-        which = "shadow" if "k_traverse_dyn<1" in name or "k_traverse_dyn<true" in name else "closest"
+        which = "shade" if "k_shade" in name else ("shadow" if "k_traverse_dyn<1" in name or "k_traverse_dyn<true" in name else ("closest" if "k_traverse_dyn" in name else None))
+        if which is None:
+            continue
         d = {"kernel": name.split("(")[0]}
         for k, m in M.items():
             if m in hdr and r[hdr.index(m)]:
