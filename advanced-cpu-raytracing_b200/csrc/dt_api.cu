@@ -237,6 +237,7 @@ DtCamDev make_cam(const dt_camera_desc* c, int flags) {
     d.focus_distance = c->focus_distance; d.aperture_size = c->aperture_size;
     d.path_tracing = c->path_tracing; d.importance_sampling = c->importance_sampling; d.nee = c->next_event_estimation; d.russian_roulette = c->russian_roulette;
     d.jitter_aa = (flags & DT_FLAG_JITTER_AA) ? 1 : 0;
+    d.keep_weightless = (flags & DT_FLAG_KEEP_WEIGHTLESS_PATHS) ? 1 : 0;
     d.row_limit = (flags & DT_FLAG_REF_ROW_BANDS) ? (c->height / 8) * 8 : c->height;      // main.cpp:15,38-39: 8 bands of H / 8 rows
     return d;
 }

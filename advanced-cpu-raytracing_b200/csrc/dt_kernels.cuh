@@ -17,6 +17,7 @@ struct DtCamDev {
     float focus_distance, aperture_size;
     int path_tracing, importance_sampling, nee, russian_roulette;
     int jitter_aa;                 // DT_FLAG_JITTER_AA: keep the sub-pixel sample position (off = the reference's int truncation, main.cpp:83)
+    int keep_weightless;           // DT_FLAG_KEEP_WEIGHTLESS_PATHS: shade hits whose path weight is exactly zero too (what the reference does)
     int row_limit;                 // rows y >= row_limit get no camera rays (DT_FLAG_REF_ROW_BANDS: the reference's 8 row bands leave the
                                    // bottom H mod 8 rows unrendered, main.cpp:38-39); height otherwise
 };
@@ -436,6 +437,13 @@ __device__ __forceinline__ void dt_shade_ray(const int i, const DtSceneDev& S, c
         W = V(W.x * expf(-pm.absorption_coefficient[0] * t), W.y * expf(-pm.absorption_coefficient[1] * t), W.z * expf(-pm.absorption_coefficient[2] * t));
     }
 
+    // A path whose weight has underflowed to exactly zero adds exact zeros from here on (every term below is W times something).
+    // Under Russian roulette, whose pure-GI chains never end (raytracer.cpp:137-147: the throughput stays 1), such paths are what
+    // the last thousands of waves of a frame consist of: rays caught inside the closed 10 M-triangle mesh keep bouncing, with W = 0
+    // after ~100 bounces.  They end here.  Bounded-depth frames keep them (their ray counts stay the reference's); the one
+    // observable difference is that a NaN produced after the underflow no longer poisons the pixel.
+    if (cam.path_tracing && cam.russian_roulette && !cam.keep_weightless && W.x == 0.0f && W.y == 0.0f && W.z == 0.0f) return;
+
     const v3 eye = primary ? F3(cam.position) : o;
     const v3 w_o = vunit(vsub(eye, hitPoint));
     const float vac = 1.00001f;
@@ -684,8 +692,16 @@ __global__ void __launch_bounds__(128, DT_SHADE_MINBLOCKS) k_shade(DtSceneDev S,
                                                DtRayQueue out, float4* out_miss, int out_capacity,
                                                DtShadowQueue sq, int shadow_capacity, DtShadeCounters counters, float4* accum) {
     const int n = n_ptr ? *n_ptr : n_fixed;
-    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x)
-        dt_shade_ray(perm ? perm[j] : j, S, cam, in, in_miss, out, out_miss, out_capacity, sq, shadow_capacity, counters, accum);
+    // The lanes of a warp take the SAME number of trips and meet again after every hit: a lane whose hit returns early (a miss, an
+    // emissive surface, a path whose weight is zero) would otherwise run ahead into its next hits on its own -- nothing reconverges
+    // a warp at a loop back-edge -- and the warp degenerates into 32 single-lane executions of this kernel (measured on config 5
+    // once a fifth of the hits returned early: k_shade 2.3x slower in the device-resident loop than with one hit per thread).
+    const int lane = threadIdx.x & 31;
+    for (int base = blockIdx.x * blockDim.x + threadIdx.x - lane; base < n; base += gridDim.x * blockDim.x) {
+        const int j = base + lane;
+        if (j < n) dt_shade_ray(perm ? perm[j] : j, S, cam, in, in_miss, out, out_miss, out_capacity, sq, shadow_capacity, counters, accum);
+        __syncwarp();
+    }
 }
 
 // ------------------------------------------------------------------ sort / compact by material
@@ -1099,8 +1115,11 @@ __global__ void __launch_bounds__(128, DT_SHADE_MINBLOCKS) k_tail(DtSceneDev S, 
             asm volatile("bar.sync 1, %0;" :: "n"(DT_TAIL_PATH_THREADS) : "memory");          // all closest hits of the wave are stored (GI children read none, but shade reads hit0 by index)
             DT_TP(0)
             const DtShadeCounters cnt = {&sc[1], &sc[3 + i % 3], &sc[2]};
-            for (int j = tid; j < cur; j += DT_TAIL_PATH_THREADS)
-                dt_shade_ray(j, S, cam, in, Lmiss[i & 1], L[(i + 1) & 1], Lmiss[(i + 1) & 1], M.capacity, B[i % 3], M.shadow_capacity, cnt, accum);
+            for (int j0 = tid & ~31; j0 < cur; j0 += DT_TAIL_PATH_THREADS) {                  // warp-uniform trip count, see k_shade
+                const int j = j0 + (tid & 31);
+                if (j < cur) dt_shade_ray(j, S, cam, in, Lmiss[i & 1], L[(i + 1) & 1], Lmiss[(i + 1) & 1], M.capacity, B[i % 3], M.shadow_capacity, cnt, accum);
+                __syncwarp();
+            }
             DT_TP(1)
         } else if (pend > 0) {
             // ---- shadow warps: the shadow rays emitted by shade(i - 2); deferred mesh-light entries look at the closest hit of

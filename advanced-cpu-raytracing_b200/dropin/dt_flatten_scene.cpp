@@ -323,6 +323,7 @@ int dt_dropin_render(void* handle, Camera& cam, unsigned char* image, float* hdr
     fill_camera(cam, c);
     dt_render_params p; memset(&p, 0, sizeof p);
     p.seed = 1234; p.tile_world = 1;
+    if (const char* e = getenv("DT_RENDER_FLAGS")) p.flags = atoi(e);        // DT_FLAG_* (dorktracer.h), e.g. 4096 = follow zero-weight paths as the CPU loop does
     dt_stats st;
     const int rc = d->multi ? dt_multi_render(d->multi, &c, &p, image, hdrImage, &st) : dt_render(d->gpu, &c, &p, image, hdrImage, &st);
     if (rc != DT_OK) { fprintf(stderr, "dorktracer: %s\n", dt_last_error()); return rc; }

@@ -32,6 +32,7 @@ DT_FLAG_HOST_WAVE_LOOP = 256
 DT_FLAG_FRAME_GRAPH = 512
 DT_FLAG_PEER_HDR = 1024
 DT_FLAG_SORT_MATERIAL_ONLY = 2048
+DT_FLAG_KEEP_WEIGHTLESS_PATHS = 4096
 
 
 class dt_scene_options(C.Structure):

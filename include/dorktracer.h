@@ -249,7 +249,13 @@ enum {
     DT_FLAG_HOST_WAVE_LOOP = 256,   /* one host round trip per wave instead of the device-resident wave loop (A/B, debugging)       */
     DT_FLAG_FRAME_GRAPH = 512,      /* bounded-depth frames: replay the enqueued frame as a CUDA graph instead of ~50 launches      */
     DT_FLAG_PEER_HDR = 1024,        /* with DT_FLAG_PEER_FRAME: gather the radiance frame too when the camera has no tonemapper      */
-    DT_FLAG_SORT_MATERIAL_ONLY = 2048 /* ignore DT_SORT_SPATIAL (the opt-in hit-cell sort, an A/B knob): sort the hits by material only */
+    DT_FLAG_SORT_MATERIAL_ONLY = 2048, /* ignore DT_SORT_SPATIAL (the opt-in hit-cell sort, an A/B knob): sort the hits by material only */
+    DT_FLAG_KEEP_WEIGHTLESS_PATHS = 4096 /* path tracing with Russian roulette: by default a hit whose path weight W is EXACTLY (0,0,0) is
+                                       not shaded -- every radiance term below it is W times something, i.e. an exact zero, and the
+                                       reference's roulette never ends such chains (raytracer.cpp:137-147), so they are a fifth of the
+                                       rays of config 5.  The image is unchanged (only a NaN produced after the underflow would no longer
+                                       poison its pixel); dt_stats then counts the rays actually traced.  With this flag the paths are
+                                       followed as the reference follows them (ray counts comparable with the oracle's; A/B)            */
 };
 
 typedef struct dt_stats {

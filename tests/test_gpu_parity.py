@@ -240,7 +240,8 @@ def test_config5_shape_path_tracing_robust_statistics(tmp_path):
     cam = hs.camera(0)
     gs = GpuScene(hs)
     oldr, ohdr, ost = oracle_render(hs, cam, seed=9)
-    for flags in (0, capi.DT_FLAG_NO_SORT):
+    # the oracle follows zero-weight paths as the reference does: ray counts are compared with DT_FLAG_KEEP_WEIGHTLESS_PATHS
+    for flags in (capi.DT_FLAG_KEEP_WEIGHTLESS_PATHS, capi.DT_FLAG_KEEP_WEIGHTLESS_PATHS | capi.DT_FLAG_NO_SORT):
         ldr, hdr, st = gs.render(cam, seed=3, flags=flags)
         cm_g, cm_o = float(np.minimum(hdr, 20).mean()), float(np.minimum(ohdr, 20).mean())
         md_g, md_o = float(np.median(hdr.reshape(-1, 3).mean(1))), float(np.median(ohdr.reshape(-1, 3).mean(1)))
@@ -250,6 +251,19 @@ def test_config5_shape_path_tracing_robust_statistics(tmp_path):
         assert abs(int(st.rays_shadow) - int(ost.rays_shadow)) / int(ost.rays_shadow) < 0.01, (st.rays_shadow, ost.rays_shadow)
         assert psnr(ldr, oldr) >= 22.0, psnr(ldr, oldr)
         assert st.nan_pixels == 0
+    # Default: hits whose path weight is exactly zero are not shaded.  Same seed -> the same ray tree minus subtrees that add exact
+    # zeros: the image is the same (float atomics reorder the sums: compared to 1e-4 of the frame's scale), with fewer rays.
+    ldr_k, hdr_k, st_k = gs.render(cam, seed=3, flags=capi.DT_FLAG_KEEP_WEIGHTLESS_PATHS)
+    ldr_d, hdr_d, st_d = gs.render(cam, seed=3)
+    gs.close()
+    assert st_d.rays_closest < st_k.rays_closest and st_d.rays_shadow < st_k.rays_shadow, (st_d.rays_closest, st_k.rays_closest)
+    fin = np.isfinite(hdr_k) & np.isfinite(hdr_d)
+    assert fin.mean() > 0.999
+    rel = np.abs(hdr_d[fin] - hdr_k[fin]) / np.maximum(1.0, np.abs(hdr_k[fin]))
+    assert rel.max() <= 1e-4, rel.max()
+    frac, mx = ldr_mismatch_fraction(ldr_d, ldr_k, 1)
+    assert frac <= 1e-3, (frac, mx)
+    print("zero-weight paths: %d of %d closest-hit rays, %d of %d shadow rays not traced" % (st_k.rays_closest - st_d.rays_closest, st_k.rays_closest, st_k.rays_shadow - st_d.rays_shadow, st_k.rays_shadow))
 
 
 def test_sort_stage_is_a_pure_reordering():
@@ -808,7 +822,10 @@ def test_dropin_reference_main_on_instances_textures_and_path_tracing(tmp_path):
     ref = run_reference(p, probe=True)
     out = run_reference(p, probe=False, exe=REF_DROPIN)
     assert psnr(out["png"], ref["png"]) >= 22.0, psnr(out["png"], ref["png"])          # two independent 64-spp estimates
-    assert abs(out["closest"] - ref["closest"]) / ref["closest"] < 0.02
+    assert out["closest"] < ref["closest"]                                             # zero-weight paths are not followed by default ...
+    keep = run_reference(p, probe=False, exe=REF_DROPIN, extra_env={"DT_RENDER_FLAGS": str(capi.DT_FLAG_KEEP_WEIGHTLESS_PATHS)})
+    assert abs(keep["closest"] - ref["closest"]) / ref["closest"] < 0.02               # ... with them the ray tree has the reference's size
+    assert psnr(keep["png"], out["png"]) >= 40.0 or np.array_equal(keep["png"], out["png"]), psnr(keep["png"], out["png"])   # same seed, same image
 
 
 # ------------------------------------------------------------------ Monte Carlo against HIGH-SPP REFERENCE renders
