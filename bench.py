@@ -467,16 +467,23 @@ def main():
         n_closest_launches += int(st.launches_traverse_closest); n_waves_roof += int(st.waves)
         bulk["waves"] += int(st.bulk_waves); bulk["ms_closest"] += st.ms_bulk_closest; bulk["ms_shadow"] += st.ms_bulk_shadow
         bulk["rays_closest"] += int(st.rays_bulk_closest); bulk["rays_shadow"] += int(st.rays_bulk_shadow)
+    # ray accounting (untimed): `value` counts the rays this library TRACES.  Under Russian roulette it does not follow paths whose
+    # weight is exactly zero (dorktracer.h, DT_FLAG_KEEP_WEIGHTLESS_PATHS); the reference does, so the size of the reference's
+    # ray tree for the same frame is measured once with the flag and reported beside it.
+    rays_ref_tree = 0
+    if cfg == 5:
+        _, st = gs.render_device(cam, tile_rank=rank, tile_world=world, flags=capi.DT_FLAG_KEEP_WEIGHTLESS_PATHS | peer_flags)
+        rays_ref_tree = int(st.rays_closest) + int(st.rays_shadow)
     barrier()
 
     # max over ranks of the times, sum over ranks of the rays
     vals = torch.tensor([ms_sum, e2e_s], dtype=torch.float64, device="cuda")
-    cnts = torch.tensor([rays_c, rays_s, launches], dtype=torch.float64, device="cuda")
+    cnts = torch.tensor([rays_c, rays_s, launches, rays_ref_tree], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
         dist.all_reduce(cnts, op=dist.ReduceOp.SUM)
     ms_sum_max, e2e_s_max = vals.tolist()
-    rays_c_all, rays_s_all, launches_all = cnts.tolist()
+    rays_c_all, rays_s_all, launches_all, rays_ref_tree_all = cnts.tolist()
 
     if rank == 0:
         rays_per_step = (rays_c_all + rays_s_all) / args.steps
@@ -546,6 +553,13 @@ def main():
                 "resolution_rendered": [W, H], "triangles": hs.n_triangles(),
                 "rays_per_step": rays_per_step, "closest_rays_per_step": rays_c_all / args.steps, "shadow_rays_per_step": rays_s_all / args.steps,
                 "waves_per_step_rank0": waves / args.steps,
+                "ray_accounting": ({"rays_per_step": "rays traced by this library (what `value` and `e2e` count)",
+                                    "rays_per_step_of_the_reference_ray_tree": rays_ref_tree_all,
+                                    "mrays_per_s_counting_the_reference_ray_tree": rays_ref_tree_all / (ms_per_step * 1e3),
+                                    "note": "under Russian roulette hits whose path weight is exactly (0,0,0) are not shaded: everything below them is an exact zero, "
+                                            "the image is the same (tests/test_gpu_parity.py::test_config5_shape_path_tracing_robust_statistics); the reference "
+                                            "follows those paths, so its ray tree for this frame is larger (one untimed frame with DT_FLAG_KEEP_WEIGHTLESS_PATHS)"}
+                                   if rays_ref_tree_all > 0 else None),
                 "timing": "CUDA events on the library stream (render + resolve + tonemap; + barrier / reduce for N > 1), max over ranks",
                 "gather": ("peer-memory stores (CUDA IPC, fused into the resolve kernel) + one barrier" if peer else "nccl-reduce") if world > 1 else "none",
                 "scene_load_s": t_load, "scene_upload_s": t_upload,

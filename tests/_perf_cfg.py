@@ -23,11 +23,11 @@ elif cfg == 'c5': p = scenegen.gen_config5('/tmp/gen/c5', spp=int(os.environ.get
 else: raise SystemExit('unknown config')
 hs = HostScene(p); cam = hs.camera(0); t1 = time.time()
 gs = GpuScene(hs); t2 = time.time()
-WAVE = int(os.environ.get('DT_AB_WAVE', '0'))
-if os.environ.get('DT_AB_WARM', '1') == '1': gs.render(cam, want_hdr=False, max_wave_rays=WAVE)
+WAVE = int(os.environ.get('DT_AB_WAVE', '0')); FLAGS = int(os.environ.get('DT_AB_FLAGS', '0'))
+if os.environ.get('DT_AB_WARM', '1') == '1': gs.render(cam, want_hdr=False, max_wave_rays=WAVE, flags=FLAGS)
 n = int(os.environ.get('DT_AB_N', '3')); acc = np.zeros(7)
 for _ in range(n):
-    ldr, hdr, st = gs.render(cam, want_hdr=False, max_wave_rays=WAVE)
+    ldr, hdr, st = gs.render(cam, want_hdr=False, max_wave_rays=WAVE, flags=FLAGS)
     acc += np.array([st.ms_total, st.ms_traverse_closest, st.ms_shade, st.ms_traverse_shadow, st.ms_sort, st.waves, st.kernel_launches])
 acc /= n
 print('%%s %%dx%%d spp %%d tris %%d (load %%.1fs create %%.1fs): total %%.1f closest %%.1f shade %%.1f shadow %%.1f sort %%.1f ms | waves %%d launches %%d | rays %%d+%%d | %%.0f Mrays/s | md5 %%s' %% (
