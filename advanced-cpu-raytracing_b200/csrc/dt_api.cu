@@ -472,6 +472,7 @@ int render_core(dt_scene* s, const dt_camera_desc* cam, const dt_render_params* 
     const int fan = s->fanout_hint + (pt ? 1 : 0);
     const int shadows_per_hit = std::max(1, s->lights_shadowed);
     int wave_max = P.max_wave_rays;
+    if (wave_max <= 0 && total <= (1ll << 23)) wave_max = 1 << 23;          // single-wave frames: nothing to size (cudaMemGetInfo costs ~1 ms, a quarter of a config-2 frame)
     if (wave_max <= 0) {
         // Default wave size: as large as HBM allows, up to 32 Mi rays.  Every wave ends in the drain of five persistent / grid-stride
         // launches, so frames of many waves (path tracing) run ~3 % faster with 32 Mi-ray waves than with 8 Mi (config 5:
