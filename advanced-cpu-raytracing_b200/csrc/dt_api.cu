@@ -238,6 +238,7 @@ DtCamDev make_cam(const dt_camera_desc* c, int flags) {
     d.path_tracing = c->path_tracing; d.importance_sampling = c->importance_sampling; d.nee = c->next_event_estimation; d.russian_roulette = c->russian_roulette;
     d.jitter_aa = (flags & DT_FLAG_JITTER_AA) ? 1 : 0;
     d.keep_weightless = (flags & DT_FLAG_KEEP_WEIGHTLESS_PATHS) ? 1 : 0;
+    d.smooth_shading = (flags & DT_FLAG_SMOOTH_SHADING) ? 1 : 0;
     d.row_limit = (flags & DT_FLAG_REF_ROW_BANDS) ? (c->height / 8) * 8 : c->height;      // main.cpp:15,38-39: 8 bands of H / 8 rows
     return d;
 }
@@ -937,6 +938,7 @@ static int scene_create_impl(const dt_scene_desc* desc, const dt_scene_options* 
     if ((rc = upload<DtShapeDev>(s->allocs, hs.shapes.data(), hs.shapes.size(), &D.shapes))) return fail(rc);
     if ((rc = upload<DtMeshDev>(s->allocs, hs.meshes.data(), hs.meshes.size(), &D.meshes))) return fail(rc);
     if ((rc = upload<float>(s->allocs, hs.uvs.data(), hs.uvs.size(), &D.uvs))) return fail(rc);
+    if ((rc = upload<float>(s->allocs, hs.vnormals.data(), hs.vnormals.size(), &D.vnormals))) return fail(rc);
     if ((rc = upload<dt_material>(s->allocs, desc->materials, (size_t)desc->n_materials, &D.materials))) return fail(rc);
     if ((rc = upload<dt_brdf>(s->allocs, desc->brdfs, (size_t)desc->n_brdfs, &D.brdfs))) return fail(rc);
     if ((rc = upload<dt_point_light>(s->allocs, desc->point_lights, (size_t)desc->n_point_lights, &D.point_lights))) return fail(rc);

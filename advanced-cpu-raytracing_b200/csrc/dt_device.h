@@ -59,6 +59,8 @@ struct DtMeshDev {
     int32_t vertex_offset, texture_offset;
     float bbox_min[3], bbox_max[3];
     double surface_area;
+    int32_t normal_base;          // index of vertex normal 0 in vnormals[] (float3 units), -1: the mesh has none (flat shading only)
+    int32_t pad_;
 };
 
 struct DtFaceDev {                // canonical (post-build) face record, read only when shading the final hit
@@ -84,6 +86,7 @@ struct DtSceneDev {
     const DtFaceDev* faces;
     const float* verts;           // xyz
     const float* uvs;             // uv
+    const float* vnormals;        // xyz per vertex of the shadingMode="smooth" meshes (DT_FLAG_SMOOTH_SHADING)
     const dt_material* materials;
     const dt_brdf* brdfs;
     const dt_point_light* point_lights;

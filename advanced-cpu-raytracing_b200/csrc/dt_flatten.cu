@@ -131,6 +131,11 @@ bool dt_flatten_scene(const dt_scene_desc* d, DtHostScene& out, std::string& err
             }
             md.uv_base = uit->second;
         }
+        md.normal_base = -1;
+        if (m.vertex_normals) {                      // shadingMode="smooth" meshes (DT_FLAG_SMOOTH_SHADING): per mesh, never shared
+            md.normal_base = (int32_t)(out.vnormals.size() / 3);
+            out.vnormals.insert(out.vnormals.end(), m.vertex_normals, m.vertex_normals + (size_t)m.n_vertices * 3);
+        }
         md.n_faces = m.n_faces; md.n_uvs = m.n_uvs;
         md.vertex_offset = m.vertex_offset; md.texture_offset = m.texture_offset;
         memcpy(md.bbox_min, m.bbox_min, 12); memcpy(md.bbox_max, m.bbox_max, 12);

@@ -34,6 +34,7 @@ struct DtHostScene {
     std::vector<DtFaceDev> faces;
     std::vector<float> verts;
     std::vector<float> uvs;
+    std::vector<float> vnormals;
     std::vector<DtImageDev> images;
     std::vector<uint8_t> image_u8;
     std::vector<float> image_f32;

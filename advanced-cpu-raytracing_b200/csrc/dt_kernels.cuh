@@ -17,6 +17,7 @@ struct DtCamDev {
     float focus_distance, aperture_size;
     int path_tracing, importance_sampling, nee, russian_roulette;
     int jitter_aa;                 // DT_FLAG_JITTER_AA: keep the sub-pixel sample position (off = the reference's int truncation, main.cpp:83)
+    int smooth_shading;            // DT_FLAG_SMOOTH_SHADING: interpolated vertex normals on meshes that carry them (not in the reference)
     int keep_weightless;           // DT_FLAG_KEEP_WEIGHTLESS_PATHS: shade hits whose path weight is exactly zero too (what the reference does)
     int row_limit;                 // rows y >= row_limit get no camera rays (DT_FLAG_REF_ROW_BANDS: the reference's 8 row bands leave the
                                    // bottom H mod 8 rows unrendered, main.cpp:38-39); height otherwise
@@ -425,7 +426,7 @@ __device__ __forceinline__ void dt_shade_ray(const int i, const DtSceneDev& S, c
         v3 ld = apply_transform(sh.inv, d, 0.0f);
         if (sh.has_motion_blur) lo = vadd(lo, vscale(F3(sh.motion_blur), mb));
         if (sh.kind == DT_SHAPE_SPHERE) sphere_surface(S, sh, t, lo, ld, V(0.f, 0.f, 0.f), sf);
-        else mesh_surface(S, sh, in.hit_face[i], t, h0.y, h0.z, lo, ld, sf);
+        else mesh_surface(S, sh, in.hit_face[i], t, h0.y, h0.z, lo, ld, cam.smooth_shading != 0, sf);
     }
     const v3 normal = sf.normal;
     const dt_material mat = S.materials[sh.material - 1];

@@ -139,11 +139,19 @@ struct DtSurface { v3 normal; float u, v; };
 // (Mesh::Intersect mesh.cpp:176-180 / InstancedMesh::Intersect instancedMesh.cpp:52-58), evaluated once for
 // the winning hit.  (lo, ld) is the ray in the shape's local space.
 __device__ inline void mesh_surface(const DtSceneDev& S, const DtShapeDev& sh, int face_index, float t, float beta, float gama,
-                                    v3 lo, v3 ld, DtSurface& out) {
+                                    v3 lo, v3 ld, bool smooth, DtSurface& out) {
     const DtShapeDev& ow = S.shapes[sh.owner];
     const DtMeshDev& m = S.meshes[sh.mesh];
     const DtFaceDev fc = S.faces[m.face_base + face_index];
     v3 N = V(fc.nx, fc.ny, fc.nz);
+    if (smooth && m.normal_base >= 0) {           // DT_FLAG_SMOOTH_SHADING: barycentric interpolation of the vertex normals
+        const float* np = S.vnormals + (size_t)m.normal_base * 3;
+        const v3 n0 = F3(np + (size_t)fc.v0 * 3), n1 = F3(np + (size_t)fc.v1 * 3), n2 = F3(np + (size_t)fc.v2 * 3);
+        const float w0 = 1.0f - beta - gama;
+        const v3 sn = V(n0.x * w0 + n1.x * beta + n2.x * gama, n0.y * w0 + n1.y * beta + n2.y * gama, n0.z * w0 + n1.z * beta + n2.z * gama);
+        const float l = vlen(sn);
+        if (l > 0.0f) N = vdiv(sn, l);
+    }
     v3 normal = N;
     out.u = 0.f; out.v = 0.f;
     if (m.n_uvs > 0) {

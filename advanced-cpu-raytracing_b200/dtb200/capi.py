@@ -33,6 +33,7 @@ DT_FLAG_FRAME_GRAPH = 512
 DT_FLAG_PEER_HDR = 1024
 DT_FLAG_SORT_MATERIAL_ONLY = 2048
 DT_FLAG_KEEP_WEIGHTLESS_PATHS = 4096
+DT_FLAG_SMOOTH_SHADING = 8192
 
 
 class dt_scene_options(C.Structure):
@@ -101,7 +102,8 @@ class dt_mesh(C.Structure):
                 ("vertex_offset", C.c_int32), ("texture_offset", C.c_int32),
                 ("faces", C.POINTER(dt_face)), ("n_faces", C.c_int32),
                 ("bvh", C.POINTER(dt_bvh2_node)), ("n_bvh_nodes", C.c_int32),
-                ("bbox_min", c_f3), ("bbox_max", c_f3), ("surface_area", C.c_double)]
+                ("bbox_min", c_f3), ("bbox_max", c_f3), ("surface_area", C.c_double),
+                ("vertex_normals", C.POINTER(C.c_float))]
 
 
 class dt_shape(C.Structure):

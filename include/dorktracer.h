@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define DT_ABI_VERSION 1
+#define DT_ABI_VERSION 2
 
 /* ---- status codes ---- */
 enum {
@@ -157,6 +157,9 @@ typedef struct dt_mesh {                /* src/mesh.hpp:11-50: geometry + the BV
     int32_t n_bvh_nodes;
     float bbox_min[3], bbox_max[3];     /* Mesh::bbox                                                    */
     double surface_area;                /* Mesh::surfaceArea                                             */
+    const float* vertex_normals;        /* SURVEY 8f-4, optional: xyz per vertex (n_vertices triples) of a shadingMode="smooth" mesh,
+                                           NULL otherwise.  The reference parses nothing of the kind and shades every mesh flat; the
+                                           normals are used only by renders that pass DT_FLAG_SMOOTH_SHADING                   */
 } dt_mesh;
 
 enum { DT_SHAPE_MESH = 0, DT_SHAPE_INSTANCE = 1, DT_SHAPE_SPHERE = 2 };
@@ -250,6 +253,9 @@ enum {
     DT_FLAG_FRAME_GRAPH = 512,      /* bounded-depth frames: replay the enqueued frame as a CUDA graph instead of ~50 launches      */
     DT_FLAG_PEER_HDR = 1024,        /* with DT_FLAG_PEER_FRAME: gather the radiance frame too when the camera has no tonemapper      */
     DT_FLAG_SORT_MATERIAL_ONLY = 2048, /* ignore DT_SORT_SPATIAL (the opt-in hit-cell sort, an A/B knob): sort the hits by material only */
+    DT_FLAG_SMOOTH_SHADING = 8192,  /* meshes that carry dt_mesh.vertex_normals (shadingMode="smooth" in the XML, which the
+                                       reference ignores) are shaded with the barycentric interpolation of their vertex normals
+                                       in place of the face normal.  Off by default: parity with the reference means flat shading */
     DT_FLAG_KEEP_WEIGHTLESS_PATHS = 4096 /* path tracing with Russian roulette: by default a hit whose path weight W is EXACTLY (0,0,0) is
                                        not shaded -- every radiance term below it is W times something, i.e. an exact zero, and the
                                        reference's roulette never ends such chains (raytracer.cpp:137-147), so they are a fifth of the

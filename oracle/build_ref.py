@@ -214,7 +214,8 @@ def copy_sources(dst):
 def build(force=False):
     want = [os.path.join(OUT, "raytracer"), os.path.join(OUT, "raytracer_probe"), os.path.join(OUT, "raytracer_dropin")]
     lib = os.path.join(PKG, "libdorktracer.so")
-    stale = os.path.exists(want[2]) and os.path.exists(DROPIN_SRC) and os.path.getmtime(DROPIN_SRC) > os.path.getmtime(want[2])
+    abi = os.path.join(REPO, "include", "dorktracer.h")         # the drop-in embeds the ABI structs: a header change makes it stale too
+    stale = os.path.exists(want[2]) and any(os.path.exists(f) and os.path.getmtime(f) > os.path.getmtime(want[2]) for f in (DROPIN_SRC, abi))
     if not force and not stale and all(os.path.exists(w) for w in want):
         return True
     if not os.path.isdir(REF_SRC):

@@ -339,6 +339,8 @@ static inline float greyscale3(v3 c) { return (c.x + c.y + c.z) / 3.0f; }     /*
 static inline v3 mesh_vertex(const dt_mesh* m, int id) { const float* p = &m->vertices[(size_t)(id - 1 + m->vertex_offset) * 3]; return V(p[0], p[1], p[2]); }
 static inline const float* mesh_uv(const dt_mesh* m, int id) { return &m->uvs[(size_t)(id - 1 + m->texture_offset) * 2]; }
 
+static int g_dto_smooth = 0;                               /* dto_set_render_flags: DT_FLAG_SMOOTH_SHADING */
+
 /* ---- Mesh::IntersectFace, mesh.cpp:201-372.  `owner` = index of the Mesh shape that owns the geometry ---- */
 static int intersect_face(const dt_scene_desc* sc, Ray* ray, int owner, uint32_t faceIdx) {
     const dt_shape* sh = &sc->shapes[owner];
@@ -362,9 +364,18 @@ static int intersect_face(const dt_scene_desc* sc, Ray* ray, int owner, uint32_t
 
     ray->hit.minT = t;
     ray->hit.hasHit = 1;
-    ray->hit.normal = F3(face->n);
-    ray->hit.hitPoint = vadd(ray->origin, vscale(ray->dir, ray->hit.minT));
     v3 N = F3(face->n);
+    if (g_dto_smooth && m->vertex_normals) {               /* DT_FLAG_SMOOTH_SHADING (not in the reference): interpolated vertex normals */
+        const float* n0 = &m->vertex_normals[(size_t)(face->v0_id - 1 + m->vertex_offset) * 3];
+        const float* n1 = &m->vertex_normals[(size_t)(face->v1_id - 1 + m->vertex_offset) * 3];
+        const float* n2 = &m->vertex_normals[(size_t)(face->v2_id - 1 + m->vertex_offset) * 3];
+        const float w0 = 1.0f - beta - gama;
+        v3 sn = V(n0[0] * w0 + n1[0] * beta + n2[0] * gama, n0[1] * w0 + n1[1] * beta + n2[1] * gama, n0[2] * w0 + n1[2] * beta + n2[2] * gama);
+        const float l = vlen(sn);
+        if (l > 0.0f) N = vdiv(sn, l);
+    }
+    ray->hit.normal = N;
+    ray->hit.hitPoint = vadd(ray->origin, vscale(ray->dir, ray->hit.minT));
     const double* invT = sh->inverse_transpose_transform;
     if (m->n_uvs > 0) {
         const float* uv0 = mesh_uv(m, face->v0_id); const float* uv1 = mesh_uv(m, face->v1_id); const float* uv2 = mesh_uv(m, face->v2_id);
@@ -1232,6 +1243,9 @@ int dto_tonemap(const float* hdr, int32_t width, int32_t height, float key, floa
 
 /* Render one camera like main.cpp:142-196.  n_threads row bands (the reference hard-codes 8; rows H mod
  * n_threads at the bottom are rendered here too).  hdr may be NULL unless the camera has a tonemapper. */
+/* Render flags of include/dorktracer.h that change the image and are not part of the reference (process-wide; tests only). */
+void dto_set_render_flags(int flags) { g_dto_smooth = (flags & DT_FLAG_SMOOTH_SHADING) ? 1 : 0; }
+
 int dto_render(const dt_scene_desc* sc, const dt_camera_desc* cam, uint64_t seed, int n_threads,
                uint8_t* ldr, float* hdr, dt_stats* stats) {
     if (!sc || !cam || !ldr) return DT_ERR_INVALID;

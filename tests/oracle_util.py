@@ -16,7 +16,7 @@ sys.path.insert(0, os.path.join(REPO, "advanced-cpu-raytracing_b200"))
 
 from dtb200 import capi  # noqa: E402
 
-DTORACLE_SYMBOLS = ["dto_render", "dto_render_reference_rng", "dto_debug_reference_rng", "dto_primary_hits", "dto_tonemap", "dto_trace_closest", "dto_trace_occluded"]
+DTORACLE_SYMBOLS = ["dto_render", "dto_render_reference_rng", "dto_debug_reference_rng", "dto_primary_hits", "dto_tonemap", "dto_trace_closest", "dto_trace_occluded", "dto_set_render_flags"]
 
 
 def load_dtoracle():
@@ -36,6 +36,8 @@ def load_dtoracle():
     lib.dto_trace_closest.restype = C.c_int
     lib.dto_trace_occluded.argtypes = [C.POINTER(capi.dt_scene_desc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     lib.dto_trace_occluded.restype = C.c_int
+    lib.dto_set_render_flags.argtypes = [C.c_int]
+    lib.dto_set_render_flags.restype = None
     return lib
 
 
@@ -49,14 +51,16 @@ def have_ref():
     return os.path.exists(REF_BIN) and os.path.exists(REF_PROBE)
 
 
-def oracle_render(host_scene, cam, seed=1234, threads=None, want_hdr=True):
+def oracle_render(host_scene, cam, seed=1234, threads=None, want_hdr=True, flags=0):
     lib = load_dtoracle()
+    lib.dto_set_render_flags(flags)          # DT_FLAG_SMOOTH_SHADING is the only flag that changes the oracle's image
     W, H = cam.width, cam.height
     ldr = np.zeros((H, W, 3), np.uint8)
     hdr = np.zeros((H, W, 3), np.float32) if want_hdr else None
     stats = capi.dt_stats()
     rc = lib.dto_render(host_scene.desc_ptr, C.byref(cam), seed, threads or (os.cpu_count() or 1),
                         ldr.ctypes.data_as(C.c_void_p), hdr.ctypes.data_as(C.c_void_p) if hdr is not None else None, C.byref(stats))
+    lib.dto_set_render_flags(0)
     if rc != 0:
         raise RuntimeError("dto_render failed %d" % rc)
     return ldr, hdr, stats

@@ -912,3 +912,24 @@ def test_env_map_on_miss_under_whitted_statistics(tmp_path, blur_instance):
     assert psnr(ldr, oldr) >= 40.0, psnr(ldr, oldr)
     assert abs(int(st.rays_closest) - int(ost.rays_closest)) / int(ost.rays_closest) < 0.01
     assert st.nan_pixels == 0
+
+
+# ------------------------------------------------------------------ shadingMode="smooth" behind DT_FLAG_SMOOTH_SHADING
+@pytest.mark.parametrize("name", ["smooth_berserker_smooth", "smooth_low_poly_smooth"])
+def test_smooth_shading_flag(name):
+    """Flag off: the compiled reference's (flat-shaded) image and ray counts.  Flag on: the CPU oracle's smooth image -- which is
+    pinned against the course's golden PNG by tests/test_cpu_smooth_shading.py -- within one level, and the golden itself."""
+    hs, g = golden_scene(name)
+    cam = hs.camera(0)
+    gs = GpuScene(hs)
+    ldr, _, st = gs.render(cam)
+    frac, mx = ldr_mismatch_fraction(ldr, g["ref_ldr"], tol=1)
+    assert frac <= 1e-4 and mx <= 1, (frac, mx)
+    assert [int(st.rays_closest), int(st.rays_shadow)] == g["rays"].tolist()
+    sm, _, st2 = gs.render(cam, flags=capi.DT_FLAG_SMOOTH_SHADING)
+    gs.close()
+    osm, _, _ = oracle_render(hs, cam, want_hdr=False, flags=capi.DT_FLAG_SMOOTH_SHADING)
+    frac, mx = ldr_mismatch_fraction(sm, osm, tol=1)
+    assert frac <= 1e-4, (frac, mx)
+    assert (int(st2.rays_closest), int(st2.rays_shadow)) == (int(st.rays_closest), int(st.rays_shadow))
+    assert psnr(sm, g["golden"]) >= 41.0 and psnr(ldr, g["golden"]) <= 32.0, (psnr(sm, g["golden"]), psnr(ldr, g["golden"]))
