@@ -253,20 +253,21 @@ enum {
     DT_FLAG_FRAME_GRAPH = 512,      /* bounded-depth frames: replay the enqueued frame as a CUDA graph instead of ~50 launches      */
     DT_FLAG_PEER_HDR = 1024,        /* with DT_FLAG_PEER_FRAME: gather the radiance frame too when the camera has no tonemapper      */
     DT_FLAG_SORT_MATERIAL_ONLY = 2048, /* ignore DT_SORT_SPATIAL (the opt-in hit-cell sort, an A/B knob): sort the hits by material only */
-    DT_FLAG_SMOOTH_SHADING = 8192,  /* meshes that carry dt_mesh.vertex_normals (shadingMode="smooth" in the XML, which the
-                                       reference ignores) are shaded with the barycentric interpolation of their vertex normals
-                                       in place of the face normal.  Off by default: parity with the reference means flat shading */
-    DT_FLAG_KEEP_WEIGHTLESS_PATHS = 4096 /* path tracing with Russian roulette: by default a hit whose path weight W is EXACTLY (0,0,0) is
+    DT_FLAG_KEEP_WEIGHTLESS_PATHS = 4096, /* path tracing with Russian roulette: by default a hit whose path weight W is EXACTLY (0,0,0) is
                                        not shaded -- every radiance term below it is W times something, i.e. an exact zero, and the
                                        reference's roulette never ends such chains (raytracer.cpp:137-147), so they are a fifth of the
                                        rays of config 5.  The image is unchanged (only a NaN produced after the underflow would no longer
                                        poison its pixel); dt_stats then counts the rays actually traced.  With this flag the paths are
                                        followed as the reference follows them (ray counts comparable with the oracle's; A/B)            */
+    DT_FLAG_SMOOTH_SHADING = 8192    /* meshes that carry dt_mesh.vertex_normals (shadingMode="smooth" in the XML, which the
+                                       reference ignores) are shaded with the barycentric interpolation of their vertex normals
+                                       in place of the face normal.  Off by default: parity with the reference means flat shading */
 };
 
 typedef struct dt_stats {
-    uint64_t rays_closest;              /* closest-hit queries  (== Raytracer::IntersectObjects calls)  */
-    uint64_t rays_shadow;               /* occlusion queries    (== Raytracer::CastShadowRay calls)     */
+    uint64_t rays_closest;              /* closest-hit queries traced (== Raytracer::IntersectObjects calls; under Russian roulette
+                                           only with DT_FLAG_KEEP_WEIGHTLESS_PATHS, see there)                                */
+    uint64_t rays_shadow;               /* occlusion queries traced (== Raytracer::CastShadowRay calls, same remark)          */
     uint64_t nan_pixels;
     uint32_t waves;
     uint32_t kernel_launches;           /* launches of this library's kernels inside the call           */

@@ -9,9 +9,11 @@
  * reference's recursion and float/double evaluation order.  Each function cites the reference file:line it
  * follows.  Compile with -ffp-contract=off (the reference build contains no FMA).
  *
- * Pinning: tests/test_oracle_pins.py checks this file against the reference's own golden
- * PNGs (archive/hw1_outputs, six "pins" scenes, committed as fixtures under tests/golden/) and — in the build
- * container — against the compiled reference oracle/_ref/raytracer_probe (hit ids, radiance, LDR bytes).
+ * Pinning: tests/test_cpu_oracle_host.py checks this file against the reference's own golden
+ * PNGs (archive/hw1_outputs, six "pins" scenes, committed as fixtures under tests/golden/) and against outputs of the
+ * compiled reference oracle/_ref/raytracer_probe (hit ids, radiance bits, LDR bytes, ray counts; fixtures + live in the
+ * build container); tests/test_cpu_monte_carlo_pin.py does the same for the Monte-Carlo path (reference-RNG mode below),
+ * tests/test_cpu_smooth_shading.py for DT_FLAG_SMOOTH_SHADING (off: the reference's image; on: the course's goldens).
  *
  * Random numbers: the reference draws from std::mt19937s that are default-seeded or seeded from an UNSEEDED rand()
  * (raytracer.cpp:10,14, main.cpp:49, areaLight.h:28, meshLight.h:17, sphericalEnvironmentLight.h:19), so with ONE render
