@@ -406,3 +406,51 @@ def test_host_loader_reports_builder_failure_instead_of_falling_back(tmp_path):
     h2 = C.c_void_p()
     assert lib.dth_scene_load_xml(os.fsencode(p), C.byref(h2)) == 0
     lib.dth_scene_free(h2)
+
+
+def test_streamed_ply_loader_equals_the_generic_reader(tmp_path):
+    """binary little-endian triangle PLYs are decoded by parallel workers straight into the scene arrays
+    (host/dth_io.cpp).  The same mesh written big-endian with double coordinates and an extra vertex property takes the generic
+    property-by-property reader; both must give the same vertices, faces (ids, normals, areas in build order), boxes and BVH2."""
+    verts, faces = scenegen.blob_mesh(400, 201, 3.0, (0.5, -0.25, 1.0))          # 160 k faces: several decode / face-property workers
+    verts = np.ascontiguousarray(verts, dtype=np.float32)
+    faces = np.ascontiguousarray(faces, dtype=np.int32)
+    le = tmp_path / "le.ply"
+    scenegen.write_ply(str(le), verts, faces)
+    be = tmp_path / "be.ply"
+    with open(be, "wb") as f:
+        f.write(("ply\nformat binary_big_endian 1.0\nelement vertex %d\nproperty double x\nproperty double y\nproperty double z\nproperty uchar quality\n"
+                 "element face %d\nproperty list uchar int vertex_indices\nend_header\n" % (len(verts), len(faces))).encode())
+        rec = np.empty(len(verts), dtype=[("p", ">f8", (3,)), ("q", "u1")])
+        rec["p"] = verts.astype(np.float64); rec["q"] = 7
+        f.write(rec.tobytes())
+        frec = np.empty(len(faces), dtype=[("n", "u1"), ("i", ">i4", (3,))])
+        frec["n"] = 3; frec["i"] = faces
+        f.write(frec.tobytes())
+    scene = ("<Scene><Cameras><Camera id=\"1\"><Position>0 0 12</Position><Gaze>0 0 -1</Gaze><Up>0 1 0</Up><NearPlane>-1 1 -1 1</NearPlane>"
+             "<NearDistance>2</NearDistance><ImageResolution>64 64</ImageResolution><ImageName>s.png</ImageName></Camera></Cameras>"
+             "<Lights><AmbientLight>25 25 25</AmbientLight><PointLight id=\"1\"><Position>5 8 10</Position><Intensity>9000 9000 9000</Intensity></PointLight></Lights>"
+             "<Materials><Material id=\"1\"><AmbientReflectance>1 1 1</AmbientReflectance><DiffuseReflectance>0.6 0.5 0.4</DiffuseReflectance>"
+             "<SpecularReflectance>0.3 0.3 0.3</SpecularReflectance><PhongExponent>20</PhongExponent></Material></Materials>"
+             "<Objects><Mesh id=\"1\" shadingMode=\"smooth\"><Material>1</Material><Faces plyFile=\"%s\" /></Mesh></Objects></Scene>")
+    out = []
+    for ply in (le, be):
+        xml = tmp_path / (ply.stem + ".xml")
+        xml.write_text(scene % ply)
+        hs = HostScene(str(xml))
+        m = hs.desc.meshes[0]
+        nf, nv, nn = m.n_faces, m.n_vertices, m.n_bvh_nodes
+        out.append((hs, {
+            "verts": np.ctypeslib.as_array(m.vertices, (nv * 3,)).copy(),
+            "faces": np.frombuffer((capi.dt_face * nf).from_address(C.addressof(m.faces.contents)), dtype=np.uint8).copy(),
+            "nodes": np.frombuffer((capi.dt_bvh2_node * nn).from_address(C.addressof(m.bvh.contents)), dtype=np.uint8).copy(),
+            "vnormals": np.ctypeslib.as_array(m.vertex_normals, (nv * 3,)).copy(),
+            "bbox": (tuple(m.bbox_min), tuple(m.bbox_max)), "area": m.surface_area, "n": (nf, nv, nn)}))
+    (hs_a, a), (hs_b, b) = out
+    assert a["n"] == b["n"] and a["n"][0] == len(faces)
+    for k in ("verts", "faces", "nodes", "vnormals"):
+        assert (a[k].view(np.uint8) == b[k].view(np.uint8)).all(), k
+    assert a["bbox"] == b["bbox"] and a["area"] == b["area"]
+    la, _, sa = oracle_render(hs_a, hs_a.camera(0), want_hdr=False)
+    lb, _, sb = oracle_render(hs_b, hs_b.camera(0), want_hdr=False)
+    assert (la == lb).all() and la.any() and int(sa.rays_closest) == int(sb.rays_closest)
