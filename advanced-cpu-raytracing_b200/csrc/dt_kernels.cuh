@@ -63,8 +63,9 @@ enum { DT_CNT_NEXT = 0, DT_CNT_SHADOW = 1, DT_CNT_FETCH_A = 2, DT_CNT_FETCH_B = 
        DT_CNT_ITERS = 24,         // executions of the WHILE body (two waves each)
        DT_CNT_TAIL_WAVES = 25,    // longest block-local wave chain of k_tail
        DT_CNT_TAIL_RAYS = 26,     // rays handed to k_tail
+       DT_CNT_SHADOW_DEAD = 28,   // 64-bit: shadow-queue entries of this frame that are not traced (zero contribution, see dt_shade_ray)
        DT_CNT_COUNT = 32 };
-struct DtShadeCounters { int* next; int* shadow; int* overflow; };
+struct DtShadeCounters { int* next; int* shadow; int* overflow; unsigned long long* shadow_dead; };
 
 #define DT_DEAD_PIXEL 0xFFFFFFFFu
 
@@ -225,6 +226,7 @@ __global__ void __launch_bounds__(128, ANY ? DT_TRAV_MINBLOCKS_ANY : DT_TRAV_MIN
             if (!ANY && q.pixel && q.pixel[i] == DT_DEAD_PIXEL) continue;
             const float4 o = ANY ? sq.o_time[i] : q.o_time[i];
             const float4 d = ANY ? sq.d_tmax[i] : q.d_tmax[i];
+            if (ANY && d.w < 0.0f) continue;                            // zero contribution: not traced (dt_shade_ray)
             DtTrav T;
             dt_trav_init<ANY>(T, S, V(o.x, o.y, o.z), V(d.x, d.y, d.z), o.w, ANY ? d.w : CUDART_INF_F);
             while (!dt_trav_step<ANY, WW>(T, stack, S, (ANY ? sq.o_time : q.o_time) + i, (ANY ? sq.d_tmax : q.d_tmax) + i)) {}
@@ -263,27 +265,40 @@ __global__ void __launch_bounds__(128, ANY ? DT_TRAV_MINBLOCKS_ANY : DT_TRAV_MIN
     const unsigned long long tl_t0 = dt_now(); unsigned long long tl_td = 0; int tl_steps = 0;
 #endif
     for (;;) {
-        if (!drained) {
-            const unsigned idle = __ballot_sync(FULL, ray < 0);
-            if (idle) {
-                const int leader = __ffs(idle) - 1;
-                int base = 0;
-                if (lane == leader) base = atomicAdd(fetch_counter, __popc(idle));
-                base = __shfl_sync(FULL, base, leader);
-                if (ray < 0) {
-                    const int i = base + __popc(idle & lanes_lt);
-                    if (i < n && (ANY || !q.pixel || q.pixel[i] != DT_DEAD_PIXEL)) {
+        // One fetch round: the idle lanes take the next rays of the queue with ONE warp-aggregated atomic.
+        auto fetch_round = [&](const unsigned idle) {
+            const int leader = __ffs(idle) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(fetch_counter, __popc(idle));
+            base = __shfl_sync(FULL, base, leader);
+            if (ray < 0) {
+                const int i = base + __popc(idle & lanes_lt);
+                if (i < n && (ANY || !q.pixel || q.pixel[i] != DT_DEAD_PIXEL)) {
+                    const float4 d = ANY ? sq.d_tmax[i] : q.d_tmax[i];
+                    if (!ANY || !(d.w < 0.0f)) {                    // tmax < 0: a shadow-queue entry that is not traced (zero contribution, dt_shade_ray)
                         const float4 o = ANY ? sq.o_time[i] : q.o_time[i];
-                        const float4 d = ANY ? sq.d_tmax[i] : q.d_tmax[i];
                         dt_trav_init<ANY>(T, S, V(o.x, o.y, o.z), V(d.x, d.y, d.z), o.w, ANY ? d.w : CUDART_INF_F);
                         ray = i;
                     }
                 }
-                if (base + __popc(idle) >= n) {
-                    drained = true;
+            }
+            if (base + __popc(idle) >= n) {
+                drained = true;
 #ifdef DT_TIMELINE
-                    tl_td = dt_now();
+                tl_td = dt_now();
 #endif
+            }
+        };
+        if (!drained) {
+            const unsigned idle = __ballot_sync(FULL, ray < 0);
+            if (idle) fetch_round(idle);
+            if (ANY) {
+                // untraced entries come in runs of 32 (a shading warp's shadow rays towards one light are neighbours in the queue):
+                // lanes that drew one fetch again, up to three more rounds while at least 8 lanes are idle
+                for (int round = 0; round < 3 && !drained; round++) {
+                    const unsigned again = __ballot_sync(FULL, ray < 0);
+                    if (__popc(again) < 8) break;
+                    fetch_round(again);
                 }
             }
         }
@@ -384,7 +399,7 @@ __device__ __forceinline__ void dt_emit_shadow(const DtShadowQueue& sq, const Dt
 // dielectric children (:208-472) turned into queue emissions.
 __device__ __forceinline__ void dt_shade_ray(const int i, const DtSceneDev& S, const DtCamDev& cam, const DtRayQueue& in, const float4* in_miss,
                                              const DtRayQueue& out, float4* out_miss, int out_capacity,
-                                             const DtShadowQueue& sq, int shadow_capacity, const DtShadeCounters& counters, float4* accum) {
+                                             const DtShadowQueue& sq, int shadow_capacity, const DtShadeCounters& counters, float4* accum, int& n_dead) {
     const uint32_t pix = in.pixel[i];
     if (pix == DT_DEAD_PIXEL) return;
     const float4 o4 = in.o_time[i], d4 = in.d_tmax[i];
@@ -592,7 +607,14 @@ __device__ __forceinline__ void dt_shade_ray(const int i, const DtSceneDev& S, c
         }
         if (mat.brdf >= 0) thr = vmul(thr, res);                                  // Shade(): ray.throughput *= res
         if (kind == 1) {
-            dt_emit_shadow(sq, counters, shadow_capacity, so, w_i, mb, lightT, vmul(W, c), pix, defer_light >= 0 ? gi_slot : -1, defer_light, shadow_slot);
+            // A shadow ray whose contribution is EXACTLY zero -- the light is below the surface's horizon, the lobe or the irradiance
+            // vanishes -- cannot change the pixel whatever it hits.  Path-traced frames do not trace it: its (already reserved) queue
+            // slot gets tmax = -1, which the any-hit kernels skip.  Whitted frames keep it (ray counts stay the reference's), and so
+            // does DT_FLAG_KEEP_WEIGHTLESS_PATHS.
+            const v3 contrib = vmul(W, c);
+            const bool dead = cam.path_tracing && !cam.keep_weightless && contrib.x == 0.0f && contrib.y == 0.0f && contrib.z == 0.0f;
+            if (dead) n_dead++;
+            dt_emit_shadow(sq, counters, shadow_capacity, so, w_i, mb, dead ? -1.0f : lightT, contrib, pix, defer_light >= 0 ? gi_slot : -1, defer_light, shadow_slot);
             shadow_slot += shadow_stride;
         } else if (kind == 2) local = vadd(local, c);
     }
@@ -698,11 +720,14 @@ __global__ void __launch_bounds__(128, DT_SHADE_MINBLOCKS) k_shade(DtSceneDev S,
     // a warp at a loop back-edge -- and the warp degenerates into 32 single-lane executions of this kernel (measured on config 5
     // once a fifth of the hits returned early: k_shade 2.3x slower in the device-resident loop than with one hit per thread).
     const int lane = threadIdx.x & 31;
+    int n_dead = 0;
     for (int base = blockIdx.x * blockDim.x + threadIdx.x - lane; base < n; base += gridDim.x * blockDim.x) {
         const int j = base + lane;
-        if (j < n) dt_shade_ray(perm ? perm[j] : j, S, cam, in, in_miss, out, out_miss, out_capacity, sq, shadow_capacity, counters, accum);
+        if (j < n) dt_shade_ray(perm ? perm[j] : j, S, cam, in, in_miss, out, out_miss, out_capacity, sq, shadow_capacity, counters, accum, n_dead);
         __syncwarp();
     }
+    n_dead = __reduce_add_sync(0xFFFFFFFFu, n_dead);
+    if (lane == 0 && n_dead > 0) atomicAdd(counters.shadow_dead, (unsigned long long)n_dead);
 }
 
 // ------------------------------------------------------------------ sort / compact by material
@@ -1088,7 +1113,7 @@ __global__ void __launch_bounds__(128, DT_SHADE_MINBLOCKS) k_tail(DtSceneDev S, 
         B[2].defer[slot] = make_int2(df.x >= 0 ? df.x - lo : -1, df.y);
     }
     __syncthreads();
-    int waves = 0;
+    int waves = 0, tail_dead = 0;
     unsigned long long n_closest = 0, n_shadow = 0;          // thread 0 only
     DT_DECLARE_STACK(stack);
 #ifdef DT_TAIL_PROFILE
@@ -1115,10 +1140,10 @@ __global__ void __launch_bounds__(128, DT_SHADE_MINBLOCKS) k_tail(DtSceneDev S, 
             }
             asm volatile("bar.sync 1, %0;" :: "n"(DT_TAIL_PATH_THREADS) : "memory");          // all closest hits of the wave are stored (GI children read none, but shade reads hit0 by index)
             DT_TP(0)
-            const DtShadeCounters cnt = {&sc[1], &sc[3 + i % 3], &sc[2]};
+            const DtShadeCounters cnt = {&sc[1], &sc[3 + i % 3], &sc[2], nullptr};
             for (int j0 = tid & ~31; j0 < cur; j0 += DT_TAIL_PATH_THREADS) {                  // warp-uniform trip count, see k_shade
                 const int j = j0 + (tid & 31);
-                if (j < cur) dt_shade_ray(j, S, cam, in, Lmiss[i & 1], L[(i + 1) & 1], Lmiss[(i + 1) & 1], M.capacity, B[i % 3], M.shadow_capacity, cnt, accum);
+                if (j < cur) dt_shade_ray(j, S, cam, in, Lmiss[i & 1], L[(i + 1) & 1], Lmiss[(i + 1) & 1], M.capacity, B[i % 3], M.shadow_capacity, cnt, accum, tail_dead);
                 __syncwarp();
             }
             DT_TP(1)
@@ -1133,6 +1158,7 @@ __global__ void __launch_bounds__(128, DT_SHADE_MINBLOCKS) k_tail(DtSceneDev S, 
             for (int e = tid - DT_TAIL_PATH_THREADS; e < pend; e += blockDim.x - DT_TAIL_PATH_THREADS) {
                 if (defer && dt_deferred_skipped(S, Q.defer[e], child_hit0)) continue;
                 const float4 o = Q.o_time[e], d = Q.d_tmax[e];
+                if (d.w < 0.0f) continue;                               // zero contribution: not traced (dt_shade_ray)
                 DtTrav T;
                 dt_trav_init<true>(T, S, V(o.x, o.y, o.z), V(d.x, d.y, d.z), o.w, d.w);
                 while (!dt_trav_step<true, true>(T, stack, S, Q.o_time + e, Q.d_tmax + e)) {}
@@ -1157,6 +1183,7 @@ __global__ void __launch_bounds__(128, DT_SHADE_MINBLOCKS) k_tail(DtSceneDev S, 
         __syncthreads();
         DT_TP(2)
     }
+    if (tail_dead > 0) atomicAdd(reinterpret_cast<unsigned long long*>(c + DT_CNT_SHADOW_DEAD), (unsigned long long)tail_dead);
     if (tid == 0) {
         atomicAdd(reinterpret_cast<unsigned long long*>(c + DT_CNT_TOT_CLOSEST), n_closest);
         atomicAdd(reinterpret_cast<unsigned long long*>(c + DT_CNT_TOT_SHADOW), n_shadow);

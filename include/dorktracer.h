@@ -258,7 +258,9 @@ enum {
                                        reference's roulette never ends such chains (raytracer.cpp:137-147), so they are a fifth of the
                                        rays of config 5.  The image is unchanged (only a NaN produced after the underflow would no longer
                                        poison its pixel); dt_stats then counts the rays actually traced.  With this flag the paths are
-                                       followed as the reference follows them (ray counts comparable with the oracle's; A/B)            */
+                                       followed as the reference follows them (ray counts comparable with the oracle's; A/B).  The same
+                                       default / flag pair governs shadow rays whose contribution W*c is exactly zero (light below the
+                                       horizon, vanishing lobe): path-traced frames do not trace them                                 */
     DT_FLAG_SMOOTH_SHADING = 8192    /* meshes that carry dt_mesh.vertex_normals (shadingMode="smooth" in the XML, which the
                                        reference ignores) are shaded with the barycentric interpolation of their vertex normals
                                        in place of the face normal.  Off by default: parity with the reference means flat shading */
