@@ -786,8 +786,8 @@ retry:
                 S.ms_bulk_shadow += ms_s; S.rays_bulk_shadow += (uint64_t)(entries - std::min(entries, dead_traced_now));
             }
             dead_prev_wave = dead_this_wave;
-            if (s->debug_timing >= 2) fprintf(stderr, "[dt-tl] wave %u: %d closest rays, %d shadow rays | closest %.3f sort %.3f shade %.3f shadow %.3f ms (cumulative)\n", S.waves - 1, count,
-                                              s->h_counters[DT_CNT_SHADOW], S.ms_traverse_closest, S.ms_sort, S.ms_shade, S.ms_traverse_shadow);
+            if (s->debug_timing >= 2) fprintf(stderr, "[dt-tl] wave %u: %d closest rays, %d shadow rays emitted (%llu of them not traced) | closest %.3f sort %.3f shade %.3f shadow %.3f ms (cumulative)\n", S.waves - 1, count,
+                                              s->h_counters[DT_CNT_SHADOW], dead_this_wave, S.ms_traverse_closest, S.ms_sort, S.ms_shade, S.ms_traverse_shadow);
             if (s->h_counters[DT_CNT_OVERFLOW] != 0) { overflow = true; break; }
             const int next_count = s->h_counters[DT_CNT_NEXT];
             const int shadow_count = std::min(s->h_counters[DT_CNT_SHADOW], pp.shadow_capacity);

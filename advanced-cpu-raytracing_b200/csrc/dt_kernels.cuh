@@ -388,8 +388,12 @@ __device__ __forceinline__ void dt_emit_shadow(const DtShadowQueue& sq, const Dt
                                                v3 contrib, uint32_t pix, int defer_slot, int defer_light, int slot = -1) {
     if (slot < 0) slot = dt_agg_inc(counters.shadow);
     if (slot >= capacity) { atomicAdd(counters.overflow, 1); return; }
-    sq.o_time[slot] = make_float4(o.x, o.y, o.z, mb);
     sq.d_tmax[slot] = make_float4(d.x, d.y, d.z, tmax);
+    if (tmax < 0.0f) {                                       // an entry that will not be traced (dt_shade_ray): the marker alone
+        if (sq.defer) sq.defer[slot] = make_int2(-1, -1);
+        return;
+    }
+    sq.o_time[slot] = make_float4(o.x, o.y, o.z, mb);
     sq.contrib_pix[slot] = make_float4(contrib.x, contrib.y, contrib.z, __int_as_float((int)pix));
     if (sq.defer) sq.defer[slot] = make_int2(defer_slot, defer_light);
 }
@@ -1106,7 +1110,7 @@ __global__ void __launch_bounds__(128, DT_SHADE_MINBLOCKS) k_tail(DtSceneDev S, 
     for (int e = tid; e < nps; e += blockDim.x) {
         const int2 df = gsq.defer[e];
         const bool mine = df.x >= 0 ? (df.x >= lo && df.x < hi) : (e % G == b);
-        if (!mine) continue;
+        if (!mine || gsq.d_tmax[e].w < 0.0f) continue;                  // (untraced entries stay behind)
         const int slot = atomicAdd(&sc[5], 1);
         if (slot >= M.shadow_capacity) { sc[2] = 1; continue; }
         B[2].o_time[slot] = gsq.o_time[e]; B[2].d_tmax[slot] = gsq.d_tmax[e]; B[2].contrib_pix[slot] = gsq.contrib_pix[e];
