@@ -403,7 +403,7 @@ __device__ __forceinline__ void dt_emit_shadow(const DtShadowQueue& sq, const Dt
 // dielectric children (:208-472) turned into queue emissions.
 __device__ __forceinline__ void dt_shade_ray(const int i, const DtSceneDev& S, const DtCamDev& cam, const DtRayQueue& in, const float4* in_miss,
                                              const DtRayQueue& out, float4* out_miss, int out_capacity,
-                                             const DtShadowQueue& sq, int shadow_capacity, const DtShadeCounters& counters, float4* accum, int& n_dead) {
+                                             const DtShadowQueue& sq, int shadow_capacity, const DtShadeCounters& counters, float4* accum, int* block_dead) {
     const uint32_t pix = in.pixel[i];
     if (pix == DT_DEAD_PIXEL) return;
     const float4 o4 = in.o_time[i], d4 = in.d_tmax[i];
@@ -617,7 +617,10 @@ __device__ __forceinline__ void dt_shade_ray(const int i, const DtSceneDev& S, c
             // does DT_FLAG_KEEP_WEIGHTLESS_PATHS.
             const v3 contrib = vmul(W, c);
             const bool dead = cam.path_tracing && !cam.keep_weightless && contrib.x == 0.0f && contrib.y == 0.0f && contrib.z == 0.0f;
-            if (dead) n_dead++;
+            {   // counted per block in shared memory (a per-thread counter carried through this function costs k_shade 7 %)
+                const unsigned dm = __ballot_sync(__activemask(), dead);
+                if (dead && (threadIdx.x & 31) == __ffs(dm) - 1) atomicAdd(block_dead, __popc(dm));
+            }
             dt_emit_shadow(sq, counters, shadow_capacity, so, w_i, mb, dead ? -1.0f : lightT, contrib, pix, defer_light >= 0 ? gi_slot : -1, defer_light, shadow_slot);
             shadow_slot += shadow_stride;
         } else if (kind == 2) local = vadd(local, c);
@@ -724,14 +727,16 @@ __global__ void __launch_bounds__(128, DT_SHADE_MINBLOCKS) k_shade(DtSceneDev S,
     // a warp at a loop back-edge -- and the warp degenerates into 32 single-lane executions of this kernel (measured on config 5
     // once a fifth of the hits returned early: k_shade 2.3x slower in the device-resident loop than with one hit per thread).
     const int lane = threadIdx.x & 31;
-    int n_dead = 0;
+    __shared__ int s_dead;                       // shadow-queue entries this block marked "not traced"
+    if (threadIdx.x == 0) s_dead = 0;
+    __syncthreads();
     for (int base = blockIdx.x * blockDim.x + threadIdx.x - lane; base < n; base += gridDim.x * blockDim.x) {
         const int j = base + lane;
-        if (j < n) dt_shade_ray(perm ? perm[j] : j, S, cam, in, in_miss, out, out_miss, out_capacity, sq, shadow_capacity, counters, accum, n_dead);
+        if (j < n) dt_shade_ray(perm ? perm[j] : j, S, cam, in, in_miss, out, out_miss, out_capacity, sq, shadow_capacity, counters, accum, &s_dead);
         __syncwarp();
     }
-    n_dead = __reduce_add_sync(0xFFFFFFFFu, n_dead);
-    if (lane == 0 && n_dead > 0) atomicAdd(counters.shadow_dead, (unsigned long long)n_dead);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_dead > 0) atomicAdd(counters.shadow_dead, (unsigned long long)s_dead);
 }
 
 // ------------------------------------------------------------------ sort / compact by material
@@ -1079,7 +1084,7 @@ __device__ __forceinline__ DtShadowQueue dt_shadow_queue_at(const DtShadowQueue&
 }
 #define DT_TAIL_PATH_THREADS 64
 __global__ void __launch_bounds__(128, DT_SHADE_MINBLOCKS) k_tail(DtSceneDev S, DtCamDev cam, DtRayQueue gq, const float4* gmiss, DtShadowQueue gsq, int* c, DtTailMem M, int defer, float4* accum) {
-    // 0 rays of this wave, 1 rays emitted for the next wave, 2 overflow, 3..5 entries of the three shadow buffers
+    // 0 rays of this wave, 1 rays emitted for the next wave, 2 overflow, 3..5 entries of the three shadow buffers, 7 untraced shadow entries
     __shared__ int sc[8];
 #ifdef DT_TAIL_PROFILE
     __shared__ long long tp_shadow;
@@ -1117,7 +1122,7 @@ __global__ void __launch_bounds__(128, DT_SHADE_MINBLOCKS) k_tail(DtSceneDev S, 
         B[2].defer[slot] = make_int2(df.x >= 0 ? df.x - lo : -1, df.y);
     }
     __syncthreads();
-    int waves = 0, tail_dead = 0;
+    int waves = 0;
     unsigned long long n_closest = 0, n_shadow = 0;          // thread 0 only
     DT_DECLARE_STACK(stack);
 #ifdef DT_TAIL_PROFILE
@@ -1147,7 +1152,7 @@ __global__ void __launch_bounds__(128, DT_SHADE_MINBLOCKS) k_tail(DtSceneDev S, 
             const DtShadeCounters cnt = {&sc[1], &sc[3 + i % 3], &sc[2], nullptr};
             for (int j0 = tid & ~31; j0 < cur; j0 += DT_TAIL_PATH_THREADS) {                  // warp-uniform trip count, see k_shade
                 const int j = j0 + (tid & 31);
-                if (j < cur) dt_shade_ray(j, S, cam, in, Lmiss[i & 1], L[(i + 1) & 1], Lmiss[(i + 1) & 1], M.capacity, B[i % 3], M.shadow_capacity, cnt, accum, tail_dead);
+                if (j < cur) dt_shade_ray(j, S, cam, in, Lmiss[i & 1], L[(i + 1) & 1], Lmiss[(i + 1) & 1], M.capacity, B[i % 3], M.shadow_capacity, cnt, accum, &sc[7]);
                 __syncwarp();
             }
             DT_TP(1)
@@ -1187,8 +1192,8 @@ __global__ void __launch_bounds__(128, DT_SHADE_MINBLOCKS) k_tail(DtSceneDev S, 
         __syncthreads();
         DT_TP(2)
     }
-    if (tail_dead > 0) atomicAdd(reinterpret_cast<unsigned long long*>(c + DT_CNT_SHADOW_DEAD), (unsigned long long)tail_dead);
     if (tid == 0) {
+        if (sc[7] > 0) atomicAdd(reinterpret_cast<unsigned long long*>(c + DT_CNT_SHADOW_DEAD), (unsigned long long)sc[7]);
         atomicAdd(reinterpret_cast<unsigned long long*>(c + DT_CNT_TOT_CLOSEST), n_closest);
         atomicAdd(reinterpret_cast<unsigned long long*>(c + DT_CNT_TOT_SHADOW), n_shadow);
         atomicMax(c + DT_CNT_TAIL_WAVES, waves);

@@ -8,7 +8,7 @@ A *step* is one frame of the workload through the hot path.
         (9 991 932 triangles: config-4 box + displaced-sphere mesh), path tracing with next-event estimation + importance
         sampling + Russian roulette, area light + mesh light + spherical HDR environment light, Torrance-Sparrow / modified
         Blinn-Phong BRDFs, photographic tonemapper, 3840x2160 — at a STATED REDUCED sample count (--spp, default 64 instead of
-        1024: a 1024-spp frame is 85 s on one B200, a 64-spp frame 5.4 s).  N > 1: THE SAME FRAME is sharded over the ranks (strips of eight
+        1024: a 1024-spp frame is 55 s on one B200, a 64-spp frame 3.5 s).  N > 1: THE SAME FRAME is sharded over the ranks (strips of eight
         8x4-pixel tiles, round-robin; what the reference does with row bands over its threads, main.cpp:38-39) -> strong
         scaling.  Every rank's resolve kernel stores its strips of radiance straight into rank 0's frame over NVLink (CUDA IPC
         peer memory, no collective), one barrier, then rank 0 tonemaps the whole frame.
@@ -16,7 +16,10 @@ A *step* is one frame of the workload through the hot path.
         headline; weak scaling: sqrt(N) x the resolution per axis).  Its N=1 numbers also ride along in `other_workloads`.
 
   value      device time only: scene + camera resident, CUDA events on the library's stream (render + resolve + tonemap,
-             + the barrier for N > 1), L2 flushed between iterations
+             + the barrier for N > 1), L2 flushed between iterations.  Rays = rays TRACED: path-traced frames do not follow paths
+             whose weight is exactly zero nor trace shadow rays whose contribution is exactly zero (same image; dorktracer.h,
+             DT_FLAG_KEEP_WEIGHTLESS_PATHS); the size of the reference's ray tree for the same frame (one untimed frame with that
+             flag) and the rate in that accounting are reported in details.ray_accounting
   e2e        the public C-ABI call dt_render() with a pinned HOST LDR buffer: camera / parameters in, D2H of the finished
              frame inside the timed region, wall clock between device synchronisations
   roofline   the dominant kernel (the traversal kernel with the larger share of the frame).  Primary bound = SM issue slots
@@ -556,9 +559,10 @@ def main():
                 "ray_accounting": ({"rays_per_step": "rays traced by this library (what `value` and `e2e` count)",
                                     "rays_per_step_of_the_reference_ray_tree": rays_ref_tree_all,
                                     "mrays_per_s_counting_the_reference_ray_tree": rays_ref_tree_all / (ms_per_step * 1e3),
-                                    "note": "under Russian roulette hits whose path weight is exactly (0,0,0) are not shaded: everything below them is an exact zero, "
-                                            "the image is the same (tests/test_gpu_parity.py::test_config5_shape_path_tracing_robust_statistics); the reference "
-                                            "follows those paths, so its ray tree for this frame is larger (one untimed frame with DT_FLAG_KEEP_WEIGHTLESS_PATHS)"}
+                                    "note": "under Russian roulette hits whose path weight is exactly (0,0,0) are not shaded (everything below them is an exact zero) and "
+                                            "shadow rays whose contribution is exactly zero are not traced; the image is the same "
+                                            "(tests/test_gpu_parity.py::test_config5_shape_path_tracing_robust_statistics); the reference follows / traces them, "
+                                            "so its ray tree for this frame is larger (one untimed frame with DT_FLAG_KEEP_WEIGHTLESS_PATHS)"}
                                    if rays_ref_tree_all > 0 else None),
                 "timing": "CUDA events on the library stream (render + resolve + tonemap; + barrier / reduce for N > 1), max over ranks",
                 "gather": ("peer-memory stores (CUDA IPC, fused into the resolve kernel) + one barrier" if peer else "nccl-reduce") if world > 1 else "none",
