@@ -616,8 +616,10 @@ __device__ __forceinline__ void dt_shade_ray(const int i, const DtSceneDev& S, c
             // slot gets tmax = -1, which the any-hit kernels skip.  Whitted frames keep it (ray counts stay the reference's), and so
             // does DT_FLAG_KEEP_WEIGHTLESS_PATHS.
             const v3 contrib = vmul(W, c);
-            const bool dead = cam.path_tracing && !cam.keep_weightless && contrib.x == 0.0f && contrib.y == 0.0f && contrib.z == 0.0f;
-            {   // counted per block in shared memory (a per-thread counter carried through this function costs k_shade 7 %)
+            bool dead = false;
+            if (cam.path_tracing && !cam.keep_weightless) {      // (frame-uniform: Whitted frames do not pay for the vote)
+                dead = contrib.x == 0.0f && contrib.y == 0.0f && contrib.z == 0.0f;
+                // counted per block in shared memory (a per-thread counter carried through this function costs k_shade 7 %)
                 const unsigned dm = __ballot_sync(__activemask(), dead);
                 if (dead && (threadIdx.x & 31) == __ffs(dm) - 1) atomicAdd(block_dead, __popc(dm));
             }
