@@ -408,7 +408,7 @@ int render_devloop(dt_scene* s, const DtCamDev& dc, const DtWaveParams& wp, long
             }
             if (do_sort) launches += launch_sort(s, pp, pp.q[cur], c + DT_CNT_CUR, 0, st, false, sort_spatial);
             {
-                DtShadeCounters sc = {c + DT_CNT_NEXT, c + DT_CNT_SHADOW, c + DT_CNT_OVERFLOW, reinterpret_cast<unsigned long long*>(c + DT_CNT_SHADOW_DEAD)};
+                DtShadeCounters sc = {c + DT_CNT_NEXT, c + DT_CNT_SHADOW, c + DT_CNT_OVERFLOW, reinterpret_cast<unsigned long long*>(c + DT_CNT_SHADOW_DEAD), reinterpret_cast<unsigned long long*>(c + DT_CNT_CLOSEST_DEAD)};
                 k_shade<<<s->grid_shade, 128, 0, st>>>(s->dev, dc, pp.q[cur], pp.miss[cur], c + DT_CNT_CUR, 0, do_sort ? pp.sort_perm : nullptr, pp.q[1 - cur], pp.miss[1 - cur], pp.capacity,
                                                         sq, pp.shadow_capacity, sc, s->accum);
                 launches++;
@@ -440,7 +440,9 @@ int render_devloop(dt_scene* s, const DtCamDev& dc, const DtWaveParams& wp, long
     unsigned long long c8 = 0, s8 = 0;
     unsigned long long dead8 = 0;
     memcpy(&c8, hc + DT_CNT_TOT_CLOSEST, 8); memcpy(&s8, hc + DT_CNT_TOT_SHADOW, 8); memcpy(&dead8, hc + DT_CNT_SHADOW_DEAD, 8);
-    S.rays_closest = c8; S.rays_shadow = s8 - std::min(s8, dead8);          // queue entries minus the ones that are not traced (zero contribution)
+    unsigned long long cdead8 = 0;
+    memcpy(&cdead8, hc + DT_CNT_CLOSEST_DEAD, 8);
+    S.rays_closest = c8 - std::min(c8, cdead8); S.rays_shadow = s8 - std::min(s8, dead8);          // queue entries minus the ones that are not traced
     S.waves = (uint32_t)(hc[DT_CNT_WAVES] + hc[DT_CNT_TAIL_WAVES]);
     S.kernel_launches = (uint32_t)hc[DT_CNT_ITERS] * s->loop_launches_per_iter + (use_tail ? 1u : 0u);
     S.launches_traverse_closest = (uint32_t)hc[DT_CNT_ITERS] * 2u;
@@ -596,7 +598,7 @@ retry:
                     if (k >= 3) CK(cudaStreamWaitEvent(pp.A, pp.ev_shadow[q], 0));           // shadow(k-3) must have drained this queue
                     if (do_sort) timed(tsort, pp.A, [&] { n_launches += launch_sort(s, pp, pp.q[cur], c + DT_CNT_CUR, 0, pp.A, true, sort_spatial); });
                     timed(th, pp.A, [&] {
-                        DtShadeCounters sc = {c + DT_CNT_NEXT, c + dt_cnt_shadow(q), c + DT_CNT_OVERFLOW, reinterpret_cast<unsigned long long*>(c + DT_CNT_SHADOW_DEAD)};
+                        DtShadeCounters sc = {c + DT_CNT_NEXT, c + dt_cnt_shadow(q), c + DT_CNT_OVERFLOW, reinterpret_cast<unsigned long long*>(c + DT_CNT_SHADOW_DEAD), reinterpret_cast<unsigned long long*>(c + DT_CNT_CLOSEST_DEAD)};
                         k_shade<<<s->grid_shade, 128, 0, pp.A>>>(s->dev, dc, pp.q[cur], pp.miss[cur], c + DT_CNT_CUR, 0, do_sort ? pp.sort_perm : nullptr, pp.q[1 - cur], pp.miss[1 - cur], pp.capacity,
                                                                 sq, pp.shadow_capacity, sc, s->accum); });
                     if (!s->shadow_order) { CK(cudaEventRecord(pp.ev_shade[q], pp.A)); CK(cudaStreamWaitEvent(pp.B, pp.ev_shade[q], 0)); launch_shadow(pp, k); }
@@ -672,7 +674,9 @@ retry:
             if (hc[DT_CNT_OVERFLOW] != 0) overflow = true;
             unsigned long long c8 = 0, s8 = 0, dead8 = 0;
             memcpy(&c8, hc + DT_CNT_TOT_CLOSEST, 8); memcpy(&s8, hc + DT_CNT_TOT_SHADOW, 8); memcpy(&dead8, hc + DT_CNT_SHADOW_DEAD, 8);
-            tot_c += c8; tot_s += s8; tot_dead += dead8;
+            unsigned long long cdead8 = 0;
+            memcpy(&cdead8, hc + DT_CNT_CLOSEST_DEAD, 8);
+            tot_c += c8 - std::min(c8, cdead8); tot_s += s8; tot_dead += dead8;
             for (int k = std::max(0, n_waves - 2); k < n_waves; k++)                          // the last two waves' queues were not recycled
                 tot_s += (unsigned long long)std::min(hc[dt_cnt_shadow(k % 3)], s->pipes[p].shadow_capacity);
         }
@@ -718,6 +722,7 @@ retry:
         int count = 0, cur = 0;
         int prev_shadow = 0;
         unsigned long long dead_total = 0, dead_prev_wave = 0;      // shadow-queue entries that are not traced (cumulative counter; those of the previous wave)
+        unsigned long long cdead_total = 0, cdead_in_wave = 0;     // the same for the closest-hit queue: untraced entries sitting in the current wave
         bool overflow = false;
         S.rays_closest = 0; S.rays_shadow = 0; S.waves = 0; S.kernel_launches = 0; S.launches_traverse_closest = 0;
         S.ms_generate = S.ms_traverse_closest = S.ms_traverse_shadow = S.ms_shade = 0.f;
@@ -751,7 +756,7 @@ retry:
             if (do_sort) { s->t_sort.start(st); S.kernel_launches += launch_sort(s, pp, pp.q[cur], nullptr, count, st, true, sort_spatial); s->t_sort.stop(st); }
             s->t_shade.start(st);
             {
-                DtShadeCounters sc = {c + DT_CNT_NEXT, c + DT_CNT_SHADOW, c + DT_CNT_OVERFLOW, reinterpret_cast<unsigned long long*>(c + DT_CNT_SHADOW_DEAD)};
+                DtShadeCounters sc = {c + DT_CNT_NEXT, c + DT_CNT_SHADOW, c + DT_CNT_OVERFLOW, reinterpret_cast<unsigned long long*>(c + DT_CNT_SHADOW_DEAD), reinterpret_cast<unsigned long long*>(c + DT_CNT_CLOSEST_DEAD)};
                 k_shade<<<(count + 127) / 128, 128, 0, st>>>(s->dev, dc, pp.q[cur], pp.miss[cur], nullptr, count, do_sort ? pp.sort_perm : nullptr, pp.q[1 - cur], pp.miss[1 - cur], pp.capacity,
                                                              sq, pp.shadow_capacity, sc, s->accum);
             }
@@ -780,12 +785,18 @@ retry:
             dead_total = dead_now;
             if (count >= wave_max / 2) {                                   // a "bulk" wave (dt_stats)
                 S.bulk_waves++;
-                S.ms_bulk_closest += ms_c; S.rays_bulk_closest += (uint64_t)count;
+                S.ms_bulk_closest += ms_c; S.rays_bulk_closest += (uint64_t)count - std::min<uint64_t>((uint64_t)count, cdead_in_wave);
                 const unsigned long long entries = (unsigned long long)(defer_mode ? prev_shadow : std::min(s->h_counters[DT_CNT_SHADOW], pp.shadow_capacity));
                 const unsigned long long dead_traced_now = defer_mode ? dead_prev_wave : dead_this_wave;      // the pass timed in ms_s traced these entries
                 S.ms_bulk_shadow += ms_s; S.rays_bulk_shadow += (uint64_t)(entries - std::min(entries, dead_traced_now));
             }
             dead_prev_wave = dead_this_wave;
+            {
+                unsigned long long cdead_now = 0;
+                memcpy(&cdead_now, s->h_counters + DT_CNT_CLOSEST_DEAD, 8);
+                cdead_in_wave = cdead_now - cdead_total;               // marked by this wave's shade pass: they sit in the NEXT wave's queue
+                cdead_total = cdead_now;
+            }
             if (s->debug_timing >= 2) fprintf(stderr, "[dt-tl] wave %u: %d closest rays, %d shadow rays emitted (%llu of them not traced) | closest %.3f sort %.3f shade %.3f shadow %.3f ms (cumulative)\n", S.waves - 1, count,
                                               s->h_counters[DT_CNT_SHADOW], dead_this_wave, S.ms_traverse_closest, S.ms_sort, S.ms_shade, S.ms_traverse_shadow);
             if (s->h_counters[DT_CNT_OVERFLOW] != 0) { overflow = true; break; }
@@ -811,6 +822,7 @@ retry:
         }
         S.rays_closest += (uint64_t)(count_valid_pixels(P, W, H, dc.row_limit) * (primary_only ? 1 : dc.spp));
         S.rays_shadow -= std::min<uint64_t>(S.rays_shadow, dead_total);
+        S.rays_closest -= std::min<uint64_t>(S.rays_closest, cdead_total);
     }
     S.retries = retries;
     if (stats) *stats = S;

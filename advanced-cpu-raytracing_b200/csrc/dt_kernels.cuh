@@ -64,8 +64,9 @@ enum { DT_CNT_NEXT = 0, DT_CNT_SHADOW = 1, DT_CNT_FETCH_A = 2, DT_CNT_FETCH_B = 
        DT_CNT_TAIL_WAVES = 25,    // longest block-local wave chain of k_tail
        DT_CNT_TAIL_RAYS = 26,     // rays handed to k_tail
        DT_CNT_SHADOW_DEAD = 28,   // 64-bit: shadow-queue entries of this frame that are not traced (zero contribution, see dt_shade_ray)
+       DT_CNT_CLOSEST_DEAD = 30,  // 64-bit: closest-hit queue entries of this frame that are not traced (GI children of zero weight)
        DT_CNT_COUNT = 32 };
-struct DtShadeCounters { int* next; int* shadow; int* overflow; unsigned long long* shadow_dead; };
+struct DtShadeCounters { int* next; int* shadow; int* overflow; unsigned long long* shadow_dead; unsigned long long* closest_dead; };
 
 #define DT_DEAD_PIXEL 0xFFFFFFFFu
 
@@ -481,6 +482,7 @@ __device__ __forceinline__ void dt_shade_ray(const int i, const DtSceneDev& S, c
     DtRng rng; rng.key = (uint32_t)misc.z; rng.ctr = 0;
     v3 thr = V(tb.x, tb.y, tb.z);
     int gi_slot = -1;
+    bool gi_weightless = false, live_deferred = false;     // the GI child's weight is exactly zero; a traced mesh-light sample waits for its hit
 
     // Queue slots are requested up front so that the atomics' round trips overlap the sampling / BRDF arithmetic below.
     // Every point / area / directional / spot / mesh light emits exactly one shadow ray per shaded hit: one reservation.
@@ -608,6 +610,7 @@ __device__ __forceinline__ void dt_shade_ray(const int i, const DtSceneDev& S, c
             ch.n_medium = n_medium; ch.thr = thr; ch.beer_thr = 0.f;
             ch.depth = depth - 1; ch.beer_mat = 0; ch.rng_key = dt_hash(rng.key, 0xA511E9B3u); ch.flags = 0; ch.miss = V(0, 0, 0);
             gi_slot = dt_emit_child(out, out_miss, counters, out_capacity, pix, ch, gi_slot);
+            gi_weightless = ch.W.x == 0.0f && ch.W.y == 0.0f && ch.W.z == 0.0f;
         }
         if (mat.brdf >= 0) thr = vmul(thr, res);                                  // Shade(): ray.throughput *= res
         if (kind == 1) {
@@ -623,11 +626,18 @@ __device__ __forceinline__ void dt_shade_ray(const int i, const DtSceneDev& S, c
                 const unsigned dm = __ballot_sync(__activemask(), dead);
                 if (dead && (threadIdx.x & 31) == __ffs(dm) - 1) atomicAdd(block_dead, __popc(dm));
             }
+            if (!dead && defer_light >= 0) live_deferred = true;
             dt_emit_shadow(sq, counters, shadow_capacity, so, w_i, mb, dead ? -1.0f : lightT, contrib, pix, defer_light >= 0 ? gi_slot : -1, defer_light, shadow_slot);
             shadow_slot += shadow_stride;
         } else if (kind == 2) local = vadd(local, c);
     }
     if (direct) dt_accum(accum, pix, vmul(W, local));
+    // A GI child of exactly zero weight (a black surface: the mirror sphere of configs 4 / 5) would be traced once and dropped when it
+    // is shaded; unless a traced mesh-light sample of this hit needs to know what it hits (deferred NEE), it is not traced at all.
+    if (gi_weightless && !live_deferred && gi_slot >= 0 && cam.russian_roulette && !cam.keep_weightless) {
+        out.pixel[gi_slot] = DT_DEAD_PIXEL;
+        atomicAdd(block_dead + 1, 1);              // shared memory, rare
+    }
 
     if (depth <= 0) return;        // all three recursive helpers start with `if(recDepth <= 0) return 0`
 
@@ -729,16 +739,17 @@ __global__ void __launch_bounds__(128, DT_SHADE_MINBLOCKS) k_shade(DtSceneDev S,
     // a warp at a loop back-edge -- and the warp degenerates into 32 single-lane executions of this kernel (measured on config 5
     // once a fifth of the hits returned early: k_shade 2.3x slower in the device-resident loop than with one hit per thread).
     const int lane = threadIdx.x & 31;
-    __shared__ int s_dead;                       // shadow-queue entries this block marked "not traced"
-    if (threadIdx.x == 0) s_dead = 0;
+    __shared__ int s_dead[2];                    // shadow-queue / closest-hit queue entries this block marked "not traced"
+    if (threadIdx.x < 2) s_dead[threadIdx.x] = 0;
     __syncthreads();
     for (int base = blockIdx.x * blockDim.x + threadIdx.x - lane; base < n; base += gridDim.x * blockDim.x) {
         const int j = base + lane;
-        if (j < n) dt_shade_ray(perm ? perm[j] : j, S, cam, in, in_miss, out, out_miss, out_capacity, sq, shadow_capacity, counters, accum, &s_dead);
+        if (j < n) dt_shade_ray(perm ? perm[j] : j, S, cam, in, in_miss, out, out_miss, out_capacity, sq, shadow_capacity, counters, accum, s_dead);
         __syncwarp();
     }
     __syncthreads();
-    if (threadIdx.x == 0 && s_dead > 0) atomicAdd(counters.shadow_dead, (unsigned long long)s_dead);
+    if (threadIdx.x == 0 && s_dead[0] > 0) atomicAdd(counters.shadow_dead, (unsigned long long)s_dead[0]);
+    if (threadIdx.x == 1 && s_dead[1] > 0) atomicAdd(counters.closest_dead, (unsigned long long)s_dead[1]);
 }
 
 // ------------------------------------------------------------------ sort / compact by material
@@ -1086,7 +1097,7 @@ __device__ __forceinline__ DtShadowQueue dt_shadow_queue_at(const DtShadowQueue&
 }
 #define DT_TAIL_PATH_THREADS 64
 __global__ void __launch_bounds__(128, DT_SHADE_MINBLOCKS) k_tail(DtSceneDev S, DtCamDev cam, DtRayQueue gq, const float4* gmiss, DtShadowQueue gsq, int* c, DtTailMem M, int defer, float4* accum) {
-    // 0 rays of this wave, 1 rays emitted for the next wave, 2 overflow, 3..5 entries of the three shadow buffers, 7 untraced shadow entries
+    // 0 rays of this wave, 1 rays emitted for the next wave, 2 overflow, 3..5 entries of the three shadow buffers, 6 / 7 untraced shadow / closest-hit entries
     __shared__ int sc[8];
 #ifdef DT_TAIL_PROFILE
     __shared__ long long tp_shadow;
@@ -1151,10 +1162,10 @@ __global__ void __launch_bounds__(128, DT_SHADE_MINBLOCKS) k_tail(DtSceneDev S, 
             }
             asm volatile("bar.sync 1, %0;" :: "n"(DT_TAIL_PATH_THREADS) : "memory");          // all closest hits of the wave are stored (GI children read none, but shade reads hit0 by index)
             DT_TP(0)
-            const DtShadeCounters cnt = {&sc[1], &sc[3 + i % 3], &sc[2], nullptr};
+            const DtShadeCounters cnt = {&sc[1], &sc[3 + i % 3], &sc[2], nullptr, nullptr};
             for (int j0 = tid & ~31; j0 < cur; j0 += DT_TAIL_PATH_THREADS) {                  // warp-uniform trip count, see k_shade
                 const int j = j0 + (tid & 31);
-                if (j < cur) dt_shade_ray(j, S, cam, in, Lmiss[i & 1], L[(i + 1) & 1], Lmiss[(i + 1) & 1], M.capacity, B[i % 3], M.shadow_capacity, cnt, accum, &sc[7]);
+                if (j < cur) dt_shade_ray(j, S, cam, in, Lmiss[i & 1], L[(i + 1) & 1], Lmiss[(i + 1) & 1], M.capacity, B[i % 3], M.shadow_capacity, cnt, accum, &sc[6]);
                 __syncwarp();
             }
             DT_TP(1)
@@ -1195,7 +1206,8 @@ __global__ void __launch_bounds__(128, DT_SHADE_MINBLOCKS) k_tail(DtSceneDev S, 
         DT_TP(2)
     }
     if (tid == 0) {
-        if (sc[7] > 0) atomicAdd(reinterpret_cast<unsigned long long*>(c + DT_CNT_SHADOW_DEAD), (unsigned long long)sc[7]);
+        if (sc[6] > 0) atomicAdd(reinterpret_cast<unsigned long long*>(c + DT_CNT_SHADOW_DEAD), (unsigned long long)sc[6]);
+        if (sc[7] > 0) atomicAdd(reinterpret_cast<unsigned long long*>(c + DT_CNT_CLOSEST_DEAD), (unsigned long long)sc[7]);
         atomicAdd(reinterpret_cast<unsigned long long*>(c + DT_CNT_TOT_CLOSEST), n_closest);
         atomicAdd(reinterpret_cast<unsigned long long*>(c + DT_CNT_TOT_SHADOW), n_shadow);
         atomicMax(c + DT_CNT_TAIL_WAVES, waves);
