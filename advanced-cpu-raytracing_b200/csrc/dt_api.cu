@@ -338,7 +338,7 @@ int ensure_tail(dt_scene* s, int shadows_per_hit, bool need_defer) {
     s->free_tail();
     s->free_loop();                      // the graph holds the old pointers
     int bps = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_tail, 128, 0));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_tail, DT_TAIL_THREADS, 0));
     const int grid = s->num_sms * std::max(1, bps);
     DtTailMem& M = s->tail;
     memset(&M, 0, sizeof M);
@@ -422,7 +422,7 @@ int render_devloop(dt_scene* s, const DtCamDev& dc, const DtWaveParams& wp, long
         if (ce != cudaSuccess) { g_err = std::string("capture of the wave-loop body failed: ") + cudaGetErrorString(ce); s->free_loop(); return DT_ERR_CUDA; }
         if (use_tail) {
             CK(cudaStreamBeginCaptureToGraph(st, g, &wnode, nullptr, 1, cudaStreamCaptureModeThreadLocal));
-            k_tail<<<s->tail_grid, 128, 0, st>>>(s->dev, dc, pp.q[0], pp.miss[0], sq, c, s->tail, defer_mode ? 1 : 0, s->accum);
+            k_tail<<<s->tail_grid, DT_TAIL_THREADS, 0, st>>>(s->dev, dc, pp.q[0], pp.miss[0], sq, c, s->tail, defer_mode ? 1 : 0, s->accum);
             ce = cudaStreamEndCapture(st, &captured);
             if (ce != cudaSuccess) { g_err = std::string("capture of the tail kernel failed: ") + cudaGetErrorString(ce); s->free_loop(); return DT_ERR_CUDA; }
         }

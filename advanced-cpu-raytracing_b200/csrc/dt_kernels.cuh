@@ -1096,6 +1096,167 @@ __device__ __forceinline__ DtShadowQueue dt_shadow_queue_at(const DtShadowQueue&
     return r;
 }
 #define DT_TAIL_PATH_THREADS 64
+#ifndef DT_TAIL_DECOUPLED
+#define DT_TAIL_DECOUPLED 1
+#endif
+#if DT_TAIL_DECOUPLED
+// Decoupled variant (default).  In the version below (kept for A/B, -DDT_TAIL_DECOUPLED=0) the shadow warps must finish the shadow
+// rays of wave i - 2 inside wave i, and they -- not the bounce chain -- were the longer side of most late waves.  Here every
+// rotating shadow buffer has its own warp, and the block-wide barrier is replaced by named barriers that express the actual hazards:
+//   FULL[k]   path -> shadow warp k: the shadow rays of batch b (emitted by shade(b), buffer k = b mod 3) are complete and their GI
+//             children (wave b + 1) have their closest hits                                         (arrive after closest(b + 1))
+//   CHECK[k]  shadow warp k -> path: the deferred mesh-light entries of batch b have looked at their child's hit record
+//             (closest(b + 3) overwrites those records: same queue parity)                          (waited for before closest(b + 3))
+//   DRAIN[k]  shadow warp k -> path: batch b is traced, buffer k may be refilled                   (waited for before shade(b + 3))
+// so a batch has shade(b + 1) + wave b + 2 + closest(b + 3) to finish, about two waves instead of one, and the bounce chain of the
+// two path warps no longer waits for shadow rays unless a batch takes twice as long as a wave.
+#define DT_TAIL_THREADS (DT_TAIL_PATH_THREADS + 96)
+#define DT_TAIL_MINBLOCKS 3                       // 3 x 160 threads at 128 registers
+__device__ __forceinline__ void dt_bar_sync(int id, int n) { __syncwarp(); asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void dt_bar_arrive(int id, int n) { __syncwarp(); __threadfence_block(); asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(n) : "memory"); }
+#define DT_BAR_PATH 1
+#define DT_BAR_FULL 2
+#define DT_BAR_CHECK 5
+#define DT_BAR_DRAIN 8
+__global__ void __launch_bounds__(DT_TAIL_THREADS, DT_TAIL_MINBLOCKS) k_tail(DtSceneDev S, DtCamDev cam, DtRayQueue gq, const float4* gmiss, DtShadowQueue gsq, int* c, DtTailMem M, int defer, float4* accum) {
+    // 0 rays of this wave, 1 rays emitted for the next wave, 2 overflow, 3..5 entries of the three shadow buffers, 6 / 7 untraced shadow / closest-hit entries
+    __shared__ int sc[8];
+    __shared__ int s_exit;
+    const int b = blockIdx.x, G = gridDim.x, tid = threadIdx.x;
+    const int n = c[DT_CNT_CUR], nps = defer ? c[DT_CNT_PREV_SHADOW] : 0;
+    if ((n == 0 && nps == 0) || c[DT_CNT_OVERFLOW] != 0) return;
+    const DtRayQueue L[2] = {dt_queue_at(M.q[0], (size_t)b * M.capacity), dt_queue_at(M.q[1], (size_t)b * M.capacity)};
+    float4* const Lmiss[2] = {M.miss[0] ? M.miss[0] + (size_t)b * M.capacity : nullptr, M.miss[1] ? M.miss[1] + (size_t)b * M.capacity : nullptr};
+    const DtShadowQueue B[3] = {dt_shadow_queue_at(M.sq, ((size_t)b * 3 + 0) * M.shadow_capacity), dt_shadow_queue_at(M.sq, ((size_t)b * 3 + 1) * M.shadow_capacity),
+                                dt_shadow_queue_at(M.sq, ((size_t)b * 3 + 2) * M.shadow_capacity)};
+    const int chunk = (n + G - 1) / G;
+    const int lo = min(n, b * chunk), hi = min(n, lo + chunk);
+    if (tid < 8) sc[tid] = 0;
+    if (tid == 8) s_exit = 0;
+    __syncthreads();
+    for (int j = tid; j < hi - lo; j += blockDim.x) {
+        const int g = lo + j;
+        L[0].o_time[j] = gq.o_time[g]; L[0].d_tmax[j] = gq.d_tmax[g]; L[0].pixel[j] = gq.pixel[g];
+        L[0].weight_n[j] = gq.weight_n[g]; L[0].thr_beer[j] = gq.thr_beer[g]; L[0].misc[j] = gq.misc[g];
+        if (Lmiss[0] && gmiss) Lmiss[0][j] = gmiss[g];
+    }
+    if (tid == 0) { sc[0] = hi - lo; if (b == 0) c[DT_CNT_TAIL_RAYS] = n; }
+    // The deferred NEE entries of the frame loop's last wave follow the block that owns their GI child; entries without a child
+    // are dealt round-robin.  They are batch -1 (buffer 2): their children are the rays of tail wave 0.
+    for (int e = tid; e < nps; e += blockDim.x) {
+        const int2 df = gsq.defer[e];
+        const bool mine = df.x >= 0 ? (df.x >= lo && df.x < hi) : (e % G == b);
+        if (!mine || gsq.d_tmax[e].w < 0.0f) continue;                  // (untraced entries stay behind)
+        const int slot = atomicAdd(&sc[5], 1);
+        if (slot >= M.shadow_capacity) { sc[2] = 1; continue; }
+        B[2].o_time[slot] = gsq.o_time[e]; B[2].d_tmax[slot] = gsq.d_tmax[e]; B[2].contrib_pix[slot] = gsq.contrib_pix[e];
+        B[2].defer[slot] = make_int2(df.x >= 0 ? df.x - lo : -1, df.y);
+    }
+    __syncthreads();
+    DT_DECLARE_STACK(stack);
+    constexpr int PT = DT_TAIL_PATH_THREADS, PS = DT_TAIL_PATH_THREADS + 32;
+    if (tid >= PT) {
+        // ---- shadow warp k: batches k, k + 3, ... (warp 2 starts with the handed-over batch -1)
+        const int k = (tid - PT) >> 5, lane = tid & 31;
+        const DtShadowQueue& Q = B[k];
+        for (int bi = (k == 2 ? -1 : k);; bi += 3) {
+            dt_bar_sync(DT_BAR_FULL + k, PS);
+            if (s_exit) break;
+            const int pend = min(sc[3 + k], M.shadow_capacity);
+            if (defer) {
+                const float4* child_hit0 = L[(bi + 1) & 1].hit0;
+                for (int e = lane; e < pend; e += 32)
+                    if (dt_deferred_skipped(S, Q.defer[e], child_hit0)) Q.d_tmax[e].w = -1.0f;          // the child found the light itself: not traced
+                __syncwarp();
+            }
+            dt_bar_arrive(DT_BAR_CHECK + k, PS);
+            for (int e = lane; e < pend; e += 32) {
+                const float4 d = Q.d_tmax[e];
+                if (d.w < 0.0f) continue;                               // zero contribution (dt_shade_ray) or skipped above
+                const float4 o = Q.o_time[e];
+                DtTrav T;
+                dt_trav_init<true>(T, S, V(o.x, o.y, o.z), V(d.x, d.y, d.z), o.w, d.w);
+                while (!dt_trav_step<true, true>(T, stack, S, Q.o_time + e, Q.d_tmax + e)) {}
+                dt_store_shadow(Q, e, T.best, accum);
+            }
+            __syncwarp();
+            dt_bar_arrive(DT_BAR_DRAIN + k, PS);
+        }
+        return;
+    }
+    // ---- path warps: closest(i) -> shade(i) -> closest(i + 1) ...
+    int waves = 0, i = 0;
+    unsigned long long n_closest = 0, n_shadow = 0;          // thread 0 only
+#ifdef DT_TAIL_PROFILE
+    long long tp[3] = {0, 0, 0}, tp_last = clock64(), tp_rays = 0;
+#define DT_TP(i) { const long long now_ = clock64(); tp[i] += now_ - tp_last; tp_last = now_; }
+#else
+#define DT_TP(i)
+#endif
+    for (;; i++) {
+        const int cur = sc[0];
+        // batches i - 1 (not announced yet) and i - 2 empty and no ray left: done (batch i - 3 may still be in flight, see the drain below)
+        if ((cur == 0 && sc[3 + (i + 2) % 3] == 0 && sc[3 + (i + 1) % 3] == 0) || sc[2] != 0) break;
+        const DtRayQueue& in = L[i & 1];
+        if (i >= 2) dt_bar_sync(DT_BAR_CHECK + i % 3, PS);            // batch i - 3 has read the hit records of wave i - 2 (this queue)
+        DT_TP(2)
+        for (int j = tid; j < cur; j += PT) {
+            if (in.pixel[j] == DT_DEAD_PIXEL) continue;
+            const float4 o = in.o_time[j], d = in.d_tmax[j];
+            DtTrav T;
+            dt_trav_init<false>(T, S, V(o.x, o.y, o.z), V(d.x, d.y, d.z), o.w, CUDART_INF_F);
+            while (!dt_trav_step<false, true>(T, stack, S, in.o_time + j, in.d_tmax + j)) {}
+            dt_store_closest(in, j, T.best);
+        }
+        dt_bar_sync(DT_BAR_PATH, PT);                                  // all closest hits of the wave are stored
+        dt_bar_arrive(DT_BAR_FULL + (i + 2) % 3, PS);                  // batch i - 1 may start
+        DT_TP(0)
+        if (i >= 2) dt_bar_sync(DT_BAR_DRAIN + i % 3, PS);            // batch i - 3 is traced: its buffer is free
+        if (tid == 0) sc[3 + i % 3] = 0;
+        dt_bar_sync(DT_BAR_PATH, PT);
+        DT_TP(2)
+        const DtShadeCounters cnt = {&sc[1], &sc[3 + i % 3], &sc[2], nullptr, nullptr};
+        for (int j0 = tid & ~31; j0 < cur; j0 += PT) {                  // warp-uniform trip count, see k_shade
+            const int j = j0 + (tid & 31);
+            if (j < cur) dt_shade_ray(j, S, cam, in, Lmiss[i & 1], L[(i + 1) & 1], Lmiss[(i + 1) & 1], M.capacity, B[i % 3], M.shadow_capacity, cnt, accum, &sc[6]);
+            __syncwarp();
+        }
+        dt_bar_sync(DT_BAR_PATH, PT);
+        DT_TP(1)
+        if (tid == 0) {
+            if (cur > 0) waves++;
+            if (sc[1] > M.capacity || sc[3 + i % 3] > M.shadow_capacity) sc[2] = 1;
+            n_closest += (unsigned long long)min(sc[1], M.capacity); n_shadow += (unsigned long long)min(sc[3 + i % 3], M.shadow_capacity);
+            sc[0] = min(sc[1], M.capacity);
+            sc[1] = 0;
+#ifdef DT_TAIL_PROFILE
+            tp_rays += cur;
+#endif
+        }
+        dt_bar_sync(DT_BAR_PATH, PT);
+    }
+    // drain: the announced batches nobody has waited for yet (i - 3, i - 2), then release the three warps from their FULL barrier
+    for (int bb = i - 3; bb <= i - 2; bb++)
+        if (bb >= -1) { dt_bar_sync(DT_BAR_CHECK + (bb + 3) % 3, PS); dt_bar_sync(DT_BAR_DRAIN + (bb + 3) % 3, PS); }
+    if (tid == 0) s_exit = 1;
+    dt_bar_sync(DT_BAR_PATH, PT);
+    for (int k = 0; k < 3; k++) dt_bar_arrive(DT_BAR_FULL + k, PS);
+    if (tid == 0) {
+        if (sc[6] > 0) atomicAdd(reinterpret_cast<unsigned long long*>(c + DT_CNT_SHADOW_DEAD), (unsigned long long)sc[6]);
+        if (sc[7] > 0) atomicAdd(reinterpret_cast<unsigned long long*>(c + DT_CNT_CLOSEST_DEAD), (unsigned long long)sc[7]);
+        atomicAdd(reinterpret_cast<unsigned long long*>(c + DT_CNT_TOT_CLOSEST), n_closest);
+        atomicAdd(reinterpret_cast<unsigned long long*>(c + DT_CNT_TOT_SHADOW), n_shadow);
+        atomicMax(c + DT_CNT_TAIL_WAVES, waves);
+        if (sc[2] != 0) atomicAdd(c + DT_CNT_OVERFLOW, 1);
+#ifdef DT_TAIL_PROFILE
+        if (waves > 1000) printf("[dt-tail] block %d: %d waves, %lld ray-waves | cycles per wave: closest %lld, shade %lld, waiting for shadow warps + bookkeeping %lld\n",
+                                 b, waves, tp_rays, tp[0] / waves, tp[1] / waves, tp[2] / waves);
+#endif
+    }
+#undef DT_TP
+}
+#else
+#define DT_TAIL_THREADS 128
 __global__ void __launch_bounds__(128, DT_SHADE_MINBLOCKS) k_tail(DtSceneDev S, DtCamDev cam, DtRayQueue gq, const float4* gmiss, DtShadowQueue gsq, int* c, DtTailMem M, int defer, float4* accum) {
     // 0 rays of this wave, 1 rays emitted for the next wave, 2 overflow, 3..5 entries of the three shadow buffers, 6 / 7 untraced shadow / closest-hit entries
     __shared__ int sc[8];
@@ -1219,6 +1380,7 @@ __global__ void __launch_bounds__(128, DT_SHADE_MINBLOCKS) k_tail(DtSceneDev S, 
     }
 #undef DT_TP
 }
+#endif
 
 // ------------------------------------------------------------------ resolve
 // main.cpp:97-125: Gaussian-weighted resolve, HDR store, LDR clamp((int)c) with cvttss2si semantics
