@@ -96,6 +96,7 @@ struct dt_scene {
     int lights_shadowed = 0;          // shadow rays per shaded hit
     int fanout_hint = 0;
     bool has_env = false;
+    bool sphere_normal_maps = false;  // a sphere carries a normal map: k_shade<true> / k_tail<true> (dt_stale_normal)
 
     // render-time buffers: up to DT_MAX_PIPES independent wavefront pipelines (queues, counters, two streams each).
     // The frame's tiles are dealt round-robin to the pipelines; their waves run concurrently so that the tail of one
@@ -338,7 +339,7 @@ int ensure_tail(dt_scene* s, int shadows_per_hit, bool need_defer) {
     s->free_tail();
     s->free_loop();                      // the graph holds the old pointers
     int bps = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_tail, DT_TAIL_THREADS, 0));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_tail<false>, DT_TAIL_THREADS, 0));
     const int grid = s->num_sms * std::max(1, bps);
     DtTailMem& M = s->tail;
     memset(&M, 0, sizeof M);
@@ -409,7 +410,7 @@ int render_devloop(dt_scene* s, const DtCamDev& dc, const DtWaveParams& wp, long
             if (do_sort) launches += launch_sort(s, pp, pp.q[cur], c + DT_CNT_CUR, 0, st, false, sort_spatial);
             {
                 DtShadeCounters sc = {c + DT_CNT_NEXT, c + DT_CNT_SHADOW, c + DT_CNT_OVERFLOW, reinterpret_cast<unsigned long long*>(c + DT_CNT_SHADOW_DEAD), reinterpret_cast<unsigned long long*>(c + DT_CNT_CLOSEST_DEAD)};
-                k_shade<<<s->grid_shade, 128, 0, st>>>(s->dev, dc, pp.q[cur], pp.miss[cur], c + DT_CNT_CUR, 0, do_sort ? pp.sort_perm : nullptr, pp.q[1 - cur], pp.miss[1 - cur], pp.capacity,
+                (s->sphere_normal_maps ? k_shade<true> : k_shade<false>)<<<s->grid_shade, 128, 0, st>>>(s->dev, dc, pp.q[cur], pp.miss[cur], c + DT_CNT_CUR, 0, do_sort ? pp.sort_perm : nullptr, pp.q[1 - cur], pp.miss[1 - cur], pp.capacity,
                                                         sq, pp.shadow_capacity, sc, s->accum);
                 launches++;
             }
@@ -422,7 +423,7 @@ int render_devloop(dt_scene* s, const DtCamDev& dc, const DtWaveParams& wp, long
         if (ce != cudaSuccess) { g_err = std::string("capture of the wave-loop body failed: ") + cudaGetErrorString(ce); s->free_loop(); return DT_ERR_CUDA; }
         if (use_tail) {
             CK(cudaStreamBeginCaptureToGraph(st, g, &wnode, nullptr, 1, cudaStreamCaptureModeThreadLocal));
-            k_tail<<<s->tail_grid, DT_TAIL_THREADS, 0, st>>>(s->dev, dc, pp.q[0], pp.miss[0], sq, c, s->tail, defer_mode ? 1 : 0, s->accum);
+            (s->sphere_normal_maps ? k_tail<true> : k_tail<false>)<<<s->tail_grid, DT_TAIL_THREADS, 0, st>>>(s->dev, dc, pp.q[0], pp.miss[0], sq, c, s->tail, defer_mode ? 1 : 0, s->accum);
             ce = cudaStreamEndCapture(st, &captured);
             if (ce != cudaSuccess) { g_err = std::string("capture of the tail kernel failed: ") + cudaGetErrorString(ce); s->free_loop(); return DT_ERR_CUDA; }
         }
@@ -599,7 +600,7 @@ retry:
                     if (do_sort) timed(tsort, pp.A, [&] { n_launches += launch_sort(s, pp, pp.q[cur], c + DT_CNT_CUR, 0, pp.A, true, sort_spatial); });
                     timed(th, pp.A, [&] {
                         DtShadeCounters sc = {c + DT_CNT_NEXT, c + dt_cnt_shadow(q), c + DT_CNT_OVERFLOW, reinterpret_cast<unsigned long long*>(c + DT_CNT_SHADOW_DEAD), reinterpret_cast<unsigned long long*>(c + DT_CNT_CLOSEST_DEAD)};
-                        k_shade<<<s->grid_shade, 128, 0, pp.A>>>(s->dev, dc, pp.q[cur], pp.miss[cur], c + DT_CNT_CUR, 0, do_sort ? pp.sort_perm : nullptr, pp.q[1 - cur], pp.miss[1 - cur], pp.capacity,
+                        (s->sphere_normal_maps ? k_shade<true> : k_shade<false>)<<<s->grid_shade, 128, 0, pp.A>>>(s->dev, dc, pp.q[cur], pp.miss[cur], c + DT_CNT_CUR, 0, do_sort ? pp.sort_perm : nullptr, pp.q[1 - cur], pp.miss[1 - cur], pp.capacity,
                                                                 sq, pp.shadow_capacity, sc, s->accum); });
                     if (!s->shadow_order) { CK(cudaEventRecord(pp.ev_shade[q], pp.A)); CK(cudaStreamWaitEvent(pp.B, pp.ev_shade[q], 0)); launch_shadow(pp, k); }
                     if (k >= 2) CK(cudaStreamWaitEvent(pp.A, pp.ev_shadow[(k + 1) % 3], 0));  // shadow(k-2): its queue is recycled for wave k+1
@@ -757,7 +758,7 @@ retry:
             s->t_shade.start(st);
             {
                 DtShadeCounters sc = {c + DT_CNT_NEXT, c + DT_CNT_SHADOW, c + DT_CNT_OVERFLOW, reinterpret_cast<unsigned long long*>(c + DT_CNT_SHADOW_DEAD), reinterpret_cast<unsigned long long*>(c + DT_CNT_CLOSEST_DEAD)};
-                k_shade<<<(count + 127) / 128, 128, 0, st>>>(s->dev, dc, pp.q[cur], pp.miss[cur], nullptr, count, do_sort ? pp.sort_perm : nullptr, pp.q[1 - cur], pp.miss[1 - cur], pp.capacity,
+                (s->sphere_normal_maps ? k_shade<true> : k_shade<false>)<<<(count + 127) / 128, 128, 0, st>>>(s->dev, dc, pp.q[cur], pp.miss[cur], nullptr, count, do_sort ? pp.sort_perm : nullptr, pp.q[1 - cur], pp.miss[1 - cur], pp.capacity,
                                                              sq, pp.shadow_capacity, sc, s->accum);
             }
             s->t_shade.stop(st);
@@ -991,6 +992,7 @@ static int scene_create_impl(const dt_scene_desc* desc, const dt_scene_options* 
     s->n_triangles = hs.n_triangles;
     s->lights_shadowed = desc->n_point_lights + desc->n_area_lights + desc->n_directional_lights + desc->n_spot_lights + desc->n_mesh_lights;
     s->has_env = desc->n_env_lights > 0;
+    for (int i = 0; i < desc->n_shapes; i++) if (desc->shapes[i].kind == DT_SHAPE_SPHERE && desc->shapes[i].tex_normal >= 0) s->sphere_normal_maps = true;
     bool any_diel = false, any_refl = false;
     for (int i = 0; i < desc->n_materials; i++) {
         if (desc->materials[i].type == DT_MAT_DIELECTRIC) any_diel = true;
@@ -1031,7 +1033,7 @@ static int scene_create_impl(const dt_scene_desc* desc, const dt_scene_options* 
             s->grid_trav[m][a] = s->num_sms * std::max(1, bps);
         }
     }
-    { int bps = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_shade, 128, 0); s->grid_shade = s->num_sms * std::max(1, bps); }
+    { int bps = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_shade<false>, 128, 0); s->grid_shade = s->num_sms * std::max(1, bps); }
     if (cudaDeviceSynchronize() != cudaSuccess) { g_err = "device sync after upload failed"; return fail(DT_ERR_CUDA); }
     *out = s;
     return DT_OK;

@@ -399,9 +399,43 @@ __device__ __forceinline__ void dt_emit_shadow(const DtShadowQueue& sq, const Dt
     if (sq.defer) sq.defer[slot] = make_int2(defer_slot, defer_light);
 }
 
+// A sphere with a normal map keeps the normal hitInfo held BEFORE Sphere::Intersect accepted the hit (sphere.cpp:95-115: the branch
+// only reads the texture, its body is commented out): the normal of the closest hit among the shapes scanned earlier (each
+// acceptance overwrites hitInfo.normal and lowers minT, so the last writer is the nearest of them), or (0,0,0) of a fresh HitInfo.
+// If that shape is such a sphere too, it passed on ITS predecessors' normal through its own transform.  Rare and slow by design
+// (one extra prefix traversal per such hit); not inlined so that the shading kernel's register allocation does not see it.
+__device__ __noinline__ void dt_stale_normal(const DtSceneDev& S, float ox, float oy, float oz, float dx, float dy, float dz, float mb, int shape_limit, int smooth, float* out) {
+    const v3 o = V(ox, oy, oz), d = V(dx, dy, dz);
+    int chain[4], n_chain = 0;
+    v3 normal = V(0.f, 0.f, 0.f);
+    for (;;) {
+        DtHit h;
+        dt_trace_prefix(S, o, d, mb, shape_limit, h);
+        if (h.shape < 0) break;
+        const DtShapeDev& sh = S.shapes[h.shape];
+        if (sh.kind == DT_SHAPE_SPHERE && sh.tex_normal >= 0) {
+            if (n_chain == 4) break;
+            chain[n_chain++] = h.shape; shape_limit = h.shape;
+            continue;
+        }
+        v3 lo = apply_transform(sh.inv, o, 1.0f);
+        v3 ld = apply_transform(sh.inv, d, 0.0f);
+        if (sh.has_motion_blur) lo = vadd(lo, vscale(F3(sh.motion_blur), mb));
+        DtSurface sf;
+        if (sh.kind == DT_SHAPE_SPHERE) sphere_surface(S, sh, h.t, lo, ld, V(0.f, 0.f, 0.f), sf);
+        else mesh_surface(S, sh, h.face, h.t, h.beta, h.gamma, lo, ld, smooth != 0, sf);
+        normal = sf.normal;
+        break;
+    }
+    while (n_chain > 0) normal = vunit(apply_transform(S.shapes[chain[--n_chain]].invT, normal, 0.0f));
+    out[0] = normal.x; out[1] = normal.y; out[2] = normal.z;
+}
+
+
 // One thread per traced ray: Raytracer::PerPixel miss handling (raytracer.cpp:49-62) and PerformShading
 // (:65-134) with ComputeGlobalIllumination (:135-191), SampleDirectLighting (:701-806), mirror / conductor /
 // dielectric children (:208-472) turned into queue emissions.
+template <bool STALE>
 __device__ __forceinline__ void dt_shade_ray(const int i, const DtSceneDev& S, const DtCamDev& cam, const DtRayQueue& in, const float4* in_miss,
                                              const DtRayQueue& out, float4* out_miss, int out_capacity,
                                              const DtShadowQueue& sq, int shadow_capacity, const DtShadeCounters& counters, float4* accum, int* block_dead) {
@@ -445,8 +479,11 @@ __device__ __forceinline__ void dt_shade_ray(const int i, const DtSceneDev& S, c
         v3 lo = apply_transform(sh.inv, o, 1.0f);
         v3 ld = apply_transform(sh.inv, d, 0.0f);
         if (sh.has_motion_blur) lo = vadd(lo, vscale(F3(sh.motion_blur), mb));
-        if (sh.kind == DT_SHAPE_SPHERE) sphere_surface(S, sh, t, lo, ld, V(0.f, 0.f, 0.f), sf);
-        else mesh_surface(S, sh, in.hit_face[i], t, h0.y, h0.z, lo, ld, cam.smooth_shading != 0, sf);
+        if (sh.kind == DT_SHAPE_SPHERE) {
+            float stale[3] = {0.f, 0.f, 0.f};
+            if (STALE && sh.tex_normal >= 0) dt_stale_normal(S, o.x, o.y, o.z, d.x, d.y, d.z, mb, hit_shape, cam.smooth_shading, stale);
+            sphere_surface(S, sh, t, lo, ld, V(stale[0], stale[1], stale[2]), sf);
+        } else mesh_surface(S, sh, in.hit_face[i], t, h0.y, h0.z, lo, ld, cam.smooth_shading != 0, sf);
     }
     const v3 normal = sf.normal;
     const dt_material mat = S.materials[sh.material - 1];
@@ -730,6 +767,8 @@ __device__ __forceinline__ void dt_shade_ray(const int i, const DtSceneDev& S, c
 #ifndef DT_SHADE_MINBLOCKS
 #define DT_SHADE_MINBLOCKS 4       // 128 registers: measured best on config 4 (shade 162 ms at 193 regs, 133 at 170, 124 at 128, 125 at 102)
 #endif
+// STALE: the scene has a sphere with a normal map (dt_stale_normal); a separate instantiation so that every other scene runs the kernel without that call
+template <bool STALE>
 __global__ void __launch_bounds__(128, DT_SHADE_MINBLOCKS) k_shade(DtSceneDev S, DtCamDev cam, DtRayQueue in, const float4* in_miss, const int* n_ptr, int n_fixed, const int* perm,
                                                DtRayQueue out, float4* out_miss, int out_capacity,
                                                DtShadowQueue sq, int shadow_capacity, DtShadeCounters counters, float4* accum) {
@@ -744,7 +783,7 @@ __global__ void __launch_bounds__(128, DT_SHADE_MINBLOCKS) k_shade(DtSceneDev S,
     __syncthreads();
     for (int base = blockIdx.x * blockDim.x + threadIdx.x - lane; base < n; base += gridDim.x * blockDim.x) {
         const int j = base + lane;
-        if (j < n) dt_shade_ray(perm ? perm[j] : j, S, cam, in, in_miss, out, out_miss, out_capacity, sq, shadow_capacity, counters, accum, s_dead);
+        if (j < n) dt_shade_ray<STALE>(perm ? perm[j] : j, S, cam, in, in_miss, out, out_miss, out_capacity, sq, shadow_capacity, counters, accum, s_dead);
         __syncwarp();
     }
     __syncthreads();
@@ -1118,6 +1157,7 @@ __device__ __forceinline__ void dt_bar_arrive(int id, int n) { __syncwarp(); __t
 #define DT_BAR_FULL 2
 #define DT_BAR_CHECK 5
 #define DT_BAR_DRAIN 8
+template <bool STALE>
 __global__ void __launch_bounds__(DT_TAIL_THREADS, DT_TAIL_MINBLOCKS) k_tail(DtSceneDev S, DtCamDev cam, DtRayQueue gq, const float4* gmiss, DtShadowQueue gsq, int* c, DtTailMem M, int defer, float4* accum) {
     // 0 rays of this wave, 1 rays emitted for the next wave, 2 overflow, 3..5 entries of the three shadow buffers, 6 / 7 untraced shadow / closest-hit entries
     __shared__ int sc[8];
@@ -1218,7 +1258,7 @@ __global__ void __launch_bounds__(DT_TAIL_THREADS, DT_TAIL_MINBLOCKS) k_tail(DtS
         const DtShadeCounters cnt = {&sc[1], &sc[3 + i % 3], &sc[2], nullptr, nullptr};
         for (int j0 = tid & ~31; j0 < cur; j0 += PT) {                  // warp-uniform trip count, see k_shade
             const int j = j0 + (tid & 31);
-            if (j < cur) dt_shade_ray(j, S, cam, in, Lmiss[i & 1], L[(i + 1) & 1], Lmiss[(i + 1) & 1], M.capacity, B[i % 3], M.shadow_capacity, cnt, accum, &sc[6]);
+            if (j < cur) dt_shade_ray<STALE>(j, S, cam, in, Lmiss[i & 1], L[(i + 1) & 1], Lmiss[(i + 1) & 1], M.capacity, B[i % 3], M.shadow_capacity, cnt, accum, &sc[6]);
             __syncwarp();
         }
         dt_bar_sync(DT_BAR_PATH, PT);
@@ -1257,6 +1297,7 @@ __global__ void __launch_bounds__(DT_TAIL_THREADS, DT_TAIL_MINBLOCKS) k_tail(DtS
 }
 #else
 #define DT_TAIL_THREADS 128
+template <bool STALE>
 __global__ void __launch_bounds__(128, DT_SHADE_MINBLOCKS) k_tail(DtSceneDev S, DtCamDev cam, DtRayQueue gq, const float4* gmiss, DtShadowQueue gsq, int* c, DtTailMem M, int defer, float4* accum) {
     // 0 rays of this wave, 1 rays emitted for the next wave, 2 overflow, 3..5 entries of the three shadow buffers, 6 / 7 untraced shadow / closest-hit entries
     __shared__ int sc[8];
@@ -1326,7 +1367,7 @@ __global__ void __launch_bounds__(128, DT_SHADE_MINBLOCKS) k_tail(DtSceneDev S, 
             const DtShadeCounters cnt = {&sc[1], &sc[3 + i % 3], &sc[2], nullptr, nullptr};
             for (int j0 = tid & ~31; j0 < cur; j0 += DT_TAIL_PATH_THREADS) {                  // warp-uniform trip count, see k_shade
                 const int j = j0 + (tid & 31);
-                if (j < cur) dt_shade_ray(j, S, cam, in, Lmiss[i & 1], L[(i + 1) & 1], Lmiss[(i + 1) & 1], M.capacity, B[i % 3], M.shadow_capacity, cnt, accum, &sc[6]);
+                if (j < cur) dt_shade_ray<STALE>(j, S, cam, in, Lmiss[i & 1], L[(i + 1) & 1], Lmiss[(i + 1) & 1], M.capacity, B[i % 3], M.shadow_capacity, cnt, accum, &sc[6]);
                 __syncwarp();
             }
             DT_TP(1)

@@ -390,8 +390,10 @@ __device__ __forceinline__ bool dt_close_behind(float t, int shape, int face, co
 }
 
 // One primitive of the current primitive group.  Returns true when an ANY query is decided (occluded).
-template <bool ANY>
-__device__ __forceinline__ bool dt_trav_prim(DtTrav& T, const DtStack& stack, const DtSceneDev& S, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d, bool& entered_blas) {
+// LIMITED: only shapes with an index below shape_limit exist (the reference's scan up to, not including, that shape: dt_stale_normal).
+template <bool ANY, bool LIMITED = false>
+__device__ __forceinline__ bool dt_trav_prim(DtTrav& T, const DtStack& stack, const DtSceneDev& S, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d, bool& entered_blas,
+                                             int shape_limit = 0x7FFFFFFF) {
     DtHit& best = T.best;
     const int bit = __ffs(T.tg.y & 0xFFu) - 1;                                   // next hit leaf slot of the group
     const uint32_t prim = T.tg.x + (uint32_t)__popc((T.tg.y >> 8) & ((1u << bit) - 1u));
@@ -437,6 +439,7 @@ __device__ __forceinline__ bool dt_trav_prim(DtTrav& T, const DtStack& stack, co
     }
     DT_STAT(2);
     const int si = __ldg(S.tlas_prims + prim);
+    if (LIMITED && si >= shape_limit) return false;
     const DtShapeDev* sh = S.shapes + si;
     if (ANY && sh->skip_shadow) return false;
     const int kind = sh->kind;
@@ -486,8 +489,9 @@ __device__ __forceinline__ bool dt_trav_prim(DtTrav& T, const DtStack& stack, co
 // WW = true: descend nodes until some primitive group is pending, then drain it ("while-while").
 // Returns true when the ray is finished (ANY: best.shape >= 0 <=> occluded).
 // ray_o / ray_d: where the world-space ray of this traversal can be re-read (queue entry or caller's copy).
-template <bool ANY, bool WW, bool ORDERED = (DT_ANYHIT_ORDERED != 0) || !ANY>
-__device__ __forceinline__ bool dt_trav_step(DtTrav& T, const DtStack& stack, const DtSceneDev& S, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d) {
+template <bool ANY, bool WW, bool ORDERED = (DT_ANYHIT_ORDERED != 0) || !ANY, bool LIMITED = false>
+__device__ __forceinline__ bool dt_trav_step(DtTrav& T, const DtStack& stack, const DtSceneDev& S, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d,
+                                             int shape_limit = 0x7FFFFFFF) {
     DT_STAT(5);
     if (WW) {
         while (T.ng.y > 0x00FFFFFFu && T.tg.y == 0u) dt_trav_node<ANY, ORDERED>(T, stack, S);
@@ -498,7 +502,7 @@ __device__ __forceinline__ bool dt_trav_step(DtTrav& T, const DtStack& stack, co
     }
     while (T.tg.y != 0u) {
         bool entered = false;
-        if (dt_trav_prim<ANY>(T, stack, S, ray_o, ray_d, entered)) return true;
+        if (dt_trav_prim<ANY, LIMITED>(T, stack, S, ray_o, ray_d, entered, shape_limit)) return true;
         if (entered) break;
     }
     if (T.ng.y <= 0x00FFFFFFu && T.tg.y == 0u) {
@@ -556,5 +560,14 @@ __device__ __forceinline__ void dt_trace(const DtSceneDev& S, v3 wo, v3 wd, floa
     dt_trav_init<ANY>(T, S, wo, wd, mb_time, tmax_in);
     const float4 ro = make_float4(wo.x, wo.y, wo.z, mb_time), rd = make_float4(wd.x, wd.y, wd.z, tmax_in);
     while (!dt_trav_step<ANY, true>(T, stack, S, &ro, &rd)) {}
+    best = T.best;
+}
+// Closest hit among the shapes [0, shape_limit) only.
+__device__ __forceinline__ void dt_trace_prefix(const DtSceneDev& S, v3 wo, v3 wd, float mb_time, int shape_limit, DtHit& best) {
+    DtTrav T;
+    DT_DECLARE_STACK(stack);
+    dt_trav_init<false>(T, S, wo, wd, mb_time, CUDART_INF_F);
+    const float4 ro = make_float4(wo.x, wo.y, wo.z, mb_time), rd = make_float4(wd.x, wd.y, wd.z, CUDART_INF_F);
+    while (!dt_trav_step<false, true, true, true>(T, stack, S, &ro, &rd, shape_limit)) {}
     best = T.best;
 }

@@ -238,3 +238,162 @@ def env_whitted_scene(out_dir, width=160, height=112, spp=4, blur_instance=False
     with open(path, "w") as f:
         f.write(xml)
     return path
+
+
+def random_scene(out_dir, seed, width=112, height=80, textures=False):
+    """A seeded random DETERMINISTIC scene (no sampling anywhere, so the reference, the oracle and the GPU path must agree bit
+    for bit on hits and ray counts): a floor, 2-5 spheres and 1-3 small meshes (boxes, tetrahedra, triangle soups, single
+    <Triangle>s) with random materials -- plain with any of the eight BRDF variants, mirror, conductor, dielectric --, random
+    composed transformations on some of them, a MeshInstance of the first mesh (with and without resetTransform), 1-2 point
+    lights and, by chance, a directional and a spot light; recursion depth 1-4 and a random camera.
+    textures=True: random texture coordinates on every vertex and, on about half of the shapes, one or two of seven texture maps
+    (image replace_kd / blend_kd / replace_all, image normal map, image bump map, Perlin replace_kd, Perlin bump map)."""
+    rng = np.random.RandomState(1000 + seed)
+    os.makedirs(os.path.join(out_dir, "inputs"), exist_ok=True)
+    u = lambda a, b: float(rng.uniform(a, b))
+    f3 = lambda v: "%.6g %.6g %.6g" % (v[0], v[1], v[2])
+    cam_pos = (u(-2.5, 2.5), u(1.5, 4.0), u(6.5, 9))
+    gaze = (-cam_pos[0] * 0.08 + u(-0.05, 0.05), -0.12 + u(-0.08, 0.05), -1.0)
+    xml = ("<Scene><MaxRecursionDepth>%d</MaxRecursionDepth><BackgroundColor>%d %d %d</BackgroundColor><ShadowRayEpsilon>1e-3</ShadowRayEpsilon>\n"
+           % (rng.randint(1, 5), rng.randint(20, 120), rng.randint(20, 120), rng.randint(30, 160)))
+    xml += ("<Cameras><Camera id=\"1\"><Position>%s</Position><Gaze>%s</Gaze><Up>0 1 0</Up><NearPlane>-1 1 -0.714 0.714</NearPlane>"
+            "<NearDistance>%.4g</NearDistance><ImageResolution>%d %d</ImageResolution><ImageName>rnd%d.png</ImageName></Camera></Cameras>\n"
+            % (f3(cam_pos), f3(gaze), u(1.6, 2.4), width, height, seed))
+    xml += "<Lights><AmbientLight>%d %d %d</AmbientLight>\n" % (rng.randint(5, 40), rng.randint(5, 40), rng.randint(5, 40))
+    for k in range(rng.randint(1, 3)):
+        xml += ("<PointLight id=\"%d\"><Position>%s</Position><Intensity>%s</Intensity></PointLight>\n"
+                % (k + 1, f3((u(-7, 7), u(4, 10), u(-2, 9))), f3((u(5e3, 3e4), u(5e3, 3e4), u(5e3, 3e4)))))
+    if rng.rand() < 0.5:
+        xml += ("<DirectionalLight id=\"7\"><Direction>%s</Direction><Radiance>%s</Radiance></DirectionalLight>\n"
+                % (f3((u(-0.6, 0.6), -1.0, u(-0.6, 0.3))), f3((u(20, 120), u(20, 120), u(20, 120)))))
+    if rng.rand() < 0.5:
+        sp = (u(-4, 4), u(5, 9), u(0, 6))
+        xml += ("<SpotLight id=\"8\"><Position>%s</Position><Direction>%s</Direction><Intensity>%s</Intensity>"
+                "<CoverageAngle>%.4g</CoverageAngle><FalloffAngle>%.4g</FalloffAngle></SpotLight>\n"
+                % (f3(sp), f3((-sp[0] * 0.15 + u(-0.1, 0.1), -1.0, -sp[2] * 0.15)), f3((u(2e4, 9e4), u(2e4, 9e4), u(2e4, 9e4))), u(35, 70), u(10, 30)))
+    xml += "</Lights>\n"
+    xml += ("<BRDFs><OriginalPhong id=\"1\"><Exponent>%.4g</Exponent></OriginalPhong><OriginalBlinnPhong id=\"2\"><Exponent>%.4g</Exponent></OriginalBlinnPhong>"
+            "<ModifiedPhong id=\"3\"><Exponent>%.4g</Exponent></ModifiedPhong><ModifiedPhong id=\"4\" normalized=\"true\"><Exponent>%.4g</Exponent></ModifiedPhong>"
+            "<ModifiedBlinnPhong id=\"5\"><Exponent>%.4g</Exponent></ModifiedBlinnPhong><ModifiedBlinnPhong id=\"6\" normalized=\"true\"><Exponent>%.4g</Exponent></ModifiedBlinnPhong>"
+            "<TorranceSparrow id=\"7\"><Exponent>%.4g</Exponent></TorranceSparrow><TorranceSparrow id=\"8\" kdfresnel=\"true\"><Exponent>%.4g</Exponent></TorranceSparrow></BRDFs>\n"
+            % tuple(u(5, 60) for _ in range(8)))
+    n_mat = 7
+    xml += "<Materials>\n"
+    for m in range(1, n_mat + 1):
+        kind = "plain" if m <= 2 else ["plain", "plain", "mirror", "conductor", "dielectric"][rng.randint(5)]
+        kd = f3((u(0.1, 0.8), u(0.1, 0.8), u(0.1, 0.8)))
+        if kind == "plain":
+            brdf = rng.randint(0, 9)
+            xml += ("<Material id=\"%d\"%s><AmbientReflectance>1 1 1</AmbientReflectance><DiffuseReflectance>%s</DiffuseReflectance>"
+                    "<SpecularReflectance>%s</SpecularReflectance><PhongExponent>%.4g</PhongExponent><RefractionIndex>%.4g</RefractionIndex></Material>\n"
+                    % (m, " BRDF=\"%d\"" % brdf if brdf else "", kd, f3((u(0, 0.6),) * 3), u(3, 60), u(1.2, 2.2)))
+        elif kind == "mirror":
+            xml += ("<Material id=\"%d\" type=\"mirror\"><AmbientReflectance>0 0 0</AmbientReflectance><DiffuseReflectance>%s</DiffuseReflectance>"
+                    "<SpecularReflectance>0.2 0.2 0.2</SpecularReflectance><PhongExponent>20</PhongExponent><MirrorReflectance>%s</MirrorReflectance></Material>\n"
+                    % (m, f3((u(0, 0.2),) * 3), f3((u(0.4, 0.95), u(0.4, 0.95), u(0.4, 0.95)))))
+        elif kind == "conductor":
+            xml += ("<Material id=\"%d\" type=\"conductor\"><AmbientReflectance>0 0 0</AmbientReflectance><DiffuseReflectance>%s</DiffuseReflectance>"
+                    "<SpecularReflectance>0 0 0</SpecularReflectance><MirrorReflectance>%s</MirrorReflectance><RefractionIndex>%.4g</RefractionIndex>"
+                    "<AbsorptionIndex>%.4g</AbsorptionIndex></Material>\n"
+                    % (m, f3((u(0, 0.2),) * 3), f3((u(0.5, 0.95), u(0.5, 0.95), u(0.4, 0.9))), u(0.2, 1.5), u(2.0, 4.0)))
+        else:
+            xml += ("<Material id=\"%d\" type=\"dielectric\"><AmbientReflectance>0 0 0</AmbientReflectance><DiffuseReflectance>0 0 0</DiffuseReflectance>"
+                    "<SpecularReflectance>0 0 0</SpecularReflectance><AbsorptionCoefficient>%s</AbsorptionCoefficient><RefractionIndex>%.4g</RefractionIndex></Material>\n"
+                    % (m, f3((u(0, 0.08), u(0, 0.08), u(0, 0.08))), u(1.2, 2.0)))
+    xml += "</Materials>\n"
+    verts = [(-11, 0, -9), (11, 0, -9), (11, 0, 9), (-11, 0, 9)]
+    objs = "<Mesh id=\"1\"><Material>%d</Material>%s<Faces>1 3 2\n1 4 3</Faces></Mesh>\n" % (rng.randint(1, 3), "PLACEHOLDER_FLOOR_TEX")
+    xml_tr = ("<Transformations>" + "".join("<Translation id=\"%d\">%s</Translation>" % (k + 1, f3((u(-2.5, 2.5), u(0, 1.5), u(-2, 2)))) for k in range(3))
+              + "".join("<Scaling id=\"%d\">%s</Scaling>" % (k + 1, f3((u(0.6, 1.5), u(0.6, 1.5), u(0.6, 1.5)))) for k in range(3))
+              + "".join("<Rotation id=\"%d\">%.4g %s</Rotation>" % (k + 1, u(-80, 80), ["1 0 0", "0 1 0", "0 0 1"][rng.randint(3)]) for k in range(3)) + "</Transformations>\n")   # axis-aligned axes only (parser.cpp:672-683)
+
+    tex_xml = ""
+    if textures:
+        from dtb200 import scenegen
+        yy, xx = np.mgrid[0:48, 0:64]
+        a = np.stack([127 + 100 * np.sin(xx / (3.0 + seed % 5)), 127 + 100 * np.cos(yy / 6.0), 90 + 2 * xx], -1).clip(0, 255).astype(np.uint8)
+        scenegen.write_png(os.path.join(out_dir, "inputs", "rnd_a.png"), a)
+        nm = np.stack([127 + 45 * np.sin(xx / 3.0), 127 + 45 * np.cos(yy / 4.0), 225 + 0 * xx], -1).clip(0, 255).astype(np.uint8)
+        scenegen.write_png(os.path.join(out_dir, "inputs", "rnd_n.png"), nm)
+        tex_xml = ("<Textures><Images><Image id=\"1\">rnd_a.png</Image><Image id=\"2\">rnd_n.png</Image></Images>\n"
+                   "<TextureMap id=\"1\" type=\"image\"><ImageId>1</ImageId><DecalMode>replace_kd</DecalMode><Interpolation>bilinear</Interpolation></TextureMap>\n"
+                   "<TextureMap id=\"2\" type=\"image\"><ImageId>1</ImageId><DecalMode>blend_kd</DecalMode><Interpolation>nearest</Interpolation></TextureMap>\n"
+                   "<TextureMap id=\"3\" type=\"image\"><ImageId>2</ImageId><DecalMode>replace_normal</DecalMode><Interpolation>bilinear</Interpolation></TextureMap>\n"
+                   "<TextureMap id=\"4\" type=\"image\"><ImageId>1</ImageId><DecalMode>bump_normal</DecalMode><BumpFactor>%.4g</BumpFactor></TextureMap>\n"
+                   "<TextureMap id=\"5\" type=\"perlin\"><DecalMode>replace_kd</DecalMode><NoiseConversion>absval</NoiseConversion><NoiseScale>%.4g</NoiseScale></TextureMap>\n"
+                   "<TextureMap id=\"6\" type=\"perlin\"><DecalMode>bump_normal</DecalMode><NoiseConversion>linear</NoiseConversion><NoiseScale>%.4g</NoiseScale><BumpFactor>%.4g</BumpFactor></TextureMap>\n"
+                   "<TextureMap id=\"7\" type=\"image\"><ImageId>1</ImageId><DecalMode>replace_all</DecalMode><Interpolation>bilinear</Interpolation></TextureMap></Textures>\n"
+                   % (u(0.5, 3), u(0.5, 4), u(1, 4), u(0.2, 1.0)))
+
+    def shape_textures():
+        if not textures or rng.rand() < 0.5:
+            return ""
+        ids = []
+        if rng.rand() < 0.75:
+            ids.append([1, 2, 5, 7][rng.randint(4)])
+        if rng.rand() < 0.5 or not ids:
+            ids.append([3, 4, 6][rng.randint(3)])
+        return "<Textures>%s</Textures>" % " ".join(str(k) for k in ids)
+
+    def transforms():
+        if rng.rand() < 0.45:
+            return ""
+        toks = [["t", "s", "r"][rng.randint(3)] + str(rng.randint(1, 4)) for _ in range(rng.randint(1, 4))]
+        return "<Transformations>%s</Transformations>" % " ".join(toks)
+
+    mesh_id = 2
+    first_mesh = None
+    for _ in range(rng.randint(1, 4)):
+        c = np.array([u(-5, 5), u(0.8, 2.4), u(-3.5, 3.5)])
+        base = len(verts)
+        kind = rng.randint(4)
+        faces = []
+        if kind == 0:                                             # box
+            h = np.array([u(0.4, 1.1), u(0.4, 1.1), u(0.4, 1.1)])
+            for dz in (-1, 1):
+                for dy in (-1, 1):
+                    for dx in (-1, 1):
+                        verts.append(tuple(c + h * (dx, dy, dz)))
+            q = [(0, 2, 3, 1), (4, 5, 7, 6), (0, 1, 5, 4), (2, 6, 7, 3), (0, 4, 6, 2), (1, 3, 7, 5)]
+            for a, b, cc, d in q:
+                faces += [(a, b, cc), (a, cc, d)]
+        elif kind == 1:                                           # tetrahedron
+            p = [c + (u(-1, 1), u(-0.7, 1.2), u(-1, 1)) for _ in range(4)]
+            verts += [tuple(x) for x in p]
+            faces = [(0, 1, 2), (0, 3, 1), (1, 3, 2), (0, 2, 3)]
+        elif kind == 2:                                           # triangle soup
+            n = rng.randint(3, 9)
+            for k in range(n):
+                o = c + (u(-1.2, 1.2), u(-0.6, 1.0), u(-1.2, 1.2))
+                verts += [tuple(o), tuple(o + (u(0.3, 1.2), u(-0.4, 0.4), u(-0.5, 0.5))), tuple(o + (u(-0.4, 0.4), u(0.3, 1.2), u(-0.5, 0.5)))]
+                faces.append((3 * k, 3 * k + 1, 3 * k + 2))
+        else:                                                     # a single <Triangle>
+            verts += [tuple(c + (-1, -0.5, 0)), tuple(c + (1, -0.5, u(-0.5, 0.5))), tuple(c + (u(-0.3, 0.3), 1.0, 0))]
+            objs += ("<Triangle id=\"%d\"><Material>%d</Material>%s%s<Indices>%d %d %d</Indices></Triangle>\n"
+                     % (mesh_id, rng.randint(1, n_mat + 1), shape_textures(), transforms(), base + 1, base + 2, base + 3))
+            mesh_id += 1
+            continue
+        objs += ("<Mesh id=\"%d\"><Material>%d</Material>%s%s<Faces>%s</Faces></Mesh>\n"
+                 % (mesh_id, rng.randint(1, n_mat + 1), shape_textures(), transforms(), "\n".join("%d %d %d" % (base + a + 1, base + b + 1, base + cc + 1) for a, b, cc in faces)))
+        if first_mesh is None:
+            first_mesh = mesh_id
+        mesh_id += 1
+    if first_mesh is not None and rng.rand() < 0.7:
+        for reset in (["true", "false"] if rng.rand() < 0.5 else ["true"]):
+            objs += ("<MeshInstance id=\"%d\" baseMeshId=\"%d\" resetTransform=\"%s\"><Material>%d</Material><Transformations>s%d r%d t%d</Transformations></MeshInstance>\n"
+                     % (mesh_id, first_mesh, reset, rng.randint(1, n_mat + 1), rng.randint(1, 4), rng.randint(1, 4), rng.randint(1, 4)))
+            mesh_id += 1
+    for k in range(rng.randint(2, 6)):
+        r = u(0.5, 1.2)
+        verts.append((u(-5.5, 5.5), r + u(0.0, 1.5), u(-3.5, 4.0)))
+        objs += ("<Sphere id=\"%d\"><Material>%d</Material>%s%s<Center>%d</Center><Radius>%.4g</Radius></Sphere>\n"
+                 % (k + 1, rng.randint(1, n_mat + 1), shape_textures(), transforms() if rng.rand() < 0.4 else "", len(verts), r))
+    objs = objs.replace("PLACEHOLDER_FLOOR_TEX", shape_textures())
+    uv_xml = ""
+    if textures:
+        uv_xml = "<TexCoordData>" + "\n".join("%.5g %.5g" % (u(0, 2), u(0, 2)) for _ in verts) + "</TexCoordData>\n"
+    xml += tex_xml + "<VertexData>" + "\n".join(f3(v) for v in verts) + "</VertexData>\n" + uv_xml + xml_tr + "<Objects>\n" + objs + "</Objects></Scene>\n"
+    path = os.path.join(out_dir, "rnd%d.xml" % seed)
+    with open(path, "w") as f:
+        f.write(xml)
+    return path

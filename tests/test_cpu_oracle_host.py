@@ -123,6 +123,24 @@ def test_motion_blur_dof_roughness_oracle_vs_reference_statistics(tmp_path):
 
 
 @needs_ref
+@pytest.mark.parametrize("textures", [False, True])
+@pytest.mark.parametrize("seed", range(16))
+def test_random_deterministic_scenes_oracle_bit_exact_vs_reference(tmp_path, seed, textures):
+    """Seeded random scenes (scenes_util.random_scene: random materials of every type, all eight BRDF variants, composed
+    transformations on meshes / spheres / <Triangle>s, MeshInstances with and without resetTransform, point / directional / spot
+    lights, depth 1-4; textures=True adds image / Perlin colour, bump and normal maps): nothing is sampled, so the C restatement must give the compiled reference's PNG, radiance bits and ray
+    counts exactly.  The same seeds are rendered by the GPU path in tests/test_gpu_parity.py."""
+    from scenes_util import random_scene
+    p = random_scene(str(tmp_path / "rnd"), seed, textures=textures)
+    hs = HostScene(p)
+    ldr, hdr, st = oracle_render(hs, hs.camera(0))
+    ref = run_reference(p)
+    assert np.array_equal(ldr, ref["png"])
+    assert np.array_equal(hdr.view(np.uint32), ref["hdr"].view(np.uint32))
+    assert (int(st.rays_closest), int(st.rays_shadow)) == (ref["closest"], ref["shadow"])
+
+
+@needs_ref
 @pytest.mark.parametrize("tonemap", [False, True])
 def test_reference_quirks_oracle_bit_exact_vs_reference(tmp_path, tonemap):
     """Behaviours no other scene renders: `replace_background` texture (raytracer.cpp:49-62), the `replace_ks`

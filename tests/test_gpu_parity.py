@@ -894,6 +894,26 @@ def test_reference_quirks_scene_parity(tmp_path, tonemap):
         assert frac <= 1e-3, ("vs compiled reference", frac, mx)
 
 
+@pytest.mark.parametrize("textures", [False, True])
+@pytest.mark.parametrize("seed", range(16))
+def test_random_deterministic_scenes_parity(tmp_path, seed, textures):
+    """Seeded random deterministic scenes (scenes_util.random_scene; the oracle is bit-exact against the compiled reference on the
+    same seeds, tests/test_cpu_oracle_host.py): primary hits bit-exact, the reference's ray counts, LDR within one level on
+    >= 99.9 % of the pixels."""
+    from scenes_util import random_scene
+    p = random_scene(str(tmp_path / "rnd"), seed, textures=textures)
+    hs = HostScene(p)
+    cam = hs.camera(0)
+    gs = GpuScene(hs)
+    _assert_hits_equal(gs.primary_hits(cam), oracle_primary_hits(hs, cam))
+    ldr, hdr, st = gs.render(cam)
+    gs.close()
+    oldr, ohdr, ost = oracle_render(hs, cam)
+    assert (int(st.rays_closest), int(st.rays_shadow)) == (int(ost.rays_closest), int(ost.rays_shadow))
+    frac, mx = ldr_mismatch_fraction(ldr, oldr, 1)
+    assert frac <= 1e-3, (frac, mx)
+
+
 @pytest.mark.parametrize("blur_instance", [False, True])
 def test_env_map_on_miss_under_whitted_statistics(tmp_path, blur_instance):
     """Whitted + spherical environment light (env lookups on the misses of mirror / dielectric children and camera rays), a
