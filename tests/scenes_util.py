@@ -240,25 +240,37 @@ def env_whitted_scene(out_dir, width=160, height=112, spp=4, blur_instance=False
     return path
 
 
-def random_scene(out_dir, seed, width=112, height=80, textures=False):
+def random_scene(out_dir, seed, width=112, height=80, textures=False, extras=False):
     """A seeded random DETERMINISTIC scene (no sampling anywhere, so the reference, the oracle and the GPU path must agree bit
     for bit on hits and ray counts): a floor, 2-5 spheres and 1-3 small meshes (boxes, tetrahedra, triangle soups, single
     <Triangle>s) with random materials -- plain with any of the eight BRDF variants, mirror, conductor, dielectric --, random
     composed transformations on some of them, a MeshInstance of the first mesh (with and without resetTransform), 1-2 point
     lights and, by chance, a directional and a spot light; recursion depth 1-4 and a random camera.
     textures=True: random texture coordinates on every vertex and, on about half of the shapes, one or two of seven texture maps
-    (image replace_kd / blend_kd / replace_all, image normal map, image bump map, Perlin replace_kd, Perlin bump map)."""
-    rng = np.random.RandomState(1000 + seed)
+    (image replace_kd / blend_kd / replace_all, image normal map, image bump map, Perlin replace_kd, Perlin bump map).
+    extras=True (a different random stream): lookAt cameras (GazePoint / FovY), a photographic tonemapper on a third of the frames,
+    `degamma` materials, recursion depth up to 6, a binary-PLY blob mesh with a MeshInstance of it and, with textures, a
+    `replace_background` map and `replace_ks` maps (always next to a diffuse map: without one the reference dereferences nullptr)."""
+    rng = np.random.RandomState(1000 + seed + (50000 if extras else 0))
     os.makedirs(os.path.join(out_dir, "inputs"), exist_ok=True)
     u = lambda a, b: float(rng.uniform(a, b))
     f3 = lambda v: "%.6g %.6g %.6g" % (v[0], v[1], v[2])
     cam_pos = (u(-2.5, 2.5), u(1.5, 4.0), u(6.5, 9))
     gaze = (-cam_pos[0] * 0.08 + u(-0.05, 0.05), -0.12 + u(-0.08, 0.05), -1.0)
     xml = ("<Scene><MaxRecursionDepth>%d</MaxRecursionDepth><BackgroundColor>%d %d %d</BackgroundColor><ShadowRayEpsilon>1e-3</ShadowRayEpsilon>\n"
-           % (rng.randint(1, 5), rng.randint(20, 120), rng.randint(20, 120), rng.randint(30, 160)))
-    xml += ("<Cameras><Camera id=\"1\"><Position>%s</Position><Gaze>%s</Gaze><Up>0 1 0</Up><NearPlane>-1 1 -0.714 0.714</NearPlane>"
-            "<NearDistance>%.4g</NearDistance><ImageResolution>%d %d</ImageResolution><ImageName>rnd%d.png</ImageName></Camera></Cameras>\n"
-            % (f3(cam_pos), f3(gaze), u(1.6, 2.4), width, height, seed))
+           % (rng.randint(1, 7 if extras else 5), rng.randint(20, 120), rng.randint(20, 120), rng.randint(30, 160)))
+    tm = ""
+    if extras and rng.rand() < 0.34:
+        tm = ("<Tonemap><TMO>Photographic</TMO><TMOOptions>%.4g %.4g</TMOOptions><Saturation>%.4g</Saturation><Gamma>%.4g</Gamma></Tonemap>"
+              % (u(0.1, 0.3), u(0.5, 3), u(0.6, 1.2), u(1.8, 2.4)))
+    if extras and rng.rand() < 0.5:
+        xml += ("<Cameras><Camera id=\"1\" type=\"lookAt\"><Position>%s</Position><GazePoint>%s</GazePoint><Up>%s</Up><FovY>%.4g</FovY>"
+                "<NearDistance>%.4g</NearDistance><ImageResolution>%d %d</ImageResolution>%s<ImageName>rnd%d.png</ImageName></Camera></Cameras>\n"
+                % (f3(cam_pos), f3((u(-1, 1), u(0.5, 1.5), u(-1, 1))), f3((u(-0.2, 0.2), 1.0, u(-0.1, 0.1))), u(35, 60), u(1.0, 2.0), width, height, tm, seed))
+    else:
+        xml += ("<Cameras><Camera id=\"1\"><Position>%s</Position><Gaze>%s</Gaze><Up>0 1 0</Up><NearPlane>-1 1 -0.714 0.714</NearPlane>"
+                "<NearDistance>%.4g</NearDistance><ImageResolution>%d %d</ImageResolution>%s<ImageName>rnd%d.png</ImageName></Camera></Cameras>\n"
+                % (f3(cam_pos), f3(gaze), u(1.6, 2.4), width, height, tm, seed))
     xml += "<Lights><AmbientLight>%d %d %d</AmbientLight>\n" % (rng.randint(5, 40), rng.randint(5, 40), rng.randint(5, 40))
     for k in range(rng.randint(1, 3)):
         xml += ("<PointLight id=\"%d\"><Position>%s</Position><Intensity>%s</Intensity></PointLight>\n"
@@ -284,9 +296,10 @@ def random_scene(out_dir, seed, width=112, height=80, textures=False):
         kd = f3((u(0.1, 0.8), u(0.1, 0.8), u(0.1, 0.8)))
         if kind == "plain":
             brdf = rng.randint(0, 9)
-            xml += ("<Material id=\"%d\"%s><AmbientReflectance>1 1 1</AmbientReflectance><DiffuseReflectance>%s</DiffuseReflectance>"
+            dg = " degamma=\"true\"" if extras and rng.rand() < 0.3 else ""
+            xml += ("<Material id=\"%d\"%s%s><AmbientReflectance>1 1 1</AmbientReflectance><DiffuseReflectance>%s</DiffuseReflectance>"
                     "<SpecularReflectance>%s</SpecularReflectance><PhongExponent>%.4g</PhongExponent><RefractionIndex>%.4g</RefractionIndex></Material>\n"
-                    % (m, " BRDF=\"%d\"" % brdf if brdf else "", kd, f3((u(0, 0.6),) * 3), u(3, 60), u(1.2, 2.2)))
+                    % (m, " BRDF=\"%d\"" % brdf if brdf else "", dg, kd, f3((u(0, 0.6),) * 3), u(3, 60), u(1.2, 2.2)))
         elif kind == "mirror":
             xml += ("<Material id=\"%d\" type=\"mirror\"><AmbientReflectance>0 0 0</AmbientReflectance><DiffuseReflectance>%s</DiffuseReflectance>"
                     "<SpecularReflectance>0.2 0.2 0.2</SpecularReflectance><PhongExponent>20</PhongExponent><MirrorReflectance>%s</MirrorReflectance></Material>\n"
@@ -322,8 +335,13 @@ def random_scene(out_dir, seed, width=112, height=80, textures=False):
                    "<TextureMap id=\"4\" type=\"image\"><ImageId>1</ImageId><DecalMode>bump_normal</DecalMode><BumpFactor>%.4g</BumpFactor></TextureMap>\n"
                    "<TextureMap id=\"5\" type=\"perlin\"><DecalMode>replace_kd</DecalMode><NoiseConversion>absval</NoiseConversion><NoiseScale>%.4g</NoiseScale></TextureMap>\n"
                    "<TextureMap id=\"6\" type=\"perlin\"><DecalMode>bump_normal</DecalMode><NoiseConversion>linear</NoiseConversion><NoiseScale>%.4g</NoiseScale><BumpFactor>%.4g</BumpFactor></TextureMap>\n"
-                   "<TextureMap id=\"7\" type=\"image\"><ImageId>1</ImageId><DecalMode>replace_all</DecalMode><Interpolation>bilinear</Interpolation></TextureMap></Textures>\n"
+                   "<TextureMap id=\"7\" type=\"image\"><ImageId>1</ImageId><DecalMode>replace_all</DecalMode><Interpolation>bilinear</Interpolation></TextureMap>\n"
                    % (u(0.5, 3), u(0.5, 4), u(1, 4), u(0.2, 1.0)))
+        if extras:
+            if rng.rand() < 0.5:
+                tex_xml += "<TextureMap id=\"8\" type=\"image\"><ImageId>1</ImageId><DecalMode>replace_background</DecalMode><Interpolation>bilinear</Interpolation></TextureMap>\n"
+            tex_xml += "<TextureMap id=\"9\" type=\"image\"><ImageId>2</ImageId><DecalMode>replace_ks</DecalMode><Interpolation>nearest</Interpolation></TextureMap>\n"
+        tex_xml += "</Textures>\n"
 
     def shape_textures():
         if not textures or rng.rand() < 0.5:
@@ -331,6 +349,8 @@ def random_scene(out_dir, seed, width=112, height=80, textures=False):
         ids = []
         if rng.rand() < 0.75:
             ids.append([1, 2, 5, 7][rng.randint(4)])
+            if extras and ids[0] in (1, 2, 5) and rng.rand() < 0.3:
+                ids.insert(0, 9)                                      # replace_ks reads the DIFFUSE slot (raytracer.cpp:516-531)
         if rng.rand() < 0.5 or not ids:
             ids.append([3, 4, 6][rng.randint(3)])
         return "<Textures>%s</Textures>" % " ".join(str(k) for k in ids)
@@ -383,6 +403,15 @@ def random_scene(out_dir, seed, width=112, height=80, textures=False):
             objs += ("<MeshInstance id=\"%d\" baseMeshId=\"%d\" resetTransform=\"%s\"><Material>%d</Material><Transformations>s%d r%d t%d</Transformations></MeshInstance>\n"
                      % (mesh_id, first_mesh, reset, rng.randint(1, n_mat + 1), rng.randint(1, 4), rng.randint(1, 4), rng.randint(1, 4)))
             mesh_id += 1
+    if extras and rng.rand() < 0.6:
+        from dtb200 import scenegen
+        bv, bf = scenegen.blob_mesh(int(rng.randint(8, 20)), int(rng.randint(5, 11)), u(0.6, 1.0), (u(-3, 3), u(1.0, 2.0), u(-2, 2)))
+        scenegen.write_ply(os.path.join(out_dir, "rnd_blob%d.ply" % seed), bv, bf)
+        objs += ("<Mesh id=\"%d\"><Material>%d</Material>%s<Faces plyFile=\"rnd_blob%d.ply\" /></Mesh>\n"
+                 % (mesh_id, rng.randint(1, n_mat + 1), transforms(), seed))
+        objs += ("<MeshInstance id=\"%d\" baseMeshId=\"%d\" resetTransform=\"%s\"><Material>%d</Material><Transformations>t%d r%d</Transformations></MeshInstance>\n"
+                 % (mesh_id + 1, mesh_id, ["true", "false"][rng.randint(2)], rng.randint(1, n_mat + 1), rng.randint(1, 4), rng.randint(1, 4)))
+        mesh_id += 2
     for k in range(rng.randint(2, 6)):
         r = u(0.5, 1.2)
         verts.append((u(-5.5, 5.5), r + u(0.0, 1.5), u(-3.5, 4.0)))

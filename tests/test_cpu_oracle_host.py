@@ -123,15 +123,15 @@ def test_motion_blur_dof_roughness_oracle_vs_reference_statistics(tmp_path):
 
 
 @needs_ref
-@pytest.mark.parametrize("textures", [False, True])
-@pytest.mark.parametrize("seed", range(16))
-def test_random_deterministic_scenes_oracle_bit_exact_vs_reference(tmp_path, seed, textures):
+@pytest.mark.parametrize("seed,textures,extras", [(k, t, False) for t in (False, True) for k in range(16)] + [(k, k % 2 == 1, True) for k in range(24)])
+def test_random_deterministic_scenes_oracle_bit_exact_vs_reference(tmp_path, seed, textures, extras):
     """Seeded random scenes (scenes_util.random_scene: random materials of every type, all eight BRDF variants, composed
     transformations on meshes / spheres / <Triangle>s, MeshInstances with and without resetTransform, point / directional / spot
-    lights, depth 1-4; textures=True adds image / Perlin colour, bump and normal maps): nothing is sampled, so the C restatement must give the compiled reference's PNG, radiance bits and ray
+    lights, depth 1-4; textures=True adds image / Perlin colour, bump and normal maps; extras=True lookAt cameras, the photographic
+    tonemapper, degamma materials, PLY meshes with instances, replace_background / replace_ks maps, depth up to 6): nothing is sampled, so the C restatement must give the compiled reference's PNG, radiance bits and ray
     counts exactly.  The same seeds are rendered by the GPU path in tests/test_gpu_parity.py."""
     from scenes_util import random_scene
-    p = random_scene(str(tmp_path / "rnd"), seed, textures=textures)
+    p = random_scene(str(tmp_path / "rnd"), seed, textures=textures, extras=extras)
     hs = HostScene(p)
     ldr, hdr, st = oracle_render(hs, hs.camera(0))
     ref = run_reference(p)

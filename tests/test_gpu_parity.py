@@ -894,14 +894,13 @@ def test_reference_quirks_scene_parity(tmp_path, tonemap):
         assert frac <= 1e-3, ("vs compiled reference", frac, mx)
 
 
-@pytest.mark.parametrize("textures", [False, True])
-@pytest.mark.parametrize("seed", range(16))
-def test_random_deterministic_scenes_parity(tmp_path, seed, textures):
+@pytest.mark.parametrize("seed,textures,extras", [(k, t, False) for t in (False, True) for k in range(16)] + [(k, k % 2 == 1, True) for k in range(24)])
+def test_random_deterministic_scenes_parity(tmp_path, seed, textures, extras):
     """Seeded random deterministic scenes (scenes_util.random_scene; the oracle is bit-exact against the compiled reference on the
     same seeds, tests/test_cpu_oracle_host.py): primary hits bit-exact, the reference's ray counts, LDR within one level on
     >= 99.9 % of the pixels."""
     from scenes_util import random_scene
-    p = random_scene(str(tmp_path / "rnd"), seed, textures=textures)
+    p = random_scene(str(tmp_path / "rnd"), seed, textures=textures, extras=extras)
     hs = HostScene(p)
     cam = hs.camera(0)
     gs = GpuScene(hs)
