@@ -328,6 +328,34 @@ def test_trace_queries_vs_oracle():
     assert gs.trace_closest(o[:0], d[:0])[0].size == 0          # empty input
 
 
+@pytest.mark.parametrize("seed", range(8))
+def test_random_scenes_ray_queries(tmp_path, seed):
+    """Generic closest-hit / occlusion queries on the random scenes (instances, PLY meshes, transformed spheres): rays from
+    random points in and around the objects, then a second generation starting exactly AT the hit points of the first (what
+    reflected / refracted / shadow rays do: origins on box faces and on triangles), bit-exact against the oracle."""
+    from scenes_util import random_scene
+    hs = HostScene(random_scene(str(tmp_path / "rnd"), seed, extras=True))
+    gs = GpuScene(hs)
+    rng = np.random.RandomState(100 + seed)
+    n = 16384
+    o = (rng.rand(n, 3).astype(np.float32) - 0.5) * np.array([14, 5, 10], np.float32) + np.array([0, 2.4, 0], np.float32)
+    d = rng.randn(n, 3).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True).astype(np.float32)
+    d[:64, rng.randint(3)] = 0.0
+    for gen in range(2):
+        s, f, t = gs.trace_closest(o, d)
+        rs, rf, rt = oracle_trace_closest(hs, o, d)
+        _assert_hits_equal((s, f, t), (rs, rf, rt))
+        tmax = np.where(np.isinf(rt), np.float32(np.inf), rt * np.float32(1.25)).astype(np.float32)
+        tmax[::4] = np.float32(np.inf)
+        assert np.array_equal(gs.trace_occluded(o, d, tmax), oracle_trace_occluded(hs, o, d, tmax))
+        hit = rs >= 0
+        o = (o[hit] + d[hit] * rt[hit][:, None]).astype(np.float32)
+        d = rng.randn(o.shape[0], 3).astype(np.float32)
+        d /= np.linalg.norm(d, axis=1, keepdims=True).astype(np.float32)
+    gs.close()
+
+
 def test_degenerate_rays_do_not_poison_the_batch():
     """NaN / infinite / zero directions and far-away origins mixed into a batch: the call must return (no hang, no CUDA
     error), and every ordinary ray of the same batch must still match the oracle bit for bit."""
