@@ -69,6 +69,10 @@ enum { DT_CNT_NEXT = 0, DT_CNT_SHADOW = 1, DT_CNT_FETCH_A = 2, DT_CNT_FETCH_B = 
 struct DtShadeCounters { int* next; int* shadow; int* overflow; unsigned long long* shadow_dead; unsigned long long* closest_dead; };
 
 #define DT_DEAD_PIXEL 0xFFFFFFFFu
+// Russian roulette never ends a path whose throughput is NaN or stays >= 1 (`probTest > maxThroughput` is false, raytracer.cpp:141-146):
+// in a closed part of a scene the reference recurses until its stack overflows (a crash after ~10^4 bounces).  The wavefront loop
+// would spin forever instead, so a path is cut this many bounces below depth 0 -- further than the reference can get.
+#define DT_RR_MAX_BOUNCES 32768
 
 __device__ __forceinline__ int dt_agg_inc(int* counter) {
     const unsigned active = __activemask();
@@ -554,6 +558,7 @@ __device__ __forceinline__ void dt_shade_ray(const int i, const DtSceneDev& S, c
                 float probTest = rng01(rng);
                 float maxT = fmaxf(thr.x, fmaxf(thr.x, thr.z));
                 if (probTest > maxT && depth <= 0) go = false;
+                else if (depth < -DT_RR_MAX_BOUNCES) go = false;           // see DT_RR_MAX_BOUNCES
                 else thr = vdiv(thr, maxT);
             } else if (depth <= 0) go = false;
             if (!go) continue;

@@ -240,7 +240,7 @@ def env_whitted_scene(out_dir, width=160, height=112, spp=4, blur_instance=False
     return path
 
 
-def random_scene(out_dir, seed, width=112, height=80, textures=False, extras=False):
+def random_scene(out_dir, seed, width=112, height=80, textures=False, extras=False, mc=False, spp=None):
     """A seeded random DETERMINISTIC scene (no sampling anywhere, so the reference, the oracle and the GPU path must agree bit
     for bit on hits and ray counts): a floor, 2-5 spheres and 1-3 small meshes (boxes, tetrahedra, triangle soups, single
     <Triangle>s) with random materials -- plain with any of the eight BRDF variants, mirror, conductor, dielectric --, random
@@ -250,8 +250,11 @@ def random_scene(out_dir, seed, width=112, height=80, textures=False, extras=Fal
     (image replace_kd / blend_kd / replace_all, image normal map, image bump map, Perlin replace_kd, Perlin bump map).
     extras=True (a different random stream): lookAt cameras (GazePoint / FovY), a photographic tonemapper on a third of the frames,
     `degamma` materials, recursion depth up to 6, a binary-PLY blob mesh with a MeshInstance of it and, with textures, a
-    `replace_background` map and `replace_ks` maps (always next to a diffuse map: without one the reference dereferences nullptr)."""
-    rng = np.random.RandomState(1000 + seed + (50000 if extras else 0))
+    `replace_background` map and `replace_ks` maps (always next to a diffuse map: without one the reference dereferences nullptr).
+    mc=True (another stream; NOT deterministic): several samples per pixel, by chance a thin lens, the path-tracing renderer with a
+    random subset of ImportanceSampling / NextEventEstimation / RussianRoulette, an area light, a spherical environment light, a
+    LightMesh, motion blur on a sphere and rough mirrors; spp overrides the sample count."""
+    rng = np.random.RandomState(1000 + seed + (50000 if extras else 0) + (90000 if mc else 0))
     os.makedirs(os.path.join(out_dir, "inputs"), exist_ok=True)
     u = lambda a, b: float(rng.uniform(a, b))
     f3 = lambda v: "%.6g %.6g %.6g" % (v[0], v[1], v[2])
@@ -263,6 +266,16 @@ def random_scene(out_dir, seed, width=112, height=80, textures=False, extras=Fal
     if extras and rng.rand() < 0.34:
         tm = ("<Tonemap><TMO>Photographic</TMO><TMOOptions>%.4g %.4g</TMOOptions><Saturation>%.4g</Saturation><Gamma>%.4g</Gamma></Tonemap>"
               % (u(0.1, 0.3), u(0.5, 3), u(0.6, 1.2), u(1.8, 2.4)))
+    env_light = False
+    if mc:
+        n_spp = spp if spp is not None else [1, 4, 4, 9][rng.randint(4)]
+        tm += "<NumSamples>%d</NumSamples>" % n_spp
+        if rng.rand() < 0.3:
+            tm += "<FocusDistance>%.4g</FocusDistance><ApertureSize>%.4g</ApertureSize>" % (u(6, 10), u(0.05, 0.3))
+        if rng.rand() < 0.75:
+            params = [w for w in ("ImportanceSampling", "NextEventEstimation", "RussianRoulette") if rng.rand() < 0.6]
+            tm += "<Renderer>PathTracing</Renderer><RendererParams>%s</RendererParams>" % " ".join(params)
+        env_light = rng.rand() < 0.4
     if extras and rng.rand() < 0.5:
         xml += ("<Cameras><Camera id=\"1\" type=\"lookAt\"><Position>%s</Position><GazePoint>%s</GazePoint><Up>%s</Up><FovY>%.4g</FovY>"
                 "<NearDistance>%.4g</NearDistance><ImageResolution>%d %d</ImageResolution>%s<ImageName>rnd%d.png</ImageName></Camera></Cameras>\n"
@@ -283,6 +296,11 @@ def random_scene(out_dir, seed, width=112, height=80, textures=False, extras=Fal
         xml += ("<SpotLight id=\"8\"><Position>%s</Position><Direction>%s</Direction><Intensity>%s</Intensity>"
                 "<CoverageAngle>%.4g</CoverageAngle><FalloffAngle>%.4g</FalloffAngle></SpotLight>\n"
                 % (f3(sp), f3((-sp[0] * 0.15 + u(-0.1, 0.1), -1.0, -sp[2] * 0.15)), f3((u(2e4, 9e4), u(2e4, 9e4), u(2e4, 9e4))), u(35, 70), u(10, 30)))
+    if mc and rng.rand() < 0.6:
+        xml += ("<AreaLight id=\"5\"><Position>%s</Position><Normal>%s</Normal><Radiance>%s</Radiance><Size>%.4g</Size></AreaLight>\n"
+                % (f3((u(-3, 3), u(5, 8), u(-2, 3))), f3((u(-0.3, 0.3), -1.0, u(-0.3, 0.3))), f3((u(8, 30), u(8, 30), u(8, 30))), u(1, 4)))
+    if env_light:
+        xml += "<SphericalDirectionalLight id=\"6\"><ImageId>3</ImageId></SphericalDirectionalLight>\n"
     xml += "</Lights>\n"
     xml += ("<BRDFs><OriginalPhong id=\"1\"><Exponent>%.4g</Exponent></OriginalPhong><OriginalBlinnPhong id=\"2\"><Exponent>%.4g</Exponent></OriginalBlinnPhong>"
             "<ModifiedPhong id=\"3\"><Exponent>%.4g</Exponent></ModifiedPhong><ModifiedPhong id=\"4\" normalized=\"true\"><Exponent>%.4g</Exponent></ModifiedPhong>"
@@ -302,8 +320,8 @@ def random_scene(out_dir, seed, width=112, height=80, textures=False, extras=Fal
                     % (m, " BRDF=\"%d\"" % brdf if brdf else "", dg, kd, f3((u(0, 0.6),) * 3), u(3, 60), u(1.2, 2.2)))
         elif kind == "mirror":
             xml += ("<Material id=\"%d\" type=\"mirror\"><AmbientReflectance>0 0 0</AmbientReflectance><DiffuseReflectance>%s</DiffuseReflectance>"
-                    "<SpecularReflectance>0.2 0.2 0.2</SpecularReflectance><PhongExponent>20</PhongExponent><MirrorReflectance>%s</MirrorReflectance></Material>\n"
-                    % (m, f3((u(0, 0.2),) * 3), f3((u(0.4, 0.95), u(0.4, 0.95), u(0.4, 0.95)))))
+                    "<SpecularReflectance>0.2 0.2 0.2</SpecularReflectance><PhongExponent>20</PhongExponent><MirrorReflectance>%s</MirrorReflectance>%s</Material>\n"
+                    % (m, f3((u(0, 0.2),) * 3), f3((u(0.4, 0.95), u(0.4, 0.95), u(0.4, 0.95))), "<Roughness>%.4g</Roughness>" % u(0.02, 0.3) if mc and rng.rand() < 0.5 else ""))
         elif kind == "conductor":
             xml += ("<Material id=\"%d\" type=\"conductor\"><AmbientReflectance>0 0 0</AmbientReflectance><DiffuseReflectance>%s</DiffuseReflectance>"
                     "<SpecularReflectance>0 0 0</SpecularReflectance><MirrorReflectance>%s</MirrorReflectance><RefractionIndex>%.4g</RefractionIndex>"
@@ -313,6 +331,9 @@ def random_scene(out_dir, seed, width=112, height=80, textures=False, extras=Fal
             xml += ("<Material id=\"%d\" type=\"dielectric\"><AmbientReflectance>0 0 0</AmbientReflectance><DiffuseReflectance>0 0 0</DiffuseReflectance>"
                     "<SpecularReflectance>0 0 0</SpecularReflectance><AbsorptionCoefficient>%s</AbsorptionCoefficient><RefractionIndex>%.4g</RefractionIndex></Material>\n"
                     % (m, f3((u(0, 0.08), u(0, 0.08), u(0, 0.08))), u(1.2, 2.0)))
+    if mc:
+        xml += ("<Material id=\"%d\"><AmbientReflectance>0 0 0</AmbientReflectance><DiffuseReflectance>0 0 0</DiffuseReflectance>"
+                "<SpecularReflectance>0 0 0</SpecularReflectance></Material>\n" % (n_mat + 1))                # becomes emissive (LightMesh)
     xml += "</Materials>\n"
     verts = [(-11, 0, -9), (11, 0, -9), (11, 0, 9), (-11, 0, 9)]
     objs = "<Mesh id=\"1\"><Material>%d</Material>%s<Faces>1 3 2\n1 4 3</Faces></Mesh>\n" % (rng.randint(1, 3), "PLACEHOLDER_FLOOR_TEX")
@@ -343,7 +364,17 @@ def random_scene(out_dir, seed, width=112, height=80, textures=False, extras=Fal
             tex_xml += "<TextureMap id=\"9\" type=\"image\"><ImageId>2</ImageId><DecalMode>replace_ks</DecalMode><Interpolation>nearest</Interpolation></TextureMap>\n"
         tex_xml += "</Textures>\n"
 
-    def shape_textures():
+    if env_light:
+        from dtb200 import scenegen
+        yy, xx = np.mgrid[0:16, 0:32].astype(np.float32)
+        sky = 6.0 + 10.0 * (1 - yy / 16) + 3.0 * np.sin(xx / 32 * 2 * np.pi + seed)
+        scenegen.write_exr(os.path.join(out_dir, "inputs", "rnd_env.exr"), np.stack([0.8 * sky, 0.9 * sky, 1.0 * sky], axis=-1).astype(np.float32))
+        if tex_xml:
+            tex_xml = tex_xml.replace("</Images>", "<Image id=\"3\">rnd_env.exr</Image></Images>")
+        else:
+            tex_xml = "<Textures><Images><Image id=\"1\">rnd_env.exr</Image><Image id=\"2\">rnd_env.exr</Image><Image id=\"3\">rnd_env.exr</Image></Images></Textures>\n"
+
+    def shape_textures(sphere=False):
         if not textures or rng.rand() < 0.5:
             return ""
         ids = []
@@ -353,6 +384,11 @@ def random_scene(out_dir, seed, width=112, height=80, textures=False, extras=Fal
                 ids.insert(0, 9)                                      # replace_ks reads the DIFFUSE slot (raytracer.cpp:516-531)
         if rng.rand() < 0.5 or not ids:
             ids.append([3, 4, 6][rng.randint(3)])
+        if mc and sphere:
+            # the image bump map of a sphere reads the texel row below the last one near the south pole (sphere.cpp:127-140 ->
+            # LDRImage.h:16-26, no bounds check): heap garbage in the reference, clamped here.  Camera rays of these scenes do not
+            # see that row, but GI rays do.
+            ids = [6 if k == 4 else k for k in ids]
         return "<Textures>%s</Textures>" % " ".join(str(k) for k in ids)
 
     def transforms():
@@ -412,11 +448,20 @@ def random_scene(out_dir, seed, width=112, height=80, textures=False, extras=Fal
         objs += ("<MeshInstance id=\"%d\" baseMeshId=\"%d\" resetTransform=\"%s\"><Material>%d</Material><Transformations>t%d r%d</Transformations></MeshInstance>\n"
                  % (mesh_id + 1, mesh_id, ["true", "false"][rng.randint(2)], rng.randint(1, n_mat + 1), rng.randint(1, 4), rng.randint(1, 4)))
         mesh_id += 2
+    if mc and rng.rand() < 0.5:
+        c = np.array([u(-3, 3), u(4.5, 7), u(-2, 2)])
+        base = len(verts)
+        h = u(0.6, 1.5)
+        verts += [tuple(c + (-h, 0, -h)), tuple(c + (h, 0, -h)), tuple(c + (h, u(-0.3, 0.3), h)), tuple(c + (-h, 0, h))]
+        objs += ("<LightMesh id=\"%d\"><Material>%d</Material><Faces>%d %d %d\n%d %d %d</Faces><Radiance>%s</Radiance></LightMesh>\n"
+                 % (mesh_id, n_mat + 1, base + 1, base + 2, base + 3, base + 3, base + 4, base + 1, f3((u(5, 20), u(5, 20), u(5, 20)))))
+        mesh_id += 1
     for k in range(rng.randint(2, 6)):
         r = u(0.5, 1.2)
         verts.append((u(-5.5, 5.5), r + u(0.0, 1.5), u(-3.5, 4.0)))
-        objs += ("<Sphere id=\"%d\"><Material>%d</Material>%s%s<Center>%d</Center><Radius>%.4g</Radius></Sphere>\n"
-                 % (k + 1, rng.randint(1, n_mat + 1), shape_textures(), transforms() if rng.rand() < 0.4 else "", len(verts), r))
+        blur = "<MotionBlur>%s</MotionBlur>" % f3((u(-0.6, 0.6), u(0, 0.5), u(-0.4, 0.4))) if mc and rng.rand() < 0.25 else ""
+        objs += ("<Sphere id=\"%d\"><Material>%d</Material>%s%s<Center>%d</Center><Radius>%.4g</Radius>%s</Sphere>\n"
+                 % (k + 1, rng.randint(1, n_mat + 1), shape_textures(sphere=True), transforms() if rng.rand() < 0.4 else "", len(verts), r, blur))
     objs = objs.replace("PLACEHOLDER_FLOOR_TEX", shape_textures())
     uv_xml = ""
     if textures:

@@ -117,6 +117,28 @@ def test_monte_carlo_radiance_bits_match_the_live_reference(tmp_path):
         assert np.array_equal(hdr.view(np.uint32), ref["hdr"].view(np.uint32))
 
 
+# scenes_util.random_scene(mc=True) seeds the reference renders (it overflows its stack or never returns on seeds 6, 13, 23, 25, 34, 43:
+# immortal Russian-roulette paths in closed geometry, rejection loops fed a NaN normal)
+RANDOM_MC_SEEDS = [k for k in range(48) if k not in (6, 13, 23, 25, 34, 43)]
+
+
+@needs_ref
+@pytest.mark.parametrize("seed", RANDOM_MC_SEEDS)
+def test_random_monte_carlo_scenes_replay_bit_exact_vs_the_live_reference(seed, tmp_path):
+    """Seeded random STOCHASTIC scenes (scenes_util.random_scene(mc=True): 1 / 4 / 9 samples, thin lens, path tracing with random
+    subsets of importance sampling / NEE / Russian roulette or Whitted with sampled lights, area + environment + mesh lights next
+    to point / directional / spot lights, motion-blurred spheres, rough mirrors, every material and BRDF, instances, textures):
+    the oracle replaying the reference's generators must give the radiance bits and ray counts of the compiled reference run on
+    one thread."""
+    from scenes_util import random_scene
+    p = random_scene(str(tmp_path / "rnd"), seed, width=56, height=40, textures=(seed % 3 == 1), extras=(seed % 2 == 1), mc=True)
+    hs = HostScene(p)
+    ref = run_reference(p, probe=True, threads=1, timeout=300)
+    _, hdr, st = oracle_render_reference_rng(hs, hs.camera(0))
+    assert (int(st.rays_closest), int(st.rays_shadow)) == (ref["closest"], ref["shadow"])
+    assert np.array_equal(hdr.view(np.uint32), ref["hdr"].view(np.uint32))
+
+
 @pytest.mark.parametrize("name,psnr_min", [("mc_all", 31.0), ("mc_mesh", 34.0), ("mc_env", 29.0)])
 def test_pixel_keyed_oracle_is_the_same_estimator_as_the_high_spp_reference(name, psnr_min, tmp_path):
     """dto_render's per-pixel SplitMix64 streams (the mode the GPU tests compare with) against the 4096-spp reference render of
