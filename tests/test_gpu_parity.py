@@ -941,6 +941,28 @@ def test_random_deterministic_scenes_parity(tmp_path, seed, textures, extras):
     assert frac <= 1e-3, (frac, mx)
 
 
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("seed", [6, 13, 23, 25, 34, 43, 0, 5, 9, 21])
+def test_random_monte_carlo_scenes_terminate(tmp_path, seed):
+    """Random stochastic scenes (scenes_util.random_scene(mc=True)), first of all the six on which the compiled reference overflows
+    its stack or never returns (immortal Russian-roulette paths -- NaN or >= 1 throughput in closed geometry --, rejection loops fed
+    a NaN normal; tests/test_cpu_monte_carlo_pin.py lists them): the GPU path must come back with a frame (paths are cut
+    DT_RR_MAX_BOUNCES below depth 0, the environment light is sampled without a loop), twice with the same ray counts bounded by
+    what the cut allows."""
+    from scenes_util import random_scene
+    p = random_scene(str(tmp_path / "rnd"), seed, width=56, height=40, textures=(seed % 3 == 1), extras=(seed % 2 == 1), mc=True)
+    hs = HostScene(p)
+    cam = hs.camera(0)
+    gs = GpuScene(hs)
+    ldr, hdr, st = gs.render(cam, seed=7)
+    ldr2, hdr2, st2 = gs.render(cam, seed=7)
+    gs.close()
+    assert ldr.shape == (40, 56, 3) and hdr.shape == (40, 56, 3)
+    n_paths = 56 * 40 * cam.samples_per_pixel
+    assert int(st.rays_closest) >= n_paths and int(st.rays_closest) <= n_paths * (32768 + 64) * 4
+    assert (int(st.rays_closest), int(st.rays_shadow)) == (int(st2.rays_closest), int(st2.rays_shadow))      # same seed, same ray tree
+
+
 @pytest.mark.parametrize("blur_instance", [False, True])
 def test_env_map_on_miss_under_whitted_statistics(tmp_path, blur_instance):
     """Whitted + spherical environment light (env lookups on the misses of mirror / dielectric children and camera rays), a
