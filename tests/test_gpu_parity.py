@@ -856,6 +856,23 @@ def test_dropin_reference_main_on_instances_textures_and_path_tracing(tmp_path):
     assert psnr(keep["png"], out["png"]) >= 40.0 or np.array_equal(keep["png"], out["png"]), psnr(keep["png"], out["png"])   # same seed, same image
 
 
+@needs_dropin
+@pytest.mark.parametrize("seed,textures,extras", [(k, k % 2 == 1, k % 4 >= 2) for k in range(12)])
+def test_dropin_reference_main_on_random_scenes(tmp_path, seed, textures, extras):
+    """The drop-in binary on the random deterministic scenes: the reference's own parser / Scene / Camera flattened by
+    dt_flatten_scene.cpp (every material, BRDF, light and texture class, <Triangle>s, instances with and without resetTransform,
+    lookAt cameras, the tonemapper, PLY meshes) and rendered by the GPU, against the oracle fed by this repository's host mirror of
+    the parser -- which is bit-exact against the compiled reference on the same seeds (tests/test_cpu_oracle_host.py)."""
+    from scenes_util import random_scene
+    p = random_scene(str(tmp_path / "rnd"), seed, textures=textures, extras=extras)
+    hs = HostScene(p)
+    oldr, _, ost = oracle_render(hs, hs.camera(0))
+    out = run_reference(p, probe=False, exe=REF_DROPIN)
+    frac, mx = ldr_mismatch_fraction(out["png"], oldr, tol=1)
+    assert frac <= 1e-3, (frac, mx)
+    assert (out["closest"], out["shadow"]) == (int(ost.rays_closest), int(ost.rays_shadow))
+
+
 # ------------------------------------------------------------------ Monte Carlo against HIGH-SPP REFERENCE renders (VERDICT r1 #3)
 # tests/golden/mc_*.npz hold renders of the compiled reference itself (8 threads, 4096 spp; 16384 for the mesh scene) made by
 # tests/golden/make_golden_mc.py, one scene per sampled light type so that a biased estimator cannot hide behind the others.
