@@ -268,7 +268,9 @@ def random_scene(out_dir, seed, width=112, height=80, textures=False, extras=Fal
               % (u(0.1, 0.3), u(0.5, 3), u(0.6, 1.2), u(1.8, 2.4)))
     env_light = False
     if mc:
-        n_spp = spp if spp is not None else [1, 4, 4, 9][rng.randint(4)]
+        n_spp = [1, 4, 4, 9][rng.randint(4)]
+        if spp is not None:
+            n_spp = spp                              # (drawn first: the rest of the scene does not depend on the override)
         tm += "<NumSamples>%d</NumSamples>" % n_spp
         if rng.rand() < 0.3:
             tm += "<FocusDistance>%.4g</FocusDistance><ApertureSize>%.4g</ApertureSize>" % (u(6, 10), u(0.05, 0.3))
