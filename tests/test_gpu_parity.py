@@ -746,6 +746,23 @@ def test_device_resident_wave_loop_on_a_tiny_frame_is_all_tail(tmp_path):
     gs.close()
 
 
+@pytest.mark.parametrize("nee", [True, False])
+def test_tail_kernel_against_the_host_loop_over_many_seeds(tmp_path, nee):
+    """k_tail's warps are synchronised by named barriers only (path warps / one shadow warp per rotating buffer: buffer full, child
+    hits read, buffer drained).  A lost or duplicated ray, a shadow ray traced against a recycled buffer or a deferred mesh-light
+    entry that read an overwritten hit record would change the ray counts or the image: 24 seeds of an all-tail frame, each
+    against the host-synchronised loop, and the two frames of a seed rendered back to back must agree too."""
+    p = scenegen.gen_config4(str(tmp_path / "c4t"), width=72, height=44, spp=4, depth=2, nee=nee)
+    hs = HostScene(p)
+    cam = hs.camera(0)
+    gs = GpuScene(hs)
+    for seed in range(24):
+        a = gs.render(cam, seed=100 + seed)
+        _assert_same_estimate(a, gs.render(cam, seed=100 + seed, flags=capi.DT_FLAG_HOST_WAVE_LOOP), "seed %d vs host loop" % seed)
+        _assert_same_estimate(a, gs.render(cam, seed=100 + seed), "seed %d twice" % seed)
+    gs.close()
+
+
 def test_multi_batch_whitted_frame_through_the_device_loop(tmp_path):
     """Bounded-depth frame of several batches (multi-sample camera, small waves): device loop == host loop == one batch."""
     hs, _ = golden_scene("spheres_mirror")
