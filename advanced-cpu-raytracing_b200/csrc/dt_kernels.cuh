@@ -154,6 +154,10 @@ __device__ __forceinline__ void dt_generate_one(const DtCamDev& cam, const DtWav
         float psi1 = rng01(rng), psi2 = rng01(rng);
         float sx = (col + psi1) / nCols;
         float sy = (row + psi2) / nRows;
+        // A non-square sample count: the reference fills nRows^2 entries of `samples` but iterates samplesPerPixel of them
+        // (main.cpp:47,63-81); the rest keep the zeros the vector was created with -- rays through the pixel with the Gaussian weight
+        // of its corner.  DT_FLAG_JITTER_AA gives them a stratum instead.
+        if (!cam.jitter_aa && s >= nRows * nCols) { sx = 0.0f; sy = 0.0f; }
         if (cam.jitter_aa) {
             // opt-in (DT_FLAG_JITTER_AA): the sample position keeps its sub-pixel jitter.  The reference means to do
             // this but RenderPixel(int,int,...) truncates it away (main.cpp:83), so parity mode leaves it off.

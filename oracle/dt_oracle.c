@@ -1149,8 +1149,8 @@ static void* render_rows(void* arg) {
     float sigma = 1.0f / 6.0f;                                  /* gaussian.h:3-21 */
     float sigmaSqr = sigma * sigma;
     float c1 = (float)(1.0f / (2.0f * M_PI * sigmaSqr));
-    float* sx = (float*)malloc(sizeof(float) * (size_t)(spp > 0 ? spp : 1));
-    float* sy = (float*)malloc(sizeof(float) * (size_t)(spp > 0 ? spp : 1));
+    float* sx = (float*)calloc((size_t)(spp > 0 ? spp : 1), sizeof(float));
+    float* sy = (float*)calloc((size_t)(spp > 0 ? spp : 1), sizeof(float));
     for (int y = job->y0; y < job->y1; y++) {
         for (int x = 0; x < width; x++) {
             if (!c.ref) c.rng = mix64(job->seed ^ mix64((uint64_t)(x + (uint64_t)y * (uint64_t)width) + 0x51ED270B7F4A7C15ull));
@@ -1164,7 +1164,10 @@ static void* render_rows(void* arg) {
                     sy[i] = (row + psi2) / nRows;
                     i++;
                 }
-                int ns = i;      /* the reference iterates samplesPerPixel entries; non-square counts read stale samples */
+                /* the reference iterates samplesPerPixel entries (main.cpp:81); with a non-square count the entries past nRows^2 are
+                   never written: they keep the zeros `std::vector<Vec2f> samples(samplesPerPixel)` was created with (main.cpp:47), i.e.
+                   extra rays through the pixel at sample position (0,0), Gaussian weight of the pixel corner */
+                int ns = spp;
                 float sumW = 0.0f;
                 for (i = 0; i < ns; i++) {
                     /* RenderPixel(int,int): the float sample position is truncated (main.cpp:83, raytracer.hpp:19) */

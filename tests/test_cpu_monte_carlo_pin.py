@@ -139,6 +139,21 @@ def test_random_monte_carlo_scenes_replay_bit_exact_vs_the_live_reference(seed, 
     assert np.array_equal(hdr.view(np.uint32), ref["hdr"].view(np.uint32))
 
 
+@needs_ref
+@pytest.mark.parametrize("seed,spp", [(0, 2), (1, 3), (2, 5), (3, 6), (4, 7), (5, 8), (7, 2), (8, 3), (9, 5), (10, 6), (11, 7), (12, 8)])
+def test_non_square_sample_counts_replay_bit_exact_vs_the_live_reference(seed, spp, tmp_path):
+    """NumSamples that is not a perfect square: the reference draws nRows^2 stratified positions but renders samplesPerPixel
+    entries of its `samples` vector; the entries past nRows^2 keep the zeros the vector was created with (main.cpp:47,63-81), so
+    every pixel gets extra rays at sample position (0,0) with the Gaussian weight of the pixel corner."""
+    from scenes_util import random_scene
+    p = random_scene(str(tmp_path / "rnd"), seed, width=40, height=28, textures=(seed % 3 == 1), extras=(seed % 2 == 1), mc=True, spp=spp)
+    hs = HostScene(p)
+    ref = run_reference(p, probe=True, threads=1, timeout=300)
+    _, hdr, st = oracle_render_reference_rng(hs, hs.camera(0))
+    assert (int(st.rays_closest), int(st.rays_shadow)) == (ref["closest"], ref["shadow"])
+    assert np.array_equal(hdr.view(np.uint32), ref["hdr"].view(np.uint32))
+
+
 @pytest.mark.parametrize("name,psnr_min", [("mc_all", 31.0), ("mc_mesh", 34.0), ("mc_env", 29.0)])
 def test_pixel_keyed_oracle_is_the_same_estimator_as_the_high_spp_reference(name, psnr_min, tmp_path):
     """dto_render's per-pixel SplitMix64 streams (the mode the GPU tests compare with) against the 4096-spp reference render of

@@ -975,6 +975,36 @@ def test_random_deterministic_scenes_parity(tmp_path, seed, textures, extras):
     assert frac <= 1e-3, (frac, mx)
 
 
+@pytest.mark.parametrize("seed,spp", [(0, 2), (1, 3), (2, 5), (3, 8), (4, 4)])
+def test_multi_sample_deterministic_scenes_and_non_square_counts(tmp_path, seed, spp):
+    """Deterministic random scenes with <NumSamples>: every sample of a pixel goes through the pixel centre (RenderPixel(int,int)
+    truncates the jitter, main.cpp:83), so the frame is the one-sample frame and the ray tree is spp times as large -- for a
+    non-square count too: the reference renders samplesPerPixel entries although it fills only nRows^2 (the rest stay (0,0)), and
+    so do the oracle and the GPU path."""
+    from scenes_util import random_scene
+    p1 = random_scene(str(tmp_path / "rnd"), seed, textures=seed % 2 == 1, extras=seed % 4 >= 2)
+    xml = open(p1).read()
+    assert "<ImageName>" in xml
+    p = str(tmp_path / "rnd" / "multi.xml")
+    open(p, "w").write(xml.replace("<ImageName>", "<NumSamples>%d</NumSamples><ImageName>" % spp))
+    hs1, hs = HostScene(p1), HostScene(p)
+    cam = hs.camera(0)
+    assert cam.samples_per_pixel == spp
+    gs = GpuScene(hs)
+    ldr, hdr, st = gs.render(cam)
+    gs.close()
+    oldr, _, ost = oracle_render(hs, cam)
+    o1, _, ost1 = oracle_render(hs1, hs1.camera(0))
+    assert (int(st.rays_closest), int(st.rays_shadow)) == (int(ost.rays_closest), int(ost.rays_shadow))
+    if not cam.has_tonemapper:
+        # (a float sample position can round up into the next pixel, main.cpp:83: a handful of rays at most)
+        assert abs(int(ost.rays_closest) - spp * int(ost1.rays_closest)) <= 64
+    frac, mx = ldr_mismatch_fraction(ldr, oldr, 1)
+    assert frac <= 1e-3, (frac, mx)
+    frac, mx = ldr_mismatch_fraction(ldr, o1, 1)
+    assert frac <= 2e-3, ("vs the one-sample frame", frac, mx)
+
+
 @pytest.mark.timeout(180)
 @pytest.mark.parametrize("seed", [6, 13, 23, 25, 34, 43, 0, 5, 9, 21])
 def test_random_monte_carlo_scenes_terminate(tmp_path, seed):
