@@ -194,6 +194,31 @@ def test_motion_blurred_instance_origin_leak_is_the_only_difference(tmp_path):
     assert abs(m_o - m_r) / m_r < 0.05, (m_o, m_r)                                  # ... and moves the image mean by a few per cent at most
 
 
+@needs_ref
+@pytest.mark.parametrize("variant", ["comments", "single_quotes", "sci", "crlf", "tabs"])
+def test_xml_formatting_variants_parse_like_the_reference(tmp_path, variant):
+    """The same random scene written differently -- XML comments, single-quoted attributes, 5e-1 for 0.5, CRLF line ends, tabs between
+    numbers -- read by this repository's parser (host/dth_scene.cpp) and by the reference's tinyxml2 + stringstream code: identical
+    radiance bits.  (An <?xml ?> declaration or a re-indented file crash the reference's parser; not tested.)"""
+    import re
+    from scenes_util import random_scene
+    fn = {"comments": lambda x: x.replace("<Lights>", "<!-- the lights -->\n<Lights>").replace("</Materials>", "<!-- end\n of materials --></Materials>").replace("<Objects>", "<Objects><!-- objects -->"),
+          "single_quotes": lambda x: re.sub(r'(\w+)="([^"]*)"', r"\1='\2'", x),
+          "sci": lambda x: re.sub(r"(?<![\w.])0\.(\d)(?![\d.])", r"\1e-1", x),
+          "crlf": lambda x: x.replace("\n", "\r\n"),
+          "tabs": lambda x: re.sub(r"(?<=[0-9]) (?=[-0-9])", "\t", x)}[variant]
+    for seed in (1, 6):
+        p0 = random_scene(str(tmp_path / "rnd"), seed, textures=True, extras=True)
+        p = str(tmp_path / "rnd" / ("v%d.xml" % seed))
+        with open(p, "w", newline="") as f:
+            f.write(fn(open(p0).read()))
+        hs = HostScene(p)
+        _, hdr, st = oracle_render(hs, hs.camera(0))
+        ref = run_reference(p)
+        assert np.array_equal(hdr.view(np.uint32), ref["hdr"].view(np.uint32))
+        assert (int(st.rays_closest), int(st.rays_shadow)) == (ref["closest"], ref["shadow"])
+
+
 # ------------------------------------------------------------------ host mirror
 def test_bvh2_invariants():
     hs, _ = golden_scene("scienceTree")
