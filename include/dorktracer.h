@@ -213,9 +213,13 @@ typedef struct dt_camera_desc {         /* src/camera.hpp:12-50, rendererParams.
     float left, right_, bottom, top;    /* m_left, m_right, m_bottom, m_top                            */
     float near_dist;
     int32_t width, height;
-    int32_t samples_per_pixel;
+    int32_t samples_per_pixel;          /* not a perfect square: the samples past floor(sqrt(n))^2 go through sample position (0,0)
+                                           like the reference's never-written `samples` entries (main.cpp:47,63-81)                  */
     float focus_distance, aperture_size;
     int32_t path_tracing, importance_sampling, next_event_estimation, russian_roulette;
+                                        /* russian_roulette: a path the roulette can never end (NaN or >= 1 throughput in closed
+                                           geometry; the reference recurses until its stack overflows) is cut 32768 bounces below
+                                           depth 0                                                                                  */
     int32_t has_tonemapper;
     float tm_key, tm_burn, tm_saturation, tm_gamma;
 } dt_camera_desc;
