@@ -161,7 +161,8 @@ def run_reference(xml_path, probe=True, threads=None, cwd=None, timeout=3600, wi
     m = re.search(r"DT_RAYS closest=(\d+) shadow=(\d+)", out)
     if m:
         res["closest"] = int(m.group(1)); res["shadow"] = int(m.group(2))
-    pngs = [f for f in set(os.listdir(tmp)) - before if f.endswith(".png")]
+    pngs = sorted(f for f in set(os.listdir(tmp)) - before if f.endswith(".png"))
+    res["pngs"] = {f: np.array(Image.open(os.path.join(tmp, f)).convert("RGB")) for f in pngs}       # every camera's image, by name
     if pngs:
         res["png"] = np.array(Image.open(os.path.join(tmp, pngs[0])).convert("RGB"))
         H, W = res["png"].shape[:2]

@@ -219,6 +219,39 @@ def test_xml_formatting_variants_parse_like_the_reference(tmp_path, variant):
         assert (int(st.rays_closest), int(st.rays_shadow)) == (ref["closest"], ref["shadow"])
 
 
+@needs_ref
+@pytest.mark.parametrize("seed", [0, 1, 5, 8, 9, 11])
+def test_multi_camera_random_scenes_every_image_matches_the_reference(tmp_path, seed):
+    """Three cameras per scene: the original, one at another position WITHOUT the optional elements of the first (the reference's
+    `camera` object persists across the loop, parser.cpp:1498-1636, so a tonemapper / lookAt set-up carries over; seed 9), and
+    one with another resolution.  Every PNG the reference writes equals the oracle's frame for that camera."""
+    import re
+    from scenes_util import random_scene
+    rng = np.random.RandomState(5 + seed)
+    x = open(random_scene(str(tmp_path / "rnd"), seed, textures=seed % 2 == 1, extras=True)).read()
+    cam = re.search(r"<Camera .*?</Camera>", x, re.S).group(0)
+    cams, names = [cam], ["rnd%d.png" % seed]
+    for k in (2, 3):
+        c = cam.replace('id="1"', 'id="%d"' % k).replace("rnd%d.png" % seed, "rnd%d_%d.png" % (seed, k))
+        c = re.sub(r"<Position>.*?</Position>", "<Position>%.3f %.3f %.3f</Position>" % (rng.uniform(-4, 4), rng.uniform(1, 5), rng.uniform(5, 9)), c)
+        if k == 2:
+            c = re.sub(r"<Tonemap>.*?</Tonemap>", "", c)
+        if k == 3:
+            c = c.replace("<ImageResolution>112 80</ImageResolution>", "<ImageResolution>80 56</ImageResolution>")
+        cams.append(c)
+        names.append("rnd%d_%d.png" % (seed, k))
+    p = str(tmp_path / "rnd" / "multi.xml")
+    with open(p, "w") as f:
+        f.write(x.replace(cam, "\n".join(cams)))
+    ref = run_reference(p, probe=False)
+    hs = HostScene(p)
+    assert hs.num_cameras == 3 and [hs.image_name(k) for k in range(3)] == names
+    for ci, name in enumerate(names):
+        ldr, _, _ = oracle_render(hs, hs.camera(ci))
+        assert name in ref["pngs"] and ref["pngs"][name].shape == ldr.shape, (name, sorted(ref["pngs"]))
+        assert np.array_equal(ref["pngs"][name], ldr), name
+
+
 # ------------------------------------------------------------------ host mirror
 def test_bvh2_invariants():
     hs, _ = golden_scene("scienceTree")
