@@ -252,6 +252,48 @@ def test_multi_camera_random_scenes_every_image_matches_the_reference(tmp_path, 
         assert np.array_equal(ref["pngs"][name], ldr), name
 
 
+@needs_ref
+@pytest.mark.parametrize("seed", range(16))
+def test_hostile_edits_of_random_scenes_oracle_bit_exact_vs_reference(tmp_path, seed):
+    """One hostile edit per scene (kind = seed mod 8): a degenerate triangle, a zero-radius sphere, a singular scaling, objects 1e5
+    away, a negative radius, a light at a sphere's centre, the camera at a sphere's centre, up parallel to the image plane's normal.
+    NaN / inf normals, matrices and distances must propagate exactly as in the compiled reference."""
+    import re
+    from scenes_util import random_scene
+    rng = np.random.RandomState(11 + seed)
+    x = open(random_scene(str(tmp_path / "rnd"), seed, textures=seed % 2 == 1, extras=seed % 4 >= 2)).read()
+    kind = seed % 8
+    v = re.search(r"<VertexData>(.*?)</VertexData>", x, re.S).group(1).strip().split("\n")
+    c = re.search(r"<Center>(\d+)</Center>", x).group(1)
+    if kind == 0:
+        m = list(re.finditer(r"(\d+) (\d+) (\d+)\n", x))
+        mm = m[rng.randint(len(m))]
+        x = x[:mm.start()] + "%s %s %s\n" % (mm.group(1), mm.group(1), mm.group(3)) + x[mm.end():]
+    elif kind == 1:
+        x = re.sub(r"<Radius>[^<]*</Radius>", "<Radius>0</Radius>", x, count=1)
+    elif kind == 2:
+        x = re.sub(r'<Scaling id="1">[^<]*</Scaling>', '<Scaling id="1">1 0 1</Scaling>', x)
+    elif kind == 3:
+        x = re.sub(r'<Translation id="1">[^<]*</Translation>', '<Translation id="1">100000 0 0</Translation>', x)
+    elif kind == 4:
+        x = re.sub(r"<Radius>([^<]*)</Radius>", r"<Radius>-\1</Radius>", x, count=1)
+    elif kind == 5:
+        x = re.sub(r'(<PointLight id="1"><Position>)[^<]*', r"\g<1>" + v[int(c) - 1], x)
+    elif kind == 6:
+        x = re.sub(r"(<Camera[^>]*><Position>)[^<]*", r"\g<1>" + v[int(c) - 1], x)
+    else:
+        x = re.sub(r"<Up>[^<]*</Up>", "<Up>0 0 -1</Up>", x)
+    p = str(tmp_path / "rnd" / "hostile.xml")
+    with open(p, "w") as f:
+        f.write(x)
+    hs = HostScene(p)
+    ldr, hdr, st = oracle_render(hs, hs.camera(0))
+    ref = run_reference(p)
+    assert np.array_equal(ldr, ref["png"])
+    assert np.array_equal(hdr.view(np.uint32), ref["hdr"].view(np.uint32))
+    assert (int(st.rays_closest), int(st.rays_shadow)) == (ref["closest"], ref["shadow"])
+
+
 # ------------------------------------------------------------------ host mirror
 def test_bvh2_invariants():
     hs, _ = golden_scene("scienceTree")
