@@ -1005,6 +1005,29 @@ def test_multi_sample_deterministic_scenes_and_non_square_counts(tmp_path, seed,
     assert frac <= 2e-3, ("vs the one-sample frame", frac, mx)
 
 
+@pytest.mark.parametrize("seed", [5, 10, 14, 15, 24])
+def test_random_monte_carlo_scenes_agree_with_the_oracle_in_the_mean(tmp_path, seed):
+    """The random stochastic scenes whose frames are (almost) free of the reference's own NaN pixels, at 64 spp: the GPU estimator
+    against the oracle's (pixel-keyed streams; the same code the reference-RNG replay pins bit for bit against the compiled
+    reference on these seeds).  Two oracle frames with different seeds differ by 0.0-0.25 % in the plain mean and < 0.05 % in the
+    mean clipped at 255; bound here: 2 % / 1 %, finite-pixel fraction within 2 points."""
+    from scenes_util import random_scene
+    p = random_scene(str(tmp_path / "rnd"), seed, width=96, height=64, textures=(seed % 3 == 1), extras=(seed % 2 == 1), mc=True, spp=64)
+    hs = HostScene(p)
+    cam = hs.camera(0)
+    gs = GpuScene(hs)
+    _, hdr, _ = gs.render(cam, seed=11)
+    gs.close()
+    _, ohdr, _ = oracle_render(hs, cam, seed=1)
+    fin_g, fin_o = np.isfinite(hdr).all(axis=2), np.isfinite(ohdr).all(axis=2)
+    assert abs(float(fin_g.mean()) - float(fin_o.mean())) <= 0.02, (float(fin_g.mean()), float(fin_o.mean()))
+    ok = fin_g & fin_o
+    a, b = hdr[ok].astype(np.float64), ohdr[ok].astype(np.float64)
+    assert abs(a.mean() - b.mean()) / b.mean() <= 0.02, (a.mean(), b.mean())
+    ca, cb = np.minimum(a, 255.0).mean(), np.minimum(b, 255.0).mean()
+    assert abs(ca - cb) / cb <= 0.01, (ca, cb)
+
+
 @pytest.mark.timeout(180)
 @pytest.mark.parametrize("seed", [6, 13, 23, 25, 34, 43, 0, 5, 9, 21])
 def test_random_monte_carlo_scenes_terminate(tmp_path, seed):
