@@ -66,14 +66,19 @@ def oracle_render(host_scene, cam, seed=1234, threads=None, want_hdr=True, flags
     return ldr, hdr, stats
 
 
-def oracle_render_reference_rng(host_scene, cam):
+DTO_FLAG_ORIGIN_LEAK = 1 << 30      # oracle only: reproduce the origin leak of motion-blurred instances (instancedMesh.cpp:22-29)
+
+
+def oracle_render_reference_rng(host_scene, cam, flags=0):
     """The oracle replaying the reference's own generators on one thread (bit-comparable with DT_THREADS=1 raytracer_probe)."""
     lib = load_dtoracle()
+    lib.dto_set_render_flags(flags)
     W, H = cam.width, cam.height
     ldr = np.zeros((H, W, 3), np.uint8)
     hdr = np.zeros((H, W, 3), np.float32)
     stats = capi.dt_stats()
     rc = lib.dto_render_reference_rng(host_scene.desc_ptr, C.byref(cam), ldr.ctypes.data_as(C.c_void_p), hdr.ctypes.data_as(C.c_void_p), C.byref(stats))
+    lib.dto_set_render_flags(0)
     if rc != 0:
         raise RuntimeError("dto_render_reference_rng failed %d" % rc)
     return ldr, hdr, stats

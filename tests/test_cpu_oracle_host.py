@@ -178,20 +178,42 @@ def test_env_map_on_miss_under_whitted_oracle_bit_exact_vs_reference(tmp_path):
 
 @needs_ref
 def test_motion_blurred_instance_origin_leak_is_the_only_difference(tmp_path):
-    """Documented deviation, bounded: InstancedMesh::Intersect leaves the ray origin shifted by motionBlurVector * time when the
-    ray misses the instance's box (instancedMesh.cpp:22-27), which displaces every shape scanned AFTER it.  Neither the oracle nor
-    the GPU path reproduces the leak.  The same scene with a static instance is bit-exact (test above); with the moving
-    instance the reference differs -- and only on pixels whose rays can reach the later shapes (the three spheres)."""
-    from oracle_util import oracle_render_reference_rng
-    from scenes_util import env_whitted_scene
+    """Documented deviation, now pinned exactly: InstancedMesh::Intersect leaves the ray origin shifted by motionBlurVector * time
+    when the ray misses the instance's box (instancedMesh.cpp:22-29; the restore sits inside the `if`), which displaces every
+    shape scanned AFTER it and the shading of the ray.  The product path does not reproduce the leak -- and it is the ONLY
+    difference: with DTO_FLAG_ORIGIN_LEAK the oracle leaves the origin shifted too and reproduces the reference bit for bit, on
+    the hand-made scene and on random stochastic scenes whose MeshInstance is made to move; without the flag the frames differ,
+    by a few per cent of the image mean at most."""
+    import re
+    from oracle_util import DTO_FLAG_ORIGIN_LEAK, oracle_render_reference_rng
+    from scenes_util import env_whitted_scene, random_scene
     p = env_whitted_scene(str(tmp_path / "b"), blur_instance=True)
     hs = HostScene(p)
-    _, hdr, _ = oracle_render_reference_rng(hs, hs.camera(0))
     ref = run_reference(p, probe=True, threads=1)
+    _, hdr, _ = oracle_render_reference_rng(hs, hs.camera(0))
     differs = (hdr.view(np.uint32) != ref["hdr"].view(np.uint32)).any(axis=2)
     assert differs.any()                                                            # the leak is real ...
     m_o, m_r = float(hdr.mean()), float(ref["hdr"].mean())
-    assert abs(m_o - m_r) / m_r < 0.05, (m_o, m_r)                                  # ... and moves the image mean by a few per cent at most
+    assert abs(m_o - m_r) / m_r < 0.05, (m_o, m_r)                                  # ... moves the image mean by a few per cent at most ...
+    _, hdr, st = oracle_render_reference_rng(hs, hs.camera(0), flags=DTO_FLAG_ORIGIN_LEAK)
+    assert np.array_equal(hdr.view(np.uint32), ref["hdr"].view(np.uint32))          # ... and is the only difference
+    assert (int(st.rays_closest), int(st.rays_shadow)) == (ref["closest"], ref["shadow"])
+    applied = 0
+    for seed in (1, 3, 4, 5, 7, 8, 10, 11):
+        x0 = open(random_scene(str(tmp_path / "rnd"), seed, width=48, height=32, textures=(seed % 3 == 1), extras=(seed % 2 == 1), mc=True)).read()
+        x = re.sub(r'(<MeshInstance id="\d+"[^>]*>)', r"\1<MotionBlur>-0.2 0.3 0.1</MotionBlur>", x0, count=1)
+        if x == x0:
+            continue
+        applied += 1
+        p = str(tmp_path / "rnd" / ("i%d.xml" % seed))
+        with open(p, "w") as f:
+            f.write(x)
+        hs = HostScene(p)
+        ref = run_reference(p, probe=True, threads=1, timeout=300)
+        _, hdr, st = oracle_render_reference_rng(hs, hs.camera(0), flags=DTO_FLAG_ORIGIN_LEAK)
+        assert np.array_equal(hdr.view(np.uint32), ref["hdr"].view(np.uint32)), seed
+        assert (int(st.rays_closest), int(st.rays_shadow)) == (ref["closest"], ref["shadow"]), seed
+    assert applied >= 4
 
 
 @needs_ref
